@@ -1,0 +1,110 @@
+// Library-wide state, element-wise utilities, fused Adam, exact negative-sampler replay.
+#include <math.h>
+
+#include "idg_common.cuh"
+
+namespace idg {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+__global__ void axpby_kernel(float* __restrict__ out, float a, const float* __restrict__ x, float b,
+                             const float* __restrict__ y, int64_t n4, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 xv = reinterpret_cast<const float4*>(x)[i], yv = reinterpret_cast<const float4*>(y)[i];
+        reinterpret_cast<float4*>(out)[i] = make_float4(a * xv.x + b * yv.x, a * xv.y + b * yv.y, a * xv.z + b * yv.z, a * xv.w + b * yv.w);
+    }
+    if (i == 0) for (int64_t k = n4 * 4; k < n; ++k) out[k] = a * x[k] + b * y[k];
+}
+
+__global__ void zero_rows_kernel(float* __restrict__ buf, const int64_t* __restrict__ idx, int n, int d4) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int r = (int)(t / d4), c = (int)(t % d4);
+    if (r < n) reinterpret_cast<float4*>(buf)[(size_t)idx[r] * d4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// torch.optim.Adam single-tensor formula (torch/optim/adam.py _single_tensor_adam, default flags):
+//   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
+//   denom = sqrt(v)/sqrt(bc2) + eps;  p.addcdiv_(m, denom, value=-(lr/bc1))
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n4, int64_t n, float b1, float b2, float eps, float step_size, float bc2_sqrt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        mm = mm + (gg - mm) * (1.f - b1);
+        vv = vv * b2 + (1.f - b2) * gg * gg;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pp = pp - step_size * (mm / denom);
+    };
+    if (i < n4) {
+        float4 pv = reinterpret_cast<float4*>(p)[i], gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+        float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        upd(pv.x, gv.x, mv.x, vv.x); upd(pv.y, gv.y, mv.y, vv.y); upd(pv.z, gv.z, mv.z, vv.z); upd(pv.w, gv.w, mv.w, vv.w);
+        reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (i == 0) for (int64_t k = n4 * 4; k < n; ++k) upd(p[k], g[k], m[k], v[k]);
+}
+}  // namespace idg
+
+using namespace idg;
+
+extern "C" int idg_version(void) { return 100; }
+extern "C" const char* idg_last_error(void) { return g_err; }
+extern "C" int64_t idg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int idg_axpby(float* d_out, float a, const float* d_x, float b, const float* d_y, int64_t n, void* stream) {
+    if (!d_out || !d_x || !d_y || n < 0) return fail(-1, "idg_axpby: bad argument%s");
+    if (n == 0) return 0;
+    if (((uintptr_t)d_out | (uintptr_t)d_x | (uintptr_t)d_y) & 15) return fail(-1, "idg_axpby: pointers must be 16-byte aligned%s");
+    const int64_t n4 = n / 4, th = (n4 > 0 ? n4 : 1);
+    axpby_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, a, d_x, b, d_y, n4, n);
+    IDG_LAUNCH_CHECK("axpby_kernel");
+    return 0;
+}
+
+extern "C" int idg_zero_rows(float* d_buf, const int64_t* d_idx, int32_t n, int32_t d, void* stream) {
+    if (!d_buf || !d_idx || n < 0 || d <= 0 || (d & 3)) return fail(-1, "idg_zero_rows: bad argument%s");
+    if (n == 0) return 0;
+    const int64_t th = (int64_t)n * (d / 4);
+    zero_rows_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_buf, d_idx, n, d / 4);
+    IDG_LAUNCH_CHECK("zero_rows_kernel");
+    return 0;
+}
+
+extern "C" int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int32_t step, void* stream) {
+    if (!d_p || !d_g || !d_m || !d_v || n < 0 || step < 1) return fail(-1, "idg_adam_step: bad argument%s");
+    if (n == 0) return 0;
+    if (((uintptr_t)d_p | (uintptr_t)d_g | (uintptr_t)d_m | (uintptr_t)d_v) & 15) return fail(-1, "idg_adam_step: pointers must be 16-byte aligned%s");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+    const int64_t n4 = n / 4, th = (n4 > 0 ? n4 : 1);
+    adam_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n4, n, beta1, beta2, eps, step_size, bc2_sqrt);
+    IDG_LAUNCH_CHECK("adam_kernel");
+    return 0;
+}
+
+// data_loader.py:108-127 replayed against a bulk candidate stream.  Host code.
+extern "C" int idg_neg_sample_replay(const int64_t* h_train_user, int64_t E, const int32_t* h_pos_indptr,
+                                     const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand, int64_t* h_neg,
+                                     int64_t* h_consumed) {
+    if (!h_train_user || !h_pos_indptr || !h_pos_indices || !h_cand || !h_neg || !h_consumed || E < 0)
+        return fail(-1, "idg_neg_sample_replay: bad argument%s");
+    int64_t j = 0;
+    for (int64_t e = 0; e < E; ++e) {
+        const int64_t u = h_train_user[e];
+        const int32_t* lo = h_pos_indices + h_pos_indptr[u];
+        const int32_t* hi = h_pos_indices + h_pos_indptr[u + 1];
+        for (;;) {
+            if (j >= n_cand) { *h_consumed = j; return fail(-2, "idg_neg_sample_replay: candidate stream exhausted%s"); }
+            const int64_t c = h_cand[j++];
+            // `neg in all_positive[user]` (data_loader.py:121): binary search in the sorted positives
+            const int32_t* a = lo; const int32_t* b = hi;
+            while (a < b) { const int32_t* m = a + (b - a) / 2; if (*m < c) a = m + 1; else b = m; }
+            if (a < hi && *a == c) continue;
+            h_neg[e] = c;
+            break;
+        }
+    }
+    *h_consumed = j;
+    return 0;
+}

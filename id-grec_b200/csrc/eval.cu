@@ -1,0 +1,414 @@
+// Full-ranking evaluation: score = <Fu[user], Fi[item]>, train positives removed, top-K by
+// (score desc, item id asc), recall/precision/ndcg sums (sm_100a).
+//
+// Replaces models/LightGCN.py:74-80 (get_rating_for_test: gather + matmul + sigmoid into a
+// [1024, I] matrix), utility_train/batch_test.py:54-68 (Python mask lists, rating[eu,ei] = -1,
+// torch.topk) and utility_function/metrics.py:4-58.  sigmoid is monotone, so ranking the raw
+// dot products ranks the ratings; the [b, I] matrix is never written.
+//
+// Exactness contract (tier T0): the returned ids equal the order defined
+// by the fp64 sequential dot product of the fp32 embeddings, ties by ascending id.
+//   pass A  candidate scores s~ with |s~ - s| <= delta_u (fp32 FMA: delta_u = g64*|u|*max|i|).
+//           Per user, every unmasked item with s~ >= (running K-th largest s~) - 2*delta_u is
+//           kept; that set provably contains the exact top-K including all boundary ties.
+//   pass B  survivors are rescored exactly (fp64, k = 0..d-1) and ordered (score desc, id asc).
+//   pass C  users whose candidate list overflowed or came up short are recomputed exhaustively.
+#include <math.h>
+
+#include "idg_common.cuh"
+
+namespace idg {
+
+constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
+constexpr int kFallbackCtas = 32;
+
+struct EvalWs {
+    float* max_norm;   // [1] max_i |Fi[i]|_2 (as float bits, atomicMax on non-negative floats)
+    int* flag_cnt;     // [1]
+    int* flag_list;    // [nu] positions (into d_users) that need the exhaustive pass
+    int* cand_cnt;     // [nu]
+    int* cand_ids;     // [nu, kCandOut]
+    double* scratch;   // [kFallbackCtas, I]
+};
+
+__host__ __device__ inline size_t ev_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+__host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
+    char* p = (char*)ws;
+    EvalWs w;
+    w.max_norm = (float*)p; p += 256;
+    w.flag_cnt = (int*)p; p += 256;
+    w.flag_list = (int*)p; p += ev_align(sizeof(int) * (size_t)nu);
+    w.cand_cnt = (int*)p; p += ev_align(sizeof(int) * (size_t)nu);
+    w.cand_ids = (int*)p; p += ev_align(sizeof(int) * (size_t)nu * kCandOut);
+    w.scratch = (double*)p;
+    return w;
+}
+
+__global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, float* __restrict__ max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= I) return;
+    float ss = 0.f;
+    for (int k = lane; k < d; k += 32) { const float v = Fi[(size_t)i * d + k]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(sqrtf(ss)));
+}
+
+__device__ __forceinline__ bool masked(const int32_t* __restrict__ ind, int lo, int hi, int item) {
+    const int end = hi;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ind + mid) < item) lo = mid + 1; else hi = mid; }
+    return lo < end && __ldg(ind + lo) == item;
+}
+
+// Prune one user's smem candidate list (one warp): tau = (K-th largest) - 2*delta; keep >= tau.
+__device__ void prune_row(float* __restrict__ ls, int* __restrict__ li, int* __restrict__ cnt_p, float* __restrict__ thr_p,
+                          float delta2, int K, int lane) {
+    const int m = *cnt_p;
+    if (m < K) return;
+    float s[4]; int id[4]; int rank[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int idx = lane + 32 * q;
+        s[q] = (idx < m) ? ls[idx] : -INFINITY; id[q] = (idx < m) ? li[idx] : 0; rank[q] = 0;
+    }
+    for (int j = 0; j < m; ++j) {
+        const float sj = ls[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && j < lane + 32 * q);
+    }
+    float vk = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = s[q];
+#pragma unroll
+    for (int mm = 16; mm >= 1; mm >>= 1) vk = fmaxf(vk, __shfl_xor_sync(0xffffffffu, vk, mm));
+    const float tau = vk - delta2;
+    __syncwarp();
+    int kept = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool keep = (lane + 32 * q < m) && (s[q] >= tau);
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) { const int p = kept + __popc(b & ((1u << lane) - 1)); ls[p] = s[q]; li[p] = id[q]; }
+        kept += __popc(b);
+    }
+    __syncwarp();
+    if (lane == 0) { *cnt_p = kept; *thr_p = (kept > kPruneAt) ? INFINITY : tau; }
+}
+
+// Pass A.  grid = ceil(nu / 64); 256 threads; thread (ty,tx) owns users ty*4.. x items tx*4..
+template <int D>
+__global__ void __launch_bounds__(256, 2) eval_candidates_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
+                                                                 const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
+                                                                 const int64_t* __restrict__ users, int nu, int K, EvalWs w) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Us = reinterpret_cast<float*>(smem_raw);   // [D][64]
+    float* Is = Us + D * kTU;                          // [D][64]
+    float* ls = Is + D * kTI;                          // [64][kCap]
+    int* li = reinterpret_cast<int*>(ls + kTU * kCap); // [64][kCap]
+    float* thr = reinterpret_cast<float*>(li + kTU * kCap);  // [64]
+    float* del2 = thr + kTU;                           // [64] 2*delta_u
+    int* cnt = reinterpret_cast<int*>(del2 + kTU);     // [64]
+    int* urow = cnt + kTU;                             // [64] user id or -1
+    __shared__ int s_overflow[kTU];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u0 = blockIdx.x * kTU;
+    if (tid < kTU) {
+        const int p = u0 + tid;
+        urow[tid] = (p < nu) ? (int)users[p] : -1;
+        cnt[tid] = 0; s_overflow[tid] = 0;
+        thr[tid] = (p < nu) ? -INFINITY : INFINITY;
+    }
+    __syncthreads();
+    // user tile, transposed: lane <-> user row (conflict-free smem stores)
+    for (int r = warp; r < 2 * (D / 4); r += 8) {
+        const int ul = (r & 1) * 32 + lane, c4 = r >> 1;
+        const int u = urow[ul];
+        float4 v = (u >= 0) ? ldg4(Fu + (size_t)u * D + c4 * 4) : f4zero();
+        Us[(c4 * 4 + 0) * kTU + ul] = v.x; Us[(c4 * 4 + 1) * kTU + ul] = v.y;
+        Us[(c4 * 4 + 2) * kTU + ul] = v.z; Us[(c4 * 4 + 3) * kTU + ul] = v.w;
+    }
+    __syncthreads();
+    if (tid < kTU) {
+        float ss = 0.f;
+        for (int k = 0; k < D; ++k) { const float v = Us[k * kTU + tid]; ss = fmaf(v, v, ss); }
+        // fp32 FMA dot of length D: |err| <= gamma_D * |u||i|, gamma_D ~ D*2^-24; 1.25x slack covers
+        // the rounding of the norms themselves and the (negligible) fp64 reference error.
+        del2[tid] = 2.f * 1.25f * (float)D * 5.9604645e-8f * sqrtf(ss) * (*w.max_norm) + 1e-30f;
+    }
+    const int ty = tid >> 4, tx = tid & 15;
+    int mlo[4], mhi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int u = urow[ty * 4 + a];
+        mlo[a] = (u >= 0) ? mptr[u] : 0; mhi[a] = (u >= 0) ? mptr[u + 1] : 0;
+    }
+
+    for (int i0 = 0; i0 < I; i0 += kTI) {
+        __syncthreads();  // previous tile fully consumed (and del2/thr visible on the first pass)
+        for (int r = warp; r < 2 * (D / 4); r += 8) {
+            const int il = (r & 1) * 32 + lane, c4 = r >> 1;
+            const int i = i0 + il;
+            float4 v = (i < I) ? ldg4(Fi + (size_t)i * D + c4 * 4) : f4zero();
+            Is[(c4 * 4 + 0) * kTI + il] = v.x; Is[(c4 * 4 + 1) * kTI + il] = v.y;
+            Is[(c4 * 4 + 2) * kTI + il] = v.z; Is[(c4 * 4 + 3) * kTI + il] = v.w;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < D; ++k) {
+            const float4 uu = *reinterpret_cast<const float4*>(Us + k * kTU + ty * 4);
+            const float4 ii = *reinterpret_cast<const float4*>(Is + k * kTI + tx * 4);
+            const float ua[4] = {uu.x, uu.y, uu.z, uu.w}, ib[4] = {ii.x, ii.y, ii.z, ii.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ua[a], ib[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int ul = ty * 4 + a;
+            const float t = thr[ul];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int item = i0 + tx * 4 + b;
+                if (acc[a][b] >= t && item < I) {
+                    if (!masked(mind, mlo[a], mhi[a], item)) {
+                        const int p = atomicAdd(&cnt[ul], 1);
+                        if (p < kCap) { ls[ul * kCap + p] = acc[a][b]; li[ul * kCap + p] = item; }
+                        else s_overflow[ul] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+            if (cnt[r] > kCap) { if (lane == 0) { cnt[r] = kCap; s_overflow[r] = 1; } __syncwarp(); }
+            if (cnt[r] > kPruneAt) prune_row(ls + r * kCap, li + r * kCap, &cnt[r], &thr[r], del2[r], K, lane);
+        }
+    }
+    __syncthreads();
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+        const int p = u0 + r;
+        if (p >= nu) continue;
+        prune_row(ls + r * kCap, li + r * kCap, &cnt[r], &thr[r], del2[r], K, lane);
+        __syncwarp();
+        const int m = cnt[r];
+        const bool bad = s_overflow[r] || m > kCandOut || m < K || !(thr[r] < INFINITY);
+        if (bad) {
+            if (lane == 0) { w.cand_cnt[p] = 0; w.flag_list[atomicAdd(w.flag_cnt, 1)] = p; }
+        } else {
+            if (lane == 0) w.cand_cnt[p] = m;
+            for (int j = lane; j < m; j += 32) w.cand_ids[(size_t)p * kCandOut + j] = li[r * kCap + j];
+        }
+    }
+}
+
+__device__ __forceinline__ double exact_dot(const float* __restrict__ a, const float* __restrict__ b, int d) {
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) acc = fma((double)a[k], (double)b[k], acc);  // products exact in fp64; order k = 0..d-1
+    return acc;
+}
+
+// Pass B: one warp per user; <= 64 candidates, exact rescore, rank by (score desc, id asc).
+__global__ void __launch_bounds__(256) eval_rescore_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int d,
+                                                           const int64_t* __restrict__ users, int nu, int K, EvalWs w,
+                                                           int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= nu) return;
+    const int m = w.cand_cnt[p];
+    if (m == 0) return;  // flagged
+    const float* urow = Fu + (size_t)users[p] * d;
+    double s[2]; int id[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int j = lane + 32 * q;
+        id[q] = (j < m) ? w.cand_ids[(size_t)p * kCandOut + j] : 0x7fffffff;
+        s[q] = (j < m) ? exact_dot(urow, Fi + (size_t)id[q] * d, d) : -INFINITY;
+    }
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int q2 = 0; q2 < 2; ++q2) {
+        for (int l = 0; l < 32; ++l) {
+            const double sj = __shfl_sync(0xffffffffu, s[q2], l);
+            const int idj = __shfl_sync(0xffffffffu, id[q2], l);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && idj < id[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (lane + 32 * q < m && rank[q] < K) {
+            out_ids[(size_t)p * K + rank[q]] = id[q];
+            if (out_scores) out_scores[(size_t)p * K + rank[q]] = (float)s[q];
+        }
+    }
+}
+
+// Pass C: exhaustive exact ranking for flagged users (rare: candidate overflow from massive ties,
+// or fewer than K unmasked items).  Masked items score -inf and stay eligible in id order, like
+// a stable sort of the reference's masked rating row.
+__global__ void __launch_bounds__(256) eval_exhaustive_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I, int d,
+                                                              const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
+                                                              const int64_t* __restrict__ users, int K, EvalWs w,
+                                                              int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
+    __shared__ double sb[8];
+    __shared__ int si[8];
+    __shared__ int s_best;
+    double* S = w.scratch + (size_t)blockIdx.x * I;
+    const int nflag = *w.flag_cnt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int f = blockIdx.x; f < nflag; f += gridDim.x) {
+        const int p = w.flag_list[f];
+        const int u = (int)users[p];
+        const float* urow = Fu + (size_t)u * d;
+        for (int i = tid; i < I; i += 256) S[i] = exact_dot(urow, Fi + (size_t)i * d, d);
+        __syncthreads();
+        for (int j = mptr[u] + tid; j < mptr[u + 1]; j += 256) S[mind[j]] = -INFINITY;
+        __syncthreads();
+        for (int r = 0; r < K; ++r) {
+            double bs = 0.0; int bi = -1;
+            for (int i = tid; i < I; i += 256) {
+                const double v = S[i];
+                if (v != v) continue;  // taken
+                if (bi < 0 || v > bs) { bs = v; bi = i; }  // ascending i: first hit wins ties
+            }
+#pragma unroll
+            for (int mm = 16; mm >= 1; mm >>= 1) {
+                const double os = __shfl_xor_sync(0xffffffffu, bs, mm);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, mm);
+                if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
+            }
+            if (lane == 0) { sb[warp] = bs; si[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                double b = sb[0]; int ii = si[0];
+                for (int q = 1; q < 8; ++q)
+                    if (si[q] >= 0 && (ii < 0 || sb[q] > b || (sb[q] == b && si[q] < ii))) { b = sb[q]; ii = si[q]; }
+                s_best = ii;
+                out_ids[(size_t)p * K + r] = (ii >= 0) ? ii : 0;
+                if (out_scores) out_scores[(size_t)p * K + r] = (ii >= 0) ? (float)b : -INFINITY;
+                if (ii >= 0) S[ii] = __longlong_as_double(0x7ff8000000000000ll);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// metrics.py:4-58 + batch_test.py:80-107: per-user recall/precision/ndcg terms, then an ordered sum.
+__global__ void __launch_bounds__(256) eval_metrics_kernel(const int64_t* __restrict__ topk, const int64_t* __restrict__ users, int nu,
+                                                           int K, const int32_t* __restrict__ tptr, const int32_t* __restrict__ tind,
+                                                           int nk, int k0, int k1, int k2, int k3, int k4, int k5, int k6, int k7,
+                                                           double* __restrict__ per_user) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (p >= nu) return;
+    const int ks[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+    const int u = (int)users[p];
+    const int lo = tptr[u], hi = tptr[u + 1], nt = hi - lo;
+    // hit bits over the K positions (K <= 64): lane handles positions lane, lane+32
+    unsigned long long hits = 0;
+    for (int q = 0; q < 2; ++q) {
+        const int j = lane + 32 * q;
+        bool h = false;
+        if (j < K) {
+            const int item = (int)topk[(size_t)p * K + j];
+            int a = lo, b = hi;
+            while (a < b) { const int mid = (a + b) >> 1; if (tind[mid] < item) a = mid + 1; else b = mid; }
+            h = (a < hi && tind[a] == item);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, h);
+        hits |= (unsigned long long)bal << (32 * q);
+    }
+    if (lane == 0) {
+        for (int t = 0; t < nk; ++t) {
+            const int k = ks[t];
+            double nh = 0, dcg = 0, idcg = 0;
+            for (int j = 0; j < k; ++j) {
+                const double disc = 1.0 / log2((double)(j + 2));
+                if ((hits >> j) & 1ull) { nh += 1.0; dcg += disc; }
+                if (j < nt) idcg += disc;
+            }
+            if (idcg == 0.0) idcg = 1.0;
+            per_user[(size_t)p * 3 * nk + 3 * t + 0] = (nt > 0) ? nh / (double)nt : 0.0;  // recall term
+            per_user[(size_t)p * 3 * nk + 3 * t + 1] = nh / (double)k;                      // precision term
+            per_user[(size_t)p * 3 * nk + 3 * t + 2] = dcg / idcg;                          // ndcg term
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) ordered_sum_kernel(const double* __restrict__ per_user, int nu, int ncol, double* __restrict__ sums) {
+    __shared__ double sh[1024];
+    for (int c = 0; c < ncol; ++c) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < nu; i += 1024) a += per_user[(size_t)i * ncol + c];
+        sh[threadIdx.x] = a;
+        __syncthreads();
+        for (int s = 512; s >= 1; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+        if (threadIdx.x == 0) sums[c] = sh[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace idg
+
+using namespace idg;
+
+extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, int32_t K) {
+    if (nu <= 0 || I <= 0) return 0;
+    const size_t metrics = ev_align(sizeof(double) * (size_t)nu * 3 * 8);
+    const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
+                       ev_align(sizeof(double) * (size_t)kFallbackCtas * I);
+    return (int64_t)(sel > metrics ? sel : metrics);
+}
+
+extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d, const int32_t* d_mask_indptr,
+                             const int32_t* d_mask_indices, const int64_t* d_users, int32_t nu, int32_t K, int64_t* d_out_ids,
+                             float* d_out_scores, void* d_ws, void* stream_) {
+    if (!d_Fu || !d_Fi || !d_mask_indptr || !d_users || !d_out_ids || !d_ws) return fail(-1, "idg_eval_topk: null argument%s");
+    if (nu <= 0 || I <= 0 || U <= 0) return fail(-1, "idg_eval_topk: bad sizes%s");
+    if (K < 1 || K > 48 || K > I) return fail(-1, "idg_eval_topk: K must be in [1, min(48, I)] (%s%lld)", "", K);
+    if (d != 64 && d != 256) return fail(-1, "idg_eval_topk: d must be 64 or 256 (%s%lld)", "", d);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EvalWs w = eval_carve(d_ws, nu, I);
+    IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm);
+    IDG_LAUNCH_CHECK("item_norm_kernel");
+    const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
+    const unsigned grid = (unsigned)((nu + kTU - 1) / kTU);
+    if (d == 64) {
+        IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_candidates_kernel<64><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
+    } else {
+        IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_candidates_kernel<256><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
+    }
+    IDG_LAUNCH_CHECK("eval_candidates_kernel");
+    eval_rescore_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_Fu, d_Fi, d, d_users, nu, K, w, d_out_ids, d_out_scores);
+    IDG_LAUNCH_CHECK("eval_rescore_kernel");
+    eval_exhaustive_kernel<<<kFallbackCtas, 256, 0, stream>>>(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w, d_out_ids, d_out_scores);
+    IDG_LAUNCH_CHECK("eval_exhaustive_kernel");
+    return 0;
+}
+
+extern "C" int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t nu, int32_t K, const int32_t* d_test_indptr,
+                                const int32_t* d_test_indices, const int32_t* h_ks, int32_t nk, double* d_sums, void* d_ws, void* stream_) {
+    if (!d_topk_ids || !d_users || !d_test_indptr || !d_test_indices || !h_ks || !d_sums || !d_ws) return fail(-1, "idg_eval_metrics: null argument%s");
+    if (nu <= 0 || K < 1 || K > 64 || nk < 1 || nk > 8) return fail(-1, "idg_eval_metrics: bad sizes%s");
+    int ks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < nk; ++t) { if (h_ks[t] < 1 || h_ks[t] > K) return fail(-1, "idg_eval_metrics: k out of range%s"); ks[t] = h_ks[t]; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* per_user = (double*)d_ws;
+    eval_metrics_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_topk_ids, d_users, nu, K, d_test_indptr, d_test_indices, nk, ks[0], ks[1], ks[2], ks[3], ks[4], ks[5], ks[6], ks[7], per_user);
+    IDG_LAUNCH_CHECK("eval_metrics_kernel");
+    ordered_sum_kernel<<<1, 1024, 0, stream>>>(per_user, nu, 3 * nk, d_sums);
+    IDG_LAUNCH_CHECK("ordered_sum_kernel");
+    return 0;
+}

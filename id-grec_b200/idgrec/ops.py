@@ -1,0 +1,159 @@
+"""torch.autograd bindings + evaluation wrappers over the C ABI.
+
+These make the CUDA kernels usable from the reference's own model code
+(``total_loss.backward()`` in utility_train/trainer.py:55 just works); the fused
+trainer path in ``idgrec.engine`` calls the same C entry points without autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+class PropagateFn(torch.autograd.Function):
+    """K x torch.sparse.mm + layer mean (LightGCN.py:36-52 / SimGCL.py:39-60 / XSimGCL.py:40-67)."""
+
+    @staticmethod
+    def forward(ctx, X0, graph, K, include_layer0, noise, eps, cl_layer):
+        X0 = _f32c(X0)
+        ctx.graph, ctx.K, ctx.inc0, ctx.cl = graph, K, include_layer0, cl_layer
+        res = graph.propagate_fwd(X0, K, include_layer0, noise=noise, eps=eps, cl_layer=cl_layer)
+        if cl_layer > 0:
+            return res[0], res[1]
+        return res
+
+    @staticmethod
+    def backward(ctx, gF, gC=None):
+        gF = _f32c(gF)
+        gC = _f32c(gC) if (ctx.cl > 0 and gC is not None) else None
+        g = ctx.graph.propagate_bwd(gF, ctx.K, ctx.inc0, Gcl=gC, cl_layer=ctx.cl if gC is not None else 0)
+        return g, None, None, None, None, None, None
+
+
+def propagate(X0, graph, K, include_layer0=True, noise=None, eps=0.0, cl_layer=0):
+    return PropagateFn.apply(X0, graph, K, include_layer0, noise, eps, cl_layer)
+
+
+class BprRegLossFn(torch.autograd.Function):
+    """[bpr, reg_lambda*reg] = fused LightGCN.py:57-70 + losses.py:4-21."""
+
+    @staticmethod
+    def forward(ctx, F, E0, users, pos, neg, num_users, reg_lambda, reg_mask):
+        l = _lib.lib()
+        F, E0 = _f32c(F), _f32c(E0)
+        users, pos, neg = (t.long().contiguous() for t in (users, pos, neg))
+        B, (N, d) = int(users.numel()), F.shape
+        ws = torch.empty(int(l.idg_bpr_workspace_bytes(B)), dtype=torch.uint8, device=F.device)
+        loss = torch.empty(2, dtype=torch.float32, device=F.device)
+        check(l.idg_bpr_forward(ptr(F), ptr(E0), ptr(users), ptr(pos), ptr(neg), B, num_users, N, d, float(reg_lambda),
+                                int(reg_mask), ptr(loss), ptr(ws), cur_stream()), "idg_bpr_forward")
+        ctx.save_for_backward(F, E0)
+        ctx.ws, ctx.B, ctx.reg_lambda, ctx.reg_mask = ws, B, float(reg_lambda), int(reg_mask)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        l = _lib.lib()
+        F, E0 = ctx.saved_tensors
+        N, d = F.shape
+        up = _f32c(gloss)
+        G = torch.zeros_like(F)
+        gE0 = torch.zeros_like(E0)
+        check(l.idg_bpr_backward(ptr(F), ctx.B, d, ctx.reg_mask, ptr(up), ptr(G), ptr(ctx.ws), cur_stream()), "idg_bpr_backward")
+        check(l.idg_bpr_finish(ptr(E0), ptr(gE0), None, ctx.B, d, ctx.reg_lambda, ptr(up), ptr(ctx.ws), cur_stream()), "idg_bpr_finish")
+        return G, gE0, None, None, None, None, None, None
+
+
+def bpr_reg_loss(F, E0, users, pos, neg, num_users, reg_lambda, reg_mask=7):
+    return BprRegLossFn.apply(F, E0, users, pos, neg, num_users, reg_lambda, reg_mask)
+
+
+class InfoNCEFn(torch.autograd.Function):
+    """losses.get_InfoNCE_loss(V1[idx], V2[idx], tau) (losses.py:24-35) on rows idx of two [N,64] views."""
+
+    @staticmethod
+    def forward(ctx, V1, V2, idx, temperature):
+        l = _lib.lib()
+        V1, V2 = _f32c(V1), _f32c(V2)
+        idx = idx.long().contiguous()
+        n, d = int(idx.numel()), V1.shape[1]
+        ws = torch.empty(int(l.idg_infonce_workspace_bytes(n, d)), dtype=torch.uint8, device=V1.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=V1.device)
+        g1, g2 = torch.zeros_like(V1), torch.zeros_like(V2)
+        check(l.idg_infonce_fwd_bwd(ptr(V1), ptr(V2), ptr(idx), n, d, float(temperature), 1.0, ptr(loss), ptr(g1), ptr(g2),
+                                    ptr(ws), cur_stream()), "idg_infonce_fwd_bwd")
+        ctx.save_for_backward(g1, g2)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        g1, g2 = ctx.saved_tensors
+        return g1 * gl, g2 * gl, None, None
+
+
+def infonce_rows(V1, V2, idx, temperature):
+    return InfoNCEFn.apply(V1, V2, idx, temperature)
+
+
+# ---------------------------------------------------------------------------------------
+# evaluation
+# ---------------------------------------------------------------------------------------
+
+def eval_topk(Fu, Fi, users, mask_indptr, mask_indices, K, want_scores=False, ws=None):
+    """ids [nu,K] int64 (and exact scores) of the top-K unmasked items per user, (score desc, id asc)."""
+    l = _lib.lib()
+    Fu, Fi = _f32c(Fu), _f32c(Fi)
+    users = users.long().contiguous()
+    nu, (U, d), I = int(users.numel()), Fu.shape, Fi.shape[0]
+    if ws is None:
+        ws = torch.empty(int(l.idg_eval_workspace_bytes(nu, I, d, K)), dtype=torch.uint8, device=Fu.device)
+    ids = torch.empty((nu, K), dtype=torch.int64, device=Fu.device)
+    sc = torch.empty((nu, K), dtype=torch.float32, device=Fu.device) if want_scores else None
+    check(l.idg_eval_topk(ptr(Fu), ptr(Fi), U, I, d, ptr(mask_indptr), ptr(mask_indices), ptr(users), nu, K, ptr(ids), ptr(sc),
+                          ptr(ws), cur_stream()), "idg_eval_topk")
+    return (ids, sc) if want_scores else ids
+
+
+def eval_metric_sums(topk_ids, users, test_indptr, test_indices, ks, ws=None):
+    """float64 [len(ks), 3] sums over users of (recall, precision, ndcg) at each k (metrics.py:4-36)."""
+    l = _lib.lib()
+    nu, K = topk_ids.shape
+    nk = len(ks)
+    if ws is None:
+        ws = torch.empty(int(l.idg_eval_workspace_bytes(nu, 1, 64, K)), dtype=torch.uint8, device=topk_ids.device)
+    sums = torch.empty(3 * nk, dtype=torch.float64, device=topk_ids.device)
+    ks_arr = (C.c_int32 * nk)(*[int(k) for k in ks])
+    check(l.idg_eval_metrics(ptr(topk_ids.contiguous()), ptr(users.long().contiguous()), nu, K, ptr(test_indptr), ptr(test_indices),
+                             ks_arr, nk, ptr(sums), ptr(ws), cur_stream()), "idg_eval_metrics")
+    return sums.view(nk, 3)
+
+
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.lib().idg_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                   int(step), cur_stream()), "idg_adam_step")
+
+
+def neg_sample_replay(train_user, pos_indptr, pos_indices, cand):
+    """Exact replay of data_loader.py:108-127 against a bulk numpy candidate stream (host)."""
+    l = _lib.lib()
+    tu = np.ascontiguousarray(train_user, dtype=np.int64)
+    ip = np.ascontiguousarray(pos_indptr, dtype=np.int32)
+    ix = np.ascontiguousarray(pos_indices, dtype=np.int32)
+    cand = np.ascontiguousarray(cand, dtype=np.int64)
+    neg = np.empty(len(tu), dtype=np.int64)
+    used = C.c_int64(0)
+    rc = l.idg_neg_sample_replay(tu.ctypes.data, len(tu), ip.ctypes.data, ix.ctypes.data, cand.ctypes.data, len(cand),
+                                 neg.ctypes.data, C.byref(used))
+    if rc == -2:
+        return None, int(used.value)
+    check(rc, "idg_neg_sample_replay")
+    return neg, int(used.value)

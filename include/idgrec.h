@@ -1,0 +1,178 @@
+/* idgrec.h -- C ABI of libidgrec_sm100.so, the B200 (sm_100a) implementation of
+ * the ID-GRec hot path: normalised-adjacency CSR build -> K-layer propagation
+ * (SpMM) and its backward -> fused BPR / InfoNCE losses -> full-ranking top-K.
+ *
+ * The reference (BlueGhostYi/ID-GRec) is pure Python and has no FFI: every entry
+ * point below replaces a *library call made from* the cited reference lines
+ * (torch.sparse.mm, torch.matmul, torch.topk, scipy dok/lil algebra, the numpy
+ * sampling loop).  The Python host mirror (id-grec_b200/{models,utility}) binds
+ * these symbols with ctypes (id-grec_b200/idgrec/_lib.py); INTEGRATION.md shows
+ * the same binding applied directly inside the reference's files.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 for an argument error, >0 for a
+ *     cudaError_t passed through; idg_last_error() returns a thread-local text.
+ *   - all `d_*` pointers are DEVICE pointers on the current CUDA device, row-major,
+ *     contiguous, caller-allocated and caller-owned; `h_*` are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and
+ *     never synchronise unless the comment says so.
+ *   - embeddings are fp32; ids are int64 at the API (the reference's LongTensors)
+ *     and int32 inside CSR structures (scipy's index dtype, data_graph.py:33-55).
+ */
+#ifndef IDGREC_H_
+#define IDGREC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct idg_graph idg_graph; /* opaque device CSR + schedule */
+
+int idg_version(void);
+const char* idg_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
+int64_t idg_launch_count(void);
+
+/* ---- a2: utility/utility_data/data_graph.py:7-55 -------------------------
+ * D^-1/2 [[0,R],[R^T,0]] D^-1/2 (add_self: +I before normalising) as canonical
+ * CSR: rows ascending, columns ascending inside a row, duplicate (u,i) pairs
+ * merged with their multiplicity as weight (data_loader.py:42-43).  Two phases,
+ * because the reference's d = np.power(deg, -0.5) is numpy's own powf/pow and is
+ * not correctly rounded: the host computes d from d_deg with
+ * numpy, exactly like data_graph.py:46, and hands it back.
+ *   structure: d_user/d_item are the E train pairs (int64, device).  Outputs hold
+ *     up to 2E(+N) entries; d_mult = multiplicity a (1.0, 2.0, ...), d_deg[N] = row
+ *     sums (incl. the self loop when add_self).  *h_nnz = merged entry count.
+ *     SYNCHRONISES the stream once (to return nnz).
+ *   normalise: data[k] = (d[row]*a[k])*d[col] evaluated in fp32 from d_dinv32
+ *     (no-self variant, data_graph.py:48-51) or in fp64 from d_dinv64 and rounded
+ *     to fp32 once (with-self variant + tools.py:101).  Exactly one of the two
+ *     dinv pointers is non-NULL. */
+int idg_csr_structure(const int64_t* d_user, const int64_t* d_item, int64_t E, int32_t U, int32_t I,
+                      int add_self, int32_t* d_indptr, int32_t* d_indices, float* d_mult, double* d_deg,
+                      int64_t* h_nnz, void* stream);
+int idg_csr_normalise(const int32_t* d_indptr, const int32_t* d_indices, const float* d_mult, int32_t n_rows,
+                      int64_t nnz, const float* d_dinv32, const double* d_dinv64, float* d_data, void* stream);
+
+/* ---- graph handle: replaces `self.Graph` (models/LightGCN.py:30-32) -------
+ * Takes rows [0,n_rows) of a CSR whose column space is [0,n_cols).  For a
+ * row-partitioned rank pass its slice (indptr rebased to 0) and set row_offset to
+ * the first global row: outputs are then written at Y[row_offset + r].  Builds the
+ * degree-sorted, chunked work schedule.  SYNCHRONISES the stream (one-off). */
+int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indices, const float* d_data,
+                     int32_t n_rows, int32_t n_cols, int64_t nnz, int32_t row_offset,
+                     idg_graph** out, void* stream);
+void idg_graph_destroy(idg_graph* g);
+int64_t idg_graph_nnz(const idg_graph* g);
+int32_t idg_graph_rows(const idg_graph* g);
+
+/* ---- a6/a7/a11: one propagation layer = torch.sparse.mm(self.Graph, X) -----
+ * (models/LightGCN.py:44, SimGCL.py:48, XSimGCL.py:51, NGCF.py:85) with the
+ * element-wise work that follows it in the reference fused into the epilogue:
+ *   y   = sum_k data[k] * X[col[k]]              (fixed order, no float atomics)
+ *   y  += addend[row]                             if d_addend  (Horner backward h <- G + A h)
+ *   y  += sign(y) * noise[row]/max(|noise[row]|_2,1e-12) * eps   if d_noise (SimGCL.py:49-51)
+ *   Y[row]       = y                              if d_Y
+ *   acc_out[row] = ((d_acc_in ? acc_in[row] : 0) + y) / acc_div   if d_acc_out (layer mean, LightGCN.py:47-48)
+ * d in {32, 64, 128}.  X must not alias Y / acc_out. */
+int idg_spmm_layer(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend,
+                   const float* d_noise, float eps, const float* d_acc_in, float* d_acc_out,
+                   float acc_div, int32_t d, void* stream);
+
+/* K-layer forward in one call (single-GPU convenience; same kernels).
+ *   include_layer0 = 1: mean over X0..XK (LightGCN.py:41); 0: X1..XK (SimGCL.py:45).
+ *   d_noise: K stacked [N,d] U[0,1) tensors or NULL.  cl_layer > 0 also copies the
+ *   post-noise output of layer cl_layer into d_out_cl (XSimGCL.py:57-58).
+ *   d_work: scratch of 2*N*d floats. */
+int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t d, int32_t K, int include_layer0,
+                      const float* d_noise, float eps, int32_t cl_layer, float* d_out_mean,
+                      float* d_out_cl, float* d_work, void* stream);
+/* Backward of the above w.r.t. X0 (A symmetric => same CSR; trainer.py:55 autograd):
+ *   gX0 = (inc0*G + A(G + A(G + ... A G)))/cnt  [+ A^cl_layer Gcl]   cnt = K + inc0. */
+int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                      int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, void* stream);
+
+/* ---- a9: models/LightGCN.py:54-72 + utility_function/losses.py:4-21 ---------
+ * Fused gather + dot + -log(sigmoid+1e-7) + L2-reg, forward and backward.
+ *   F  [N,d]  final embeddings (users rows 0..U-1, items U..N-1)
+ *   E0 [N,d]  ego embeddings (cat(user_w,item_w))
+ *   d_loss[0] = bpr, d_loss[1] = reg_lambda * reg     (losses.py:13,19-21)
+ *   d_G  [N,d]: dL/dF.  Only the rows touched by the batch are written (each row is
+ *               the ordered sum of its samples' contributions: deterministic, no
+ *               float atomics); every other row must already be ZERO.  The caller
+ *               zero-fills G once; idg_bpr_finish re-zeroes the touched rows.
+ * reg_mask bit0/1/2 = include user/pos/neg ego rows (NGCF.py:120-125 uses 0b110).
+ * d_ws: workspace of idg_bpr_workspace_bytes(B) bytes, private to one forward/backward/finish triple. */
+int64_t idg_bpr_workspace_bytes(int32_t B);
+/* forward: d_loss[0] = bpr, d_loss[1] = reg_lambda * reg; keeps c_b and the row keys in d_ws */
+int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
+                    const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda,
+                    int reg_mask, float* d_loss, void* d_ws, void* stream);
+/* backward: writes the touched rows of d_G = upstream[0] * d bpr / dF.  d_upstream: device float[2]
+ * = (dL/d bpr, dL/d reg) handed down by autograd, or NULL for (1, 1). */
+int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_mask, const float* d_upstream,
+                     float* d_G, void* d_ws, void* stream);
+/* After the propagation backward has consumed G: adds the L2-reg gradient
+ * (upstream[1] * reg_lambda/B * multiplicity * E0[row]) into d_gE0 (may be NULL) and zeroes the
+ * touched rows of d_G (may be NULL).  Same B / d_ws as the matching forward/backward calls. */
+int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
+                   const float* d_upstream, void* d_ws, void* stream);
+
+/* small utilities used between the fused kernels */
+int idg_axpby(float* d_out, float a, const float* d_x, float b, const float* d_y, int64_t n, void* stream);
+int idg_zero_rows(float* d_buf, const int64_t* d_idx, int32_t n, int32_t d, void* stream);
+
+/* ---- a10: utility_function/losses.py:24-35 (in-batch InfoNCE) --------------
+ * V1,V2 [N,d] views; d_idx n sorted-unique row ids (torch.unique, SimGCL.py:80-81)
+ * already offset into [0,N).  loss_scale multiplies the loss and the gradients
+ * (ssl_lambda).  d_loss[0] += loss_scale * mean(-log(pos/ttl + 1e-5)).
+ * Gradients are ACCUMULATED into rows d_idx of d_gV1 / d_gV2 (both [N,d]).
+ * The n x n matrix is never materialised (tile-wise recompute in shared memory). */
+int64_t idg_infonce_workspace_bytes(int32_t n, int32_t d);
+int idg_infonce_fwd_bwd(const float* d_V1, const float* d_V2, const int64_t* d_idx, int32_t n, int32_t d,
+                        float temperature, float loss_scale, float* d_loss, float* d_gV1, float* d_gV2,
+                        void* d_ws, void* stream);
+
+/* ---- a13/a14: get_rating_for_test + Test (models/LightGCN.py:74-80,
+ * utility_train/batch_test.py:52-68) fused: score = <Fu[user], Fi[item]>, train
+ * positives removed, top-K by (score desc, item id asc).  No [b, I] matrix is
+ * materialised.  Exactness: candidates come from an fp32 (or tensor-core) pass,
+ * the survivors are rescored with the fp64 sequential dot product of the fp32
+ * embeddings and every user whose candidate margin cannot be proven is recomputed
+ * exhaustively, so ids equal the exact-rank oracle bit for bit.
+ *   d_users [nu] int64 user ids; mask CSR = user_item_net (int32, U rows, sorted)
+ *   d_out_ids [nu,K] int64, d_out_scores [nu,K] fp32 (may be NULL). K <= 64. */
+int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, int32_t K);
+int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d,
+                  const int32_t* d_mask_indptr, const int32_t* d_mask_indices, const int64_t* d_users,
+                  int32_t nu, int32_t K, int64_t* d_out_ids, float* d_out_scores, void* d_ws, void* stream);
+
+/* metrics.py:4-58 + batch_test.py:80-91 on device: sums over users of
+ * recall/precision/ndcg at each k in h_ks (nk <= 8) -> d_sums[3*nk] (float64).
+ * test CSR = test_dict rows (int32, sorted inside a row, duplicates kept: metrics.py:27 uses
+ * the list length).  d_ws: idg_eval_workspace_bytes(nu, ...) bytes (may be the top-k workspace). */
+int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t nu, int32_t K,
+                     const int32_t* d_test_indptr, const int32_t* d_test_indices, const int32_t* h_ks,
+                     int32_t nk, double* d_sums, void* d_ws, void* stream);
+
+/* ---- a12: torch.optim.Adam step (trainer.py:11,54-56) fused, fp32 ----------
+ * p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps), torch's non-capturable formula order. */
+int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, void* stream);
+
+/* ---- a4: data_loader.py:108-127, exact replay on the HOST -------------------
+ * h_cand: candidate stream = np.random.randint(0, I, size=n_cand) drawn from the
+ * reference's RNG state.  Walks the train edges in file order, skipping candidates
+ * that are positives of the current user (CSR of user_item_net, sorted).  Writes
+ * h_neg[E]; *h_consumed = number of candidates used (caller re-winds the numpy
+ * stream to exactly that many draws).  Returns -2 if the stream ran out. */
+int idg_neg_sample_replay(const int64_t* h_train_user, int64_t E, const int32_t* h_pos_indptr,
+                          const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand,
+                          int64_t* h_neg, int64_t* h_consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDGREC_H_ */
