@@ -43,6 +43,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
     if (i == 0) for (int64_t k = n4 * 4; k < n; ++k) upd(p[k], g[k], m[k], v[k]);
 }
+
+// CUDA-graph friendly variant: the step number lives on the device (d_step holds the number of
+// steps already taken) so a captured launch keeps advancing the bias corrections.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                int64_t n4, int64_t n, float lr, float b1, float b2, float eps, const int* __restrict__ d_step) {
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const double t = (double)(*d_step + 1);
+        s_step_size = (float)((double)lr / (1.0 - pow((double)b1, t)));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        mm = mm + (gg - mm) * (1.f - b1);
+        vv = vv * b2 + (1.f - b2) * gg * gg;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pp = pp - step_size * (mm / denom);
+    };
+    if (i < n4) {
+        float4 pv = reinterpret_cast<float4*>(p)[i], gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+        float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        upd(pv.x, gv.x, mv.x, vv.x); upd(pv.y, gv.y, mv.y, vv.y); upd(pv.z, gv.z, mv.z, vv.z); upd(pv.w, gv.w, mv.w, vv.w);
+        reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (i == 0) for (int64_t k = n4 * 4; k < n; ++k) upd(p[k], g[k], m[k], v[k]);
+}
+__global__ void incr_kernel(int* c) { *c += 1; }
 }  // namespace idg
 
 using namespace idg;
@@ -80,6 +109,19 @@ extern "C" int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_
     const int64_t n4 = n / 4, th = (n4 > 0 ? n4 : 1);
     adam_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n4, n, beta1, beta2, eps, step_size, bc2_sqrt);
     IDG_LAUNCH_CHECK("adam_kernel");
+    return 0;
+}
+
+extern "C" int idg_adam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                                 float beta2, float eps, int32_t* d_step, void* stream) {
+    if (!d_p || !d_g || !d_m || !d_v || !d_step || n < 0) return fail(-1, "idg_adam_step_dev: bad argument%s");
+    if (n == 0) return 0;
+    if (((uintptr_t)d_p | (uintptr_t)d_g | (uintptr_t)d_m | (uintptr_t)d_v) & 15) return fail(-1, "idg_adam_step_dev: pointers must be 16-byte aligned%s");
+    const int64_t n4 = n / 4, th = (n4 > 0 ? n4 : 1);
+    adam_dev_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_p, d_g, d_m, d_v, n4, n, lr, beta1, beta2, eps, d_step);
+    IDG_LAUNCH_CHECK("adam_dev_kernel");
+    incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step);
+    IDG_LAUNCH_CHECK("incr_kernel");
     return 0;
 }
 

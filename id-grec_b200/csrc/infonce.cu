@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(1024) nce_rows_kernel(NceWs w, int n, float lo
 
 // final gradients, through the normalisation, accumulated into rows idx of gV1/gV2; one warp per row
 __global__ void __launch_bounds__(256) nce_grad_kernel(NceWs w, const int64_t* __restrict__ idx, int n, float inv_tau, float scale,
-                                                       float* __restrict__ gV1, float* __restrict__ gV2) {
+                                                       float* gV1, float* gV2) {  // may alias (SimGCL accumulates both views into one buffer)
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;

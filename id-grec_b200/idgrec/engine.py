@@ -1,0 +1,169 @@
+"""Fused training step of the propagation models (LightGCN / SimGCL / XSimGCL / MFBPR).
+
+One object owns the device state of a model's hot path -- the fused [N,d] parameter table
+(user rows then item rows; ``user_embedding.weight`` / ``item_embedding.weight`` are views of
+it), its gradient, the Adam moments, the layer work buffers -- and runs
+    propagate -> BPR (+InfoNCE) -> backward propagate -> Adam
+through the C ABI without autograd, Python-side tensor ops or host syncs, optionally replayed
+from a CUDA graph.  It is what ``utility_train.trainer.universal_trainer`` drives; the autograd
+path in the model classes computes the same values for the reference's own trainer loop
+(trainer.py:40-56).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+
+class FusedTrainer:
+    def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
+                 eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8):
+        assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR")
+        self.l = _lib.lib()
+        self.kind, self.graph, self.E0 = kind, graph, table
+        self.U, (self.N, self.d), self.K = num_users, table.shape, K
+        self.reg_lambda, self.lr, self.betas, self.adam_eps = reg_lambda, lr, betas, adam_eps
+        self.ssl_lambda, self.temperature, self.eps, self.cl_layer = ssl_lambda, temperature, eps, cl_layer
+        dev = table.device
+        self.dev = dev
+        z = lambda: torch.zeros_like(table)
+        self.gE0, self.m, self.v, self.G = z(), z(), z(), z()
+        self.F = table if kind == "MFBPR" else torch.empty_like(table)
+        self.step_count = 0
+        self.max_batch = max_batch
+        self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
+        self.n_loss = 3 if kind in ("SimGCL", "XSimGCL") else 2
+        self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
+        if kind in ("SimGCL", "XSimGCL"):
+            self.noise = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev)
+            self.nce_ws = torch.empty(int(self.l.idg_infonce_workspace_bytes(max_batch, self.d)), dtype=torch.uint8, device=dev)
+            self.V1 = torch.empty_like(table)
+            self.V2 = torch.empty_like(table) if kind == "SimGCL" else None
+            self.Gcl = z() if kind == "XSimGCL" else None
+        if kind != "MFBPR":
+            graph.work(self.d)  # allocate the layer ping-pong buffers before any graph capture
+        self.use_cuda_graph = use_cuda_graph and kind in ("LightGCN", "MFBPR")
+        self._graphs = {}
+        self.injected_noise = None  # parity tests: list of per-view [K,N,d] tensors
+
+    # ------------------------------------------------------------------ pieces
+    def _adam(self):
+        self.step_count += 1
+        check(self.l.idg_adam_step(ptr(self.E0), ptr(self.gE0), ptr(self.m), ptr(self.v), self.E0.numel(), self.lr,
+                                   self.betas[0], self.betas[1], self.adam_eps, self.step_count, cur_stream()), "idg_adam_step")
+
+    def _bpr(self, B, u, p, n):
+        l, s = self.l, cur_stream()
+        check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, 7,
+                                ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
+        check(l.idg_bpr_backward(ptr(self.F), B, self.d, 7, None, ptr(self.G), ptr(self.ws), s), "idg_bpr_backward")
+
+    def _finish(self, B):
+        check(self.l.idg_bpr_finish(ptr(self.E0), ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None, ptr(self.ws),
+                                    cur_stream()), "idg_bpr_finish")
+
+    def _draw_noise(self, view):
+        if self.injected_noise is not None:
+            self.noise.copy_(self.injected_noise[view])
+        else:  # same call pattern as SimGCL.py:50: one rand_like([N,d]) per layer, views in order
+            for k in range(self.K):
+                self.noise[k].uniform_()
+
+    def _body(self, B, u, p, n, users_t=None, pos_t=None):
+        """Kernels of one step for batch pointers u/p/n (device int64)."""
+        g, K = self.graph, self.K
+        if self.kind == "LightGCN":
+            g.propagate_fwd(self.E0, K, True, out_mean=self.F)
+            self._bpr(B, u, p, n)
+            g.propagate_bwd(self.G, K, True, out=self.gE0)
+        elif self.kind == "MFBPR":
+            self._bpr(B, u, p, n)
+            self.gE0.copy_(self.G)
+        else:
+            l, s = self.l, cur_stream()
+            uidx = torch.unique(users_t)
+            iidx = torch.unique(pos_t) + self.U
+            if self.kind == "SimGCL":
+                g.propagate_fwd(self.E0, K, False, out_mean=self.F)
+                self._draw_noise(0)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1)
+                self._draw_noise(1)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2)
+                self._bpr(B, u, p, n)
+                self.loss[2] = 0.0
+                # the three propagations share one linear backward operator: accumulate all row
+                # gradients into G and back-propagate once (9 backward SpMMs of the reference -> 3)
+                for idx in (uidx, iidx):
+                    check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.V2), ptr(idx), idx.numel(), self.d, self.temperature,
+                                                self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
+                          "idg_infonce_fwd_bwd")
+                g.propagate_bwd(self.G, K, False, out=self.gE0)
+            else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
+                self._draw_noise(0)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1)
+                self._bpr(B, u, p, n)
+                self.loss[2] = 0.0
+                for idx in (uidx, iidx):
+                    check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.F), ptr(idx), idx.numel(), self.d, self.temperature,
+                                                self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
+                          "idg_infonce_fwd_bwd")
+                g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=self.gE0)
+                for idx in (uidx, iidx):
+                    check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), idx.numel(), self.d, s), "idg_zero_rows")
+        self._finish(B)
+
+    # ------------------------------------------------------------------ public
+    def step(self, users, pos, neg, apply_adam=True):
+        """One training step on device int64 index tensors; losses land in self.loss[:n_loss]."""
+        B = int(users.numel())
+        assert B <= self.max_batch
+        if self.use_cuda_graph and apply_adam:
+            return self._step_graph(B, users, pos, neg)
+        users, pos, neg = users.contiguous(), pos.contiguous(), neg.contiguous()
+        self._body(B, ptr(users), ptr(pos), ptr(neg), users, pos)
+        if apply_adam:
+            self._adam()
+        self.loss_acc += self.loss
+        return self.loss[:self.n_loss]
+
+    def _step_graph(self, B, users, pos, neg):
+        """CUDA-graph replay: the step's kernels (incl. the device-side Adam step counter) are captured
+        once per batch size; each call only copies the batch into the static slab and replays."""
+        self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
+        if B not in self._graphs:
+            self._capture(B)
+        self._graphs[B].replay()
+        self.step_count += 1
+        return self.loss[:self.n_loss]
+
+    def _capture(self, B):
+        if not hasattr(self, "d_step"):
+            self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.d_step.fill_(self.step_count)
+        u, p, n = (self.batch[k].data_ptr() for k in range(3))
+
+        def run():
+            self._body(B, u, p, n)
+            check(self.l.idg_adam_step_dev(ptr(self.E0), ptr(self.gE0), ptr(self.m), ptr(self.v), self.E0.numel(), self.lr,
+                                           self.betas[0], self.betas[1], self.adam_eps, ptr(self.d_step), cur_stream()), "idg_adam_step_dev")
+            check(self.l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, cur_stream()), "idg_axpby")
+
+        # warm-up outside capture would advance the model; capture directly (kernels are launched lazily at replay)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            run()
+        self._graphs[B] = gr
+
+    def sync_step_counter(self):
+        if hasattr(self, "d_step"):
+            self.d_step.fill_(self.step_count)
+
+    def pop_epoch_losses(self):
+        out = self.loss_acc[:self.n_loss].tolist()
+        self.loss_acc.zero_()
+        return out

@@ -1,0 +1,101 @@
+"""Shared machinery of the propagation models (the per-model files under models/ keep the
+reference's class names, constructor and method signatures; SURVEY.md section 8 b)."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .engine import FusedTrainer
+
+
+class PropagationModel(nn.Module):
+    """nn.Module with the reference's duck-typed model contract:
+    ``forward(user, pos, neg) -> [losses]``, ``aggregate(...) -> (users_emb, items_emb)``,
+    ``get_rating_for_test(user) -> [b, I]``; attributes Graph, user_embedding, item_embedding,
+    activation, config, dataset, device."""
+
+    kind = "LightGCN"
+    include_layer0 = True
+
+    def __init__(self, config, dataset, device, graph_fn=None):
+        super().__init__()
+        self.config, self.dataset, self.device = config, dataset, device
+        self.reg_lambda = float(config['reg_lambda'])
+        dim = int(config['embedding_size'])
+        self.user_embedding = nn.Embedding(num_embeddings=dataset.num_users, embedding_dim=dim)
+        self.item_embedding = nn.Embedding(num_embeddings=dataset.num_items, embedding_dim=dim)
+        # same draw order from the torch CPU generator as the reference (LightGCN.py:27-28)
+        nn.init.xavier_uniform_(self.user_embedding.weight, gain=1)
+        nn.init.xavier_uniform_(self.item_embedding.weight, gain=1)
+        self.activation = nn.Sigmoid()
+        self._table = None
+        self._fused = None
+        self.Graph = None
+        if graph_fn is not None:
+            import utility.utility_function.tools as tools
+            self.Graph = graph_fn(dataset)
+            self.Graph = tools.convert_sp_mat_to_sp_tensor(self.Graph)
+            self.Graph = self.Graph.coalesce().to(self.device)
+
+    @property
+    def num_layers(self):
+        return int(self.config.get('GCN_layer', 0))
+
+    # -- one [N,d] table behind both embedding weights (no torch.cat per step) -----------------
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        self._fuse_tables()
+        return self
+
+    def _fuse_tables(self):
+        uw, iw = self.user_embedding.weight, self.item_embedding.weight
+        if not uw.is_cuda:
+            self._table = None
+            return
+        U = uw.shape[0]
+        t = self._table
+        if t is not None and uw.data_ptr() == t.data_ptr() and iw.data_ptr() == t[U:].data_ptr():
+            return
+        t = torch.cat([uw.data, iw.data]).contiguous()
+        uw.data, iw.data = t[:U], t[U:]
+        self._table, self._fused = t, None
+
+    def table(self):
+        """[N,d] ego embeddings: the fused buffer on CUDA, an autograd-tracked cat when grads are needed."""
+        if torch.is_grad_enabled() and self.user_embedding.weight.requires_grad:
+            return torch.cat([self.user_embedding.weight, self.item_embedding.weight])
+        if self._table is None:
+            raise RuntimeError("model parameters are not on a CUDA device; the ID-GRec hot path has no CPU fallback")
+        return self._table
+
+    def _split(self, X):
+        return torch.split(X, [self.dataset.num_users, self.dataset.num_items])
+
+    # -- fused trainer (used by utility_train.trainer.universal_trainer) -------------------------
+    def fused_trainer(self, lr, max_batch):
+        if self._fused is None or self._fused.lr != lr or self._fused.max_batch < max_batch:
+            if self._table is None:
+                self._fuse_tables()
+            if self._table is None:
+                raise RuntimeError("model must be moved to a CUDA device first (model.to(device))")
+            cfg = self.config
+            self._fused = FusedTrainer(
+                self.kind, self.Graph, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda, lr,
+                ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),
+                eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)), max_batch=max_batch,
+                use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'))
+        return self._fused
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def final_embeddings(self):
+        """(users_emb, items_emb) for evaluation: clean propagation, no grad."""
+        with torch.no_grad():
+            return self.aggregate()[:2]
+
+    def get_rating_for_test(self, user):
+        """LightGCN.py:74-80: sigmoid(U_b . F_i^T) as a dense [b, I] matrix.  Kept for API
+        completeness; Test() ranks through the fused top-K kernel and never materialises it."""
+        with torch.no_grad():
+            users_emb, items_emb = self.aggregate()[:2]
+            return self.activation(torch.matmul(users_emb[user.long()], items_emb.t()))

@@ -1,0 +1,179 @@
+"""utility_data/data_loader.py of the reference, hot-path subset (data_loader.py:8-70,108-133,151-159).
+
+``Data`` keeps the reference's attributes (num_users, num_items, num_nodes, user_item_net,
+all_positive, test_dict, train_user, train_item, ...) and adds device-resident copies used by the
+CUDA evaluator.  ``sample_data_to_train_all`` reproduces the reference's negative samples and its
+numpy global-RNG stream bit for bit, in milliseconds instead of a Python loop over every edge.
+"""
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+warnings.filterwarnings('ignore')
+
+
+class Data(object):
+    def __init__(self, path, config):
+        self.path = path
+        self.num_users = 0
+        self.num_items = 0
+        self.num_entities = 0
+        self.num_relations = 0
+        self.num_nodes = 0
+        self.num_train = 0
+        self.num_test = 0
+        self.config = config
+        self._dev = {}
+        self.load_data()
+        if config:
+            self.split_test_dict = None
+            self.split_state = None
+            if "sparsity_test" in config.keys() and int(config["sparsity_test"]) == 1:
+                raise NotImplementedError("sparsity_test = 1 is outside the accelerated hot path (SURVEY.md section 8 f)")
+
+    # -- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, num_users, num_items, train_user, train_item, test_user, test_item, config=None, path="<memory>"):
+        """Same object from in-memory COO arrays (synthetic graphs never go through text)."""
+        self = cls.__new__(cls)
+        self.path, self.config, self._dev = path, config, {}
+        self.num_entities = self.num_relations = 0
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        self.train_user = np.ascontiguousarray(train_user, dtype=np.int64)
+        self.train_item = np.ascontiguousarray(train_item, dtype=np.int64)
+        self.test_user = np.ascontiguousarray(test_user, dtype=np.int64)
+        self.test_item = np.ascontiguousarray(test_item, dtype=np.int64)
+        self.num_train, self.num_test = len(self.train_user), len(self.test_user)
+        self.pos_length = None
+        self.split_test_dict = self.split_state = None
+        self._finish()
+        return self
+
+    def load_data(self):
+        """data_loader.py:27-46."""
+        _, self.train_user, self.train_item, self.num_train, self.pos_length = self.read_ratings(self.path + "/train.txt")
+        _, self.test_user, self.test_item, self.num_test, _ = self.read_ratings(self.path + "/test.txt")
+        self.num_users += 1
+        self.num_items += 1
+        self.data_statistics_on_load = True
+        self._finish()
+        self.data_statistics()
+
+    def _finish(self):
+        self.num_nodes = self.num_users + self.num_items
+        assert len(self.train_user) == len(self.train_item)
+        # duplicate (u,i) pairs sum to 2.0 exactly like the reference's csr_matrix call (data_loader.py:42-43)
+        self.user_item_net = sp.csr_matrix((np.ones(len(self.train_user)), (self.train_user, self.train_item)),
+                                           shape=(self.num_users, self.num_items))
+        self.user_item_net.sum_duplicates()
+        self.user_item_net.sort_indices()
+        self.all_positive = self.get_user_pos_items(range(self.num_users))
+        self.test_dict = self.build_test()
+
+    def read_ratings(self, file_name):
+        """data_loader.py:48-70: ``user item item ...`` per line; max ids tracked over both files."""
+        unique_users, pos_length, chunks_u, chunks_i = [], [], [], []
+        with open(file_name, "r") as f:
+            for line in f:
+                tok = line.split()
+                if not tok:
+                    if line == "":
+                        break
+                    continue
+                arr = np.array(tok, dtype=np.int64)
+                user_id, pos_id = int(arr[0]), arr[1:]
+                unique_users.append(user_id)
+                if len(pos_id) < 1:
+                    continue
+                self.num_users = max(self.num_users, user_id)
+                self.num_items = max(self.num_items, int(pos_id.max()))
+                chunks_u.append(np.full(len(pos_id), user_id, dtype=np.int64))
+                chunks_i.append(pos_id)
+                pos_length.append(len(pos_id))
+        users = np.concatenate(chunks_u) if chunks_u else np.zeros(0, np.int64)
+        items = np.concatenate(chunks_i) if chunks_i else np.zeros(0, np.int64)
+        return np.array(unique_users), users, items, len(items), pos_length
+
+    def data_statistics(self):
+        print("\t num_users:", self.num_users)
+        print("\t num_items:", self.num_items)
+        print("\t num_nodes:", self.num_nodes)
+        print("\t num_train:", self.num_train)
+        print("\t num_test: ", self.num_test)
+        print("\t sparisty: ", 1 - (self.num_train + self.num_test) / self.num_users / self.num_items)
+
+    def get_statistics(self):
+        strs = "dataset:" + self.config['dataset'] + "\t"
+        strs += "num_users:%d, num_items:%d \t" % (self.num_users, self.num_items)
+        strs += ("|num_train:%d, num_test:%d, sparsity: %.6f"
+                 % (self.num_train, self.num_test, 1 - (self.num_train + self.num_test) / self.num_users / self.num_items))
+        return strs
+
+    # -- sampling ----------------------------------------------------------------------------
+    def sample_data_to_train_all(self):
+        """data_loader.py:108-127, exact.  The reference draws np.random.randint(0, num_items) once
+        per attempt; scalar draws equal one bulk draw (same values, same final generator state), so a
+        bulk candidate stream is replayed against the sorted positives of each edge's user by the C
+        entry point idg_neg_sample_replay and the global numpy generator is then advanced by exactly the
+        number of candidates the reference would have consumed (tools.shuffle reads it next)."""
+        from idgrec import ops
+        E = len(self.train_user)
+        if E == 0:
+            return np.zeros((0, 3), dtype=np.int64)
+        net = self.user_item_net
+        state = np.random.get_state()
+        slack = max(4096, E // 16)
+        while True:
+            np.random.set_state(state)
+            cand = np.random.randint(0, self.num_items, size=E + slack)
+            neg, used = ops.neg_sample_replay(self.train_user, net.indptr, net.indices, cand)
+            if neg is not None:
+                break
+            slack *= 4
+        np.random.set_state(state)
+        np.random.randint(0, self.num_items, size=used)
+        return np.stack([self.train_user, self.train_item, neg], axis=1)
+
+    def get_user_pos_items(self, users):
+        """data_loader.py:129-133: sorted train items of each user (views into the CSR)."""
+        ip, ix = self.user_item_net.indptr, self.user_item_net.indices
+        return [ix[ip[u]:ip[u + 1]] for u in users]
+
+    def build_test(self):
+        """data_loader.py:151-159: {user: [items in file order]} for users with a non-empty line."""
+        test_data = {}
+        if len(self.test_user) == 0:
+            return test_data
+        order = np.argsort(self.test_user, kind="stable")
+        su, si = self.test_user[order], self.test_item[order]
+        starts = np.flatnonzero(np.concatenate([[True], su[1:] != su[:-1]]))
+        ends = np.concatenate([starts[1:], [len(su)]])
+        first_seen = {}
+        for s, e in zip(starts, ends):
+            first_seen[int(su[s])] = (int(order[s]), si[s:e].tolist())
+        for u, (_, items) in sorted(first_seen.items(), key=lambda kv: kv[1][0]):
+            test_data[u] = items
+        return test_data
+
+    # -- device-side copies for the CUDA evaluator ------------------------------------------
+    def device_cache(self, device):
+        """mask CSR (train positives), test CSR (sorted, duplicates kept) and the test-user list."""
+        import torch
+        key = str(device)
+        if key not in self._dev:
+            net = self.user_item_net
+            users = np.fromiter(self.test_dict.keys(), dtype=np.int64, count=len(self.test_dict))
+            tu, ti = self.test_user, self.test_item
+            order = np.lexsort((ti, tu))
+            tptr = np.zeros(self.num_users + 1, dtype=np.int64)
+            np.add.at(tptr, tu + 1, 1)
+            tptr = np.cumsum(tptr)
+            self._dev[key] = {
+                "mask_indptr": torch.from_numpy(net.indptr.astype(np.int32)).to(device),
+                "mask_indices": torch.from_numpy(net.indices.astype(np.int32)).to(device),
+                "test_indptr": torch.from_numpy(tptr.astype(np.int32)).to(device),
+                "test_indices": torch.from_numpy(ti[order].astype(np.int32)).to(device),
+                "test_users": torch.from_numpy(users).to(device),
+            }
+        return self._dev[key]

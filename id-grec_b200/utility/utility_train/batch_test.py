@@ -1,0 +1,67 @@
+"""utility_train/batch_test.py of the reference (batch_test.py:8-107): ``general_test`` and
+``Test`` keep their signatures and return values.  ``Test`` propagates ONCE (the reference
+re-runs the K SpMMs for every 1024-user batch, batch_test.py:59), then ranks all test users with
+the fused score + train-mask + top-K kernel and reduces recall/precision/ndcg on the device; the
+only device->host traffic is 3*len(top_K) float64 sums."""
+import numpy as np
+import torch
+
+from idgrec import ops
+
+
+def general_test(dataset, model, device, config, epoch, best_results):
+    """batch_test.py:8-34 (early-stop bookkeeping on the first K of top_K)."""
+    if int(config["sparsity_test"]) == 0:
+        result = Test(dataset, model, device, config)
+        if result['recall'][0] > best_results['recall'][0]:
+            best_results['count'] = 0
+            best_results['epoch'] = epoch + 1
+            best_results['recall'] = result['recall']
+            best_results['ndcg'] = result['ndcg']
+        else:
+            best_results['count'] += 1
+            if best_results['count'] >= int(config['early_stopping']):
+                print("Early stop......")
+                print("Best epoch:   ", best_results['epoch'], " Best recall:", best_results['recall'], "Best NDCG:", best_results['ndcg'])
+                best_results['stop'] = 99999
+                return result, best_results
+        print("Current epoch:", epoch + 1, " Test recall:", result['recall'], "Test NDCG:", result['ndcg'])
+        print("Best epoch:   ", best_results['epoch'], " Best recall:", best_results['recall'], "Best NDCG:", best_results['ndcg'])
+    else:
+        raise NotImplementedError("sparsity_test = 1 is outside the accelerated hot path (SURVEY.md section 8 f)")
+    return result, best_results
+
+
+def rank_all(dataset, model, device, K, users=None):
+    """ids [n_test_users, K] int64 on the device, ordered (score desc, item id asc), train positives removed."""
+    cache = dataset.device_cache(device)
+    users = cache["test_users"] if users is None else users
+    users_emb, items_emb = model.final_embeddings()
+    return ops.eval_topk(users_emb, items_emb, users, cache["mask_indptr"], cache["mask_indices"], K), users
+
+
+def Test(dataset, model, device, config):
+    """batch_test.py:37-93 -> {'precision','recall','hit','ndcg'} (float64 arrays, one entry per K)."""
+    model = model.eval()
+    topK = eval(config['top_K'])
+    device = torch.device(device)
+    cache = dataset.device_cache(device)
+    with torch.no_grad():
+        ids, users = rank_all(dataset, model, device, max(topK))
+        sums = ops.eval_metric_sums(ids, users, cache["test_indptr"], cache["test_indices"], topK).cpu().numpy()
+    n = float(len(users))
+    return {'precision': sums[:, 1] / n, 'recall': sums[:, 0] / n, 'hit': np.zeros(len(topK)), 'ndcg': sums[:, 2] / n}
+
+
+def test_one_batch(X, topK):
+    """batch_test.py:96-107 on host arrays (kept for callers that already hold top-K ids)."""
+    import utility.utility_function.metrics as metrics
+    recommender_items = X[0].numpy() if torch.is_tensor(X[0]) else np.asarray(X[0])
+    ground_true_items = X[1]
+    r = metrics.get_label(ground_true_items, recommender_items)
+    precision, recall, ndcg = [], [], []
+    for k_size in topK:
+        recall.append(metrics.recall_at_k(r, k_size, ground_true_items))
+        precision.append(metrics.precision_at_k(r, k_size, ground_true_items))
+        ndcg.append(metrics.ndcg_at_k(r, k_size, ground_true_items))
+    return {'recall': np.array(recall), 'precision': np.array(precision), 'ndcg': np.array(ndcg)}

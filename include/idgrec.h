@@ -162,6 +162,11 @@ int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t 
 int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, void* stream);
 
+/* Same update with the step counter on the device (*d_step = steps already taken; incremented by
+ * the call): lets a captured CUDA graph of the whole train step be replayed unchanged. */
+int idg_adam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int32_t* d_step, void* stream);
+
 /* ---- a4: data_loader.py:108-127, exact replay on the HOST -------------------
  * h_cand: candidate stream = np.random.randint(0, I, size=n_cand) drawn from the
  * reference's RNG state.  Walks the train edges in file order, skipping candidates

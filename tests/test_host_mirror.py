@@ -1,0 +1,133 @@
+"""CPU tests of the host-side mirror (no GPU): data loader / sampler stream / config / metrics
+against golden vectors of the unmodified reference, and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+
+def _cfg(name="LightGCN"):
+    import utility.utility_function.tools as tools
+    return tools.read_configuration(os.path.join(REPO, "id-grec_b200", "configure", name + ".txt"), name)
+
+
+@pytest.mark.parametrize("name", ["LightGCN", "SimGCL", "XSimGCL", "NGCF", "MFBPR"])
+def test_configuration_files_parse_like_reference(name):
+    cfg = _cfg(name)
+    assert all(isinstance(v, str) for v in cfg.values())
+    assert eval(cfg["top_K"]) in ([10, 20], [20, 40])
+    assert int(cfg["embedding_size"]) == 64 and float(cfg["reg_lambda"]) == 1e-4
+    if name == "XSimGCL":
+        assert (float(cfg["epsilon"]), float(cfg["temperature"]), float(cfg["ssl_lambda"]), int(cfg["cl_layer"])) == (0.2, 0.15, 0.2, 1)
+    if name == "SimGCL":
+        assert (float(cfg["epsilon"]), float(cfg["temperature"]), float(cfg["ssl_lambda"]), int(cfg["batch_size"])) == (0.05, 0.2, 0.5, 2048)
+
+
+@pytest.mark.parametrize("name", ["tiny", "quirks"])
+def test_data_loader_matches_reference(golden_dirs, golden_tiny, golden_quirks, name):
+    from utility.utility_data.data_loader import Data
+    g = golden_tiny if name == "tiny" else golden_quirks
+    cfg = dict(_cfg(), dataset=name)
+    d = Data(golden_dirs[name], cfg)
+    assert (d.num_users, d.num_items, d.num_train, d.num_test) == tuple(int(g[k]) for k in ("num_users", "num_items", "num_train", "num_test"))
+    assert d.num_nodes == d.num_users + d.num_items
+    assert d.get_statistics() == str(g["stats"])
+    np.testing.assert_array_equal(d.train_user, g["train_user"])
+    np.testing.assert_array_equal(d.train_item, g["train_item"])
+    ptr = g["allpos_ptr"]
+    for u in range(d.num_users):
+        np.testing.assert_array_equal(d.all_positive[u], g["allpos_flat"][ptr[u]:ptr[u + 1]])
+    assert list(d.test_dict.keys()) == g["test_users"].tolist()
+    tp = g["test_ptr"]
+    for j, u in enumerate(g["test_users"].tolist()):
+        assert d.test_dict[u] == g["test_flat"][tp[j]:tp[j + 1]].tolist()
+    np.testing.assert_array_equal(d.user_item_net.indptr, g["net_indptr"])
+    np.testing.assert_array_equal(d.user_item_net.indices, g["net_indices"])
+    np.testing.assert_array_equal(d.user_item_net.data, g["net_data"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "quirks"])
+def test_sampler_and_shuffle_stream_bit_exact(golden_dirs, golden_tiny, golden_quirks, name):
+    """a4/a5: negatives, shuffle permutation and the numpy generator state after two epochs equal the
+    reference's (data_loader.py:108-127 + tools.py:41-42), through the C entry point."""
+    from utility.utility_data.data_loader import Data
+    import utility.utility_function.tools as tools
+    g = golden_tiny if name == "tiny" else golden_quirks
+    d = Data(golden_dirs[name], dict(_cfg(), dataset=name))
+    tools.set_seed(2024)
+    for ep in range(2):
+        s = d.sample_data_to_train_all()
+        np.testing.assert_array_equal(s, g["sample_ep%d" % ep])
+        _, perm = tools.shuffle(s[:, 0], indices=True)
+        np.testing.assert_array_equal(perm, g["perm_ep%d" % ep])
+    st = np.random.get_state()
+    assert st[2] == int(g["rng_after_pos"])
+    np.testing.assert_array_equal(st[1], g["rng_after_key"])
+
+
+def test_from_arrays_equals_text_loader(golden_dirs):
+    from utility.utility_data.data_loader import Data
+    d = Data(golden_dirs["tiny"], dict(_cfg(), dataset="tiny"))
+    e = Data.from_arrays(d.num_users, d.num_items, d.train_user, d.train_item, d.test_user, d.test_item, d.config)
+    assert list(e.test_dict.items()) == list(d.test_dict.items())
+    assert (e.user_item_net != d.user_item_net).nnz == 0
+
+
+def test_metrics_known_answers(golden_tiny):
+    import utility.utility_function.metrics as metrics
+    g = golden_tiny
+    truth = [[1, 2, 3], [7], list(range(4, 7)) + list(range(8, 27))]
+    pred = np.array([[1, 9, 2, 8, 3], [0, 1, 2, 3, 4], [4, 5, 6, 8, 9]])
+    r = metrics.get_label(truth, pred)
+    np.testing.assert_array_equal(r, g["mt_r"])
+    for j, k in enumerate((3, 5)):
+        got = (metrics.recall_at_k(r, k, truth), metrics.precision_at_k(r, k, truth), metrics.ndcg_at_k(r, k, truth))
+        np.testing.assert_allclose(got, g["mt_vals"][j], rtol=1e-12)
+
+
+def test_mini_batch_and_parser():
+    import Parser
+    import utility.utility_function.tools as tools
+    a = Parser.parse_args(["--model=LightGCN"])
+    assert (a.model, a.seed, a.gpu_id, a.cuda, a.seed_flag) == ("LightGCN", 2024, 0, True, True)
+    x = np.arange(10)
+    assert [len(b) for b in tools.mini_batch(x, batch_size=4)] == [4, 4, 2]
+    assert [tuple(len(t) for t in b) for b in tools.mini_batch(x, x, batch_size=5)] == [(5, 5), (5, 5)]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports exactly what include/idgrec.h declares."""
+    from idgrec import _lib
+    hdr = open(os.path.join(REPO, "include", "idgrec.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(idg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    _lib.build()
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(l, name), name
+    assert _lib.lib().idg_version() >= 100
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "id-grec_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert "ref_oracle" not in src and "from oracle" not in src and "import oracle" not in src, os.path.join(root, f)
+
+
+def test_models_fail_loudly_without_cuda(golden_dirs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from utility.utility_data.data_loader import Data
+    from models.LightGCN import LightGCN
+    d = Data(golden_dirs["tiny"], dict(_cfg(), dataset="tiny"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        LightGCN(dict(_cfg(), dataset="tiny"), d, torch.device("cpu"))
