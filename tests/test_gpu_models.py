@@ -88,8 +88,10 @@ def test_lightgcn_two_steps_vs_reference(dev, golden_dirs, golden_tiny, path):
             np.testing.assert_allclose(loss.cpu().numpy(), g["lg_loss_s%d" % st], rtol=RTOL)
             _close(ft.gE0[:d.num_users].cpu().numpy(), g["lg_gu_s%d" % st])
             _close(ft.gE0[d.num_users:].cpu().numpy(), g["lg_gi_s%d" % st])
-        np.testing.assert_allclose(m.user_embedding.weight.detach().cpu().numpy(), g["lg_user_w_s%d" % st], rtol=1e-5, atol=1e-8)
-        np.testing.assert_allclose(m.item_embedding.weight.detach().cpu().numpy(), g["lg_item_w_s%d" % st], rtol=1e-5, atol=1e-8)
+        # Adam's first steps move every weight by ~lr*g/(|g|+1e-8): entries with |g| ~ 1e-8 amplify the
+        # 1e-5 gradient tolerance, so the updated tables are compared at 1e-5 of the table scale
+        _close(m.user_embedding.weight.detach().cpu().numpy(), g["lg_user_w_s%d" % st])
+        _close(m.item_embedding.weight.detach().cpu().numpy(), g["lg_item_w_s%d" % st])
     if ft is not None:
         acc = ft.pop_epoch_losses()
         np.testing.assert_allclose(acc, g["lg_loss_s0"] + g["lg_loss_s1"], rtol=RTOL)
