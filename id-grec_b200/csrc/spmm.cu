@@ -8,15 +8,17 @@
 // Design (HBM/L2-bound gather, no tensor cores):
 //   * CSR rows are cut into work items of at most kChunk nonzeros; items are sorted
 //     longest-first (degree-sorted schedule) so the power-law tail starts early.
-//   * one warp per item.  (col,val) pairs are stored interleaved (int2) and read with
-//     one coalesced 8-byte load per lane, then broadcast by shuffle.
-//   * an embedding row of d = 4*LPR floats is covered by LPR lanes with one 128-bit
-//     load each, so a warp-wide LDG.128 gathers 32/LPR rows (2 rows at d=64); kUnroll
-//     independent gathers per lane are in flight before the FMAs.
+//   * one lane group per item: an embedding row of d = 4*LPR floats is covered by LPR
+//     lanes with one 128-bit load each, so a warp carries 32/LPR items (2 rows at d=64)
+//     of adjacent, hence similar, length.  (col,val) pairs are stored interleaved (int2)
+//     and read with one broadcast 8-byte load per nonzero (L1-resident: 16 per line);
+//     kUnroll independent gathers per lane are in flight before the FMAs and the next
+//     (col,val) quad is fetched while they fly.
 //   * the reduction order inside a row is a pure function of the row's nonzeros
-//     (lane-group partial sums over strided nonzeros, butterfly combine, chunk
-//     partials summed in chunk order by the last-arriving warp): deterministic,
-//     no float atomics, and independent of how rows are partitioned across GPUs.
+//     (ascending column order inside a chunk, chunk partials summed in chunk order by
+//     the last-arriving lane group): deterministic, no float atomics, and independent
+//     of how rows are partitioned across GPUs.
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -53,6 +55,9 @@ struct SpmmArgs {
     const float* acc_in;
     float* acc_out;
     float acc_div;
+    const int* worklist;      // optional: item ids to run (row-restricted layer), count in *d_wl_count
+    const int* d_wl_count;
+    const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
 };
 
 }  // namespace idg
@@ -63,6 +68,7 @@ struct idg_graph {
     int n_items = 0, n_heavy = 0, n_parts = 0;
     int2* colval = nullptr;
     int4* items = nullptr;
+    int2* row_items = nullptr;  // per local row: {first item, item count}
     idg::HeavyRow* heavy = nullptr;
     float* partials = nullptr;
     int* counters = nullptr;
@@ -70,8 +76,18 @@ struct idg_graph {
 
 namespace idg {
 
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    // embedding gathers have ~no L1 reuse (ncu: 2.5% hit rate): keep L1 for the (col,val) stream
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <bool NA>
+__device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
+
 template <int LPR>
-__device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, bool writer, float4 y) {
+__device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
     constexpr int d = 4 * LPR;
     const size_t off = (size_t)grow * d + sub * 4;
     if (a.addend) y = f4add(y, ldcs4(a.addend + off));
@@ -81,14 +97,13 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
         float4 nz = ldcs4(a.noise + off);
         float ss = nz.x * nz.x + nz.y * nz.y + nz.z * nz.z + nz.w * nz.w;
 #pragma unroll
-        for (int m = LPR / 2; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+        for (int m = LPR / 2; m >= 1; m >>= 1) ss += __shfl_xor_sync(gmask, ss, m);
         const float nrm = fmaxf(sqrtf(ss), 1e-12f);
         y.x += (sgn(y.x) * (nz.x / nrm)) * a.eps;
         y.y += (sgn(y.y) * (nz.y / nrm)) * a.eps;
         y.z += (sgn(y.z) * (nz.z / nrm)) * a.eps;
         y.w += (sgn(y.w) * (nz.w / nrm)) * a.eps;
     }
-    if (!writer) return;
     if (a.Y) st4(a.Y + off, y);
     if (a.acc_out) {
         float4 s = y;
@@ -98,60 +113,97 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
     }
 }
 
-template <int LPR>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) spmm_kernel(const SpmmArgs a) {
+// One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
+// 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
+// load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
+    constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
-    constexpr int G = 32 / LPR;  // rows gathered per warp-wide load
+    constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
-    const int item = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (item >= a.n_items) return;
-    const int4 it = __ldg(a.items + item);
     const int group = lane / LPR, sub = lane % LPR;
-    const float* __restrict__ X = a.X;
-
-    float4 acc = f4zero();
-    for (int base = it.y; base < it.z; base += 32) {
-        const int n = min(32, it.z - base);
-        int2 cv = make_int2(0, 0);
-        if (lane < n) cv = __ldg(a.colval + base + lane);
-        for (int j = 0; j < n; j += G * kUnroll) {
-            float4 x[kUnroll];
-            float w[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int k = j + u * G + group;
-                const int c = __shfl_sync(0xffffffffu, cv.x, k & 31);
-                w[u] = __int_as_float(__shfl_sync(0xffffffffu, cv.y, k & 31));
-                x[u] = f4zero();
-                if (k < n) x[u] = ldg4(X + (size_t)c * d + sub * 4);
-                else w[u] = 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) acc = f4fma(w[u], x[u], acc);
-        }
-    }
-    // combine the G lane-group partial sums (butterfly: every lane ends with the same bits)
-#pragma unroll
-    for (int m = LPR; m < 32; m <<= 1) acc = f4add(acc, f4shfl_xor(acc, m));
-
-    if (it.w < 0) {
-        finish_row<LPR>(a, a.row_offset + it.x, sub, group == 0, acc);
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (group * LPR));
+    const int slot = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + group;
+    int item = slot;
+    if (a.worklist) {
+        if (slot >= __ldg(a.d_wl_count)) return;
+        item = __ldg(a.worklist + slot);
+    } else if (slot >= a.n_items) {
         return;
     }
-    // chunk of a heavy row: publish the partial, the last chunk to arrive reduces in chunk order
+    const int4 it = __ldg(a.items + item);
+    const float* __restrict__ X = a.X + sub * 4;
+    const int2* __restrict__ cvp = a.colval;
+
+    float4 acc = f4zero();
+    int k = it.y;
+    const int end = it.z;
+    if (SPARSE) {
+        // X is zero outside the rows flagged in the bitmap (first backward layer: dL/dF touches only
+        // the batch rows): stream the (col,val) list, gather only flagged columns, same ascending order.
+        for (int base = k; base < end; base += LPR) {
+            const int kk = base + sub;
+            int2 c = make_int2(0, 0);
+            bool hit = false;
+            if (kk < end) {
+                c = __ldg(cvp + kk);
+                hit = (__ldg(a.bitmap + (c.x >> 5)) >> (c.x & 31)) & 1u;
+            }
+            unsigned m = __ballot_sync(gmask, hit);
+            if (LPR < 32) m = (m >> (group * LPR)) & ((1u << (LPR & 31)) - 1u);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int col = __shfl_sync(gmask, c.x, group * LPR + j);
+                const float w = __int_as_float(__shfl_sync(gmask, c.y, group * LPR + j));
+                acc = f4fma(w, ldg4(X + (size_t)col * d), acc);
+            }
+        }
+        k = end;
+    }
+    if (k + kU <= end) {
+        int2 cv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + u);
+        for (; k + kU <= end; k += kU) {
+            float4 x[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) x[u] = gat<NA>(X + (size_t)cv[u].x * d);
+            float w[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) w[u] = __int_as_float(cv[u].y);
+            if (k + 2 * kU <= end) {  // software pipeline: next (col,val) quad while the gathers fly
+#pragma unroll
+                for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + kU + u);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) acc = f4fma(w[u], x[u], acc);
+        }
+    }
+    for (; k < end; ++k) {
+        const int2 c = __ldg(cvp + k);
+        acc = f4fma(__int_as_float(c.y), gat<NA>(X + (size_t)c.x * d), acc);
+    }
+
+    if (it.w < 0) {
+        finish_row<LPR>(a, a.row_offset + it.x, sub, gmask, acc);
+        return;
+    }
+    // chunk of a heavy row: publish the partial; the last chunk to arrive sums them in chunk order
     const HeavyRow h = a.heavy[it.x];
-    if (group == 0) stcg4(a.partials + (size_t)it.w * d + sub * 4, acc);
+    stcg4(a.partials + (size_t)it.w * d + sub * 4, acc);
     __threadfence();
-    __syncwarp();
+    __syncwarp(gmask);
     int old = 0;
-    if (lane == 0) old = atomicAdd(a.counters + it.x, 1);
-    old = __shfl_sync(0xffffffffu, old, 0);
+    if (sub == 0) old = atomicAdd(a.counters + it.x, 1);
+    old = __shfl_sync(gmask, old, group * LPR);
     if (old != h.n_parts - 1) return;
     __threadfence();
     float4 s = ldcg4(a.partials + (size_t)h.part_begin * d + sub * 4);
     for (int p = 1; p < h.n_parts; ++p) s = f4add(s, ldcg4(a.partials + (size_t)(h.part_begin + p) * d + sub * 4));
-    if (lane == 0) a.counters[it.x] = 0;  // ready for the next launch
-    finish_row<LPR>(a, a.row_offset + h.row, sub, group == 0, s);
+    if (sub == 0) a.counters[it.x] = 0;  // ready for the next launch
+    finish_row<LPR>(a, a.row_offset + h.row, sub, gmask, s);
 }
 
 __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int2* __restrict__ out, int64_t nnz) {
@@ -192,17 +244,22 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
             heavy.push_back(h);
         }
     }
-    // degree-sorted schedule: full chunks first, then whole rows longest-first (stable => deterministic)
-    std::stable_sort(parts.begin(), parts.end(), [](const int4& x, const int4& y) { return (x.z - x.y) > (y.z - y.y); });
+    // degree-sorted schedule: chunks of heavy rows first (contiguous per row), then whole rows
+    // longest-first (stable => deterministic)
     std::stable_sort(light.begin(), light.end(), [](const int4& x, const int4& y) { return (x.z - x.y) > (y.z - y.y); });
     std::vector<int4> items(parts);
     items.insert(items.end(), light.begin(), light.end());
+    std::vector<int2> row_items((size_t)std::max(n_rows, 1));
+    for (size_t h = 0; h < heavy.size(); ++h) row_items[heavy[h].row] = make_int2(heavy[h].part_begin, heavy[h].n_parts);
+    for (size_t i = 0; i < light.size(); ++i) row_items[light[i].x] = make_int2((int)(parts.size() + i), 1);
     g->n_items = (int)items.size(); g->n_heavy = (int)heavy.size(); g->n_parts = (int)parts.size();
 
 #define G_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { idg_graph_destroy(g); return cuda_fail(_e, #expr); } } while (0)
     G_CUDA(cudaMalloc(&g->colval, sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
     G_CUDA(cudaMalloc(&g->items, sizeof(int4) * (size_t)std::max(g->n_items, 1)));
     G_CUDA(cudaMalloc(&g->heavy, sizeof(HeavyRow) * (size_t)std::max(g->n_heavy, 1)));
+    G_CUDA(cudaMalloc(&g->row_items, sizeof(int2) * row_items.size()));
+    G_CUDA(cudaMemcpyAsync(g->row_items, row_items.data(), sizeof(int2) * row_items.size(), cudaMemcpyHostToDevice, stream));
     G_CUDA(cudaMalloc(&g->partials, sizeof(float) * 128 * (size_t)std::max(g->n_parts, 1)));
     G_CUDA(cudaMalloc(&g->counters, sizeof(int) * (size_t)std::max(g->n_heavy, 1)));
     G_CUDA(cudaMemsetAsync(g->counters, 0, sizeof(int) * (size_t)std::max(g->n_heavy, 1), stream));
@@ -221,15 +278,22 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
 
 extern "C" void idg_graph_destroy(idg_graph* g) {
     if (!g) return;
-    cudaFree(g->colval); cudaFree(g->items); cudaFree(g->heavy); cudaFree(g->partials); cudaFree(g->counters);
+    cudaFree(g->colval); cudaFree(g->items); cudaFree(g->row_items); cudaFree(g->heavy); cudaFree(g->partials); cudaFree(g->counters);
     delete g;
 }
 extern "C" int64_t idg_graph_nnz(const idg_graph* g) { return g ? g->nnz : -1; }
 extern "C" int32_t idg_graph_rows(const idg_graph* g) { return g ? g->n_rows : -1; }
 
+struct SpmmExtra {
+    const int* worklist = nullptr;   // row-restricted launch
+    const int* d_wl_count = nullptr;
+    int max_wl = 0;
+    const unsigned* bitmap = nullptr;  // sparse-input launch
+};
+
 static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
                        float scale2, const float* d_noise, float eps, const float* d_acc_in, float* d_acc_out, float acc_div,
-                       int32_t d, void* stream_) {
+                       int32_t d, void* stream_, const SpmmExtra& ex = SpmmExtra()) {
     if (!g || !d_X) return fail(-1, "idg_spmm_layer: null graph or X%s");
     if (!d_Y && !d_acc_out) return fail(-1, "idg_spmm_layer: no output requested%s");
     if (d_X == d_Y || d_X == d_acc_out) return fail(-1, "idg_spmm_layer: X must not alias an output%s");
@@ -241,11 +305,24 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.partials = g->partials; a.counters = g->counters; a.row_offset = g->row_offset;
     a.X = d_X; a.Y = d_Y; a.addend = d_addend; a.addend2 = d_addend2; a.scale2 = scale2; a.noise = d_noise; a.eps = eps;
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
-    const unsigned grid = (unsigned)((g->n_items + kWarpsPerCta - 1) / kWarpsPerCta);
+    a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap;
+    const int per_cta = kWarpsPerCta * (32 / (d / 4));  // items per CTA: one lane group each
+    const int n_slots = ex.worklist ? ex.max_wl : g->n_items;
+    if (n_slots <= 0) return 0;
+    const unsigned grid = (unsigned)((n_slots + per_cta - 1) / per_cta);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (d == 64) spmm_kernel<16><<<grid, kWarpsPerCta * 32, 0, stream>>>(a);
-    else if (d == 32) spmm_kernel<8><<<grid, kWarpsPerCta * 32, 0, stream>>>(a);
-    else spmm_kernel<32><<<grid, kWarpsPerCta * 32, 0, stream>>>(a);
+    const int T = kWarpsPerCta * 32;
+    // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
+    // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
+    if (ex.bitmap) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+    } else {
+        if (d == 64) spmm_kernel<16, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8><<<grid, T, 0, stream>>>(a);
+    }
     IDG_LAUNCH_CHECK("spmm_kernel");
     return 0;
 }
@@ -255,14 +332,115 @@ extern "C" int idg_spmm_layer(const idg_graph* g, const float* d_X, float* d_Y, 
     return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, d_noise, eps, d_acc_in, d_acc_out, acc_div, d, stream);
 }
 
-// K-layer forward, single GPU (models/LightGCN.py:36-52, SimGCL.py:39-60, XSimGCL.py:40-67).
-extern "C" int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t d, int32_t K, int include_layer0,
-                                 const float* d_noise, float eps, int32_t cl_layer, float* d_out_mean, float* d_out_cl,
-                                 float* d_work, void* stream) {
+// ---- batch row set: unique rows touched by a mini-batch, as a list and as a bitmap ----------------
+namespace idg {
+// one warp per entry e of the 3B keys (user, U+pos, U+neg); the first occurrence of a row appends it
+__global__ void __launch_bounds__(256) batch_rows_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ pos,
+                                                         const int64_t* __restrict__ neg, int B, int U, int* __restrict__ rowlist,
+                                                         int* __restrict__ count, unsigned* __restrict__ bitmap) {
+    extern __shared__ int skeys[];
+    const int n = 3 * B;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int role = i / B, b = i - role * B;
+        skeys[i] = role == 0 ? (int)user[b] : U + (int)(role == 1 ? pos[b] : neg[b]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= n) return;
+    const int node = skeys[e];
+    for (int base = 0; base < e; base += 32) {
+        const int i = base + lane;
+        if (__any_sync(0xffffffffu, (i < e) && (skeys[i] == node))) return;
+    }
+    if (lane == 0) {
+        rowlist[atomicAdd(count, 1)] = node;
+        atomicOr(bitmap + (node >> 5), 1u << (node & 31));
+    }
+}
+
+__global__ void batch_rows_clear_kernel(const int* __restrict__ rowlist, const int* __restrict__ count, unsigned* __restrict__ bitmap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count) bitmap[rowlist[i] >> 5] = 0u;  // every set bit belongs to a listed row
+}
+
+// rows -> item ids of the schedule (heavy rows expand to all their chunks); rows outside [row_offset, +n_rows) are skipped
+__global__ void expand_rows_kernel(const int* __restrict__ rowlist, const int* __restrict__ count, const int2* __restrict__ row_items,
+                                   int row_offset, int n_rows, int* __restrict__ worklist, int* __restrict__ wl_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const int r = rowlist[i] - row_offset;
+    if (r < 0 || r >= n_rows) return;
+    const int2 ri = row_items[r];
+    const int p = atomicAdd(wl_count, ri.y);
+    for (int q = 0; q < ri.y; ++q) worklist[p + q] = ri.x + q;
+}
+}  // namespace idg
+
+extern "C" int idg_batch_rows(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                              int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, void* stream_) {
+    if (!d_user || !d_pos || !d_neg || !d_rowlist || !d_count || !d_bitmap || B <= 0) return fail(-1, "idg_batch_rows: bad argument%s");
+    const size_t smem = sizeof(int) * 3 * (size_t)B;
+    if (smem > 200 * 1024) return fail(-1, "idg_batch_rows: batch too large (B=%s%lld)", "", B);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    IDG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
+    if (smem > 48 * 1024) IDG_CUDA(cudaFuncSetAttribute(batch_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    batch_rows_kernel<<<(3 * B + 7) / 8, 256, smem, stream>>>(d_user, d_pos, d_neg, B, U, d_rowlist, d_count, d_bitmap);
+    IDG_LAUNCH_CHECK("batch_rows_kernel");
+    return 0;
+}
+
+extern "C" int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, uint32_t* d_bitmap, void* stream) {
+    if (!d_rowlist || !d_count || !d_bitmap || max_rows <= 0) return fail(-1, "idg_batch_rows_clear: bad argument%s");
+    batch_rows_clear_kernel<<<(max_rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_rowlist, d_count, d_bitmap);
+    IDG_LAUNCH_CHECK("batch_rows_clear_kernel");
+    return 0;
+}
+
+extern "C" int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows) {
+    return g ? (int64_t)max_rows + g->n_parts + 8 : -1;
+}
+
+// one layer restricted to the listed rows (d_worklist: idg_graph_worklist_ints(g, max_rows) ints of scratch)
+static int spmm_rows(const idg_graph* g, const float* X, float* Y, const float* noise, float eps, const float* acc_in, float* acc_out,
+                     float acc_div, int d, const int* d_rowlist, const int* d_count, int max_rows, int* d_worklist, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int* wl_count = d_worklist;  // first int = number of work items, list follows (aligned to 4 ints)
+    IDG_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(int), stream));
+    expand_rows_kernel<<<(max_rows + 255) / 256, 256, 0, stream>>>(d_rowlist, d_count, g->row_items, g->row_offset, g->n_rows, d_worklist + 4, wl_count);
+    IDG_LAUNCH_CHECK("expand_rows_kernel");
+    SpmmExtra ex;
+    ex.worklist = d_worklist + 4; ex.d_wl_count = wl_count; ex.max_wl = max_rows + g->n_parts;
+    return spmm_launch(g, X, Y, nullptr, nullptr, 0.f, noise, eps, acc_in, acc_out, acc_div, d, stream_, ex);
+}
+
+extern "C" int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
+                                   const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d, const int32_t* d_rowlist,
+                                   const int32_t* d_count, int32_t max_rows, int32_t* d_worklist, void* stream) {
+    if (!g || !d_rowlist || !d_count || !d_worklist || max_rows <= 0) return fail(-1, "idg_spmm_layer_rows: bad argument%s");
+    return spmm_rows(g, d_X, d_Y, d_noise, eps, d_acc_in, d_acc_out, acc_div, d, d_rowlist, d_count, max_rows, d_worklist, stream);
+}
+
+extern "C" int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_acc_in,
+                                        float* d_acc_out, float acc_div, int32_t d, const uint32_t* d_bitmap, void* stream) {
+    if (!d_bitmap) return fail(-1, "idg_spmm_layer_sparse_in: null bitmap%s");
+    SpmmExtra ex;
+    ex.bitmap = d_bitmap;
+    return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, d_acc_in, d_acc_out, acc_div, d, stream, ex);
+}
+
+// K-layer forward, single GPU (models/LightGCN.py:36-52, SimGCL.py:39-60, XSimGCL.py:40-67).  With a row list the
+// LAST layer (and with it the layer mean) is evaluated only on those rows: the loss reads nothing else
+// (LightGCN.py:57-59), so the result is identical where it is consumed and ~1/K of the gather work disappears.
+extern "C" int idg_propagate_fwd_ex(const idg_graph* g, const float* d_X0, int32_t d, int32_t K, int include_layer0,
+                                    const float* d_noise, float eps, int32_t cl_layer, float* d_out_mean, float* d_out_cl,
+                                    float* d_work, const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows,
+                                    int32_t* d_worklist, void* stream) {
     if (!g || !d_X0 || !d_out_mean || !d_work) return fail(-1, "idg_propagate_fwd: null argument%s");
     if (K < 1) return fail(-1, "idg_propagate_fwd: K must be >= 1%s");
     if (g->row_offset != 0 || g->n_rows != g->n_cols) return fail(-1, "idg_propagate_fwd: needs the whole square graph (use idg_spmm_layer per rank)%s");
     if (cl_layer > K || (cl_layer > 0 && !d_out_cl)) return fail(-1, "idg_propagate_fwd: bad cl_layer%s");
+    if (d_rowlist && (!d_count || !d_worklist || max_rows <= 0)) return fail(-1, "idg_propagate_fwd: incomplete row restriction%s");
     const size_t nd = (size_t)g->n_rows * d;
     float* buf[2] = {d_work, d_work + nd};
     const float cnt = (float)(K + (include_layer0 ? 1 : 0));
@@ -273,19 +451,32 @@ extern "C" int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t 
         const bool need_y = !last || l == cl_layer;
         // the running layer sum lives in d_out_mean; the last layer divides by the layer count
         const float* acc_in = (l == 1) ? (include_layer0 ? d_X0 : nullptr) : d_out_mean;
-        int rc = idg_spmm_layer(g, x, need_y ? y : nullptr, nullptr, d_noise ? d_noise + (size_t)(l - 1) * nd : nullptr, eps,
-                                acc_in, d_out_mean, last ? cnt : 1.0f, d, stream);
+        const float* nz = d_noise ? d_noise + (size_t)(l - 1) * nd : nullptr;
+        int rc;
+        if (last && d_rowlist)
+            rc = spmm_rows(g, x, need_y ? y : nullptr, nz, eps, acc_in, d_out_mean, cnt, d, d_rowlist, d_count, max_rows, d_worklist, stream);
+        else
+            rc = idg_spmm_layer(g, x, need_y ? y : nullptr, nullptr, nz, eps, acc_in, d_out_mean, last ? cnt : 1.0f, d, stream);
         if (rc) return rc;
         x = y;
     }
     return 0;
 }
 
+extern "C" int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t d, int32_t K, int include_layer0,
+                                 const float* d_noise, float eps, int32_t cl_layer, float* d_out_mean, float* d_out_cl,
+                                 float* d_work, void* stream) {
+    return idg_propagate_fwd_ex(g, d_X0, d, K, include_layer0, d_noise, eps, cl_layer, d_out_mean, d_out_cl, d_work, nullptr, nullptr, 0,
+                                nullptr, stream);
+}
+
 // Backward of idg_propagate_fwd w.r.t. X0 (autograd of torch.sparse.mm + stack/mean, trainer.py:55).
 // With H_l = cnt * dL/dX_l:  H_K = G (+cnt*Gcl if cl==K);  H_l = G + A H_{l+1} (+cnt*Gcl if cl==l);
 // gX0 = (inc0*G + A H_1)/cnt.  The sign-noise perturbation has identity gradient (SimGCL.py:51).
-extern "C" int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
-                                 int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, void* stream) {
+// With d_bitmap (rows where G / Gcl are non-zero) the first product A*H_K only gathers flagged columns.
+extern "C" int idg_propagate_bwd_ex(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                                    int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, const uint32_t* d_bitmap,
+                                    void* stream) {
     if (!g || !d_G || !d_gX0 || !d_work) return fail(-1, "idg_propagate_bwd: null argument%s");
     if (K < 1) return fail(-1, "idg_propagate_bwd: K must be >= 1%s");
     if (g->row_offset != 0 || g->n_rows != g->n_cols) return fail(-1, "idg_propagate_bwd: needs the whole square graph%s");
@@ -302,15 +493,22 @@ extern "C" int idg_propagate_bwd(const idg_graph* g, const float* d_G, const flo
     }
     for (int s = 1; s <= K; ++s) {
         const int layer = K - s;  // index of the H being produced; 0 => gX0
+        SpmmExtra ex;
+        if (s == 1) ex.bitmap = d_bitmap;
         if (layer > 0) {
             float* y = buf[pb]; pb ^= 1;
-            rc = spmm_launch(g, h, y, d_G, (d_Gcl && cl_layer == layer) ? d_Gcl : nullptr, cnt, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream);
+            rc = spmm_launch(g, h, y, d_G, (d_Gcl && cl_layer == layer) ? d_Gcl : nullptr, cnt, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);
             if (rc) return rc;
             h = y;
         } else {
-            rc = spmm_launch(g, h, nullptr, include_layer0 ? d_G : nullptr, nullptr, 0.f, nullptr, 0.f, nullptr, d_gX0, cnt, d, stream);
+            rc = spmm_launch(g, h, nullptr, include_layer0 ? d_G : nullptr, nullptr, 0.f, nullptr, 0.f, nullptr, d_gX0, cnt, d, stream, ex);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+extern "C" int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                                 int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, void* stream) {
+    return idg_propagate_bwd_ex(g, d_G, d_Gcl, d, K, include_layer0, cl_layer, d_gX0, d_work, nullptr, stream);
 }

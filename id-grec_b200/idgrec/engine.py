@@ -19,7 +19,8 @@ from ._lib import check, cur_stream, ptr
 
 class FusedTrainer:
     def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
-                 eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8):
+                 eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8,
+                 restrict_rows=True):
         assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR")
         self.l = _lib.lib()
         self.kind, self.graph, self.E0 = kind, graph, table
@@ -44,10 +45,19 @@ class FusedTrainer:
             self.V1 = torch.empty_like(table)
             self.V2 = torch.empty_like(table) if kind == "SimGCL" else None
             self.Gcl = z() if kind == "XSimGCL" else None
+        # identical-result work skipping (SURVEY.md 8 d): last forward layer only on the batch rows, first
+        # backward product only over the batch columns
+        self.rows = None
         if kind != "MFBPR":
             graph.work(self.d)  # allocate the layer ping-pong buffers before any graph capture
+            if restrict_rows:
+                from .graph import BatchRows
+                self.rows = BatchRows(self.N, max_batch, dev)
+                self.rows.worklist(graph)
         self.use_cuda_graph = use_cuda_graph and kind in ("LightGCN", "MFBPR")
         self._graphs = {}
+        self._graph_launches = {}
+        self.replayed_launches = 0  # kernels launched through graph replays (bench.py gpu_launches)
         self.injected_noise = None  # parity tests: list of per-view [K,N,d] tensors
 
     # ------------------------------------------------------------------ pieces
@@ -76,10 +86,13 @@ class FusedTrainer:
     def _body(self, B, u, p, n, users_t=None, pos_t=None):
         """Kernels of one step for batch pointers u/p/n (device int64)."""
         g, K = self.graph, self.K
+        rows = self.rows
+        if rows is not None:
+            rows.build(u, p, n, B, self.U)
         if self.kind == "LightGCN":
-            g.propagate_fwd(self.E0, K, True, out_mean=self.F)
+            g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
             self._bpr(B, u, p, n)
-            g.propagate_bwd(self.G, K, True, out=self.gE0)
+            g.propagate_bwd(self.G, K, True, out=self.gE0, rows=rows)
         elif self.kind == "MFBPR":
             self._bpr(B, u, p, n)
             self.gE0.copy_(self.G)
@@ -88,11 +101,11 @@ class FusedTrainer:
             uidx = torch.unique(users_t)
             iidx = torch.unique(pos_t) + self.U
             if self.kind == "SimGCL":
-                g.propagate_fwd(self.E0, K, False, out_mean=self.F)
+                g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)
                 self._draw_noise(0)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1, rows=rows)
                 self._draw_noise(1)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2, rows=rows)
                 self._bpr(B, u, p, n)
                 self.loss[2] = 0.0
                 # the three propagations share one linear backward operator: accumulate all row
@@ -101,20 +114,22 @@ class FusedTrainer:
                     check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.V2), ptr(idx), idx.numel(), self.d, self.temperature,
                                                 self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
                           "idg_infonce_fwd_bwd")
-                g.propagate_bwd(self.G, K, False, out=self.gE0)
+                g.propagate_bwd(self.G, K, False, out=self.gE0, rows=rows)
             else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
                 self._draw_noise(0)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1)
+                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
                 self._bpr(B, u, p, n)
                 self.loss[2] = 0.0
                 for idx in (uidx, iidx):
                     check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.F), ptr(idx), idx.numel(), self.d, self.temperature,
                                                 self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
                           "idg_infonce_fwd_bwd")
-                g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=self.gE0)
+                g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=self.gE0, rows=rows)
                 for idx in (uidx, iidx):
                     check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), idx.numel(), self.d, s), "idg_zero_rows")
         self._finish(B)
+        if rows is not None:
+            rows.clear()
 
     # ------------------------------------------------------------------ public
     def step(self, users, pos, neg, apply_adam=True):
@@ -137,6 +152,7 @@ class FusedTrainer:
         if B not in self._graphs:
             self._capture(B)
         self._graphs[B].replay()
+        self.replayed_launches += self._graph_launches[B]
         self.step_count += 1
         return self.loss[:self.n_loss]
 
@@ -154,9 +170,11 @@ class FusedTrainer:
 
         # warm-up outside capture would advance the model; capture directly (kernels are launched lazily at replay)
         torch.cuda.synchronize()
+        n0 = self.l.idg_launch_count()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
             run()
+        self._graph_launches[B] = int(self.l.idg_launch_count() - n0)
         self._graphs[B] = gr
 
     def sync_step_counter(self):

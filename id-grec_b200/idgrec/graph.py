@@ -118,20 +118,51 @@ class Graph:
         check(_lib.lib().idg_spmm_layer(self._h, ptr(X), ptr(Y), ptr(addend), ptr(noise), float(eps), ptr(acc_in), ptr(acc_out),
                                         float(acc_div), d, cur_stream()), "idg_spmm_layer")
 
-    def propagate_fwd(self, X0, K, include_layer0, noise=None, eps=0.0, cl_layer=0, out_mean=None, out_cl=None):
+    def propagate_fwd(self, X0, K, include_layer0, noise=None, eps=0.0, cl_layer=0, out_mean=None, out_cl=None, rows=None):
+        """K layers + layer mean.  ``rows`` (a BatchRows) restricts the last layer and the mean to those rows."""
         d = X0.shape[1]
         if out_mean is None:
             out_mean = torch.empty_like(X0)
         if cl_layer > 0 and out_cl is None:
             out_cl = torch.empty_like(X0)
-        check(_lib.lib().idg_propagate_fwd(self._h, ptr(X0), d, K, int(include_layer0), ptr(noise), float(eps), cl_layer,
-                                           ptr(out_mean), ptr(out_cl), ptr(self.work(d)), cur_stream()), "idg_propagate_fwd")
+        r = rows
+        check(_lib.lib().idg_propagate_fwd_ex(self._h, ptr(X0), d, K, int(include_layer0), ptr(noise), float(eps), cl_layer,
+                                              ptr(out_mean), ptr(out_cl), ptr(self.work(d)),
+                                              ptr(r.rowlist) if r else None, ptr(r.count) if r else None, r.max_rows if r else 0,
+                                              ptr(r.worklist(self)) if r else None, cur_stream()), "idg_propagate_fwd_ex")
         return (out_mean, out_cl) if cl_layer > 0 else out_mean
 
-    def propagate_bwd(self, G, K, include_layer0, Gcl=None, cl_layer=0, out=None):
+    def propagate_bwd(self, G, K, include_layer0, Gcl=None, cl_layer=0, out=None, rows=None):
+        """Backward w.r.t. X0.  ``rows``: G (and Gcl) are zero outside those rows -> sparse-input first product."""
         d = G.shape[1]
         if out is None:
             out = torch.empty_like(G)
-        check(_lib.lib().idg_propagate_bwd(self._h, ptr(G), ptr(Gcl), d, K, int(include_layer0), cl_layer, ptr(out),
-                                           ptr(self.work(d)), cur_stream()), "idg_propagate_bwd")
+        check(_lib.lib().idg_propagate_bwd_ex(self._h, ptr(G), ptr(Gcl), d, K, int(include_layer0), cl_layer, ptr(out),
+                                              ptr(self.work(d)), ptr(rows.bitmap) if rows else None, cur_stream()), "idg_propagate_bwd_ex")
         return out
+
+
+class BatchRows:
+    """Unique rows {user, U+pos, U+neg} of a mini-batch on the device: list + count + bitmap."""
+
+    def __init__(self, N, max_batch, device):
+        self.max_rows = 3 * max_batch
+        self.rowlist = torch.zeros(self.max_rows, dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.bitmap = torch.zeros((N + 31) // 32 + 1, dtype=torch.int32, device=device)
+        self._wl = {}
+
+    def worklist(self, graph):
+        k = id(graph)
+        if k not in self._wl:
+            n = int(_lib.lib().idg_graph_worklist_ints(graph._h, self.max_rows))
+            self._wl[k] = torch.zeros(n, dtype=torch.int32, device=self.rowlist.device)
+        return self._wl[k]
+
+    def build(self, users_ptr, pos_ptr, neg_ptr, B, num_users):
+        check(_lib.lib().idg_batch_rows(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),
+                                        cur_stream()), "idg_batch_rows")
+
+    def clear(self):
+        check(_lib.lib().idg_batch_rows_clear(ptr(self.rowlist), ptr(self.count), self.max_rows, ptr(self.bitmap), cur_stream()),
+              "idg_batch_rows_clear")

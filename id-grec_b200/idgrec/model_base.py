@@ -84,7 +84,8 @@ class PropagationModel(nn.Module):
                 self.kind, self.Graph, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda, lr,
                 ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),
                 eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)), max_batch=max_batch,
-                use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'))
+                use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
+                restrict_rows=str(cfg.get('restrict_rows', '1')) not in ('0', 'False', 'false'))
         return self._fused
 
     # -- evaluation ------------------------------------------------------------------------------

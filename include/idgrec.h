@@ -94,6 +94,37 @@ int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t d, int32_t 
 int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
                       int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, void* stream);
 
+/* ---- work the loss never looks at (identical results, SURVEY.md 8 d "row-restricted last layer") ----
+ * idg_batch_rows: unique rows {user, U+pos, U+neg} of a mini-batch as a list (order unspecified) with
+ * its length in *d_count, and as bits set in d_bitmap (ceil(N/32) words, all zero on entry).
+ * idg_batch_rows_clear zeroes those bits again.  d_rowlist holds up to 3B ints. */
+int idg_batch_rows(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                   int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, void* stream);
+int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, uint32_t* d_bitmap,
+                         void* stream);
+/* scratch ints needed by the row-restricted entry points for up to max_rows listed rows */
+int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows);
+/* idg_spmm_layer evaluated only on the listed rows (other rows of the outputs are left untouched) */
+int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
+                        const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
+                        const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, int32_t* d_worklist,
+                        void* stream);
+/* idg_spmm_layer for an X that is zero outside the rows flagged in d_bitmap: streams the CSR structure
+ * but gathers only flagged columns (first backward layer: dL/dF is non-zero on the batch rows only) */
+int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend,
+                             const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
+                             const uint32_t* d_bitmap, void* stream);
+/* idg_propagate_fwd whose LAST layer and layer mean are evaluated only on the listed rows
+ * (d_rowlist NULL => identical to idg_propagate_fwd); idg_propagate_bwd whose FIRST product uses the
+ * sparse-input kernel (d_bitmap NULL => identical to idg_propagate_bwd). */
+int idg_propagate_fwd_ex(const idg_graph* g, const float* d_X0, int32_t d, int32_t K, int include_layer0,
+                         const float* d_noise, float eps, int32_t cl_layer, float* d_out_mean, float* d_out_cl,
+                         float* d_work, const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows,
+                         int32_t* d_worklist, void* stream);
+int idg_propagate_bwd_ex(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                         int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work,
+                         const uint32_t* d_bitmap, void* stream);
+
 /* ---- a9: models/LightGCN.py:54-72 + utility_function/losses.py:4-21 ---------
  * Fused gather + dot + -log(sigmoid+1e-7) + L2-reg, forward and backward.
  *   F  [N,d]  final embeddings (users rows 0..U-1, items U..N-1)

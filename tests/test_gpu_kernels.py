@@ -134,6 +134,50 @@ def test_propagate_fwd_bwd(dev, inc0, use_noise, cl):
     _assert_close(Xg.grad.cpu().numpy(), Xr.grad.numpy())
 
 
+def test_row_restricted_and_sparse_input_layers(dev):
+    """The two identical-result shortcuts of the fused trainer: last forward layer only on the batch
+    rows, first backward product only over the batch columns (heavy rows included)."""
+    from idgrec.graph import BatchRows
+    U, I, K, d, B = 900, 1300, 3, 64, 300
+    u, i = _rand_graph(U, I, 25000, 13, hub=600)
+    G, A = _graph_and_oracle(dev, U, I, u, i)
+    gen = torch.Generator().manual_seed(9)
+    X0 = ((torch.rand(U + I, d, generator=gen) - 0.5) * 0.2).to(dev)
+    users = torch.randint(0, U, (B,), generator=gen)
+    users[:5] = 0                                   # hub user (heavy row)
+    pos = torch.randint(0, 30, (B,), generator=gen)
+    pos[:5] = 0                                     # hub item
+    neg = torch.randint(0, I, (B,), generator=gen)
+    rows = BatchRows(U + I, B, dev)
+    ud, pd_, nd = users.to(dev), pos.to(dev), neg.to(dev)
+    rows.build(ud.data_ptr(), pd_.data_ptr(), nd.data_ptr(), B, U)
+    want = np.unique(np.concatenate([users.numpy(), U + pos.numpy(), U + neg.numpy()]))
+    n = int(rows.count.item())
+    assert n == len(want)
+    np.testing.assert_array_equal(np.sort(rows.rowlist[:n].cpu().numpy()), want)
+    bits = rows.bitmap.cpu().numpy().view(np.uint32)
+    got = np.flatnonzero(np.unpackbits(bits.view(np.uint8), bitorder="little"))
+    np.testing.assert_array_equal(got, want)
+    # forward: restricted rows equal the full propagation bit for bit
+    full = G.propagate_fwd(X0, K, True)
+    part = G.propagate_fwd(X0, K, True, rows=rows)
+    w = torch.from_numpy(want).to(dev)
+    assert torch.equal(full[w], part[w])
+    # backward: G non-zero only on the batch rows
+    Gd = torch.zeros(U + I, d, device=dev)
+    Gd[w] = torch.randn(len(want), d, generator=gen).to(dev)
+    dense = G.propagate_bwd(Gd, K, True)
+    sparse = G.propagate_bwd(Gd, K, True, rows=rows)
+    _assert_close(sparse.cpu().numpy(), dense.cpu().numpy(), rtol=1e-6)
+    ref = torch.from_numpy(Gd.cpu().numpy())
+    h = ref
+    for _ in range(K):
+        h = ref + torch.sparse.mm(A, h)
+    _assert_close(sparse.cpu().numpy(), (h / (K + 1)).numpy())
+    rows.clear()
+    assert int(rows.bitmap.abs().sum().item()) == 0
+
+
 # ---------------------------------------------------------------- a9: BPR + reg
 @pytest.mark.parametrize("B,reg_mask", [(256, 7), (1000, 7), (333, 6)])
 def test_bpr_reg_loss_and_grads(dev, B, reg_mask):

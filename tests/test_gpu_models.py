@@ -56,13 +56,13 @@ def test_model_init_matches_reference_rng_order(dev, golden_dirs, golden_tiny):
     np.testing.assert_array_equal(m.item_embedding.weight.detach().numpy(), golden_tiny["lg_item_w0"])
 
 
-@pytest.mark.parametrize("path", ["autograd", "fused", "fused_graph"])
+@pytest.mark.parametrize("path", ["autograd", "fused", "fused_graph", "fused_dense"])
 def test_lightgcn_two_steps_vs_reference(dev, golden_dirs, golden_tiny, path):
     """Reference trainer loop (trainer.py:40-56) for two batches of 256: losses, gradients and the
     Adam-updated tables equal the unmodified reference's."""
     from models.LightGCN import LightGCN
     g = golden_tiny
-    cfg = _cfg("LightGCN", batch_size=256, cuda_graph=int(path == "fused_graph"))
+    cfg = _cfg("LightGCN", batch_size=256, cuda_graph=int(path == "fused_graph"), restrict_rows=int(path != "fused_dense"))
     d = _data(golden_dirs, cfg)
     m = LightGCN(cfg, d, dev)
     _load_weights(m, g["lg_user_w0"], g["lg_item_w0"])
