@@ -7,6 +7,14 @@
 
 #include "../../include/idgrec.h"
 
+// symmetric peer slabs of the row-partitioned multi-GPU path (csrc/peers.cu)
+struct idg_peers {
+    char* local_base = nullptr;
+    int64_t bytes = 0;
+    int rank = 0, world = 1;
+    char* bases[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 namespace idg {
 
 extern thread_local char g_err[512];

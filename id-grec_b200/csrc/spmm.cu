@@ -55,6 +55,10 @@ struct SpmmArgs {
     const float* acc_in;
     float* acc_out;
     float acc_div;
+    const float* acc_in2;     // optional further layer-sum inputs: s = ((acc_in + acc_in2) + acc_in3) + y
+    const float* acc_in3;
+    float* peerY[7];          // Y is also stored at the same slab offset of every peer GPU (fused all-gather)
+    int n_peers;
     const int* worklist;      // optional: item ids to run (row-restricted layer), count in *d_wl_count
     const int* d_wl_count;
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
@@ -63,6 +67,7 @@ struct SpmmArgs {
 }  // namespace idg
 
 struct idg_graph {
+    const idg_peers* peers = nullptr;
     int32_t n_rows = 0, n_cols = 0, row_offset = 0;
     int64_t nnz = 0;
     int n_items = 0, n_heavy = 0, n_parts = 0;
@@ -104,10 +109,19 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
         y.z += (sgn(y.z) * (nz.z / nrm)) * a.eps;
         y.w += (sgn(y.w) * (nz.w / nrm)) * a.eps;
     }
-    if (a.Y) st4(a.Y + off, y);
+    if (a.Y) {
+        st4(a.Y + off, y);
+#pragma unroll 1
+        for (int p = 0; p < a.n_peers; ++p) st4(a.peerY[p] + off, y);  // NVLink peer stores, fire-and-forget
+    }
     if (a.acc_out) {
         float4 s = y;
-        if (a.acc_in) s = f4add(ldcs4(a.acc_in + off), y);
+        if (a.acc_in) {
+            float4 t = ldcs4(a.acc_in + off);
+            if (a.acc_in2) t = f4add(t, ldcs4(a.acc_in2 + off));
+            if (a.acc_in3) t = f4add(t, ldcs4(a.acc_in3 + off));
+            s = f4add(t, y);
+        }
         s.x /= a.acc_div; s.y /= a.acc_div; s.z /= a.acc_div; s.w /= a.acc_div;
         stcs4(a.acc_out + off, s);
     }
@@ -281,10 +295,17 @@ extern "C" void idg_graph_destroy(idg_graph* g) {
     cudaFree(g->colval); cudaFree(g->items); cudaFree(g->row_items); cudaFree(g->heavy); cudaFree(g->partials); cudaFree(g->counters);
     delete g;
 }
+extern "C" int idg_graph_set_peers(idg_graph* g, const idg_peers* p) {
+    if (!g) return fail(-1, "idg_graph_set_peers: null graph%s");
+    g->peers = p;
+    return 0;
+}
 extern "C" int64_t idg_graph_nnz(const idg_graph* g) { return g ? g->nnz : -1; }
 extern "C" int32_t idg_graph_rows(const idg_graph* g) { return g ? g->n_rows : -1; }
 
 struct SpmmExtra {
+    const float* acc_in2 = nullptr;
+    const float* acc_in3 = nullptr;
     const int* worklist = nullptr;   // row-restricted launch
     const int* d_wl_count = nullptr;
     int max_wl = 0;
@@ -306,6 +327,17 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.X = d_X; a.Y = d_Y; a.addend = d_addend; a.addend2 = d_addend2; a.scale2 = scale2; a.noise = d_noise; a.eps = eps;
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap;
+    a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
+    a.n_peers = 0;
+    for (int p = 0; p < 7; ++p) a.peerY[p] = nullptr;
+    if (g->peers && d_Y) {
+        const idg_peers* P = g->peers;
+        const char* y = (const char*)d_Y;
+        if (y >= P->local_base && y < P->local_base + P->bytes) {
+            for (int q = 0; q < P->world; ++q)
+                if (q != P->rank) a.peerY[a.n_peers++] = (float*)(P->bases[q] + (y - P->local_base));
+        }
+    }
     const int per_cta = kWarpsPerCta * (32 / (d / 4));  // items per CTA: one lane group each
     const int n_slots = ex.worklist ? ex.max_wl : g->n_items;
     if (n_slots <= 0) return 0;
@@ -403,7 +435,8 @@ extern "C" int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows)
 
 // one layer restricted to the listed rows (d_worklist: idg_graph_worklist_ints(g, max_rows) ints of scratch)
 static int spmm_rows(const idg_graph* g, const float* X, float* Y, const float* noise, float eps, const float* acc_in, float* acc_out,
-                     float acc_div, int d, const int* d_rowlist, const int* d_count, int max_rows, int* d_worklist, void* stream_) {
+                     float acc_div, int d, const int* d_rowlist, const int* d_count, int max_rows, int* d_worklist, void* stream_,
+                     const float* acc_in2 = nullptr, const float* acc_in3 = nullptr) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int* wl_count = d_worklist;  // first int = number of work items, list follows (aligned to 4 ints)
     IDG_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(int), stream));
@@ -411,14 +444,18 @@ static int spmm_rows(const idg_graph* g, const float* X, float* Y, const float* 
     IDG_LAUNCH_CHECK("expand_rows_kernel");
     SpmmExtra ex;
     ex.worklist = d_worklist + 4; ex.d_wl_count = wl_count; ex.max_wl = max_rows + g->n_parts;
+    ex.acc_in2 = acc_in2; ex.acc_in3 = acc_in3;
     return spmm_launch(g, X, Y, nullptr, nullptr, 0.f, noise, eps, acc_in, acc_out, acc_div, d, stream_, ex);
 }
 
 extern "C" int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
-                                   const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d, const int32_t* d_rowlist,
-                                   const int32_t* d_count, int32_t max_rows, int32_t* d_worklist, void* stream) {
+                                   const float* d_acc_in, const float* d_acc_in2, const float* d_acc_in3, float* d_acc_out,
+                                   float acc_div, int32_t d, const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows,
+                                   int32_t* d_worklist, void* stream) {
     if (!g || !d_rowlist || !d_count || !d_worklist || max_rows <= 0) return fail(-1, "idg_spmm_layer_rows: bad argument%s");
-    return spmm_rows(g, d_X, d_Y, d_noise, eps, d_acc_in, d_acc_out, acc_div, d, d_rowlist, d_count, max_rows, d_worklist, stream);
+    if ((d_acc_in2 || d_acc_in3) && !d_acc_in) return fail(-1, "idg_spmm_layer_rows: acc_in2/3 need acc_in%s");
+    return spmm_rows(g, d_X, d_Y, d_noise, eps, d_acc_in, d_acc_out, acc_div, d, d_rowlist, d_count, max_rows, d_worklist, stream,
+                     d_acc_in2, d_acc_in3);
 }
 
 extern "C" int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_acc_in,

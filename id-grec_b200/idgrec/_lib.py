@@ -73,7 +73,7 @@ SIGNATURES = {
     "idg_batch_rows": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_batch_rows_clear": (C.c_int, [_p, _p, _i32, _p, _p]),
     "idg_graph_worklist_ints": (_i64, [_p, _i32]),
-    "idg_spmm_layer_rows": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _f32, _i32, _p, _p, _i32, _p, _p]),
+    "idg_spmm_layer_rows": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _f32, _i32, _p, _p, _i32, _p, _p]),
     "idg_spmm_layer_sparse_in": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i32, _p, _p]),
     "idg_propagate_fwd_ex": (C.c_int, [_p, _p, _i32, _i32, C.c_int, _p, _f32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "idg_propagate_bwd_ex": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
@@ -90,6 +90,16 @@ SIGNATURES = {
     "idg_eval_metrics": (C.c_int, [_p, _p, _i32, _i32, _p, _p, C.POINTER(_i32), _i32, _p, _p, _p]),
     "idg_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i32, _p]),
     "idg_adam_step_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p]),
+    "idg_device_alloc": (C.c_int, [_i64, C.POINTER(_p)]),
+    "idg_device_free": (C.c_int, [_p]),
+    "idg_ipc_get_handle": (C.c_int, [_p, _p]),
+    "idg_ipc_open": (C.c_int, [_p, C.POINTER(_p)]),
+    "idg_ipc_close": (C.c_int, [_p]),
+    "idg_peers_create": (C.c_int, [_p, _i64, _i32, _i32, C.POINTER(_p), C.POINTER(_p)]),
+    "idg_peers_destroy": (None, [_p]),
+    "idg_graph_set_peers": (C.c_int, [_p, _p]),
+    "idg_peers_push": (C.c_int, [_p, _p, _i64, _p]),
+    "idg_peers_barrier": (C.c_int, [_p, _p, _p]),
     "idg_neg_sample_replay": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64)]),
 }
 

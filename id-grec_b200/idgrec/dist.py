@@ -1,0 +1,226 @@
+"""Row-partitioned multi-GPU training (SURVEY.md section 8 e): one process per GPU on one NVSwitch box.
+
+Nodes (rows of the normalised adjacency, of every layer buffer, of the parameter table and of the
+Adam state) are split into contiguous, nnz-balanced ranges.  Each propagation layer computes the
+local rows and its SpMM epilogue stores every finished row into all peers' layer buffers over
+NVLink (CUDA-IPC symmetric slab, csrc/peers.cu + SpmmArgs::peerY), followed by a device-side flag
+barrier -- the per-layer all-gather is fused into the kernel that produces the rows.  The loss is
+evaluated redundantly on every rank from the (complete) final rows of the mini-batch, so there is no
+gradient reduction; each rank applies Adam to the rows it owns and pushes them to its peers.
+torch.distributed (NCCL) is used only for bootstrap and scalar metric reductions.  Results are
+bit-identical to one GPU: a row's reduction order is a function of the row alone.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+from .graph import BatchRows, Graph
+
+
+def partition_rows(indptr, world: int):
+    """Contiguous row ranges balanced by nonzeros (+ one unit per row for the epilogue traffic).
+    Returns world+1 boundaries; boundaries are multiples of 4 rows so every range is 16-byte aligned."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    n = len(indptr) - 1
+    cost = indptr + 8 * np.arange(n + 1, dtype=np.int64)      # cumulative work up to each row boundary
+    bounds = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(cost, cost[-1] * r / world))
+        b = min(n, max(bounds[-1], (b + 3) // 4 * 4))
+        bounds.append(b)
+    bounds.append(n)
+    return bounds
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous shard of n units for user-sharded evaluation."""
+    per = (n + world - 1) // world
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
+class _CudaBuffer:
+    """Exposes raw device memory to torch through __cuda_array_interface__."""
+
+    def __init__(self, p, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(p), False), "version": 3, "strides": None}
+
+
+class PeerSlab:
+    """One cudaMalloc'd slab per rank, mapped on every rank; tensors carved at identical offsets."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group=None, device=None):
+        import torch.distributed as dist
+        self.l = _lib.lib()
+        self.rank, self.world, self.nbytes = rank, world, int((nbytes + 4095) // 4096 * 4096)
+        self.device = device
+        base = C.c_void_p()
+        check(self.l.idg_device_alloc(self.nbytes, C.byref(base)), "idg_device_alloc")
+        self.base = base.value
+        handle = (C.c_char * 64)()
+        check(self.l.idg_ipc_get_handle(self.base, handle), "idg_ipc_get_handle")
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        else:
+            handles[0] = bytes(handle.raw)
+        self.peer_bases = []
+        for r in range(world):
+            if r == rank:
+                self.peer_bases.append(self.base)
+            else:
+                out = C.c_void_p()
+                buf = C.create_string_buffer(handles[r], 64)
+                check(self.l.idg_ipc_open(buf, C.byref(out)), "idg_ipc_open")
+                self.peer_bases.append(out.value)
+        arr = (C.c_void_p * world)(*self.peer_bases)
+        h = C.c_void_p()
+        check(self.l.idg_peers_create(self.base, self.nbytes, rank, world, arr, C.byref(h)), "idg_peers_create")
+        self.handle = h
+        self._bytes = torch.as_tensor(_CudaBuffer(self.base, self.nbytes), device=device)
+        self._off = 0
+        self.state = self.carve((64,), torch.int32)
+
+    def carve(self, shape, dtype=torch.float32):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        off = (self._off + 255) // 256 * 256
+        if off + n > self.nbytes:
+            raise RuntimeError("PeerSlab exhausted")
+        self._off = off + n
+        return self._bytes[off:off + n].view(dtype).view(*shape)
+
+    def barrier(self):
+        check(self.l.idg_peers_barrier(self.handle, ptr(self.state), cur_stream()), "idg_peers_barrier")
+
+    def push(self, t):
+        check(self.l.idg_peers_push(self.handle, ptr(t), t.numel() * t.element_size(), cur_stream()), "idg_peers_push")
+
+
+class DistFusedTrainer:
+    """LightGCN training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer)."""
+
+    def __init__(self, kind, csr, table, num_users, K, reg_lambda, lr, rank, world, group=None, max_batch=1024,
+                 betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None):
+        if kind != "LightGCN":
+            raise NotImplementedError("multi-GPU training is implemented for LightGCN (BASELINE.json configs 2 and 5)")
+        if not 1 <= K <= 3:
+            raise NotImplementedError("row-restricted distributed forward supports 1..3 layers")
+        self.l = _lib.lib()
+        self.kind, self.rank, self.world = kind, rank, world
+        self.U, (self.N, self.d), self.K = num_users, table.shape, K
+        self.reg_lambda, self.lr, self.betas, self.adam_eps = reg_lambda, lr, betas, adam_eps
+        dev = table.device
+        self.dev = dev
+        N, d = self.N, self.d
+        nd = N * d * 4
+        self.slab = PeerSlab((1 + 2 * max(K - 1, 1)) * (nd + 4096) + (1 << 20), rank, world, group, dev)
+        self.E0 = self.slab.carve((N, d))
+        self.E0.copy_(table)
+        self.W = [self.slab.carve((N, d)) for _ in range(K - 1)]     # forward layer outputs X1..X_{K-1}
+        self.H = [self.slab.carve((N, d)) for _ in range(K - 1)]     # backward chain H_{K-1}..H_1
+        self.bounds = partition_rows(csr.indptr.cpu().numpy(), world)
+        self.b0, self.b1 = self.bounds[rank], self.bounds[rank + 1]
+        self.local = Graph(csr, self.b0, self.b1)
+        check(self.l.idg_graph_set_peers(self.local._h, self.slab.handle), "idg_graph_set_peers")
+        self.full = full_graph if full_graph is not None else Graph(csr)   # row-restricted last layer + evaluation
+        z = lambda: torch.zeros(N, d, dtype=torch.float32, device=dev)
+        self.gE0, self.m, self.v, self.G, self.F = z(), z(), z(), z(), z()
+        self.rows = BatchRows(N, max_batch, dev)
+        self.rows.worklist(self.full)
+        self.max_batch, self.step_count = max_batch, 0
+        self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
+        self.n_loss = 2
+        self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
+        self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs, self._graph_launches, self.replayed_launches = {}, {}, 0
+        torch.cuda.synchronize()
+        self._host_barrier(group)
+        self.group = group
+
+    @staticmethod
+    def _host_barrier(group):
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.barrier(group=group)
+
+    # ------------------------------------------------------------------
+    def _body(self, B, u, p, n):
+        l, s, K, d = self.l, cur_stream(), self.K, self.d
+        loc, rows, slab = self.local, self.rows, self.slab
+        rows.build(u, p, n, B, self.U)
+        # forward: layers 1..K-1 on the local rows, rows pushed to every peer by the epilogue
+        x = self.E0
+        for k in range(K - 1):
+            loc.spmm_layer(x, Y=self.W[k])
+            slab.barrier()
+            x = self.W[k]
+        # last layer + mean only on the batch rows, every rank computes all of them (no exchange)
+        acc = [self.E0] + self.W
+        check(l.idg_spmm_layer_rows(self.full._h, ptr(x), None, None, 0.0, ptr(acc[0]), ptr(acc[1]) if K > 1 else None,
+                                    ptr(acc[2]) if K > 2 else None, ptr(self.F), float(K + 1), d, ptr(rows.rowlist), ptr(rows.count),
+                                    rows.max_rows, ptr(rows.worklist(self.full)), s), "idg_spmm_layer_rows")
+        check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, d, self.reg_lambda, 7, ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
+        check(l.idg_bpr_backward(ptr(self.F), B, d, 7, None, ptr(self.G), ptr(self.ws), s), "idg_bpr_backward")
+        # backward Horner chain on the local rows; the first product only gathers batch columns
+        off = self.b0 * d
+        g_loc = self.gE0  # full-size buffer, local rows written at their global position
+        if K == 1:
+            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), None, ptr(self.G), None, ptr(g_loc), float(K + 1), d, ptr(rows.bitmap), s), "idg_spmm_layer_sparse_in")
+        else:
+            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), s), "idg_spmm_layer_sparse_in")
+            slab.barrier()
+            h = self.H[0]
+            for k in range(1, K - 1):
+                loc.spmm_layer(h, Y=self.H[k], addend=self.G)
+                slab.barrier()
+                h = self.H[k]
+            loc.spmm_layer(h, Y=None, addend=self.G, acc_out=g_loc, acc_div=float(K + 1))
+        check(l.idg_bpr_finish(ptr(self.E0), ptr(self.gE0), ptr(self.G), B, d, self.reg_lambda, None, ptr(self.ws), s), "idg_bpr_finish")
+        rows.clear()
+        # Adam on the rows this rank owns, then hand them to the peers
+        nloc = (self.b1 - self.b0) * d
+        if nloc > 0:
+            fp = lambda t: t.data_ptr() + off * 4
+            check(l.idg_adam_step_dev(fp(self.E0), fp(self.gE0), fp(self.m), fp(self.v), nloc, self.lr, self.betas[0], self.betas[1],
+                                      self.adam_eps, ptr(self.d_step), s), "idg_adam_step_dev")
+            slab.push(self.E0[self.b0:self.b1])
+        slab.barrier()
+        check(l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, s), "idg_axpby")
+
+    def step(self, users, pos, neg, apply_adam=True):
+        assert apply_adam, "the distributed step always applies Adam"
+        B = int(users.numel())
+        self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
+        u, p, n = (self.batch[k].data_ptr() for k in range(3))
+        if not self.use_cuda_graph:
+            self._body(B, u, p, n)
+        else:
+            if B not in self._graphs:
+                torch.cuda.synchronize()
+                n0 = self.l.idg_launch_count()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._body(B, u, p, n)
+                self._graph_launches[B] = int(self.l.idg_launch_count() - n0)
+                self._graphs[B] = gr
+            self._graphs[B].replay()
+            self.replayed_launches += self._graph_launches[B]
+        self.step_count += 1
+        return self.loss[:2]
+
+    def pop_epoch_losses(self):
+        out = self.loss_acc[:2].tolist()
+        self.loss_acc.zero_()
+        return out
+
+    @torch.no_grad()
+    def final_embeddings(self):
+        """Clean propagation of the current table on the whole graph (every rank, for its evaluation shard)."""
+        return self.full.propagate_fwd(self.E0, self.K, True)

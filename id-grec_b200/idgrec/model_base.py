@@ -80,6 +80,19 @@ class PropagationModel(nn.Module):
             if self._table is None:
                 raise RuntimeError("model must be moved to a CUDA device first (model.to(device))")
             cfg = self.config
+            import torch.distributed as dist
+            world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+            if world > 1 and int(cfg.get('num_gpus', world)) > 1:
+                # row-partitioned over the process group: the parameter table moves into the peer slab
+                from .dist import DistFusedTrainer
+                ft = DistFusedTrainer(self.kind, self.Graph.csr, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda,
+                                      lr, dist.get_rank(), world, max_batch=max_batch, full_graph=self.Graph,
+                                      use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'))
+                U = self.dataset.num_users
+                self._table = ft.E0
+                self.user_embedding.weight.data, self.item_embedding.weight.data = ft.E0[:U], ft.E0[U:]
+                self._fused = ft
+                return ft
             self._fused = FusedTrainer(
                 self.kind, self.Graph, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda, lr,
                 ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),

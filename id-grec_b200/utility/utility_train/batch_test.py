@@ -46,10 +46,24 @@ def Test(dataset, model, device, config):
     topK = eval(config['top_K'])
     device = torch.device(device)
     cache = dataset.device_cache(device)
+    import torch.distributed as dist
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    all_users = cache["test_users"]
+    n = float(len(all_users))
     with torch.no_grad():
-        ids, users = rank_all(dataset, model, device, max(topK))
-        sums = ops.eval_metric_sums(ids, users, cache["test_indptr"], cache["test_indices"], topK).cpu().numpy()
-    n = float(len(users))
+        if world > 1:
+            # user-sharded evaluation: no data-path communication, one all-reduce of 3*len(top_K) float64 sums
+            from idgrec.dist import shard_range
+            s, e = shard_range(len(all_users), dist.get_rank(), world)
+            sums = torch.zeros(len(topK), 3, dtype=torch.float64, device=device)
+            if e > s:
+                ids, users = rank_all(dataset, model, device, max(topK), users=all_users[s:e].contiguous())
+                sums = ops.eval_metric_sums(ids, users, cache["test_indptr"], cache["test_indices"], topK).clone()
+            dist.all_reduce(sums)
+            sums = sums.cpu().numpy()
+        else:
+            ids, users = rank_all(dataset, model, device, max(topK))
+            sums = ops.eval_metric_sums(ids, users, cache["test_indptr"], cache["test_indices"], topK).cpu().numpy()
     return {'precision': sums[:, 1] / n, 'recall': sums[:, 0] / n, 'hit': np.zeros(len(topK)), 'ndcg': sums[:, 2] / n}
 
 

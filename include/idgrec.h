@@ -29,6 +29,7 @@ extern "C" {
 #endif
 
 typedef struct idg_graph idg_graph; /* opaque device CSR + schedule */
+typedef struct idg_peers idg_peers; /* opaque table of IPC-mapped peer slabs (multi-GPU) */
 
 int idg_version(void);
 const char* idg_last_error(void);
@@ -104,11 +105,12 @@ int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32
                          void* stream);
 /* scratch ints needed by the row-restricted entry points for up to max_rows listed rows */
 int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows);
-/* idg_spmm_layer evaluated only on the listed rows (other rows of the outputs are left untouched) */
+/* idg_spmm_layer evaluated only on the listed rows (other rows of the outputs are left untouched);
+ * the layer sum may take up to three inputs: acc_out = (((acc_in + acc_in2) + acc_in3) + y) / acc_div */
 int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
-                        const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
-                        const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, int32_t* d_worklist,
-                        void* stream);
+                        const float* d_acc_in, const float* d_acc_in2, const float* d_acc_in3, float* d_acc_out,
+                        float acc_div, int32_t d, const int32_t* d_rowlist, const int32_t* d_count,
+                        int32_t max_rows, int32_t* d_worklist, void* stream);
 /* idg_spmm_layer for an X that is zero outside the rows flagged in d_bitmap: streams the CSR structure
  * but gathers only flagged columns (first backward layer: dL/dF is non-zero on the batch rows only) */
 int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend,
@@ -197,6 +199,25 @@ int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t 
  * the call): lets a captured CUDA graph of the whole train step be replayed unchanged. */
 int idg_adam_step_dev(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
                       float beta2, float eps, int32_t* d_step, void* stream);
+
+/* ---- multi-GPU (SURVEY.md 8 e): row-partitioned nodes, one process per GPU --------------------
+ * Each rank allocates one slab (idg_device_alloc), exports it (idg_ipc_get_handle, 64 bytes), opens the
+ * peers' (idg_ipc_open) and registers the table (idg_peers_create; bases[rank] is ignored).  After
+ * idg_graph_set_peers, every idg_spmm_layer* call whose d_Y lies inside the slab ALSO stores each finished
+ * row at the same offset of every peer's slab over NVLink: the per-layer all-gather is fused into the SpMM
+ * epilogue.  idg_peers_barrier is a device-side flag barrier over the slabs (d_state: 64 ints inside the
+ * slab, zero-initialised, same offset on every rank); idg_peers_push copies a byte range of the local slab
+ * to the same offset of all peers (parameter rows after the Adam step). */
+int idg_device_alloc(int64_t bytes, void** out);
+int idg_device_free(void* p);
+int idg_ipc_get_handle(const void* d_ptr, void* handle64);
+int idg_ipc_open(const void* handle64, void** out);
+int idg_ipc_close(void* p);
+int idg_peers_create(void* local_base, int64_t bytes, int32_t rank, int32_t world, void* const* bases, idg_peers** out);
+void idg_peers_destroy(idg_peers* p);
+int idg_graph_set_peers(idg_graph* g, const idg_peers* p);
+int idg_peers_push(const idg_peers* p, const void* d_src, int64_t bytes, void* stream);
+int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* stream);
 
 /* ---- a4: data_loader.py:108-127, exact replay on the HOST -------------------
  * h_cand: candidate stream = np.random.randint(0, I, size=n_cand) drawn from the

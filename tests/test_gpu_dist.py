@@ -1,0 +1,22 @@
+"""Multi-GPU parity (needs >= 2 GPUs): the row-partitioned trainer reproduces the 1-GPU trainer bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_two_gpu_training_bit_identical(graph):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, IDG_GRAPH=graph)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", os.path.join(REPO, "tools", "dist_check.py"), "small", "4"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
