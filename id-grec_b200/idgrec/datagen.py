@@ -113,3 +113,33 @@ def write_dataset(root: str, name: str, g: SynthGraph) -> str:
     _write(os.path.join(d, "train.txt"), g.train_user, g.train_item, g.num_users)
     _write(os.path.join(d, "test.txt"), g.test_user, g.test_item, g.num_users)
     return d
+
+
+def gen_edges_device(num_users: int, num_items: int, num_edges: int, seed: int = 2024, device="cuda"):
+    """Scale-up graphs (SURVEY.md section 8 d, XL: 1M x 1M, 100M edges) generated directly on the device as
+    sorted unique (user, item) pairs -- same degree families as gen_graph (lognormal user activity sigma 0.9,
+    item popularity sigma 1.1), never through text or scipy.  Deterministic for a given seed and GPU model, so
+    every rank of a multi-GPU run builds the identical graph."""
+    import torch
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    wu = torch.exp(torch.randn(num_users, generator=gen, device=dev, dtype=torch.float64) * 0.9 + 3.3)
+    wi = torch.exp(torch.randn(num_items, generator=gen, device=dev, dtype=torch.float64) * 1.1)
+    cu = torch.cumsum(wu / wu.sum(), 0)
+    ci = torch.cumsum(wi / wi.sum(), 0)
+    keys = (torch.arange(num_users, device=dev, dtype=torch.int64) * num_items
+            + torch.randint(0, num_items, (num_users,), generator=gen, device=dev))      # every user has an edge
+    while True:
+        need = num_edges - keys.numel()
+        if need <= 0:
+            break
+        n = int(need * 1.1) + 4096
+        u = torch.searchsorted(cu, torch.rand(n, generator=gen, device=dev, dtype=torch.float64)).clamp_(max=num_users - 1)
+        i = torch.searchsorted(ci, torch.rand(n, generator=gen, device=dev, dtype=torch.float64)).clamp_(max=num_items - 1)
+        keys = torch.unique(torch.cat([keys, u * num_items + i]))
+        del u, i
+    if keys.numel() > num_edges:
+        keep = torch.randperm(keys.numel(), generator=gen, device=dev)[:num_edges]
+        keys = torch.sort(keys[keep]).values
+    return keys // num_items, keys % num_items

@@ -38,8 +38,11 @@ def build_norm_adjacency(train_user, train_item, num_users: int, num_items: int,
     """data_graph.py:33-55 (``add_self=False``) / :7-30 (``add_self=True``) on the device."""
     l = _lib.lib()
     dev = torch.device(device)
-    u = torch.as_tensor(np.ascontiguousarray(train_user), dtype=torch.int64).to(dev)
-    i = torch.as_tensor(np.ascontiguousarray(train_item), dtype=torch.int64).to(dev)
+    if torch.is_tensor(train_user):
+        u, i = train_user.to(dev, torch.int64).contiguous(), train_item.to(dev, torch.int64).contiguous()
+    else:
+        u = torch.as_tensor(np.ascontiguousarray(train_user), dtype=torch.int64).to(dev)
+        i = torch.as_tensor(np.ascontiguousarray(train_item), dtype=torch.int64).to(dev)
     E = int(u.numel())
     N = num_users + num_items
     cap = 2 * E + (N if add_self else 0)
