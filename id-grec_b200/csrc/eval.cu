@@ -14,10 +14,17 @@
 //   pass B  survivors are rescored exactly (fp64, k = 0..d-1) and ordered (score desc, id asc).
 //   pass C  users whose candidate list overflowed or came up short are recomputed exhaustively.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "idg_common.cuh"
 
 namespace idg {
+
+// csrc/eval_tc.cu: the same candidate pass on tcgen05 tensor cores (d = 64)
+int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
+                              int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
+                              cudaStream_t stream);
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
 constexpr int kFallbackCtas = 32;
@@ -383,14 +390,20 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     IDG_LAUNCH_CHECK("item_norm_kernel");
     const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
     const unsigned grid = (unsigned)((nu + kTU - 1) / kTU);
-    if (d == 64) {
+    // IDG_EVAL_IMPL=fma selects the CUDA-core candidate pass (kept as a cross-check of the tensor-core one)
+    static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
+    if (d == 64 && use_tc) {
+        if (int rc = launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
+                                               w.flag_list, w.cand_cnt, w.cand_ids, stream))
+            return rc;
+    } else if (d == 64) {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_candidates_kernel<64><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
     } else {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_candidates_kernel<256><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
     }
-    IDG_LAUNCH_CHECK("eval_candidates_kernel");
+    if (!(d == 64 && use_tc)) IDG_LAUNCH_CHECK("eval_candidates_kernel");
     eval_rescore_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_Fu, d_Fi, d, d_users, nu, K, w, d_out_ids, d_out_scores);
     IDG_LAUNCH_CHECK("eval_rescore_kernel");
     eval_exhaustive_kernel<<<kFallbackCtas, 256, 0, stream>>>(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w, d_out_ids, d_out_scores);

@@ -1,0 +1,336 @@
+// Full-ranking candidate pass on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as eval_candidates_kernel (csrc/eval.cu): per user keep every unmasked item whose
+// approximate score can still belong to the exact top-K; the survivors are rescored exactly in fp64
+// by eval_rescore_kernel, so the returned ids do not depend on the tensor-core rounding.
+//
+//   scores:  S[128 users, 128 items] = Fu_tile . Fi_tile^T, d = 64, one tcgen05.mma.kind::tf32 chain
+//            (8 instructions of K = 8) per item tile, accumulators in TMEM (4 buffers x 128 columns).
+//            fp32 operands are read as tf32 (low 13 mantissa bits ignored):
+//            |s~ - s| <= (2^-9 + small) * |u||i|  -> candidate margin 2*delta_u.
+//   roles:   warp 0      MMA issuer (one elected thread) + TMEM alloc/dealloc
+//            warps 2-3   operand loaders: cp.async 16-byte chunks into the 128B-swizzled K-major
+//                        UMMA layout, 3-stage ring, mbarrier full/empty
+//            warps 4-7   epilogue: thread <-> user row (TMEM lane), tcgen05.ld 32 columns at a time,
+//                        train-mask by a per-row cursor over the sorted positives, threshold filter
+//                        in registers, per-row candidate lists in shared memory, warp-cooperative prune
+//   bound:   TMEM drain (64 B/clk/SM = 16 scores/clk/SM), not the MMA rate.
+#include <math.h>
+
+#include "idg_common.cuh"
+
+namespace idg {
+
+constexpr int kTcM = 128, kTcN = 128, kTcD = 64;
+constexpr int kTcStages = 3, kTcBufs = 4;
+constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
+constexpr int kTcLoaders = 64;
+constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
+
+struct EvalWsTc {
+    float* max_norm;
+    int* flag_cnt;
+    int* flag_list;
+    int* cand_cnt;
+    int* cand_ids;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle: 8-row groups are 1024 B apart (SBO), version 1 (sm_100), layout type 2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+__device__ __forceinline__ uint32_t umma_idesc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// smem byte offset of the 16-byte chunk kc (0..15) of row r inside an operand tile [128 rows x 64 fp32]
+__device__ __forceinline__ uint32_t sw128_offset(int r, int kc) {
+    return (uint32_t)(kc >> 3) * kSubTile + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((kc & 7) ^ (r & 7)) << 4);
+}
+
+// warp-cooperative prune of one row's candidate list: tau = (K-th largest) - 2*delta, keep >= tau
+__device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2, int K, int lane, int& new_cnt, float& new_tau) {
+    float s[3]; int id[3]; int rank[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int idx = lane + 32 * q;
+        s[q] = (idx < m) ? ls[idx] : -INFINITY; id[q] = (idx < m) ? li[idx] : 0; rank[q] = 0;
+    }
+    for (int j = 0; j < m; ++j) {
+        const float sj = ls[j];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && j < lane + 32 * q);
+    }
+    float vk = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = s[q];
+#pragma unroll
+    for (int mm = 16; mm >= 1; mm >>= 1) vk = fmaxf(vk, __shfl_xor_sync(0xffffffffu, vk, mm));
+    const float tau = vk - delta2;
+    __syncwarp();
+    int kept = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const bool keep = (lane + 32 * q < m) && (s[q] >= tau);
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (keep) { const int p = kept + __popc(b & ((1u << lane) - 1)); ls[p] = s[q]; li[p] = id[q]; }
+        kept += __popc(b);
+    }
+    __syncwarp();
+    new_cnt = kept; new_tau = tau;
+}
+
+__global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
+                                                                    const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
+                                                                    const int64_t* __restrict__ users, int nu, int K, EvalWsTc w) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;                                        // 32 KB
+    unsigned char* sB = smem + 2 * kSubTile;                         // kTcStages x 32 KB
+    float* ls = reinterpret_cast<float*>(sB + kTcStages * 2 * kSubTile);  // [128][kTcCap]
+    int* li = reinterpret_cast<int*>(ls + kTcM * kTcCap);            // [128][kTcCap]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li + kTcM * kTcCap);
+    uint64_t* full = bars;                   // [kTcStages] loaders -> MMA
+    uint64_t* empty = bars + kTcStages;      // [kTcStages] MMA -> loaders
+    uint64_t* tfull = empty + kTcStages;     // [kTcBufs]   MMA -> epilogue
+    uint64_t* tempty = tfull + kTcBufs;      // [kTcBufs]   epilogue -> MMA
+    uint64_t* afull = tempty + kTcBufs;      // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(afull + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u0 = blockIdx.x * kTcM;
+    const int ntiles = (I + kTcN - 1) / kTcN;
+
+    if (tid == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, kTcLoaders); mbar_init(empty + s, 1); }
+        for (int b = 0; b < kTcBufs; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+        mbar_init(afull, kTcLoaders);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc();
+            mbar_wait(afull, 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kTcStages, b = t % kTcBufs;
+                mbar_wait(full + s, (t / kTcStages) & 1);
+                mbar_wait(tempty + b, ((t / kTcBufs) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * 2 * kSubTile);
+#pragma unroll
+                for (int k = 0; k < kTcD / 8; ++k) {
+                    const uint32_t koff = (uint32_t)(k >> 2) * kSubTile + (uint32_t)(k & 3) * 32u;
+                    umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc(a0 + koff), umma_desc(b0 + koff), idesc, k > 0);
+                }
+                umma_commit(empty + s);
+                umma_commit(tfull + b);
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== operand loaders =====================
+        const int lt = tid - 64;  // 0..63
+        // A: the CTA's 128 user rows (gathered through users[]), once
+        for (int c = lt; c < kTcM * 16; c += kTcLoaders) {
+            const int r = c >> 4, kc = c & 15;
+            const int p = u0 + r;
+            const int64_t u = (p < nu) ? users[p] : users[0];
+            cp_async16(smem_u32(sA) + sw128_offset(r, kc), Fu + (size_t)u * kTcD + kc * 4, (p < nu) ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(afull);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % kTcStages;
+            mbar_wait(empty + s, ((t / kTcStages) & 1) ^ 1);
+            const uint32_t dst = smem_u32(sB + (size_t)s * 2 * kSubTile);
+            const int i0 = t * kTcN;
+#pragma unroll 4
+            for (int c = lt; c < kTcN * 16; c += kTcLoaders) {
+                const int r = c >> 4, kc = c & 15;
+                const int i = i0 + r;
+                cp_async16(dst + sw128_offset(r, kc), Fi + (size_t)min(i, I - 1) * kTcD + kc * 4, (i < I) ? 16 : 0);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (t > 0) {  // keep two tiles in flight: publish the previous one
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(full + (t - 1) % kTcStages);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full + (ntiles - 1) % kTcStages);
+    } else if (warp >= 4) {
+        // ===================== epilogue: one thread per user row =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int p = u0 + row;
+        const bool valid = p < nu;
+        const int u = valid ? (int)users[p] : 0;
+        float ss = 0.f;
+        if (valid) for (int k = 0; k < kTcD; ++k) { const float v = __ldg(Fu + (size_t)u * kTcD + k); ss = fmaf(v, v, ss); }
+        // tf32 operand truncation: |err| <= (2*2^-10 + 2^-20)|u||i| plus fp32 accumulation; 1.25x slack
+        const float delta2 = 2.f * 1.25f * (0.001953125f + 0.0001f) * sqrtf(ss) * (*w.max_norm) + 1e-30f;
+        float tau = valid ? -3.0e38f : INFINITY;  // finite: masked scores (-inf) never pass
+        int cnt = 0, overflow = 0;
+        int cur = valid ? mptr[u] : 0;
+        const int cend = valid ? mptr[u + 1] : 0;
+        int next_mask = (cur < cend) ? __ldg(mind + cur) : 0x7fffffff;
+        float* my_ls = ls + row * kTcCap;
+        int* my_li = li + row * kTcCap;
+        const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
+
+        for (int t = 0; t < ntiles; ++t) {
+            const int b = t % kTcBufs;
+            mbar_wait(tfull + b, (t / kTcBufs) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < kTcN / 32; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(b * kTcN + c * 32), raw);
+                if (c == kTcN / 32 - 1) {  // accumulator fully read: hand the buffer back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tempty + b);
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                const int c0 = t * kTcN + c * 32;
+                // train positives of this row that fall into [c0, c0+32): remove (batch_test.py:62-65)
+                while (next_mask < c0 + 32) {
+                    const int j = next_mask - c0;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) if (jj == j) v[jj] = -INFINITY;
+                    ++cur;
+                    next_mask = (cur < cend) ? __ldg(mind + cur) : 0x7fffffff;
+                }
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                if (m >= tau) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] >= tau && c0 + j < I) { my_ls[cnt] = v[j]; my_li[cnt] = c0 + j; ++cnt; }
+                    }
+                }
+                unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrig);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int mL = __shfl_sync(0xffffffffu, cnt, L);
+                    const float dL = __shfl_sync(0xffffffffu, delta2, L);
+                    int nc; float nt;
+                    __syncwarp();
+                    tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, K, lane, nc, nt);
+                    if (lane == L) {
+                        cnt = nc;
+                        if (nc > kTcTrig) { overflow = 1; tau = INFINITY; } else tau = nt;
+                    }
+                }
+            }
+        }
+        // final prune of every row, then publish the candidate ids
+        for (int L = 0; L < 32; ++L) {
+            const int mL = __shfl_sync(0xffffffffu, cnt, L);
+            const float dL = __shfl_sync(0xffffffffu, delta2, L);
+            if (mL >= K) {
+                int nc; float nt;
+                __syncwarp();
+                tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, K, lane, nc, nt);
+                if (lane == L) cnt = nc;
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            const bool bad = overflow || cnt > kTcCandOut || cnt < K;
+            if (bad) {
+                w.cand_cnt[p] = 0;
+                w.flag_list[atomicAdd(w.flag_cnt, 1)] = p;
+            } else {
+                w.cand_cnt[p] = cnt;
+                for (int j = 0; j < cnt; ++j) w.cand_ids[(size_t)p * kTcCandOut + j] = my_li[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
+                              int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
+                              cudaStream_t stream) {
+    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids};
+    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + sizeof(float) * kTcM * kTcCap + sizeof(int) * kTcM * kTcCap +
+                        sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
+    IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w);
+    IDG_LAUNCH_CHECK("eval_candidates_tc_kernel");
+    return 0;
+}
+
+}  // namespace idg
