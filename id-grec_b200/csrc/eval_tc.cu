@@ -91,8 +91,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // smem byte offset of the 16-byte chunk kc (0..15) of row r inside an operand tile [128 rows x 64 fp32]
 __device__ __forceinline__ uint32_t sw128_offset(int r, int kc) {
@@ -241,14 +241,16 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
         int* my_li = li + row * kTcCap;
         const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
 
+        int next2 = (cur + 1 < cend) ? __ldg(mind + cur + 1) : 0x7fffffff;  // one positive of look-ahead: no exposed load latency
         for (int t = 0; t < ntiles; ++t) {
             const int b = t % kTcBufs;
             mbar_wait(tfull + b, (t / kTcBufs) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < kTcN / 32; ++c) {
+            for (int c = 0; c < kTcN / 32; ++c) {  // kept rolled: the epilogue is instruction-cache sensitive (ncu: no_instruction stalls)
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + lane_base + (uint32_t)(b * kTcN + c * 32), raw);
+                tmem_ld_wait();
                 if (c == kTcN / 32 - 1) {  // accumulator fully read: hand the buffer back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(tempty + b);
@@ -263,11 +265,13 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) if (jj == j) v[jj] = -INFINITY;
                     ++cur;
-                    next_mask = (cur < cend) ? __ldg(mind + cur) : 0x7fffffff;
+                    next_mask = next2;
+                    next2 = (cur + 1 < cend) ? __ldg(mind + cur + 1) : 0x7fffffff;
                 }
-                float m = v[0];
+                float m8[8];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+                for (int j = 0; j < 8; ++j) m8[j] = fmaxf(fmaxf(v[j], v[j + 8]), fmaxf(v[j + 16], v[j + 24]));
+                const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 if (m >= tau) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {

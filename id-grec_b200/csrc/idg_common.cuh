@@ -13,6 +13,7 @@ struct idg_peers {
     int64_t bytes = 0;
     int rank = 0, world = 1;
     char* bases[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    char* mc_base = nullptr;  // NVSwitch multicast mapping of the same slab (NVLS): one store reaches every GPU
 };
 
 namespace idg {
@@ -50,6 +51,10 @@ __device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterp
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void stcg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
+// store through an NVSwitch multicast address: the switch replicates it into every GPU's copy of the slab
+__device__ __forceinline__ void multimem_st4(float* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }

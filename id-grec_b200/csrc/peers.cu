@@ -19,6 +19,11 @@ __global__ void peer_push_kernel(const float4* __restrict__ src, PeerPtrs dst, i
     const float4 v = src[i];
     for (int q = 0; q < n_dst; ++q) reinterpret_cast<float4*>(dst.p[q])[i] = v;
 }
+__global__ void mc_push_kernel(const float4* __restrict__ src, float* mc_dst, int64_t n4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    multimem_st4(mc_dst + 4 * i, src[i]);
+}
 
 // state layout (ints, inside the slab): [0] = epoch counter (local), [8 + r] = last epoch announced by rank r
 __global__ void peer_barrier_kernel(int* state, PeerPtrs peer_states, int rank, int world) {
@@ -79,6 +84,11 @@ extern "C" int idg_peers_create(void* local_base, int64_t bytes, int32_t rank, i
     return 0;
 }
 extern "C" void idg_peers_destroy(idg_peers* p) { delete p; }
+extern "C" int idg_peers_set_multicast(idg_peers* p, void* mc_base) {
+    if (!p) return fail(-1, "idg_peers_set_multicast: null argument%s");
+    p->mc_base = (char*)mc_base;
+    return 0;
+}
 
 static int slab_offset(const idg_peers* p, const void* ptr, int64_t bytes, int64_t* off) {
     const char* c = (const char*)ptr;
@@ -92,10 +102,15 @@ extern "C" int idg_peers_push(const idg_peers* p, const void* d_src, int64_t byt
     if (bytes == 0 || p->world == 1) return 0;
     int64_t off;
     if (int rc = slab_offset(p, d_src, bytes, &off)) return rc;
+    const int64_t n4 = bytes / 16;
+    if (p->mc_base) {
+        mc_push_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_src, (float*)(p->mc_base + off), n4);
+        IDG_LAUNCH_CHECK("mc_push_kernel");
+        return 0;
+    }
     PeerPtrs dst;
     int n = 0;
     for (int q = 0; q < p->world; ++q) if (q != p->rank) dst.p[n++] = p->bases[q] + off;
-    const int64_t n4 = bytes / 16;
     peer_push_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_src, dst, n, n4);
     IDG_LAUNCH_CHECK("peer_push_kernel");
     return 0;

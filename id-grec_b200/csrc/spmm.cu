@@ -59,6 +59,7 @@ struct SpmmArgs {
     const float* acc_in3;
     float* peerY[7];          // Y is also stored at the same slab offset of every peer GPU (fused all-gather)
     int n_peers;
+    float* mcY;               // ... or once through the NVSwitch multicast mapping (reaches all GPUs incl. this one)
     const int* worklist;      // optional: item ids to run (row-restricted layer), count in *d_wl_count
     const int* d_wl_count;
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
@@ -109,7 +110,9 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
         y.z += (sgn(y.z) * (nz.z / nrm)) * a.eps;
         y.w += (sgn(y.w) * (nz.w / nrm)) * a.eps;
     }
-    if (a.Y) {
+    if (a.mcY) {
+        multimem_st4(a.mcY + off, y);  // one NVLink store, replicated by the switch (NVLS)
+    } else if (a.Y) {
         st4(a.Y + off, y);
 #pragma unroll 1
         for (int p = 0; p < a.n_peers; ++p) st4(a.peerY[p] + off, y);  // NVLink peer stores, fire-and-forget
@@ -329,13 +332,18 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap;
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
     a.n_peers = 0;
+    a.mcY = nullptr;
     for (int p = 0; p < 7; ++p) a.peerY[p] = nullptr;
-    if (g->peers && d_Y) {
+    if (g->peers && d_Y && g->peers->world > 1) {
         const idg_peers* P = g->peers;
         const char* y = (const char*)d_Y;
         if (y >= P->local_base && y < P->local_base + P->bytes) {
-            for (int q = 0; q < P->world; ++q)
-                if (q != P->rank) a.peerY[a.n_peers++] = (float*)(P->bases[q] + (y - P->local_base));
+            if (P->mc_base) {
+                a.mcY = (float*)(P->mc_base + (y - P->local_base));
+            } else {
+                for (int q = 0; q < P->world; ++q)
+                    if (q != P->rank) a.peerY[a.n_peers++] = (float*)(P->bases[q] + (y - P->local_base));
+            }
         }
     }
     const int per_cta = kWarpsPerCta * (32 / (d / 4));  // items per CTA: one lane group each

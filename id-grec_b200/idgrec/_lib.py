@@ -97,6 +97,7 @@ SIGNATURES = {
     "idg_ipc_close": (C.c_int, [_p]),
     "idg_peers_create": (C.c_int, [_p, _i64, _i32, _i32, C.POINTER(_p), C.POINTER(_p)]),
     "idg_peers_destroy": (None, [_p]),
+    "idg_peers_set_multicast": (C.c_int, [_p, _p]),
     "idg_graph_set_peers": (C.c_int, [_p, _p]),
     "idg_peers_push": (C.c_int, [_p, _p, _i64, _p]),
     "idg_peers_barrier": (C.c_int, [_p, _p, _p]),

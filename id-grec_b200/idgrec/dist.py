@@ -51,39 +51,74 @@ class _CudaBuffer:
 
 
 class PeerSlab:
-    """One cudaMalloc'd slab per rank, mapped on every rank; tensors carved at identical offsets."""
+    """One slab per rank, mapped on every rank; tensors carved at identical offsets.
+
+    Backends: ``symm`` -- torch.distributed._symmetric_memory (CUDA VMM); when the fabric supports it this also
+    yields an NVSwitch multicast address, so a finished row leaves the GPU once (multimem.st) and the switch
+    replicates it (NVLS).  ``ipc`` -- plain cudaMalloc + CUDA IPC handles, unicast peer stores.  IDG_SLAB
+    selects one; the default tries ``symm`` and falls back to ``ipc``."""
 
     def __init__(self, nbytes: int, rank: int, world: int, group=None, device=None):
+        import os
         import torch.distributed as dist
         self.l = _lib.lib()
-        self.rank, self.world, self.nbytes = rank, world, int((nbytes + 4095) // 4096 * 4096)
+        self.rank, self.world, self.nbytes = rank, world, int((nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20))
         self.device = device
-        base = C.c_void_p()
-        check(self.l.idg_device_alloc(self.nbytes, C.byref(base)), "idg_device_alloc")
-        self.base = base.value
-        handle = (C.c_char * 64)()
-        check(self.l.idg_ipc_get_handle(self.base, handle), "idg_ipc_get_handle")
-        handles = [None] * world
-        if world > 1:
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-        else:
-            handles[0] = bytes(handle.raw)
-        self.peer_bases = []
-        for r in range(world):
-            if r == rank:
-                self.peer_bases.append(self.base)
+        self.multicast = False
+        mode = os.environ.get("IDG_SLAB", "auto")
+        self._bytes = None
+        if world > 1 and mode in ("auto", "symm"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD if group is None else group)
+                t.zero_()
+                self._symm = (t, hdl)
+                self._bytes, self.base = t, t.data_ptr()
+                self.peer_bases = [int(p) for p in hdl.buffer_ptrs]
+                self.peer_bases[rank] = self.base
+                mc = int(hdl.multicast_ptr) if os.environ.get("IDG_MULTICAST", "1") != "0" else 0
+                self.backend = "symm"
+            except Exception as e:  # noqa: BLE001 -- any failure of the optional backend falls back to IPC
+                if mode == "symm":
+                    raise
+                self._bytes = None
+                self._symm_error = repr(e)
+        if self._bytes is None:
+            mc = 0
+            self.backend = "ipc"
+            base = C.c_void_p()
+            check(self.l.idg_device_alloc(self.nbytes, C.byref(base)), "idg_device_alloc")
+            self.base = base.value
+            handle = (C.c_char * 64)()
+            check(self.l.idg_ipc_get_handle(self.base, handle), "idg_ipc_get_handle")
+            handles = [None] * world
+            if world > 1:
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
             else:
-                out = C.c_void_p()
-                buf = C.create_string_buffer(handles[r], 64)
-                check(self.l.idg_ipc_open(buf, C.byref(out)), "idg_ipc_open")
-                self.peer_bases.append(out.value)
+                handles[0] = bytes(handle.raw)
+            self.peer_bases = []
+            for r in range(world):
+                if r == rank:
+                    self.peer_bases.append(self.base)
+                else:
+                    out = C.c_void_p()
+                    buf = C.create_string_buffer(handles[r], 64)
+                    check(self.l.idg_ipc_open(buf, C.byref(out)), "idg_ipc_open")
+                    self.peer_bases.append(out.value)
+            self._bytes = torch.as_tensor(_CudaBuffer(self.base, self.nbytes), device=device)
         arr = (C.c_void_p * world)(*self.peer_bases)
         h = C.c_void_p()
         check(self.l.idg_peers_create(self.base, self.nbytes, rank, world, arr, C.byref(h)), "idg_peers_create")
         self.handle = h
-        self._bytes = torch.as_tensor(_CudaBuffer(self.base, self.nbytes), device=device)
+        if mc:
+            check(self.l.idg_peers_set_multicast(h, mc), "idg_peers_set_multicast")
+            self.multicast = True
         self._off = 0
         self.state = self.carve((64,), torch.int32)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=group)
 
     def carve(self, shape, dtype=torch.float32):
         n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()

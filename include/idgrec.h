@@ -215,6 +215,9 @@ int idg_ipc_open(const void* handle64, void** out);
 int idg_ipc_close(void* p);
 int idg_peers_create(void* local_base, int64_t bytes, int32_t rank, int32_t world, void* const* bases, idg_peers** out);
 void idg_peers_destroy(idg_peers* p);
+/* optional: the NVSwitch multicast (NVLS) mapping of the same slab; row stores and pushes then go out once
+ * as multimem.st and the switch replicates them into every GPU's copy (1/(G-1) of the NVLink egress) */
+int idg_peers_set_multicast(idg_peers* p, void* mc_base);
 int idg_graph_set_peers(idg_graph* g, const idg_peers* p);
 int idg_peers_push(const idg_peers* p, const void* d_src, int64_t bytes, void* stream);
 int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* stream);

@@ -69,7 +69,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("recall@20", res["recall"][1], "ndcg@20", res["ndcg"][1], "bounds", ft.bounds)
+        print("recall@20", res["recall"][1], "ndcg@20", res["ndcg"][1], "bounds", ft.bounds, "slab", ft.slab.backend, "multicast", ft.slab.multicast)
         print("DIST_CHECK", "PASS" if int(flag.item()) == 1 else "FAIL")
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
