@@ -62,6 +62,7 @@ struct SpmmArgs {
     float* mcY;               // ... or once through the NVSwitch multicast mapping (reaches all GPUs incl. this one)
     const int* worklist;      // optional: item ids to run (row-restricted layer), count in *d_wl_count
     const int* d_wl_count;
+    int skip_zero_rows;       // SPARSE kernels: rows that come out exactly zero are not stored (outputs pre-zeroed by the caller)
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
 };
 
@@ -204,6 +205,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     }
 
     if (it.w < 0) {
+        if (SPARSE && a.skip_zero_rows) {
+            // first backward product: most rows have no batch neighbour and a zero addend -> nothing to publish
+            const size_t off = (size_t)(a.row_offset + it.x) * d + sub * 4;
+            float4 g = a.addend ? ldcs4(a.addend + off) : f4zero();
+            const bool nz = (acc.x != 0.f) | (acc.y != 0.f) | (acc.z != 0.f) | (acc.w != 0.f) | (g.x != 0.f) | (g.y != 0.f) | (g.z != 0.f) | (g.w != 0.f);
+            if (!__any_sync(gmask, nz)) return;
+        }
         finish_row<LPR>(a, a.row_offset + it.x, sub, gmask, acc);
         return;
     }
@@ -313,6 +321,7 @@ struct SpmmExtra {
     const int* d_wl_count = nullptr;
     int max_wl = 0;
     const unsigned* bitmap = nullptr;  // sparse-input launch
+    int skip_zero_rows = 0;
 };
 
 static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
@@ -329,7 +338,7 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.partials = g->partials; a.counters = g->counters; a.row_offset = g->row_offset;
     a.X = d_X; a.Y = d_Y; a.addend = d_addend; a.addend2 = d_addend2; a.scale2 = scale2; a.noise = d_noise; a.eps = eps;
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
-    a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap;
+    a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap; a.skip_zero_rows = ex.skip_zero_rows;
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
     a.n_peers = 0;
     a.mcY = nullptr;
@@ -467,10 +476,13 @@ extern "C" int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* 
 }
 
 extern "C" int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_acc_in,
-                                        float* d_acc_out, float acc_div, int32_t d, const uint32_t* d_bitmap, void* stream) {
+                                        float* d_acc_out, float acc_div, int32_t d, const uint32_t* d_bitmap, int skip_zero_rows,
+                                        void* stream) {
     if (!d_bitmap) return fail(-1, "idg_spmm_layer_sparse_in: null bitmap%s");
+    if (skip_zero_rows && d_acc_out) return fail(-1, "idg_spmm_layer_sparse_in: skip_zero_rows only with a plain Y output%s");
     SpmmExtra ex;
     ex.bitmap = d_bitmap;
+    ex.skip_zero_rows = skip_zero_rows;
     return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, d_acc_in, d_acc_out, acc_div, d, stream, ex);
 }
 

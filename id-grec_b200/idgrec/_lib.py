@@ -74,7 +74,7 @@ SIGNATURES = {
     "idg_batch_rows_clear": (C.c_int, [_p, _p, _i32, _p, _p]),
     "idg_graph_worklist_ints": (_i64, [_p, _i32]),
     "idg_spmm_layer_rows": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _f32, _i32, _p, _p, _i32, _p, _p]),
-    "idg_spmm_layer_sparse_in": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i32, _p, _p]),
+    "idg_spmm_layer_sparse_in": (C.c_int, [_p, _p, _p, _p, _p, _p, _f32, _i32, _p, C.c_int, _p]),
     "idg_propagate_fwd_ex": (C.c_int, [_p, _p, _i32, _i32, C.c_int, _p, _f32, _i32, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "idg_propagate_bwd_ex": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
     "idg_bpr_workspace_bytes": (_i64, [_i32]),

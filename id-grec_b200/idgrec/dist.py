@@ -175,6 +175,7 @@ class DistFusedTrainer:
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.use_cuda_graph = use_cuda_graph
         self._graphs, self._graph_launches, self.replayed_launches = {}, {}, 0
+        self._prof = None
         torch.cuda.synchronize()
         self._host_barrier(group)
         self.group = group
@@ -186,47 +187,72 @@ class DistFusedTrainer:
             dist.barrier(group=group)
 
     # ------------------------------------------------------------------
+    def _mark(self, name):
+        if self._prof is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._prof.append((name, e))
+
     def _body(self, B, u, p, n):
         l, s, K, d = self.l, cur_stream(), self.K, self.d
+        self._mark('start')
         loc, rows, slab = self.local, self.rows, self.slab
         rows.build(u, p, n, B, self.U)
+        if K > 1:
+            # the first backward product only publishes non-zero rows: clear this rank's copy of its output now; every
+            # peer passes two barriers (after this point in stream order) before it writes into it
+            self.H[0].zero_()
+        self._mark('batch_rows')
         # forward: layers 1..K-1 on the local rows, rows pushed to every peer by the epilogue
         x = self.E0
         for k in range(K - 1):
             loc.spmm_layer(x, Y=self.W[k])
+            self._mark('fwd_layer%d' % (k + 1))
             slab.barrier()
+            self._mark('barrier')
             x = self.W[k]
         # last layer + mean only on the batch rows, every rank computes all of them (no exchange)
         acc = [self.E0] + self.W
         check(l.idg_spmm_layer_rows(self.full._h, ptr(x), None, None, 0.0, ptr(acc[0]), ptr(acc[1]) if K > 1 else None,
                                     ptr(acc[2]) if K > 2 else None, ptr(self.F), float(K + 1), d, ptr(rows.rowlist), ptr(rows.count),
                                     rows.max_rows, ptr(rows.worklist(self.full)), s), "idg_spmm_layer_rows")
+        self._mark('fwd_last_rows')
         check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, d, self.reg_lambda, 7, ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
         check(l.idg_bpr_backward(ptr(self.F), B, d, 7, None, ptr(self.G), ptr(self.ws), s), "idg_bpr_backward")
+        self._mark('bpr')
         # backward Horner chain on the local rows; the first product only gathers batch columns
         off = self.b0 * d
         g_loc = self.gE0  # full-size buffer, local rows written at their global position
         if K == 1:
-            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), None, ptr(self.G), None, ptr(g_loc), float(K + 1), d, ptr(rows.bitmap), s), "idg_spmm_layer_sparse_in")
+            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), None, ptr(self.G), None, ptr(g_loc), float(K + 1), d, ptr(rows.bitmap), 0, s), "idg_spmm_layer_sparse_in")
         else:
-            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), s), "idg_spmm_layer_sparse_in")
+            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
+            self._mark('bwd_sparse')
             slab.barrier()
+            self._mark('barrier')
             h = self.H[0]
             for k in range(1, K - 1):
                 loc.spmm_layer(h, Y=self.H[k], addend=self.G)
+                self._mark('bwd_layer')
                 slab.barrier()
+                self._mark('barrier')
                 h = self.H[k]
             loc.spmm_layer(h, Y=None, addend=self.G, acc_out=g_loc, acc_div=float(K + 1))
+            self._mark('bwd_last')
         check(l.idg_bpr_finish(ptr(self.E0), ptr(self.gE0), ptr(self.G), B, d, self.reg_lambda, None, ptr(self.ws), s), "idg_bpr_finish")
         rows.clear()
+        self._mark('finish')
         # Adam on the rows this rank owns, then hand them to the peers
         nloc = (self.b1 - self.b0) * d
         if nloc > 0:
             fp = lambda t: t.data_ptr() + off * 4
             check(l.idg_adam_step_dev(fp(self.E0), fp(self.gE0), fp(self.m), fp(self.v), nloc, self.lr, self.betas[0], self.betas[1],
                                       self.adam_eps, ptr(self.d_step), s), "idg_adam_step_dev")
+            self._mark('adam')
             slab.push(self.E0[self.b0:self.b1])
+            self._mark('push')
         slab.barrier()
+        self._mark('barrier')
         check(l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, s), "idg_axpby")
 
     def step(self, users, pos, neg, apply_adam=True):
@@ -259,3 +285,18 @@ class DistFusedTrainer:
     def final_embeddings(self):
         """Clean propagation of the current table on the whole graph (every rank, for its evaluation shard)."""
         return self.full.propagate_fwd(self.E0, self.K, True)
+
+    def profile_steps(self, batches):
+        """Eager steps with CUDA events between phases -> {phase: mean ms} (diagnostics)."""
+        graph, self.use_cuda_graph = self.use_cuda_graph, False
+        acc, n = {}, 0
+        for b in batches:
+            self._prof = []
+            self.step(*b)
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(self._prof[:-1], self._prof[1:]):
+                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+            n += 1
+        self._prof = None
+        self.use_cuda_graph = graph
+        return {k: v / n for k, v in acc.items()}

@@ -43,6 +43,29 @@ def propagate(X0, graph, K, include_layer0=True, noise=None, eps=0.0, cl_layer=0
     return PropagateFn.apply(X0, graph, K, include_layer0, noise, eps, cl_layer)
 
 
+class SpmmFn(torch.autograd.Function):
+    """One torch.sparse.mm(self.Graph, X) (NGCF.py:85); the adjacency is symmetric, so backward is the same product."""
+
+    @staticmethod
+    def forward(ctx, X, graph):
+        X = _f32c(X)
+        ctx.graph = graph
+        Y = torch.empty_like(X)
+        graph.spmm_layer(X, Y=Y)
+        return Y
+
+    @staticmethod
+    def backward(ctx, gY):
+        gY = _f32c(gY)
+        gX = torch.empty_like(gY)
+        ctx.graph.spmm_layer(gY, Y=gX)
+        return gX, None
+
+
+def spmm(X, graph):
+    return SpmmFn.apply(X, graph)
+
+
 class BprRegLossFn(torch.autograd.Function):
     """[bpr, reg_lambda*reg] = fused LightGCN.py:57-70 + losses.py:4-21."""
 

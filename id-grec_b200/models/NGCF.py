@@ -1,0 +1,76 @@
+"""NGCF (Wang et al., SIGIR'19) -- same class interface as the reference's models/NGCF.py:17-153.
+Graph D^-1/2 (A+I) D^-1/2; per layer side = A.E (hand-written SpMM kernel), sum = side W_gcn + b,
+bi = (E * side) W_bi + b, LeakyReLU(0.2), message dropout, row-normalise; final = concat of the
+K+1 blocks (256-d).  The two 64x64 dense products per layer are plain library GEMMs (torch.matmul);
+BPR / regulariser / full-ranking evaluation run on the fused kernels (d = 256 for scores)."""
+import torch
+from torch import nn
+
+import utility.utility_data.data_graph
+import utility.utility_train.trainer as trainer
+from idgrec import ops
+from idgrec.model_base import PropagationModel
+
+
+class NGCF(PropagationModel):
+    kind = "NGCF"
+    fused_trainer = None  # trained through autograd + torch.optim.Adam (dense weights), reference loop trainer.py:40-56
+
+    def __init__(self, config, dataset, device):
+        super(NGCF, self).__init__(config, dataset, device, None)
+        initializer = nn.init.xavier_uniform_
+        self.weight_dict = nn.ParameterDict()
+        layers = [int(config['embedding_size'])] + eval(config['layer_size'])
+        # same parameter order (and torch RNG draws) as NGCF.py:36-44
+        for layer in range(int(config['GCN_layer'])):
+            self.weight_dict.update({'W_gcn_%d' % layer: nn.Parameter(initializer(torch.empty(layers[layer], layers[layer + 1])))})
+            self.weight_dict.update({'b_gcn_%d' % layer: nn.Parameter(initializer(torch.empty(1, layers[layer + 1])))})
+            self.weight_dict.update({'W_bi_%d' % layer: nn.Parameter(initializer(torch.empty(layers[layer], layers[layer + 1])))})
+            self.weight_dict.update({'b_bi_%d' % layer: nn.Parameter(initializer(torch.empty(1, layers[layer + 1])))})
+        if eval(config['mess_dropout']):
+            self.mess_dropout = eval(config['mess_drop_prob'])
+        if eval(config['node_dropout']):
+            raise NotImplementedError("node_dropout = True is not part of the accelerated path (the reference's default is False)")
+        import utility.utility_function.tools as tools
+        self.Graph = utility.utility_data.data_graph.sparse_adjacency_matrix_with_self(dataset)
+        self.Graph = tools.convert_sp_mat_to_sp_tensor(self.Graph)
+        self.Graph = self.Graph.coalesce().to(self.device)
+        self.activation_layer = nn.Tanh()
+
+    def aggregate(self, keep_masks=None):
+        """NGCF.py:67-111.  ``keep_masks`` (K tensors of 0/1) injects the dropout draws for parity tests;
+        otherwise nn.Dropout is constructed inline exactly like the reference -- i.e. ALWAYS active, also in
+        eval mode."""
+        ego = self.table()
+        outs = [ego]
+        for layer in range(int(self.config['GCN_layer'])):
+            side = ops.spmm(ego, self.Graph)
+            s = torch.matmul(side, self.weight_dict['W_gcn_%d' % layer]) + self.weight_dict['b_gcn_%d' % layer]
+            bi = torch.matmul(torch.mul(ego, side), self.weight_dict['W_bi_%d' % layer]) + self.weight_dict['b_bi_%d' % layer]
+            ego = nn.LeakyReLU(negative_slope=0.2)(s + bi)
+            if keep_masks is not None:
+                ego = ego * keep_masks[layer] / (1.0 - self.mess_dropout[layer])
+            else:
+                ego = nn.Dropout(self.mess_dropout[layer])(ego)
+            outs.append(nn.functional.normalize(ego, p=2, dim=1))
+        final = torch.cat(outs, dim=1)
+        return self._split(final)
+
+    def forward(self, user, positive, negative, keep_masks=None):
+        """NGCF.py:113-130 -> [bpr, reg]; the regulariser covers the item ego rows only (NGCF.py:120-125)."""
+        U = self.dataset.num_users
+        users_emb, items_emb = self.aggregate(keep_masks)
+        final = torch.cat([users_emb, items_emb])
+        E0 = self.table()
+        bpr = ops.bpr_reg_loss(final, final, user, positive, negative, U, 0.0, 0)[0]
+        reg = ops.bpr_reg_loss(E0.detach(), E0, user, positive, negative, U, self.reg_lambda, 6)[1]
+        return [bpr, reg]
+
+
+class Trainer():
+    def __init__(self, args, config, dataset, device, logger):
+        self.model = NGCF(config, dataset, device)
+        self.args, self.device, self.config, self.dataset, self.logger = args, device, config, dataset, logger
+
+    def train(self):
+        trainer.universal_trainer(self.model, self.args, self.config, self.dataset, self.device, self.logger)

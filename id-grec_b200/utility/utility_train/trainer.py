@@ -30,7 +30,7 @@ def universal_trainer(model, args, config, dataset, device, logger):
     model.to(device)
     lr = float(config['learn_rate'])
     batch_size = int(config['batch_size'])
-    fused = model.fused_trainer(lr, batch_size) if hasattr(model, "fused_trainer") else None
+    fused = model.fused_trainer(lr, batch_size) if getattr(model, "fused_trainer", None) is not None else None
     Optim = None if fused is not None else torch.optim.Adam(model.parameters(), lr=lr)
 
     best_results = dict()

@@ -112,10 +112,12 @@ int idg_spmm_layer_rows(const idg_graph* g, const float* d_X, float* d_Y, const 
                         float acc_div, int32_t d, const int32_t* d_rowlist, const int32_t* d_count,
                         int32_t max_rows, int32_t* d_worklist, void* stream);
 /* idg_spmm_layer for an X that is zero outside the rows flagged in d_bitmap: streams the CSR structure
- * but gathers only flagged columns (first backward layer: dL/dF is non-zero on the batch rows only) */
+ * but gathers only flagged columns (first backward layer: dL/dF is non-zero on the batch rows only).
+ * skip_zero_rows: rows whose result is exactly zero are not stored (d_Y must be zero-filled by the caller);
+ * on the multi-GPU path this keeps them off NVLink. */
 int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend,
                              const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
-                             const uint32_t* d_bitmap, void* stream);
+                             const uint32_t* d_bitmap, int skip_zero_rows, void* stream);
 /* idg_propagate_fwd whose LAST layer and layer mean are evaluated only on the listed rows
  * (d_rowlist NULL => identical to idg_propagate_fwd); idg_propagate_bwd whose FIRST product uses the
  * sparse-input kernel (d_bitmap NULL => identical to idg_propagate_bwd). */

@@ -159,6 +159,45 @@ def test_contrastive_models_vs_reference(dev, golden_dirs, golden_tiny, kind, pr
     _close(fu.cpu().numpy(), g[prefix + "_fu"]); _close(fi.cpu().numpy(), g[prefix + "_fi"])
 
 
+def test_ngcf_vs_reference(dev, golden_dirs, golden_tiny):
+    """NGCF forward + backward with the reference's dropout masks injected (ngcf_* in tiny.npz), then the
+    256-d full-ranking evaluation against the exact-rank oracle."""
+    from models.NGCF import NGCF
+    import utility.utility_train.batch_test as batch_test
+    g = golden_tiny
+    cfg = _cfg("NGCF")
+    d = _data(golden_dirs, cfg)
+    m = NGCF(cfg, d, dev)
+    _load_weights(m, g["ngcf_user_w0"], g["ngcf_item_w0"])
+    with torch.no_grad():
+        for l in range(3):
+            for k in ("W_gcn", "b_gcn", "W_bi", "b_bi"):
+                m.weight_dict["%s_%d" % (k, l)].copy_(torch.from_numpy(g["ngcf_%s_%d" % (k, l)]))
+    m.to(dev)
+    masks = [torch.from_numpy(x).to(dev) for x in g["ngcf_masks"]]
+    b = torch.from_numpy(g["batch"].copy()).to(dev)
+    losses = m(b[:, 0], b[:, 1], b[:, 2], keep_masks=masks)
+    (losses[0] + losses[1]).backward()
+    np.testing.assert_allclose([l.item() for l in losses], g["ngcf_loss"], rtol=RTOL)
+    _close(m.user_embedding.weight.grad.cpu().numpy(), g["ngcf_gu"], rtol=1e-4)
+    _close(m.item_embedding.weight.grad.cpu().numpy(), g["ngcf_gi"], rtol=1e-4)
+    for l in range(3):
+        for k in ("W_gcn", "b_gcn", "W_bi", "b_bi"):
+            _close(m.weight_dict["%s_%d" % (k, l)].grad.cpu().numpy(), g["ngcf_g_%s_%d" % (k, l)], rtol=1e-4)
+    # 256-d ranking through the fused evaluator (dropout is live at eval in the reference: fix the masks)
+    with torch.no_grad():
+        fu, fi = m.aggregate(masks)
+    od = O.load_dataset(golden_dirs["tiny"])
+    users = np.array(list(od.test_dict.keys()), dtype=np.int64)
+    cache = d.device_cache(dev)
+    from idgrec import ops
+    ids = ops.eval_topk(fu.contiguous(), fi.contiguous(), cache["test_users"], cache["mask_indptr"], cache["mask_indices"], 20)
+    ref_ids, _ = O.topk_exact(fu.cpu().numpy(), fi.cpu().numpy(), users, od.user_item_net.indptr, od.user_item_net.indices, 20)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids)
+    res = batch_test.Test(d, m, dev, cfg)
+    assert 0.0 <= res["recall"][1] <= 1.0
+
+
 def test_mfbpr_vs_reference(dev, golden_dirs, golden_tiny):
     from models.MFBPR import MFBPR
     g = golden_tiny

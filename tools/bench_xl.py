@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--eval-users", type=int, default=16384, help="test users ranked per rank")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -76,6 +77,8 @@ def main():
     b.record()
     sync()
     step_ms = a.elapsed_time(b) / args.steps
+    breakdown = ft.profile_steps([(bu[s], bp[s], negs[s]) for s in range(min(8, nb))]) if args.breakdown else None
+    sync()
     # one local propagation layer (local rows, peer stores on) timed alone
     evs = []
     for _ in range(8):
@@ -120,7 +123,7 @@ def main():
                           "layer_ms_local_rows": layer_ms, "layer_alg_GBs_per_gpu": alg / layer_ms / 1e6, "layer_gather_GBs_per_gpu": gat / layer_ms / 1e6,
                           "layer_gather_frac_of_hbm": gat / layer_ms / 1e6 / hbm, "hbm_peak_GBs": hbm,
                           "eval_users_per_s_total": nu * world / eval_ms * 1e3, "eval_ms": eval_ms, "eval_users_per_rank": nu,
-                          "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": not args.no_graph, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}))
+                          "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": not args.no_graph, "breakdown_ms": breakdown, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}))
     if world > 1:
         dist.destroy_process_group()
 
