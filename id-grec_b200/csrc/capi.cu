@@ -72,6 +72,13 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
     if (i == 0) for (int64_t k = n4 * 4; k < n; ++k) upd(p[k], g[k], m[k], v[k]);
 }
 __global__ void incr_kernel(int* c) { *c += 1; }
+// bias-corrected step scalars for the Adam-fused SpMM epilogue: scalars[0] = lr/(1-b1^t), scalars[1] = sqrt(1-b2^t)
+__global__ void adam_prepare_kernel(int* d_step, float* scalars, float lr, float b1, float b2) {
+    const double t = (double)(*d_step + 1);
+    scalars[0] = (float)((double)lr / (1.0 - pow((double)b1, t)));
+    scalars[1] = (float)sqrt(1.0 - pow((double)b2, t));
+    *d_step += 1;
+}
 }  // namespace idg
 
 using namespace idg;
@@ -122,6 +129,13 @@ extern "C" int idg_adam_step_dev(float* d_p, const float* d_g, float* d_m, float
     IDG_LAUNCH_CHECK("adam_dev_kernel");
     incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step);
     IDG_LAUNCH_CHECK("incr_kernel");
+    return 0;
+}
+
+extern "C" int idg_adam_prepare(int32_t* d_step, float* d_scalars, float lr, float beta1, float beta2, void* stream) {
+    if (!d_step || !d_scalars) return fail(-1, "idg_adam_prepare: null argument%s");
+    adam_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_step, d_scalars, lr, beta1, beta2);
+    IDG_LAUNCH_CHECK("adam_prepare_kernel");
     return 0;
 }
 

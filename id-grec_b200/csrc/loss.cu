@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(1024) bpr_reduce_kernel(BprWs w, int B, float 
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ F, int B, int reg_mask, const float* __restrict__ upstream, BprWs w, float* __restrict__ G) {
+__global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ F, int B, int reg_mask, const float* __restrict__ upstream, BprWs w, float* __restrict__ G,
+                                                      float* __restrict__ regc, float reg_coef) {
     constexpr int d = 32 * VPL;
     extern __shared__ int skeys[];  // [3B]
     const int n = 3 * B;
@@ -139,12 +140,17 @@ __global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ 
     }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) G[(size_t)node * d + lane * VPL + v] = acc[v];
-    if (lane == 0) { w.lead_node[e] = node; w.lead_mult[e] = mult; }
+    if (lane == 0) {
+        w.lead_node[e] = node; w.lead_mult[e] = mult;
+        // per-row L2-reg coefficient for the Adam-fused last backward layer: g += regc[row] * E0[row]
+        if (regc) regc[node] = reg_coef * (upstream ? upstream[1] : 1.f) * (float)mult;
+    }
 }
 
 template <int VPL>
 __global__ void __launch_bounds__(256) bpr_finish_kernel(const float* __restrict__ E0, float* __restrict__ gE0, float* __restrict__ G,
-                                                         int n, float coef, const float* __restrict__ upstream, BprWs w) {
+                                                         int n, float coef, const float* __restrict__ upstream, BprWs w,
+                                                         float* __restrict__ regc) {
     constexpr int d = 32 * VPL;
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(256) bpr_finish_kernel(const float* __restrict
         if (gE0 && m != 0.f) gE0[o] += m * E0[o];
         if (G) G[o] = 0.f;
     }
+    if (regc && lane == 0) regc[node] = 0.f;
 }
 
 }  // namespace idg
@@ -194,27 +201,27 @@ extern "C" int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_
 }
 
 extern "C" int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_mask, const float* d_upstream, float* d_G,
-                                void* d_ws, void* stream_) {
+                                float reg_lambda, float* d_regc, void* d_ws, void* stream_) {
     if (!d_F || !d_G || !d_ws || B <= 0) return fail(-1, "idg_bpr_backward: bad argument%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     BprWs w = bpr_carve(d_ws, B);
     const size_t smem = sizeof(int) * 3 * (size_t)B;
     IDG_DISPATCH_D(d, {
         if (smem > 48 * 1024) IDG_CUDA(cudaFuncSetAttribute(bpr_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bpr_bwd_kernel<VPL><<<(3 * B + 7) / 8, 256, smem, stream>>>(d_F, B, reg_mask, d_upstream, w, d_G);
+        bpr_bwd_kernel<VPL><<<(3 * B + 7) / 8, 256, smem, stream>>>(d_F, B, reg_mask, d_upstream, w, d_G, d_regc, reg_lambda / (float)B);
     });
     IDG_LAUNCH_CHECK("bpr_bwd_kernel");
     return 0;
 }
 
 extern "C" int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
-                              const float* d_upstream, void* d_ws, void* stream_) {
+                              const float* d_upstream, float* d_regc, void* d_ws, void* stream_) {
     if (!d_ws || B <= 0 || (d_gE0 && !d_E0)) return fail(-1, "idg_bpr_finish: bad argument%s");
-    if (!d_gE0 && !d_G) return 0;
+    if (!d_gE0 && !d_G && !d_regc) return 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     BprWs w = bpr_carve(d_ws, B);
     const float coef = reg_lambda / (float)B;
-    IDG_DISPATCH_D(d, (bpr_finish_kernel<VPL><<<(3 * B + 7) / 8, 256, 0, stream>>>(d_E0, d_gE0, d_G, 3 * B, coef, d_upstream, w)));
+    IDG_DISPATCH_D(d, (bpr_finish_kernel<VPL><<<(3 * B + 7) / 8, 256, 0, stream>>>(d_E0, d_gE0, d_G, 3 * B, coef, d_upstream, w, d_regc)));
     IDG_LAUNCH_CHECK("bpr_finish_kernel");
     return 0;
 }

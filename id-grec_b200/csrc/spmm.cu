@@ -62,6 +62,10 @@ struct SpmmArgs {
     float* mcY;               // ... or once through the NVSwitch multicast mapping (reaches all GPUs incl. this one)
     const int* worklist;      // optional: item ids to run (row-restricted layer), count in *d_wl_count
     const int* d_wl_count;
+    // Adam fused into the last backward layer: the row gradient never goes to memory
+    float* adam_p; float* adam_m; float* adam_v; const float* adam_regc; const float* adam_scalars;
+    float adam_b1, adam_b2, adam_eps;
+    float* adam_peer_p[7]; float* adam_mc_p;
     int skip_zero_rows;       // SPARSE kernels: rows that come out exactly zero are not stored (outputs pre-zeroed by the caller)
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
 };
@@ -93,7 +97,7 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
 template <bool NA>
 __device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
 
-template <int LPR>
+template <int LPR, bool ADAM>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
     constexpr int d = 4 * LPR;
     const size_t off = (size_t)grow * d + sub * 4;
@@ -118,6 +122,31 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 #pragma unroll 1
         for (int p = 0; p < a.n_peers; ++p) st4(a.peerY[p] + off, y);  // NVLink peer stores, fire-and-forget
     }
+    if (ADAM) {
+        // g = y/acc_div + regc[row]*p ; torch.optim.Adam update (same formula as adam_dev_kernel); publish p
+        float4 g = make_float4(y.x / a.acc_div, y.y / a.acc_div, y.z / a.acc_div, y.w / a.acc_div);
+        float4 pv = *reinterpret_cast<const float4*>(a.adam_p + off);
+        const float rc = a.adam_regc ? __ldg(a.adam_regc + grow) : 0.f;
+        if (rc != 0.f) { g.x = fmaf(rc, pv.x, g.x); g.y = fmaf(rc, pv.y, g.y); g.z = fmaf(rc, pv.z, g.z); g.w = fmaf(rc, pv.w, g.w); }
+        float4 mv = *reinterpret_cast<const float4*>(a.adam_m + off), vv = *reinterpret_cast<const float4*>(a.adam_v + off);
+        const float step_size = __ldg(a.adam_scalars), bc2_sqrt = __ldg(a.adam_scalars + 1);
+        const float b1 = a.adam_b1, b2 = a.adam_b2, eps = a.adam_eps;
+        auto upd = [&](float& pp, float gg, float& mm, float& v2) {
+            mm = mm + (gg - mm) * (1.f - b1);
+            v2 = v2 * b2 + (1.f - b2) * gg * gg;
+            const float denom = sqrtf(v2) / bc2_sqrt + eps;
+            pp = pp - step_size * (mm / denom);
+        };
+        upd(pv.x, g.x, mv.x, vv.x); upd(pv.y, g.y, mv.y, vv.y); upd(pv.z, g.z, mv.z, vv.z); upd(pv.w, g.w, mv.w, vv.w);
+        st4(a.adam_m + off, mv); st4(a.adam_v + off, vv);
+        if (a.adam_mc_p) {
+            multimem_st4(a.adam_mc_p + off, pv);
+        } else {
+            st4(a.adam_p + off, pv);
+#pragma unroll 1
+            for (int q = 0; q < a.n_peers; ++q) st4(a.adam_peer_p[q] + off, pv);
+        }
+    }
     if (a.acc_out) {
         float4 s = y;
         if (a.acc_in) {
@@ -134,7 +163,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -212,7 +241,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             const bool nz = (acc.x != 0.f) | (acc.y != 0.f) | (acc.z != 0.f) | (acc.w != 0.f) | (g.x != 0.f) | (g.y != 0.f) | (g.z != 0.f) | (g.w != 0.f);
             if (!__any_sync(gmask, nz)) return;
         }
-        finish_row<LPR>(a, a.row_offset + it.x, sub, gmask, acc);
+        finish_row<LPR, ADAM>(a, a.row_offset + it.x, sub, gmask, acc);
         return;
     }
     // chunk of a heavy row: publish the partial; the last chunk to arrive sums them in chunk order
@@ -228,7 +257,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     float4 s = ldcg4(a.partials + (size_t)h.part_begin * d + sub * 4);
     for (int p = 1; p < h.n_parts; ++p) s = f4add(s, ldcg4(a.partials + (size_t)(h.part_begin + p) * d + sub * 4));
     if (sub == 0) a.counters[it.x] = 0;  // ready for the next launch
-    finish_row<LPR>(a, a.row_offset + h.row, sub, gmask, s);
+    finish_row<LPR, ADAM>(a, a.row_offset + h.row, sub, gmask, s);
 }
 
 __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int2* __restrict__ out, int64_t nnz) {
@@ -322,13 +351,14 @@ struct SpmmExtra {
     int max_wl = 0;
     const unsigned* bitmap = nullptr;  // sparse-input launch
     int skip_zero_rows = 0;
+    const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
 
 static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
                        float scale2, const float* d_noise, float eps, const float* d_acc_in, float* d_acc_out, float acc_div,
                        int32_t d, void* stream_, const SpmmExtra& ex = SpmmExtra()) {
     if (!g || !d_X) return fail(-1, "idg_spmm_layer: null graph or X%s");
-    if (!d_Y && !d_acc_out) return fail(-1, "idg_spmm_layer: no output requested%s");
+    if (!d_Y && !d_acc_out && !ex.adam) return fail(-1, "idg_spmm_layer: no output requested%s");
     if (d_X == d_Y || d_X == d_acc_out) return fail(-1, "idg_spmm_layer: X must not alias an output%s");
     if (d != 32 && d != 64 && d != 128) return fail(-1, "idg_spmm_layer: d must be 32, 64 or 128 (%s%lld)", "", d);
     if (d_acc_out && !(acc_div > 0.f)) return fail(-1, "idg_spmm_layer: acc_div must be > 0%s");
@@ -340,6 +370,9 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap; a.skip_zero_rows = ex.skip_zero_rows;
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
+    a.adam_p = nullptr; a.adam_m = a.adam_v = nullptr; a.adam_regc = a.adam_scalars = nullptr; a.adam_mc_p = nullptr;
+    a.adam_b1 = a.adam_b2 = a.adam_eps = 0.f;
+    for (int p = 0; p < 7; ++p) a.adam_peer_p[p] = nullptr;
     a.n_peers = 0;
     a.mcY = nullptr;
     for (int p = 0; p < 7; ++p) a.peerY[p] = nullptr;
@@ -355,6 +388,20 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
             }
         }
     }
+    if (ex.adam) {
+        const idg_adam_args* A = ex.adam;
+        if (!A->p || !A->m || !A->v || !A->d_scalars || !(acc_div > 0.f)) return fail(-1, "idg_spmm_layer_adam: incomplete Adam arguments%s");
+        a.adam_p = A->p; a.adam_m = A->m; a.adam_v = A->v; a.adam_regc = A->regc; a.adam_scalars = A->d_scalars;
+        a.adam_b1 = A->beta1; a.adam_b2 = A->beta2; a.adam_eps = A->eps; a.acc_div = acc_div;
+        if (g->peers && g->peers->world > 1) {  // parameter rows go straight to the peers as well (replaces the push)
+            const idg_peers* P = g->peers;
+            const char* pp = (const char*)A->p;
+            if (pp >= P->local_base && pp < P->local_base + P->bytes) {
+                if (P->mc_base) a.adam_mc_p = (float*)(P->mc_base + (pp - P->local_base));
+                else { a.n_peers = 0; for (int q = 0; q < P->world; ++q) if (q != P->rank) a.adam_peer_p[a.n_peers++] = (float*)(P->bases[q] + (pp - P->local_base)); }
+            }
+        }
+    }
     const int per_cta = kWarpsPerCta * (32 / (d / 4));  // items per CTA: one lane group each
     const int n_slots = ex.worklist ? ex.max_wl : g->n_items;
     if (n_slots <= 0) return 0;
@@ -363,10 +410,20 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     const int T = kWarpsPerCta * 32;
     // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
     // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
-    if (ex.bitmap) {
+    if (ex.adam) {
+        if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
+        if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap) {
         if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
         else spmm_kernel<32, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.worklist) {
+        // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
+        if (d == 64) spmm_kernel<16, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 8, false, 1><<<grid, T, 0, stream>>>(a);
     } else {
         if (d == 64) spmm_kernel<16, 2, false, 8><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 8><<<grid, T, 0, stream>>>(a);
@@ -486,6 +543,14 @@ extern "C" int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, fl
     return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, d_acc_in, d_acc_out, acc_div, d, stream, ex);
 }
 
+extern "C" int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
+                                   const idg_adam_args* adam, void* stream) {
+    if (!adam) return fail(-1, "idg_spmm_layer_adam: null adam%s");
+    SpmmExtra ex;
+    ex.adam = adam;
+    return spmm_launch(g, d_X, nullptr, d_addend, nullptr, 0.f, nullptr, 0.f, nullptr, nullptr, acc_div, d, stream, ex);
+}
+
 // K-layer forward, single GPU (models/LightGCN.py:36-52, SimGCL.py:39-60, XSimGCL.py:40-67).  With a row list the
 // LAST layer (and with it the layer mean) is evaluated only on those rows: the loss reads nothing else
 // (LightGCN.py:57-59), so the result is identical where it is consumed and ~1/K of the gather work disappears.
@@ -531,10 +596,10 @@ extern "C" int idg_propagate_fwd(const idg_graph* g, const float* d_X0, int32_t 
 // With H_l = cnt * dL/dX_l:  H_K = G (+cnt*Gcl if cl==K);  H_l = G + A H_{l+1} (+cnt*Gcl if cl==l);
 // gX0 = (inc0*G + A H_1)/cnt.  The sign-noise perturbation has identity gradient (SimGCL.py:51).
 // With d_bitmap (rows where G / Gcl are non-zero) the first product A*H_K only gathers flagged columns.
-extern "C" int idg_propagate_bwd_ex(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
-                                    int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, const uint32_t* d_bitmap,
-                                    void* stream) {
-    if (!g || !d_G || !d_gX0 || !d_work) return fail(-1, "idg_propagate_bwd: null argument%s");
+static int propagate_bwd_impl(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K, int include_layer0,
+                              int32_t cl_layer, float* d_gX0, float* d_work, const uint32_t* d_bitmap, const idg_adam_args* adam,
+                              void* stream) {
+    if (!g || !d_G || (!d_gX0 && !adam) || !d_work) return fail(-1, "idg_propagate_bwd: null argument%s");
     if (K < 1) return fail(-1, "idg_propagate_bwd: K must be >= 1%s");
     if (g->row_offset != 0 || g->n_rows != g->n_cols) return fail(-1, "idg_propagate_bwd: needs the whole square graph%s");
     if (d_Gcl && (cl_layer < 1 || cl_layer > K)) return fail(-1, "idg_propagate_bwd: bad cl_layer%s");
@@ -558,11 +623,26 @@ extern "C" int idg_propagate_bwd_ex(const idg_graph* g, const float* d_G, const 
             if (rc) return rc;
             h = y;
         } else {
-            rc = spmm_launch(g, h, nullptr, include_layer0 ? d_G : nullptr, nullptr, 0.f, nullptr, 0.f, nullptr, d_gX0, cnt, d, stream, ex);
+            ex.adam = adam;
+            rc = spmm_launch(g, h, nullptr, include_layer0 ? d_G : nullptr, nullptr, 0.f, nullptr, 0.f, nullptr, adam ? nullptr : d_gX0, cnt, d, stream, ex);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+extern "C" int idg_propagate_bwd_ex(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                                    int include_layer0, int32_t cl_layer, float* d_gX0, float* d_work, const uint32_t* d_bitmap,
+                                    void* stream) {
+    return propagate_bwd_impl(g, d_G, d_Gcl, d, K, include_layer0, cl_layer, d_gX0, d_work, d_bitmap, nullptr, stream);
+}
+
+// Same chain, but the last product's epilogue applies the Adam update in place of writing the gradient.
+extern "C" int idg_propagate_bwd_adam(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                                      int include_layer0, int32_t cl_layer, float* d_work, const uint32_t* d_bitmap,
+                                      const idg_adam_args* adam, void* stream) {
+    if (!adam) return fail(-1, "idg_propagate_bwd_adam: null adam%s");
+    return propagate_bwd_impl(g, d_G, d_Gcl, d, K, include_layer0, cl_layer, nullptr, d_work, d_bitmap, adam, stream);
 }
 
 extern "C" int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,

@@ -79,8 +79,8 @@ SIGNATURES = {
     "idg_propagate_bwd_ex": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
     "idg_bpr_workspace_bytes": (_i64, [_i32]),
     "idg_bpr_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, C.c_int, _p, _p, _p]),
-    "idg_bpr_backward": (C.c_int, [_p, _i32, _i32, C.c_int, _p, _p, _p, _p]),
-    "idg_bpr_finish": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _p, _p, _p]),
+    "idg_bpr_backward": (C.c_int, [_p, _i32, _i32, C.c_int, _p, _p, _f32, _p, _p, _p]),
+    "idg_bpr_finish": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _p, _p, _p, _p]),
     "idg_axpby": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
     "idg_zero_rows": (C.c_int, [_p, _p, _i32, _i32, _p]),
     "idg_infonce_workspace_bytes": (_i64, [_i32, _i32]),
@@ -89,6 +89,9 @@ SIGNATURES = {
     "idg_eval_topk": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_eval_metrics": (C.c_int, [_p, _p, _i32, _i32, _p, _p, C.POINTER(_i32), _i32, _p, _p, _p]),
     "idg_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i32, _p]),
+    "idg_adam_prepare": (C.c_int, [_p, _p, _f32, _f32, _f32, _p]),
+    "idg_propagate_bwd_adam": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
+    "idg_spmm_layer_adam": (C.c_int, [_p, _p, _p, _f32, _i32, _p, _p]),
     "idg_adam_step_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p]),
     "idg_device_alloc": (C.c_int, [_i64, C.POINTER(_p)]),
     "idg_device_free": (C.c_int, [_p]),
@@ -103,6 +106,13 @@ SIGNATURES = {
     "idg_peers_barrier": (C.c_int, [_p, _p, _p]),
     "idg_neg_sample_replay": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64)]),
 }
+
+
+
+class AdamArgs(C.Structure):
+    """idg_adam_args of include/idgrec.h."""
+    _fields_ = [("p", _p), ("m", _p), ("v", _p), ("regc", _p), ("d_scalars", _p), ("beta1", _f32), ("beta2", _f32), ("eps", _f32)]
+
 
 _lib = None
 

@@ -142,7 +142,7 @@ class DistFusedTrainer:
                  betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None):
         if kind != "LightGCN":
             raise NotImplementedError("multi-GPU training is implemented for LightGCN (BASELINE.json configs 2 and 5)")
-        if not 1 <= K <= 3:
+        if not 2 <= K <= 3:
             raise NotImplementedError("row-restricted distributed forward supports 1..3 layers")
         self.l = _lib.lib()
         self.kind, self.rank, self.world = kind, rank, world
@@ -173,6 +173,9 @@ class DistFusedTrainer:
         self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.regc = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
         self.use_cuda_graph = use_cuda_graph
         self._graphs, self._graph_launches, self.replayed_launches = {}, {}, 0
         self._prof = None
@@ -218,39 +221,32 @@ class DistFusedTrainer:
                                     rows.max_rows, ptr(rows.worklist(self.full)), s), "idg_spmm_layer_rows")
         self._mark('fwd_last_rows')
         check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, d, self.reg_lambda, 7, ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
-        check(l.idg_bpr_backward(ptr(self.F), B, d, 7, None, ptr(self.G), ptr(self.ws), s), "idg_bpr_backward")
+        check(l.idg_bpr_backward(ptr(self.F), B, d, 7, None, ptr(self.G), self.reg_lambda, ptr(self.regc), ptr(self.ws), s), "idg_bpr_backward")
+        check(l.idg_adam_prepare(ptr(self.d_step), ptr(self.adam_scalars), self.lr, self.betas[0], self.betas[1], s), "idg_adam_prepare")
         self._mark('bpr')
-        # backward Horner chain on the local rows; the first product only gathers batch columns
-        off = self.b0 * d
-        g_loc = self.gE0  # full-size buffer, local rows written at their global position
+        # backward Horner chain on the local rows; the first product only gathers batch columns.  The last
+        # product applies Adam in its epilogue and stores the updated parameter rows to every peer: the
+        # gradient never goes to memory and the parameter exchange overlaps the last layer's gathers.
+        import ctypes as _C
+        adam = _C.byref(self.adam_args)
         if K == 1:
-            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), None, ptr(self.G), None, ptr(g_loc), float(K + 1), d, ptr(rows.bitmap), 0, s), "idg_spmm_layer_sparse_in")
-        else:
-            check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
-            self._mark('bwd_sparse')
+            raise NotImplementedError("distributed Adam-fused path needs K >= 2")
+        check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
+        self._mark('bwd_sparse')
+        slab.barrier()
+        self._mark('barrier')
+        h = self.H[0]
+        for k in range(1, K - 1):
+            loc.spmm_layer(h, Y=self.H[k], addend=self.G)
+            self._mark('bwd_layer')
             slab.barrier()
             self._mark('barrier')
-            h = self.H[0]
-            for k in range(1, K - 1):
-                loc.spmm_layer(h, Y=self.H[k], addend=self.G)
-                self._mark('bwd_layer')
-                slab.barrier()
-                self._mark('barrier')
-                h = self.H[k]
-            loc.spmm_layer(h, Y=None, addend=self.G, acc_out=g_loc, acc_div=float(K + 1))
-            self._mark('bwd_last')
-        check(l.idg_bpr_finish(ptr(self.E0), ptr(self.gE0), ptr(self.G), B, d, self.reg_lambda, None, ptr(self.ws), s), "idg_bpr_finish")
+            h = self.H[k]
+        check(l.idg_spmm_layer_adam(loc._h, ptr(h), ptr(self.G), float(K + 1), d, adam, s), "idg_spmm_layer_adam")
+        self._mark('bwd_last_adam_push')
+        check(l.idg_bpr_finish(ptr(self.E0), None, ptr(self.G), B, d, self.reg_lambda, None, ptr(self.regc), ptr(self.ws), s), "idg_bpr_finish")
         rows.clear()
         self._mark('finish')
-        # Adam on the rows this rank owns, then hand them to the peers
-        nloc = (self.b1 - self.b0) * d
-        if nloc > 0:
-            fp = lambda t: t.data_ptr() + off * 4
-            check(l.idg_adam_step_dev(fp(self.E0), fp(self.gE0), fp(self.m), fp(self.v), nloc, self.lr, self.betas[0], self.betas[1],
-                                      self.adam_eps, ptr(self.d_step), s), "idg_adam_step_dev")
-            self._mark('adam')
-            slab.push(self.E0[self.b0:self.b1])
-            self._mark('push')
         slab.barrier()
         self._mark('barrier')
         check(l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, s), "idg_axpby")

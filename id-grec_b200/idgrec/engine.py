@@ -20,7 +20,7 @@ from ._lib import check, cur_stream, ptr
 class FusedTrainer:
     def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
                  eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8,
-                 restrict_rows=True):
+                 restrict_rows=True, fuse_adam=True):
         assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR")
         self.l = _lib.lib()
         self.kind, self.graph, self.E0 = kind, graph, table
@@ -54,6 +54,12 @@ class FusedTrainer:
                 from .graph import BatchRows
                 self.rows = BatchRows(self.N, max_batch, dev)
                 self.rows.worklist(graph)
+        # Adam applied in the epilogue of the last backward layer (no gradient pass through memory)
+        self.fuse_adam = fuse_adam and kind != "MFBPR"
+        self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.regc = torch.zeros(self.N, dtype=torch.float32, device=dev)
+        self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
         self.use_cuda_graph = use_cuda_graph and kind in ("LightGCN", "MFBPR")
         self._graphs = {}
         self._graph_launches = {}
@@ -62,19 +68,21 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ pieces
     def _adam(self):
-        self.step_count += 1
-        check(self.l.idg_adam_step(ptr(self.E0), ptr(self.gE0), ptr(self.m), ptr(self.v), self.E0.numel(), self.lr,
-                                   self.betas[0], self.betas[1], self.adam_eps, self.step_count, cur_stream()), "idg_adam_step")
+        check(self.l.idg_adam_step_dev(ptr(self.E0), ptr(self.gE0), ptr(self.m), ptr(self.v), self.E0.numel(), self.lr,
+                                       self.betas[0], self.betas[1], self.adam_eps, ptr(self.d_step), cur_stream()), "idg_adam_step_dev")
 
-    def _bpr(self, B, u, p, n):
+    def _bpr(self, B, u, p, n, fused):
         l, s = self.l, cur_stream()
         check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, 7,
                                 ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
-        check(l.idg_bpr_backward(ptr(self.F), B, self.d, 7, None, ptr(self.G), ptr(self.ws), s), "idg_bpr_backward")
+        check(l.idg_bpr_backward(ptr(self.F), B, self.d, 7, None, ptr(self.G), self.reg_lambda, ptr(self.regc) if fused else None,
+                                 ptr(self.ws), s), "idg_bpr_backward")
+        if fused:
+            check(l.idg_adam_prepare(ptr(self.d_step), ptr(self.adam_scalars), self.lr, self.betas[0], self.betas[1], s), "idg_adam_prepare")
 
-    def _finish(self, B):
-        check(self.l.idg_bpr_finish(ptr(self.E0), ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None, ptr(self.ws),
-                                    cur_stream()), "idg_bpr_finish")
+    def _finish(self, B, fused):
+        check(self.l.idg_bpr_finish(ptr(self.E0), None if fused else ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None,
+                                    ptr(self.regc) if fused else None, ptr(self.ws), cur_stream()), "idg_bpr_finish")
 
     def _draw_noise(self, view):
         if self.injected_noise is not None:
@@ -83,18 +91,20 @@ class FusedTrainer:
             for k in range(self.K):
                 self.noise[k].uniform_()
 
-    def _body(self, B, u, p, n, users_t=None, pos_t=None):
-        """Kernels of one step for batch pointers u/p/n (device int64)."""
+    def _body(self, B, u, p, n, users_t=None, pos_t=None, fused=False):
+        """Kernels of one step for batch pointers u/p/n (device int64).  ``fused``: Adam inside the last backward layer."""
         g, K = self.graph, self.K
+        adam = self.adam_args if fused else None
+        out = None if fused else self.gE0
         rows = self.rows
         if rows is not None:
             rows.build(u, p, n, B, self.U)
         if self.kind == "LightGCN":
             g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
-            self._bpr(B, u, p, n)
-            g.propagate_bwd(self.G, K, True, out=self.gE0, rows=rows)
+            self._bpr(B, u, p, n, fused)
+            g.propagate_bwd(self.G, K, True, out=out, rows=rows, adam=adam)
         elif self.kind == "MFBPR":
-            self._bpr(B, u, p, n)
+            self._bpr(B, u, p, n, False)
             self.gE0.copy_(self.G)
         else:
             l, s = self.l, cur_stream()
@@ -106,7 +116,7 @@ class FusedTrainer:
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1, rows=rows)
                 self._draw_noise(1)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2, rows=rows)
-                self._bpr(B, u, p, n)
+                self._bpr(B, u, p, n, fused)
                 self.loss[2] = 0.0
                 # the three propagations share one linear backward operator: accumulate all row
                 # gradients into G and back-propagate once (9 backward SpMMs of the reference -> 3)
@@ -114,20 +124,20 @@ class FusedTrainer:
                     check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.V2), ptr(idx), idx.numel(), self.d, self.temperature,
                                                 self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
                           "idg_infonce_fwd_bwd")
-                g.propagate_bwd(self.G, K, False, out=self.gE0, rows=rows)
+                g.propagate_bwd(self.G, K, False, out=out, rows=rows, adam=adam)
             else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
                 self._draw_noise(0)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
-                self._bpr(B, u, p, n)
+                self._bpr(B, u, p, n, fused)
                 self.loss[2] = 0.0
                 for idx in (uidx, iidx):
                     check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.F), ptr(idx), idx.numel(), self.d, self.temperature,
                                                 self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
                           "idg_infonce_fwd_bwd")
-                g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=self.gE0, rows=rows)
+                g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=out, rows=rows, adam=adam)
                 for idx in (uidx, iidx):
                     check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), idx.numel(), self.d, s), "idg_zero_rows")
-        self._finish(B)
+        self._finish(B, fused)
         if rows is not None:
             rows.clear()
 
@@ -139,9 +149,12 @@ class FusedTrainer:
         if self.use_cuda_graph and apply_adam:
             return self._step_graph(B, users, pos, neg)
         users, pos, neg = users.contiguous(), pos.contiguous(), neg.contiguous()
-        self._body(B, ptr(users), ptr(pos), ptr(neg), users, pos)
+        fused = apply_adam and self.fuse_adam
+        self._body(B, ptr(users), ptr(pos), ptr(neg), users, pos, fused=fused)
         if apply_adam:
-            self._adam()
+            if not fused:
+                self._adam()
+            self.step_count += 1
         self.loss_acc += self.loss
         return self.loss[:self.n_loss]
 
@@ -157,15 +170,12 @@ class FusedTrainer:
         return self.loss[:self.n_loss]
 
     def _capture(self, B):
-        if not hasattr(self, "d_step"):
-            self.d_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.d_step.fill_(self.step_count)
         u, p, n = (self.batch[k].data_ptr() for k in range(3))
 
         def run():
-            self._body(B, u, p, n)
-            check(self.l.idg_adam_step_dev(ptr(self.E0), ptr(self.gE0), ptr(self.m), ptr(self.v), self.E0.numel(), self.lr,
-                                           self.betas[0], self.betas[1], self.adam_eps, ptr(self.d_step), cur_stream()), "idg_adam_step_dev")
+            self._body(B, u, p, n, fused=self.fuse_adam)
+            if not self.fuse_adam:
+                self._adam()
             check(self.l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, cur_stream()), "idg_axpby")
 
         # warm-up outside capture would advance the model; capture directly (kernels are launched lazily at replay)
@@ -176,10 +186,6 @@ class FusedTrainer:
             run()
         self._graph_launches[B] = int(self.l.idg_launch_count() - n0)
         self._graphs[B] = gr
-
-    def sync_step_counter(self):
-        if hasattr(self, "d_step"):
-            self.d_step.fill_(self.step_count)
 
     def pop_epoch_losses(self):
         out = self.loss_acc[:self.n_loss].tolist()

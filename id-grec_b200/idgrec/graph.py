@@ -135,9 +135,15 @@ class Graph:
                                               ptr(r.worklist(self)) if r else None, cur_stream()), "idg_propagate_fwd_ex")
         return (out_mean, out_cl) if cl_layer > 0 else out_mean
 
-    def propagate_bwd(self, G, K, include_layer0, Gcl=None, cl_layer=0, out=None, rows=None):
-        """Backward w.r.t. X0.  ``rows``: G (and Gcl) are zero outside those rows -> sparse-input first product."""
+    def propagate_bwd(self, G, K, include_layer0, Gcl=None, cl_layer=0, out=None, rows=None, adam=None):
+        """Backward w.r.t. X0.  ``rows``: G (and Gcl) are zero outside those rows -> sparse-input first product.
+        ``adam`` (an _lib.AdamArgs): the last product applies the Adam update in its epilogue, no gradient is written."""
         d = G.shape[1]
+        if adam is not None:
+            import ctypes as _C
+            check(_lib.lib().idg_propagate_bwd_adam(self._h, ptr(G), ptr(Gcl), d, K, int(include_layer0), cl_layer, ptr(self.work(d)),
+                                                    ptr(rows.bitmap) if rows else None, _C.byref(adam), cur_stream()), "idg_propagate_bwd_adam")
+            return None
         if out is None:
             out = torch.empty_like(G)
         check(_lib.lib().idg_propagate_bwd_ex(self._h, ptr(G), ptr(Gcl), d, K, int(include_layer0), cl_layer, ptr(out),

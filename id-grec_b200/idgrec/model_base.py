@@ -98,7 +98,8 @@ class PropagationModel(nn.Module):
                 ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),
                 eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)), max_batch=max_batch,
                 use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
-                restrict_rows=str(cfg.get('restrict_rows', '1')) not in ('0', 'False', 'false'))
+                restrict_rows=str(cfg.get('restrict_rows', '1')) not in ('0', 'False', 'false'),
+                fuse_adam=str(cfg.get('fuse_adam', '1')) not in ('0', 'False', 'false'))
         return self._fused
 
     # -- evaluation ------------------------------------------------------------------------------

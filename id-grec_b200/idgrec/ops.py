@@ -91,8 +91,8 @@ class BprRegLossFn(torch.autograd.Function):
         up = _f32c(gloss)
         G = torch.zeros_like(F)
         gE0 = torch.zeros_like(E0)
-        check(l.idg_bpr_backward(ptr(F), ctx.B, d, ctx.reg_mask, ptr(up), ptr(G), ptr(ctx.ws), cur_stream()), "idg_bpr_backward")
-        check(l.idg_bpr_finish(ptr(E0), ptr(gE0), None, ctx.B, d, ctx.reg_lambda, ptr(up), ptr(ctx.ws), cur_stream()), "idg_bpr_finish")
+        check(l.idg_bpr_backward(ptr(F), ctx.B, d, ctx.reg_mask, ptr(up), ptr(G), 0.0, None, ptr(ctx.ws), cur_stream()), "idg_bpr_backward")
+        check(l.idg_bpr_finish(ptr(E0), ptr(gE0), None, ctx.B, d, ctx.reg_lambda, ptr(up), None, ptr(ctx.ws), cur_stream()), "idg_bpr_finish")
         return G, gE0, None, None, None, None, None, None
 
 

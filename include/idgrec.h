@@ -30,6 +30,15 @@ extern "C" {
 
 typedef struct idg_graph idg_graph; /* opaque device CSR + schedule */
 typedef struct idg_peers idg_peers; /* opaque table of IPC-mapped peer slabs (multi-GPU) */
+/* Adam fused into the epilogue of the last backward propagation layer (trainer.py:54-56 without a gradient pass):
+ * p/m/v [N,d] tables, regc [N] per-row L2-reg coefficient (written by idg_bpr_backward, may be NULL),
+ * d_scalars = {lr/(1-beta1^t), sqrt(1-beta2^t)} produced by idg_adam_prepare for the current step. */
+typedef struct idg_adam_args {
+    float* p; float* m; float* v;
+    const float* regc;
+    const float* d_scalars;
+    float beta1, beta2, eps;
+} idg_adam_args;
 
 int idg_version(void);
 const char* idg_last_error(void);
@@ -146,14 +155,15 @@ int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_t* d_user, 
                     const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda,
                     int reg_mask, float* d_loss, void* d_ws, void* stream);
 /* backward: writes the touched rows of d_G = upstream[0] * d bpr / dF.  d_upstream: device float[2]
- * = (dL/d bpr, dL/d reg) handed down by autograd, or NULL for (1, 1). */
+ * = (dL/d bpr, dL/d reg) handed down by autograd, or NULL for (1, 1).  d_regc (may be NULL): [N] floats, all
+ * zero on entry; receives upstream[1]*reg_lambda/B*multiplicity for the touched rows (Adam-fused path). */
 int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_mask, const float* d_upstream,
-                     float* d_G, void* d_ws, void* stream);
+                     float* d_G, float reg_lambda, float* d_regc, void* d_ws, void* stream);
 /* After the propagation backward has consumed G: adds the L2-reg gradient
  * (upstream[1] * reg_lambda/B * multiplicity * E0[row]) into d_gE0 (may be NULL) and zeroes the
- * touched rows of d_G (may be NULL).  Same B / d_ws as the matching forward/backward calls. */
+ * touched rows of d_G and of d_regc (each may be NULL).  Same B / d_ws as the matching forward/backward calls. */
 int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
-                   const float* d_upstream, void* d_ws, void* stream);
+                   const float* d_upstream, float* d_regc, void* d_ws, void* stream);
 
 /* small utilities used between the fused kernels */
 int idg_axpby(float* d_out, float a, const float* d_x, float b, const float* d_y, int64_t n, void* stream);
@@ -196,6 +206,17 @@ int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t 
  * p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps), torch's non-capturable formula order. */
 int idg_adam_step(float* d_p, const float* d_g, float* d_m, float* d_v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, void* stream);
+
+/* Adam fused into the last backward layer: idg_adam_prepare computes the step scalars on the device (and
+ * advances *d_step); idg_propagate_bwd_adam is idg_propagate_bwd_ex whose last product updates p/m/v in its
+ * epilogue instead of writing the gradient; idg_spmm_layer_adam is that last product alone (multi-GPU path:
+ * updated parameter rows inside the peer slab are stored to every peer as well). */
+int idg_adam_prepare(int32_t* d_step, float* d_scalars, float lr, float beta1, float beta2, void* stream);
+int idg_propagate_bwd_adam(const idg_graph* g, const float* d_G, const float* d_Gcl, int32_t d, int32_t K,
+                           int include_layer0, int32_t cl_layer, float* d_work, const uint32_t* d_bitmap,
+                           const idg_adam_args* adam, void* stream);
+int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
+                        const idg_adam_args* adam, void* stream);
 
 /* Same update with the step counter on the device (*d_step = steps already taken; incremented by
  * the call): lets a captured CUDA graph of the whole train step be replayed unchanged. */

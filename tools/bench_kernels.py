@@ -82,8 +82,8 @@ def main():
 
     def bpr():
         _lib.check(l.idg_bpr_forward(X.data_ptr(), X.data_ptr(), users.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, U, N, d, 1e-4, 7, loss.data_ptr(), ws.data_ptr(), st()))
-        _lib.check(l.idg_bpr_backward(X.data_ptr(), B, d, 7, None, Gz.data_ptr(), ws.data_ptr(), st()))
-        _lib.check(l.idg_bpr_finish(X.data_ptr(), gE.data_ptr(), Gz.data_ptr(), B, d, 1e-4, None, ws.data_ptr(), st()))
+        _lib.check(l.idg_bpr_backward(X.data_ptr(), B, d, 7, None, Gz.data_ptr(), 0.0, None, ws.data_ptr(), st()))
+        _lib.check(l.idg_bpr_finish(X.data_ptr(), gE.data_ptr(), Gz.data_ptr(), B, d, 1e-4, None, None, ws.data_ptr(), st()))
     out["bpr_fwd_bwd_finish_ms"], _ = timed(bpr)
     m, v = torch.zeros_like(X), torch.zeros_like(X)
     out["adam_ms"], _ = timed(lambda: ops.adam_step(X, Gd, m, v, 1e-3, 1))
