@@ -27,7 +27,7 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
                               cudaStream_t stream);
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
-constexpr int kFallbackCtas = 32;
+constexpr int kFallbackCtas = 148;  // one per SM; scratch = 148 x I doubles
 
 struct EvalWs {
     float* max_norm;   // [1] max_i |Fi[i]|_2 (as float bits, atomicMax on non-negative floats)

@@ -87,6 +87,21 @@ def main():
     out["bpr_fwd_bwd_finish_ms"], _ = timed(bpr)
     m, v = torch.zeros_like(X), torch.zeros_like(X)
     out["adam_ms"], _ = timed(lambda: ops.adam_step(X, Gd, m, v, 1e-3, 1))
+    # InfoNCE alone (n ~ unique users of a 2048 batch) and the contrastive models' fused steps
+    n = 1900
+    idx = torch.sort(torch.randperm(U, device=dev)[:n]).values
+    V1, V2 = torch.randn(N, d, device=dev), torch.randn(N, d, device=dev)
+    g1 = torch.zeros(N, d, device=dev)
+    wsn = torch.empty(int(l.idg_infonce_workspace_bytes(n, d)), dtype=torch.uint8, device=dev)
+    lossn = torch.zeros(1, device=dev)
+    out["infonce_n1900_ms"], _ = timed(lambda: _lib.check(l.idg_infonce_fwd_bwd(V1.data_ptr(), V2.data_ptr(), idx.data_ptr(), n, d, 0.2, 0.5, lossn.data_ptr(), g1.data_ptr(), g1.data_ptr(), wsn.data_ptr(), st())))
+    from idgrec.engine import FusedTrainer
+    Bc = 2048
+    uc, pc, nc = (torch.randint(0, U, (Bc,), device=dev), torch.randint(0, I, (Bc,), device=dev), torch.randint(0, I, (Bc,), device=dev))
+    for kind, kw in (("LightGCN", {}), ("SimGCL", dict(ssl_lambda=0.5, temperature=0.2, eps=0.05)), ("XSimGCL", dict(ssl_lambda=0.2, temperature=0.15, eps=0.2, cl_layer=1))):
+        ftc = FusedTrainer(kind, G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=Bc, use_cuda_graph=False, **kw)
+        out["step_%s_B2048_eager_ms" % kind], _ = timed(lambda: ftc.step(uc, pc, nc), iters=10, warm=2)
+        del ftc
     # eval
     import scipy.sparse as sp
     net = sp.csr_matrix((np.ones(len(g.train_user)), (g.train_user, g.train_item)), shape=(U, I))
