@@ -53,7 +53,8 @@ __host__ inline NceWs nce_carve(void* ws, int n, int d) {
 
 // gather + F.normalize (eps 1e-12) + diagonal term; one warp per row, d = 64
 __global__ void __launch_bounds__(256) nce_prep_kernel(const float* __restrict__ V1, const float* __restrict__ V2,
-                                                       const int64_t* __restrict__ idx, int n, float inv_tau, NceWs w) {
+                                                       const int64_t* __restrict__ idx, const int* __restrict__ d_n, int n_in, float inv_tau, NceWs w) {
+    const int n = d_n ? *d_n : n_in;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -79,7 +80,10 @@ __global__ void __launch_bounds__(256) nce_prep_kernel(const float* __restrict__
 // TRANS = 0: rows = X, S = <x_r, y_c>;  (S is symmetric in its arguments so TRANS is only naming)
 template <int MODE>
 __global__ void __launch_bounds__(256) nce_pass_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ beta,
-                                                       int n, float inv_tau, float* __restrict__ part_sum, float* __restrict__ part_out) {
+                                                       const int* __restrict__ d_n, int n_in, int nstride, float inv_tau,
+                                                       float* __restrict__ part_sum, float* __restrict__ part_out) {
+    const int n = d_n ? *d_n : n_in;
+    if ((int)blockIdx.x * kNT >= n) return;
     extern __shared__ __align__(16) float nce_smem[];
     float* Xt = nce_smem;            // [k][r]
     float* Yt = Xt + 64 * kNT;       // [k][c]
@@ -165,24 +169,25 @@ __global__ void __launch_bounds__(256) nce_pass_kernel(const float* __restrict__
         if (tid < kNT && r0 + tid < n) {
             float s = 0.f;
             for (int q = 0; q < 16; ++q) s += Et[tid * 16 + q];
-            part_sum[(size_t)split * n + r0 + tid] = s;
+            part_sum[(size_t)split * nstride + r0 + tid] = s;
         }
     } else {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int r = r0 + ty * 4 + a;
-            if (r < n) *reinterpret_cast<float4*>(part_out + ((size_t)split * n + r) * 64 + tx * 4) = make_float4(out[a][0], out[a][1], out[a][2], out[a][3]);
+            if (r < n) *reinterpret_cast<float4*>(part_out + ((size_t)split * nstride + r) * 64 + tx * 4) = make_float4(out[a][0], out[a][1], out[a][2], out[a][3]);
         }
     }
 }
 
 // ttl, loss terms, backward row weights; single CTA, fixed-order loss reduction
-__global__ void __launch_bounds__(1024) nce_rows_kernel(NceWs w, int n, float loss_scale, float* __restrict__ loss) {
+__global__ void __launch_bounds__(1024) nce_rows_kernel(NceWs w, const int* __restrict__ d_n, int n_in, int nstride, float loss_scale, float* __restrict__ loss) {
+    const int n = d_n ? *d_n : n_in;
     __shared__ float sh[1024];
     float a = 0.f;
     for (int i = threadIdx.x; i < n; i += 1024) {
         float ttl = 0.f;
-        for (int s = 0; s < kNceSplits; ++s) ttl += w.part_sum[(size_t)s * n + i];
+        for (int s = 0; s < kNceSplits; ++s) ttl += w.part_sum[(size_t)s * nstride + i];
         const float r = w.pos[i] / ttl;
         const float li = -logf(r + 1e-5f);
         const float wi = -r / ((float)n * (r + 1e-5f));
@@ -192,20 +197,21 @@ __global__ void __launch_bounds__(1024) nce_rows_kernel(NceWs w, int n, float lo
     sh[threadIdx.x] = a;
     __syncthreads();
     for (int s = 512; s >= 1; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
-    if (threadIdx.x == 0) loss[0] += loss_scale * (sh[0] / (float)n);
+    if (threadIdx.x == 0 && n > 0) loss[0] += loss_scale * (sh[0] / (float)n);
 }
 
 // final gradients, through the normalisation, accumulated into rows idx of gV1/gV2; one warp per row
-__global__ void __launch_bounds__(256) nce_grad_kernel(NceWs w, const int64_t* __restrict__ idx, int n, float inv_tau, float scale,
+__global__ void __launch_bounds__(256) nce_grad_kernel(NceWs w, const int64_t* __restrict__ idx, const int* __restrict__ d_n, int n_in, int nstride, float inv_tau, float scale,
                                                        float* gV1, float* gV2) {  // may alias (SimGCL accumulates both views into one buffer)
+    const int n = d_n ? *d_n : n_in;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
     const size_t o = (size_t)i * 64 + lane * 2;
     float2 pb = make_float2(0.f, 0.f), qa = make_float2(0.f, 0.f);
     for (int s = 0; s < kNceSplits; ++s) {
-        const float2 x = *reinterpret_cast<const float2*>(w.part_pb + (size_t)s * n * 64 + o);
-        const float2 y = *reinterpret_cast<const float2*>(w.part_qa + (size_t)s * n * 64 + o);
+        const float2 x = *reinterpret_cast<const float2*>(w.part_pb + (size_t)s * nstride * 64 + o);
+        const float2 y = *reinterpret_cast<const float2*>(w.part_qa + (size_t)s * nstride * 64 + o);
         pb.x += x.x; pb.y += x.y; qa.x += y.x; qa.y += y.y;
     }
     const float2 a = *reinterpret_cast<const float2*>(w.A + o), b = *reinterpret_cast<const float2*>(w.Bm + o);
@@ -231,8 +237,8 @@ extern "C" int64_t idg_infonce_workspace_bytes(int32_t n, int32_t d) {
                      nce_align(sizeof(float) * (size_t)kNceSplits * n) + 2 * nce_align(sizeof(float) * (size_t)kNceSplits * n * d));
 }
 
-extern "C" int idg_infonce_fwd_bwd(const float* d_V1, const float* d_V2, const int64_t* d_idx, int32_t n, int32_t d, float temperature,
-                                   float loss_scale, float* d_loss, float* d_gV1, float* d_gV2, void* d_ws, void* stream_) {
+static int infonce_impl(const float* d_V1, const float* d_V2, const int64_t* d_idx, const int* d_n, int32_t n, int32_t d, float temperature,
+                        float loss_scale, float* d_loss, float* d_gV1, float* d_gV2, void* d_ws, void* stream_) {
     if (!d_V1 || !d_V2 || !d_idx || !d_loss || !d_ws) return fail(-1, "idg_infonce_fwd_bwd: null argument%s");
     if (n <= 0) return fail(-1, "idg_infonce_fwd_bwd: n must be > 0%s");
     if (d != 64) return fail(-1, "idg_infonce_fwd_bwd: d must be 64 (%s%lld)", "", d);
@@ -241,22 +247,74 @@ extern "C" int idg_infonce_fwd_bwd(const float* d_V1, const float* d_V2, const i
     NceWs w = nce_carve(d_ws, n, d);
     const float inv_tau = 1.f / temperature;
     const dim3 grid((n + kNT - 1) / kNT, kNceSplits);
-    nce_prep_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_V1, d_V2, d_idx, n, inv_tau, w);
+    nce_prep_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_V1, d_V2, d_idx, d_n, n, inv_tau, w);
     IDG_LAUNCH_CHECK("nce_prep_kernel");
     const size_t smem = sizeof(float) * 4 * 64 * kNT;
     IDG_CUDA(cudaFuncSetAttribute(nce_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IDG_CUDA(cudaFuncSetAttribute(nce_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nce_pass_kernel<0><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, n, inv_tau, w.part_sum, nullptr);
+    nce_pass_kernel<0><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, n, inv_tau, w.part_sum, nullptr);
     IDG_LAUNCH_CHECK("nce_pass_kernel<0>");
-    nce_rows_kernel<<<1, 1024, 0, stream>>>(w, n, loss_scale, d_loss);
+    nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, n, loss_scale, d_loss);
     IDG_LAUNCH_CHECK("nce_rows_kernel");
     if (d_gV1 || d_gV2) {
-        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, n, inv_tau, nullptr, w.part_pb);   // sum_j e_ij b_j
+        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, n, inv_tau, nullptr, w.part_pb);   // sum_j e_ij b_j
         IDG_LAUNCH_CHECK("nce_pass_kernel<1>");
-        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.Bm, w.A, w.beta, n, inv_tau, nullptr, w.part_qa);    // sum_i beta_i e_ij a_i
+        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.Bm, w.A, w.beta, d_n, n, n, inv_tau, nullptr, w.part_qa);    // sum_i beta_i e_ij a_i
         IDG_LAUNCH_CHECK("nce_pass_kernel<1>");
-        nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, n, inv_tau, loss_scale, d_gV1, d_gV2);
+        nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, n, inv_tau, loss_scale, d_gV1, d_gV2);
         IDG_LAUNCH_CHECK("nce_grad_kernel");
     }
+    return 0;
+}
+
+extern "C" int idg_infonce_fwd_bwd(const float* d_V1, const float* d_V2, const int64_t* d_idx, int32_t n, int32_t d, float temperature,
+                                   float loss_scale, float* d_loss, float* d_gV1, float* d_gV2, void* d_ws, void* stream) {
+    return infonce_impl(d_V1, d_V2, d_idx, nullptr, n, d, temperature, loss_scale, d_loss, d_gV1, d_gV2, d_ws, stream);
+}
+
+// Same, with the row count on the device (*d_n <= n_max): no host sync between torch.unique's job and the loss,
+// so the whole contrastive step can be captured in a CUDA graph.  Workspace sized for n_max.
+extern "C" int idg_infonce_fwd_bwd_dev(const float* d_V1, const float* d_V2, const int64_t* d_idx, const int32_t* d_n, int32_t n_max,
+                                       int32_t d, float temperature, float loss_scale, float* d_loss, float* d_gV1, float* d_gV2,
+                                       void* d_ws, void* stream) {
+    if (!d_n) return fail(-1, "idg_infonce_fwd_bwd_dev: null d_n%s");
+    return infonce_impl(d_V1, d_V2, d_idx, d_n, n_max, d, temperature, loss_scale, d_loss, d_gV1, d_gV2, d_ws, stream);
+}
+
+// torch.unique(ids) (SimGCL.py:80-81) on the device without a host sync: sorted distinct values (+offset) and
+// their count.  One CTA; n <= 4096.  Deterministic: rank = number of distinct smaller values.
+namespace idg {
+__global__ void __launch_bounds__(1024) unique_rows_kernel(const int64_t* __restrict__ ids, int n, int64_t offset, int64_t* __restrict__ out,
+                                                           int* __restrict__ out_count) {
+    __shared__ int key[4096];
+    __shared__ unsigned char lead[4096];
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    for (int i = threadIdx.x; i < n; i += 1024) key[i] = (int)ids[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const int k = key[i];
+        bool first = true;
+        for (int j = 0; j < i; ++j) if (key[j] == k) { first = false; break; }
+        lead[i] = first;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        if (!lead[i]) continue;
+        const int k = key[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (lead[j] && key[j] < k);
+        out[rank] = (int64_t)k + offset;
+        atomicAdd(&total, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *out_count = total;
+}
+}  // namespace idg
+
+extern "C" int idg_unique_rows(const int64_t* d_ids, int32_t n, int64_t offset, int64_t* d_out, int32_t* d_out_count, void* stream) {
+    if (!d_ids || !d_out || !d_out_count || n <= 0 || n > 4096) return fail(-1, "idg_unique_rows: bad argument (n in 1..4096)%s");
+    unique_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_ids, n, offset, d_out, d_out_count);
+    IDG_LAUNCH_CHECK("unique_rows_kernel");
     return 0;
 }

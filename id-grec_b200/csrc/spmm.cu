@@ -443,7 +443,8 @@ namespace idg {
 // one warp per entry e of the 3B keys (user, U+pos, U+neg); the first occurrence of a row appends it
 __global__ void __launch_bounds__(256) batch_rows_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ pos,
                                                          const int64_t* __restrict__ neg, int B, int U, int* __restrict__ rowlist,
-                                                         int* __restrict__ count, unsigned* __restrict__ bitmap) {
+                                                         int* __restrict__ count, unsigned* __restrict__ bitmap,
+                                                         unsigned char* __restrict__ lead) {
     extern __shared__ int skeys[];
     const int n = 3 * B;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -457,11 +458,40 @@ __global__ void __launch_bounds__(256) batch_rows_kernel(const int64_t* __restri
     const int node = skeys[e];
     for (int base = 0; base < e; base += 32) {
         const int i = base + lane;
-        if (__any_sync(0xffffffffu, (i < e) && (skeys[i] == node))) return;
+        if (__any_sync(0xffffffffu, (i < e) && (skeys[i] == node))) {
+            if (lead && lane == 0) lead[e] = 0;
+            return;
+        }
     }
     if (lane == 0) {
+        if (lead) lead[e] = 1;
         rowlist[atomicAdd(count, 1)] = node;
         atomicOr(bitmap + (node >> 5), 1u << (node & 31));
+    }
+}
+
+// distinct users / positive items of the batch in order of first appearance (the job of torch.unique at
+// SimGCL.py:80-81; InfoNCE is permutation-invariant, the order only has to be deterministic).
+// One warp per entry e of the user and positive segments; lead[] comes from batch_rows_kernel.
+__global__ void __launch_bounds__(256) batch_unique_kernel(const int64_t* __restrict__ user, const int64_t* __restrict__ pos, int B, int U,
+                                                           const unsigned char* __restrict__ lead, int64_t* __restrict__ uidx,
+                                                           int* __restrict__ ucnt, int64_t* __restrict__ iidx, int* __restrict__ icnt) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= 2 * B) return;
+    const int seg = e / B, b = e - seg * B;
+    const unsigned char* ld = lead + seg * B;
+    int before = 0;
+    for (int base = 0; base < b; base += 32) {
+        const int i = base + lane;
+        before += __popc(__ballot_sync(0xffffffffu, (i < b) && ld[i]));
+    }
+    if (lane == 0) {
+        const bool mine = ld[b] != 0;
+        if (mine) {
+            if (seg == 0) uidx[before] = user[b]; else iidx[before] = (int64_t)U + pos[b];
+        }
+        if (b == B - 1) { if (seg == 0) *ucnt = before + (mine ? 1 : 0); else *icnt = before + (mine ? 1 : 0); }
     }
 }
 
@@ -483,16 +513,33 @@ __global__ void expand_rows_kernel(const int* __restrict__ rowlist, const int* _
 }
 }  // namespace idg
 
-extern "C" int idg_batch_rows(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
-                              int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, void* stream_) {
+static int batch_rows_impl(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                           int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, unsigned char* d_lead, void* stream_) {
     if (!d_user || !d_pos || !d_neg || !d_rowlist || !d_count || !d_bitmap || B <= 0) return fail(-1, "idg_batch_rows: bad argument%s");
     const size_t smem = sizeof(int) * 3 * (size_t)B;
     if (smem > 200 * 1024) return fail(-1, "idg_batch_rows: batch too large (B=%s%lld)", "", B);
     cudaStream_t stream = (cudaStream_t)stream_;
     IDG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));
     if (smem > 48 * 1024) IDG_CUDA(cudaFuncSetAttribute(batch_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    batch_rows_kernel<<<(3 * B + 7) / 8, 256, smem, stream>>>(d_user, d_pos, d_neg, B, U, d_rowlist, d_count, d_bitmap);
+    batch_rows_kernel<<<(3 * B + 7) / 8, 256, smem, stream>>>(d_user, d_pos, d_neg, B, U, d_rowlist, d_count, d_bitmap, d_lead);
     IDG_LAUNCH_CHECK("batch_rows_kernel");
+    return 0;
+}
+
+extern "C" int idg_batch_rows(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                              int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, void* stream) {
+    return batch_rows_impl(d_user, d_pos, d_neg, B, U, d_rowlist, d_count, d_bitmap, nullptr, stream);
+}
+
+// idg_batch_rows + the distinct users / (U + positive items) of the batch, in order of first appearance, with their
+// counts on the device (d_lead: 3B bytes of scratch).
+extern "C" int idg_batch_rows_unique(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                                     int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, unsigned char* d_lead,
+                                     int64_t* d_uidx, int32_t* d_ucnt, int64_t* d_iidx, int32_t* d_icnt, void* stream) {
+    if (!d_lead || !d_uidx || !d_ucnt || !d_iidx || !d_icnt) return fail(-1, "idg_batch_rows_unique: null argument%s");
+    if (int rc = batch_rows_impl(d_user, d_pos, d_neg, B, U, d_rowlist, d_count, d_bitmap, d_lead, stream)) return rc;
+    batch_unique_kernel<<<(2 * B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_user, d_pos, B, U, d_lead, d_uidx, d_ucnt, d_iidx, d_icnt);
+    IDG_LAUNCH_CHECK("batch_unique_kernel");
     return 0;
 }
 

@@ -71,6 +71,7 @@ SIGNATURES = {
     "idg_propagate_fwd": (C.c_int, [_p, _p, _i32, _i32, C.c_int, _p, _f32, _i32, _p, _p, _p, _p]),
     "idg_propagate_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p]),
     "idg_batch_rows": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
+    "idg_batch_rows_unique": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "idg_batch_rows_clear": (C.c_int, [_p, _p, _i32, _p, _p]),
     "idg_graph_worklist_ints": (_i64, [_p, _i32]),
     "idg_spmm_layer_rows": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _f32, _i32, _p, _p, _i32, _p, _p]),
@@ -85,6 +86,8 @@ SIGNATURES = {
     "idg_zero_rows": (C.c_int, [_p, _p, _i32, _i32, _p]),
     "idg_infonce_workspace_bytes": (_i64, [_i32, _i32]),
     "idg_infonce_fwd_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
+    "idg_unique_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _p]),
+    "idg_infonce_fwd_bwd_dev": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
     "idg_eval_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "idg_eval_topk": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_eval_metrics": (C.c_int, [_p, _p, _i32, _i32, _p, _p, C.POINTER(_i32), _i32, _p, _p, _p]),

@@ -45,6 +45,11 @@ class FusedTrainer:
             self.V1 = torch.empty_like(table)
             self.V2 = torch.empty_like(table) if kind == "SimGCL" else None
             self.Gcl = z() if kind == "XSimGCL" else None
+            # torch.unique(user) / torch.unique(positive) on the device, no host sync (SimGCL.py:80-81)
+            self.uidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
+            self.iidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
+            self.ucnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.icnt = torch.zeros(1, dtype=torch.int32, device=dev)
         # identical-result work skipping (SURVEY.md 8 d): last forward layer only on the batch rows, first
         # backward product only over the batch columns
         self.rows = None
@@ -60,7 +65,7 @@ class FusedTrainer:
         self.regc = torch.zeros(self.N, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
-        self.use_cuda_graph = use_cuda_graph and kind in ("LightGCN", "MFBPR")
+        self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
         self.replayed_launches = 0  # kernels launched through graph replays (bench.py gpu_launches)
@@ -97,7 +102,10 @@ class FusedTrainer:
         adam = self.adam_args if fused else None
         out = None if fused else self.gE0
         rows = self.rows
-        if rows is not None:
+        contrastive = self.kind in ("SimGCL", "XSimGCL")
+        if rows is not None and contrastive:
+            rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
+        elif rows is not None:
             rows.build(u, p, n, B, self.U)
         if self.kind == "LightGCN":
             g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
@@ -108,8 +116,10 @@ class FusedTrainer:
             self.gE0.copy_(self.G)
         else:
             l, s = self.l, cur_stream()
-            uidx = torch.unique(users_t)
-            iidx = torch.unique(pos_t) + self.U
+            if rows is None:  # no batch row set: stand-alone (sorted) unique
+                check(l.idg_unique_rows(u, B, 0, ptr(self.uidx), ptr(self.ucnt), s), "idg_unique_rows")
+                check(l.idg_unique_rows(p, B, self.U, ptr(self.iidx), ptr(self.icnt), s), "idg_unique_rows")
+            uniq = ((self.uidx, self.ucnt), (self.iidx, self.icnt))
             if self.kind == "SimGCL":
                 g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)
                 self._draw_noise(0)
@@ -117,26 +127,26 @@ class FusedTrainer:
                 self._draw_noise(1)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2, rows=rows)
                 self._bpr(B, u, p, n, fused)
-                self.loss[2] = 0.0
+                self.loss[2:3].zero_()
                 # the three propagations share one linear backward operator: accumulate all row
                 # gradients into G and back-propagate once (9 backward SpMMs of the reference -> 3)
-                for idx in (uidx, iidx):
-                    check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.V2), ptr(idx), idx.numel(), self.d, self.temperature,
-                                                self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
-                          "idg_infonce_fwd_bwd")
+                for idx, cnt in uniq:
+                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.V2), ptr(idx), ptr(cnt), B, self.d, self.temperature,
+                                                    self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
+                          "idg_infonce_fwd_bwd_dev")
                 g.propagate_bwd(self.G, K, False, out=out, rows=rows, adam=adam)
             else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
                 self._draw_noise(0)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
                 self._bpr(B, u, p, n, fused)
-                self.loss[2] = 0.0
-                for idx in (uidx, iidx):
-                    check(l.idg_infonce_fwd_bwd(ptr(self.V1), ptr(self.F), ptr(idx), idx.numel(), self.d, self.temperature,
-                                                self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
-                          "idg_infonce_fwd_bwd")
+                self.loss[2:3].zero_()
+                for idx, cnt in uniq:
+                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.F), ptr(idx), ptr(cnt), B, self.d, self.temperature,
+                                                    self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
+                          "idg_infonce_fwd_bwd_dev")
                 g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=out, rows=rows, adam=adam)
-                for idx in (uidx, iidx):
-                    check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), idx.numel(), self.d, s), "idg_zero_rows")
+                for idx, _ in uniq:  # entries past the count are stale but valid rows of an all-zero table: harmless
+                    check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), B, self.d, s), "idg_zero_rows")
         self._finish(B, fused)
         if rows is not None:
             rows.clear()

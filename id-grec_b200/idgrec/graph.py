@@ -159,6 +159,7 @@ class BatchRows:
         self.rowlist = torch.zeros(self.max_rows, dtype=torch.int32, device=device)
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
         self.bitmap = torch.zeros((N + 31) // 32 + 1, dtype=torch.int32, device=device)
+        self.lead = torch.zeros(3 * max_batch, dtype=torch.uint8, device=device)
         self._wl = {}
 
     def worklist(self, graph):
@@ -171,6 +172,10 @@ class BatchRows:
     def build(self, users_ptr, pos_ptr, neg_ptr, B, num_users):
         check(_lib.lib().idg_batch_rows(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),
                                         cur_stream()), "idg_batch_rows")
+
+    def build_unique(self, users_ptr, pos_ptr, neg_ptr, B, num_users, uidx, ucnt, iidx, icnt):
+        check(_lib.lib().idg_batch_rows_unique(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),
+                                               ptr(self.lead), ptr(uidx), ptr(ucnt), ptr(iidx), ptr(icnt), cur_stream()), "idg_batch_rows_unique")
 
     def clear(self):
         check(_lib.lib().idg_batch_rows_clear(ptr(self.rowlist), ptr(self.count), self.max_rows, ptr(self.bitmap), cur_stream()),

@@ -110,6 +110,11 @@ int idg_propagate_bwd(const idg_graph* g, const float* d_G, const float* d_Gcl, 
  * idg_batch_rows_clear zeroes those bits again.  d_rowlist holds up to 3B ints. */
 int idg_batch_rows(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
                    int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, void* stream);
+/* same + the distinct users and (U + positive item) rows of the batch, in order of first appearance, counts on
+ * the device: replaces torch.unique(user) / torch.unique(positive) (SimGCL.py:80-81) without a host sync */
+int idg_batch_rows_unique(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
+                          int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, unsigned char* d_lead,
+                          int64_t* d_uidx, int32_t* d_ucnt, int64_t* d_iidx, int32_t* d_icnt, void* stream);
 int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, uint32_t* d_bitmap,
                          void* stream);
 /* scratch ints needed by the row-restricted entry points for up to max_rows listed rows */
@@ -179,6 +184,14 @@ int64_t idg_infonce_workspace_bytes(int32_t n, int32_t d);
 int idg_infonce_fwd_bwd(const float* d_V1, const float* d_V2, const int64_t* d_idx, int32_t n, int32_t d,
                         float temperature, float loss_scale, float* d_loss, float* d_gV1, float* d_gV2,
                         void* d_ws, void* stream);
+
+/* Device-side variants for CUDA-graph capture of the contrastive steps: idg_unique_rows = torch.unique(ids)
+ * + offset (sorted distinct values, count in *d_out_count, n <= 4096, no host sync); idg_infonce_fwd_bwd_dev takes
+ * the row count from the device (*d_n <= n_max; workspace sized with idg_infonce_workspace_bytes(n_max, d)). */
+int idg_unique_rows(const int64_t* d_ids, int32_t n, int64_t offset, int64_t* d_out, int32_t* d_out_count, void* stream);
+int idg_infonce_fwd_bwd_dev(const float* d_V1, const float* d_V2, const int64_t* d_idx, const int32_t* d_n, int32_t n_max,
+                            int32_t d, float temperature, float loss_scale, float* d_loss, float* d_gV1, float* d_gV2,
+                            void* d_ws, void* stream);
 
 /* ---- a13/a14: get_rating_for_test + Test (models/LightGCN.py:74-80,
  * utility_train/batch_test.py:52-68) fused: score = <Fu[user], Fi[item]>, train

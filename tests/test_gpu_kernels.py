@@ -238,6 +238,20 @@ def test_infonce_loss_and_grads(dev, n, tau):
     _assert_close(g2.grad.cpu().numpy(), r2.grad.numpy(), rtol=5e-5)
 
 
+def test_unique_rows_matches_torch_unique(dev):
+    from idgrec import _lib
+    l = _lib.lib()
+    gen = torch.Generator().manual_seed(4)
+    for n, hi in ((1, 5), (257, 40), (2048, 900), (4096, 100000)):
+        ids = torch.randint(0, hi, (n,), generator=gen).to(dev)
+        out = torch.zeros(n, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(l.idg_unique_rows(ids.data_ptr(), n, 7, out.data_ptr(), cnt.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        want = torch.unique(ids) + 7
+        assert int(cnt.item()) == want.numel()
+        assert torch.equal(out[:want.numel()], want)
+
+
 # ---------------------------------------------------------------- a12: Adam
 def test_adam_matches_torch(dev):
     from idgrec import ops
