@@ -10,10 +10,17 @@
 // The n x n matrix is never written: each pass recomputes a 64x64 tile of exp(S) in shared memory
 // and contracts it immediately.  Column splits write partials that are summed in split order.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "idg_common.cuh"
 
 namespace idg {
+
+// csrc/infonce_tc.cu: the four n x n x 64 contractions on tcgen05 tensor cores (3xTF32)
+size_t nce_tc_extra_bytes(int n_max);
+int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, const int* d_n, int n_max, float inv_tau, float* part_sum,
+                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream);
 
 constexpr int kNT = 64;      // tile edge
 constexpr int kNceSplits = 4;
@@ -31,6 +38,7 @@ struct NceWs {
     float* part_sum;  // [splits, n]
     float* part_pb;   // [splits, n, d]  sum_j exp(S_ij) b_j
     float* part_qa;   // [splits, n, d]  sum_i beta_i exp(S_ij) a_i
+    char* extra;      // tensor-core path scratch (splits of the operands, E / E^T)
 };
 
 __host__ __device__ inline size_t nce_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -48,6 +56,7 @@ __host__ inline NceWs nce_carve(void* ws, int n, int d) {
     w.part_sum = (float*)take(sizeof(float) * (size_t)kNceSplits * n);
     w.part_pb = (float*)take(sizeof(float) * (size_t)kNceSplits * n * d);
     w.part_qa = (float*)take(sizeof(float) * (size_t)kNceSplits * n * d);
+    w.extra = p;
     return w;
 }
 
@@ -231,9 +240,15 @@ __global__ void __launch_bounds__(256) nce_grad_kernel(NceWs w, const int64_t* _
 
 using namespace idg;
 
+static bool nce_use_tc(int n_max) {
+    static const bool off = getenv("IDG_NCE_IMPL") && strcmp(getenv("IDG_NCE_IMPL"), "fma") == 0;
+    return !off && n_max >= 256;  // below that the tiled CUDA-core passes are launch-bound anyway
+}
+
 extern "C" int64_t idg_infonce_workspace_bytes(int32_t n, int32_t d) {
     if (n <= 0 || d <= 0) return 0;
-    return (int64_t)(2 * nce_align(sizeof(float) * (size_t)n * d) + 7 * nce_align(sizeof(float) * (size_t)n) +
+    n = (n + 127) / 128 * 128;
+    return (int64_t)nce_tc_extra_bytes(n) + (int64_t)(2 * nce_align(sizeof(float) * (size_t)n * d) + 7 * nce_align(sizeof(float) * (size_t)n) +
                      nce_align(sizeof(float) * (size_t)kNceSplits * n) + 2 * nce_align(sizeof(float) * (size_t)kNceSplits * n * d));
 }
 
@@ -244,24 +259,37 @@ static int infonce_impl(const float* d_V1, const float* d_V2, const int64_t* d_i
     if (d != 64) return fail(-1, "idg_infonce_fwd_bwd: d must be 64 (%s%lld)", "", d);
     if (!(temperature > 0.f)) return fail(-1, "idg_infonce_fwd_bwd: temperature must be > 0%s");
     cudaStream_t stream = (cudaStream_t)stream_;
-    NceWs w = nce_carve(d_ws, n, d);
+    const int np = (n + 127) / 128 * 128;  // partial buffers use the padded row stride on both paths
+    NceWs w = nce_carve(d_ws, np, d);
     const float inv_tau = 1.f / temperature;
     const dim3 grid((n + kNT - 1) / kNT, kNceSplits);
     nce_prep_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_V1, d_V2, d_idx, d_n, n, inv_tau, w);
     IDG_LAUNCH_CHECK("nce_prep_kernel");
+    if (nce_use_tc(n)) {
+        // tensor-core path: E = exp(A B^T/tau) and its row sums, then (if gradients are wanted) E^T, PB = E B, QA = E^T (beta A)
+        if (int rc = nce_tc_stage(0, w.A, w.Bm, nullptr, d_n, n, inv_tau, w.part_sum, nullptr, nullptr, w.extra, stream)) return rc;
+        nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, np, loss_scale, d_loss);
+        IDG_LAUNCH_CHECK("nce_rows_kernel");
+        if (d_gV1 || d_gV2) {
+            if (int rc = nce_tc_stage(1, w.A, w.Bm, w.beta, d_n, n, inv_tau, nullptr, w.part_pb, w.part_qa, w.extra, stream)) return rc;
+            nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, np, inv_tau, loss_scale, d_gV1, d_gV2);
+            IDG_LAUNCH_CHECK("nce_grad_kernel");
+        }
+        return 0;
+    }
     const size_t smem = sizeof(float) * 4 * 64 * kNT;
     IDG_CUDA(cudaFuncSetAttribute(nce_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IDG_CUDA(cudaFuncSetAttribute(nce_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nce_pass_kernel<0><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, n, inv_tau, w.part_sum, nullptr);
+    nce_pass_kernel<0><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, np, inv_tau, w.part_sum, nullptr);
     IDG_LAUNCH_CHECK("nce_pass_kernel<0>");
-    nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, n, loss_scale, d_loss);
+    nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, np, loss_scale, d_loss);
     IDG_LAUNCH_CHECK("nce_rows_kernel");
     if (d_gV1 || d_gV2) {
-        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, n, inv_tau, nullptr, w.part_pb);   // sum_j e_ij b_j
+        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.A, w.Bm, nullptr, d_n, n, np, inv_tau, nullptr, w.part_pb);   // sum_j e_ij b_j
         IDG_LAUNCH_CHECK("nce_pass_kernel<1>");
-        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.Bm, w.A, w.beta, d_n, n, n, inv_tau, nullptr, w.part_qa);    // sum_i beta_i e_ij a_i
+        nce_pass_kernel<1><<<grid, 256, smem, stream>>>(w.Bm, w.A, w.beta, d_n, n, np, inv_tau, nullptr, w.part_qa);    // sum_i beta_i e_ij a_i
         IDG_LAUNCH_CHECK("nce_pass_kernel<1>");
-        nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, n, inv_tau, loss_scale, d_gV1, d_gV2);
+        nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, np, inv_tau, loss_scale, d_gV1, d_gV2);
         IDG_LAUNCH_CHECK("nce_grad_kernel");
     }
     return 0;
