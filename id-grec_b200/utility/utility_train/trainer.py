@@ -19,11 +19,23 @@ def sample_epoch(dataset, device):
     sample_data = dataset.sample_data_to_train_all()
     perm = np.arange(len(sample_data))
     np.random.shuffle(perm)                       # tools.shuffle (tools.py:41-42), same stream position
-    shuffled = np.ascontiguousarray(sample_data[perm].T)   # [3, E]
-    t = torch.from_numpy(shuffled)
-    if device.type == "cuda":
-        t = t.pin_memory().to(device, non_blocking=True)
+    E = len(sample_data)
+    if device.type != "cuda":
+        t = torch.from_numpy(np.ascontiguousarray(sample_data[perm].T))
+        return t[0], t[1], t[2]
+    # gather straight into a reused pinned staging buffer, one async H2D copy of [3, E] int64
+    stage = _PINNED.get(E)
+    if stage is None:
+        stage = _PINNED[E] = torch.empty((3, E), dtype=torch.int64).pin_memory()
+    host = stage.numpy()
+    for c in range(3):
+        np.take(sample_data[:, c], perm, out=host[c])
+    t = stage.to(device, non_blocking=True)
+    torch.cuda.current_stream().synchronize()      # the staging buffer is reused by the next epoch's prefetch
     return t[0], t[1], t[2]
+
+
+_PINNED = {}
 
 
 def universal_trainer(model, args, config, dataset, device, logger):
@@ -40,17 +52,24 @@ def universal_trainer(model, args, config, dataset, device, logger):
     best_results['ndcg'] = [0. for _ in eval(config['top_K'])]
     best_results['stop'] = 0
 
-    for epoch in range(int(config['training_epochs'])):
+    n_epochs = int(config['training_epochs'])
+    prefetched = None
+    for epoch in range(n_epochs):
         print('-' * 100)
         start_time = time()
         model.train()
 
-        users, pos_items, neg_items = sample_epoch(dataset, device)
+        users, pos_items, neg_items = prefetched if prefetched is not None else sample_epoch(dataset, device)
+        prefetched = None
         num_batch = len(users) // batch_size + 1          # trainer.py:36 (over-counts when divisible)
 
         if fused is not None:
             for bu, bp, bn in tools.mini_batch(users, pos_items, neg_items, batch_size=batch_size):
                 fused.step(bu, bp, bn)
+            # the steps are only enqueued: draw the next epoch's samples on the host while the GPU trains.  Nothing else
+            # reads the numpy global generator in between, so the stream (and every batch) stays the reference's.
+            if epoch + 1 < n_epochs:
+                prefetched = sample_epoch(dataset, device)
             total_loss_list = fused.pop_epoch_losses()    # one device read per epoch
         else:
             total_loss_list = []
