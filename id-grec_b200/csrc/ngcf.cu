@@ -1,0 +1,261 @@
+// NGCF dense layer epilogue, forward and backward (sm_100a).
+//
+// Replaces the per-layer element-wise / small-GEMM chain of models/NGCF.py:87-106 (two [N,64]x[64,64] matmuls,
+// two bias adds, E*side, LeakyReLU(0.2), Dropout, F.normalize, torch.cat) and its autograd backward:
+//   Z    = [side | E (*) side]                       [N,128]          side = A_hat . E from the SpMM kernel
+//   S    = Z . [W_gcn ; W_bi] + b_gcn + b_bi         [N,64]
+//   D    = LeakyReLU_0.2(S) (*) keep / (1-p)          next layer's E
+//   O    = D / max(|D|_2, 1e-12)                      written into the layer's 64-column block of the [N,256] concat
+// backward (given dO and the gradient dD_ext arriving from the next layer):
+//   dD   = dD_ext + (dO - O <O,dO>)/|D| ;  dS = dD (*) keep/(1-p) (*) (S>0 ? 1 : 0.2)
+//   dZ   = dS . [W_gcn ; W_bi]^T ;  dside = dZ1 + dZ2 (*) E ;  dE_direct = dZ2 (*) side
+//   dW   = Z^T . dS ,  db = colsum(dS)                per-CTA partials, summed in CTA order (deterministic)
+// fp32 CUDA-core tiles: the 1e-5 parity bar needs fp32 products and these GEMMs (1.2 GFLOP per layer at the
+// amazon-book shape) are a small fraction of the layer's SpMM time.
+#include <math.h>
+
+#include "idg_common.cuh"
+
+namespace idg {
+
+constexpr int kNgTile = 64;     // rows per tile
+constexpr int kNgCtas = 296;    // persistent grid of the backward kernel (2 per SM)
+
+// ---- forward: one CTA per 64-row tile, 256 threads, thread (ty,tx) -> rows ty*4.., columns tx*4..
+__global__ void __launch_bounds__(256) ngcf_dense_fwd_kernel(const float* __restrict__ E, const float* __restrict__ side,
+                                                             const float* __restrict__ Wg, const float* __restrict__ bg,
+                                                             const float* __restrict__ Wb, const float* __restrict__ bb,
+                                                             const float* __restrict__ keep, float inv_keep, int N,
+                                                             float* __restrict__ S_pre, float* __restrict__ D, float* __restrict__ out,
+                                                             int out_stride) {
+    extern __shared__ __align__(16) float sm[];
+    float* Zt = sm;                  // [128 k][64 rows]
+    float* W = Zt + 128 * kNgTile;   // [128 k][64 cols]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int r0 = blockIdx.x * kNgTile;
+    for (int q = tid; q < 64 * 64; q += 256) { W[q] = Wg[q]; W[64 * 64 + q] = Wb[q]; }
+    for (int q = tid; q < kNgTile * 16; q += 256) {
+        const int r = q & 63, c4 = q >> 6;  // lane <-> row: conflict-free transposed stores
+        float4 s = f4zero(), e = f4zero();
+        if (r0 + r < N) { s = ldg4(side + (size_t)(r0 + r) * 64 + c4 * 4); e = ldg4(E + (size_t)(r0 + r) * 64 + c4 * 4); }
+        const float sv[4] = {s.x, s.y, s.z, s.w}, ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { Zt[(c4 * 4 + j) * kNgTile + r] = sv[j]; Zt[(64 + c4 * 4 + j) * kNgTile + r] = ev[j] * sv[j]; }
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 128; ++k) {
+        const float4 z = *reinterpret_cast<const float4*>(Zt + k * kNgTile + ty * 4);
+        const float4 w = *reinterpret_cast<const float4*>(W + k * 64 + tx * 4);
+        const float za[4] = {z.x, z.y, z.z, z.w}, wb[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(za[a], wb[b], acc[a][b]);
+    }
+    const float4 b1 = ldg4(bg + tx * 4), b2 = ldg4(bb + tx * 4);
+    const float bias[4] = {b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = r0 + ty * 4 + a;
+        float s[4], dv[4], ss = 0.f;
+        float4 kp = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (keep && r < N) kp = ldg4(keep + (size_t)r * 64 + tx * 4);
+        const float kv[4] = {kp.x, kp.y, kp.z, kp.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            s[b] = acc[a][b] + bias[b];
+            const float act = s[b] > 0.f ? s[b] : 0.2f * s[b];
+            dv[b] = keep ? act * kv[b] * inv_keep : act;
+            ss = fmaf(dv[b], dv[b], ss);
+        }
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);  // 16 lanes share a row
+        const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+        if (r < N) {
+            st4(S_pre + (size_t)r * 64 + tx * 4, make_float4(s[0], s[1], s[2], s[3]));
+            st4(D + (size_t)r * 64 + tx * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
+            st4(out + (size_t)r * out_stride + tx * 4, make_float4(dv[0] / nrm, dv[1] / nrm, dv[2] / nrm, dv[3] / nrm));
+        }
+    }
+}
+
+// ---- backward: persistent CTAs loop over 64-row tiles, accumulating dW/db partials in registers
+__global__ void __launch_bounds__(256) ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ side,
+                                                             const float* __restrict__ Wg, const float* __restrict__ Wb,
+                                                             const float* __restrict__ keep, float inv_keep, const float* __restrict__ S_pre,
+                                                             const float* __restrict__ D, const float* __restrict__ dO, int dO_stride,
+                                                             const float* __restrict__ dD_ext, int N, float* __restrict__ dside,
+                                                             float* __restrict__ dE_direct, float* __restrict__ dW_part,
+                                                             float* __restrict__ db_part) {
+    extern __shared__ __align__(16) float sm[];
+    float* Zt = sm;                         // [64 rows][128 k]  (row-major here: used as Z^T . dS with rows as the contraction)
+    float* dSs = Zt + kNgTile * 128;        // [64 rows][64 cols]
+    float* Wt = dSs + kNgTile * 64;         // [64 cols][128 k]   Wcat^T: Wt[c][k] = Wcat[k][c]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    for (int q = tid; q < 64 * 64; q += 256) {
+        const int k = q >> 6, c = q & 63;
+        Wt[c * 128 + k] = Wg[q];
+        Wt[c * 128 + 64 + k] = Wb[q];
+    }
+    // dW partial owned by this thread: Wcat rows k = ty*8 .. ty*8+7, columns tx*4 .. tx*4+3  (128 x 64 = 256 threads x 32)
+    float dw[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dw[a][b] = 0.f;
+    float dbv = 0.f;  // threads 0..63: column tid
+    const int ntiles = (N + kNgTile - 1) / kNgTile;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int r0 = t * kNgTile;
+        __syncthreads();
+        // phase 1: per row (16 threads per row, 4 rows per warp-pass): dD, dS, Z
+        for (int rr = ty; rr < kNgTile; rr += 16) {
+            const int r = r0 + rr;
+            float4 d4 = f4zero(), o4 = f4zero(), x4 = f4zero(), s4 = f4zero(), k4 = make_float4(1.f, 1.f, 1.f, 1.f), e4 = f4zero(), sd4 = f4zero();
+            if (r < N) {
+                d4 = ldg4(D + (size_t)r * 64 + tx * 4);
+                o4 = ldg4(dO + (size_t)r * dO_stride + tx * 4);
+                if (dD_ext) x4 = ldg4(dD_ext + (size_t)r * 64 + tx * 4);
+                s4 = ldg4(S_pre + (size_t)r * 64 + tx * 4);
+                if (keep) k4 = ldg4(keep + (size_t)r * 64 + tx * 4);
+                e4 = ldg4(E + (size_t)r * 64 + tx * 4);
+                sd4 = ldg4(side + (size_t)r * 64 + tx * 4);
+            }
+            float ss = d4.x * d4.x + d4.y * d4.y + d4.z * d4.z + d4.w * d4.w;
+            float dot = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;  // <D, dO>
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, m); dot += __shfl_xor_sync(0xffffffffu, dot, m); }
+            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+            const float proj = dot / (nrm * nrm);  // <O,dO>/|D| with O = D/|D|
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, kv[4] = {k4.x, k4.y, k4.z, k4.w};
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, sdv[4] = {sd4.x, sd4.y, sd4.z, sd4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float dD = xv[j] + (ov[j] - dv[j] * proj) / nrm;
+                float dS = keep ? dD * kv[j] * inv_keep : dD;
+                dS *= (sv[j] > 0.f) ? 1.f : 0.2f;
+                if (r >= N) dS = 0.f;
+                dSs[rr * 64 + tx * 4 + j] = dS;
+                Zt[rr * 128 + tx * 4 + j] = sdv[j];
+                Zt[rr * 128 + 64 + tx * 4 + j] = ev[j] * sdv[j];
+            }
+        }
+        __syncthreads();
+        // phase 2: dZ = dS . Wcat^T  (64 x 128); thread -> rows ty*4.., k columns tx*8..  then dside / dE_direct
+        {
+            float dz[4][8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) dz[a][b] = 0.f;
+            for (int c = 0; c < 64; ++c) {
+                float sa[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) sa[a] = dSs[(ty * 4 + a) * 64 + c];
+                const float4 w0 = *reinterpret_cast<const float4*>(Wt + c * 128 + tx * 8), w1 = *reinterpret_cast<const float4*>(Wt + c * 128 + tx * 8 + 4);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) dz[a][b] = fmaf(sa[a], wv[b], dz[a][b]);
+            }
+            // thread tx < 8 holds dZ1[:, tx*8..], its partner lane tx+8 holds dZ2[:, tx*8..]: exchange by shuffle
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int rr = ty * 4 + a, r = r0 + rr;
+                float o1[8], o2[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const float other = __shfl_xor_sync(0xffffffffu, dz[a][b], 8);
+                    const int k = (tx & 7) * 8 + b;
+                    const float sdv = Zt[rr * 128 + k];
+                    const float ev = (r < N && tx < 8) ? __ldg(E + (size_t)r * 64 + k) : 0.f;
+                    o1[b] = dz[a][b] + other * ev;   // dside = dZ1 + dZ2 (*) E        (valid for tx < 8)
+                    o2[b] = other * sdv;             // dE_direct = dZ2 (*) side
+                }
+                if (tx < 8 && r < N) {
+                    float* ps = dside + (size_t)r * 64 + tx * 8;
+                    float* pe = dE_direct + (size_t)r * 64 + tx * 8;
+                    st4(ps, make_float4(o1[0], o1[1], o1[2], o1[3])); st4(ps + 4, make_float4(o1[4], o1[5], o1[6], o1[7]));
+                    st4(pe, make_float4(o2[0], o2[1], o2[2], o2[3])); st4(pe + 4, make_float4(o2[4], o2[5], o2[6], o2[7]));
+                }
+            }
+        }
+        // phase 3: dWcat[k][c] += sum_rows Z[row][k] * dS[row][c]; thread -> k = ty*8.., c = tx*4..
+        for (int rr = 0; rr < kNgTile; ++rr) {
+            const float4 s = *reinterpret_cast<const float4*>(dSs + rr * 64 + tx * 4);
+            const float sc[4] = {s.x, s.y, s.z, s.w};
+            const float4 z0 = *reinterpret_cast<const float4*>(Zt + rr * 128 + ty * 8), z1 = *reinterpret_cast<const float4*>(Zt + rr * 128 + ty * 8 + 4);
+            const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dw[a][b] = fmaf(zv[a], sc[b], dw[a][b]);
+        }
+        if (tid < 64) for (int rr = 0; rr < kNgTile; ++rr) dbv += dSs[rr * 64 + tid];
+    }
+    float* wp = dW_part + (size_t)blockIdx.x * 128 * 64;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) st4(wp + (size_t)(ty * 8 + a) * 64 + tx * 4, make_float4(dw[a][0], dw[a][1], dw[a][2], dw[a][3]));
+    if (tid < 64) db_part[(size_t)blockIdx.x * 64 + tid] = dbv;
+}
+
+// ordered sum of the per-CTA partials: dWg, dWb [64,64], db [64] (shared by b_gcn and b_bi)
+__global__ void ngcf_reduce_kernel(const float* __restrict__ dW_part, const float* __restrict__ db_part, int n_parts, float* __restrict__ dWg,
+                                   float* __restrict__ dWb, float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 128 * 64) {
+        float a = 0.f;
+        for (int p = 0; p < n_parts; ++p) a += dW_part[(size_t)p * 128 * 64 + i];
+        if (i < 64 * 64) dWg[i] = a; else dWb[i - 64 * 64] = a;
+    } else if (i < 128 * 64 + 64) {
+        const int c = i - 128 * 64;
+        float a = 0.f;
+        for (int p = 0; p < n_parts; ++p) a += db_part[(size_t)p * 64 + c];
+        db[c] = a;
+    }
+}
+
+}  // namespace idg
+
+using namespace idg;
+
+extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
+                                  const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,
+                                  int32_t out_stride, void* stream) {
+    if (!d_E || !d_side || !d_Wg || !d_bg || !d_Wb || !d_bb || !d_S || !d_D || !d_out || N <= 0) return fail(-1, "idg_ngcf_dense_fwd: bad argument%s");
+    if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "idg_ngcf_dense_fwd: drop_p must be in [0,1)%s");
+    const size_t smem = sizeof(float) * (128 * kNgTile + 128 * 64);
+    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ngcf_dense_fwd_kernel<<<(N + kNgTile - 1) / kNgTile, 256, smem, (cudaStream_t)stream>>>(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, 1.f / (1.f - drop_p), N, d_S,
+                                                                                          d_D, d_out, out_stride);
+    IDG_LAUNCH_CHECK("ngcf_dense_fwd_kernel");
+    return 0;
+}
+
+extern "C" int64_t idg_ngcf_workspace_bytes(void) { return (int64_t)sizeof(float) * kNgCtas * (128 * 64 + 64); }
+
+extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep, float drop_p,
+                                  const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
+                                  float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream_) {
+    if (!d_E || !d_side || !d_Wg || !d_Wb || !d_S || !d_D || !d_dO || !d_dside || !d_dE_direct || !d_dWg || !d_dWb || !d_db || !d_ws || N <= 0)
+        return fail(-1, "idg_ngcf_dense_bwd: bad argument%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    float* dW_part = (float*)d_ws;
+    float* db_part = dW_part + (size_t)kNgCtas * 128 * 64;
+    const size_t smem = sizeof(float) * (kNgTile * 128 + kNgTile * 64 + 64 * 128);
+    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ngcf_dense_bwd_kernel<<<kNgCtas, 256, smem, stream>>>(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside,
+                                                          d_dE_direct, dW_part, db_part);
+    IDG_LAUNCH_CHECK("ngcf_dense_bwd_kernel");
+    ngcf_reduce_kernel<<<(128 * 64 + 64 + 255) / 256, 256, 0, stream>>>(dW_part, db_part, kNgCtas, d_dWg, d_dWb, d_db);
+    IDG_LAUNCH_CHECK("ngcf_reduce_kernel");
+    return 0;
+}

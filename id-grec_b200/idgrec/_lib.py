@@ -88,6 +88,9 @@ SIGNATURES = {
     "idg_infonce_fwd_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
     "idg_unique_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _p]),
     "idg_infonce_fwd_bwd_dev": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
+    "idg_ngcf_dense_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i32, _p]),
+    "idg_ngcf_workspace_bytes": (_i64, []),
+    "idg_ngcf_dense_bwd": (C.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "idg_eval_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "idg_eval_topk": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_eval_metrics": (C.c_int, [_p, _p, _i32, _i32, _p, _p, C.POINTER(_i32), _i32, _p, _p, _p]),

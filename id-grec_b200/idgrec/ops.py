@@ -66,6 +66,47 @@ def spmm(X, graph):
     return SpmmFn.apply(X, graph)
 
 
+class NgcfLayerFn(torch.autograd.Function):
+    """One NGCF layer (NGCF.py:85-106): SpMM + fused dense epilogue kernels, forward and backward.
+    Returns (D, O): the next layer's input and the row-normalised block of the final concat."""
+
+    @staticmethod
+    def forward(ctx, E, Wg, bg, Wb, bb, graph, keep, drop_p):
+        l = _lib.lib()
+        E, Wg, bg, Wb, bb = (_f32c(t) for t in (E, Wg, bg, Wb, bb))
+        keep = _f32c(keep) if keep is not None else None
+        N = E.shape[0]
+        side = torch.empty_like(E)
+        graph.spmm_layer(E, Y=side)
+        S, D, O = torch.empty_like(E), torch.empty_like(E), torch.empty_like(E)
+        check(l.idg_ngcf_dense_fwd(ptr(E), ptr(side), ptr(Wg), ptr(bg), ptr(Wb), ptr(bb), ptr(keep), float(drop_p), N, ptr(S), ptr(D), ptr(O), 64,
+                                   cur_stream()), "idg_ngcf_dense_fwd")
+        ctx.save_for_backward(E, side, S, D, Wg, Wb, keep if keep is not None else torch.empty(0, device=E.device))
+        ctx.graph, ctx.drop_p, ctx.has_keep = graph, float(drop_p), keep is not None
+        return D, O
+
+    @staticmethod
+    def backward(ctx, gD, gO):
+        l = _lib.lib()
+        E, side, S, D, Wg, Wb, keep = ctx.saved_tensors
+        N = E.shape[0]
+        gO = _f32c(gO) if gO is not None else torch.zeros_like(E)
+        gD = _f32c(gD) if gD is not None else None
+        dside, dEd = torch.empty_like(E), torch.empty_like(E)
+        dWg, dWb = torch.empty_like(Wg), torch.empty_like(Wb)
+        db = torch.empty(64, dtype=torch.float32, device=E.device)
+        ws = torch.empty(int(l.idg_ngcf_workspace_bytes()), dtype=torch.uint8, device=E.device)
+        check(l.idg_ngcf_dense_bwd(ptr(E), ptr(side), ptr(Wg), ptr(Wb), ptr(keep) if ctx.has_keep else None, ctx.drop_p, ptr(S), ptr(D), ptr(gO), 64,
+                                   ptr(gD), N, ptr(dside), ptr(dEd), ptr(dWg), ptr(dWb), ptr(db), ptr(ws), cur_stream()), "idg_ngcf_dense_bwd")
+        dE = torch.empty_like(E)
+        ctx.graph.spmm_layer(dside, Y=dE, addend=dEd)   # dE = dE_direct + A_hat . dside (A_hat symmetric)
+        return dE, dWg, db.view(1, 64), dWb, db.view(1, 64).clone(), None, None, None
+
+
+def ngcf_layer(E, Wg, bg, Wb, bb, graph, keep=None, drop_p=0.0):
+    return NgcfLayerFn.apply(E, Wg, bg, Wb, bb, graph, keep, drop_p)
+
+
 class BprRegLossFn(torch.autograd.Function):
     """[bpr, reg_lambda*reg] = fused LightGCN.py:57-70 + losses.py:4-21."""
 

@@ -1,8 +1,8 @@
 """NGCF (Wang et al., SIGIR'19) -- same class interface as the reference's models/NGCF.py:17-153.
-Graph D^-1/2 (A+I) D^-1/2; per layer side = A.E (hand-written SpMM kernel), sum = side W_gcn + b,
-bi = (E * side) W_bi + b, LeakyReLU(0.2), message dropout, row-normalise; final = concat of the
-K+1 blocks (256-d).  The two 64x64 dense products per layer are plain library GEMMs (torch.matmul);
-BPR / regulariser / full-ranking evaluation run on the fused kernels (d = 256 for scores)."""
+Graph D^-1/2 (A+I) D^-1/2; per layer side = A.E (hand-written SpMM kernel), then one fused
+dense kernel per layer: sum = side W_gcn + b, bi = (E * side) W_bi + b, LeakyReLU(0.2), message dropout,
+row-normalise (csrc/ngcf.cu, forward and backward); final = concat of the K+1 blocks (256-d).  BPR / regulariser /
+full-ranking evaluation run on the fused kernels (d = 256 for scores)."""
 import torch
 from torch import nn
 
@@ -43,16 +43,17 @@ class NGCF(PropagationModel):
         eval mode."""
         ego = self.table()
         outs = [ego]
+        wd = self.weight_dict
         for layer in range(int(self.config['GCN_layer'])):
-            side = ops.spmm(ego, self.Graph)
-            s = torch.matmul(side, self.weight_dict['W_gcn_%d' % layer]) + self.weight_dict['b_gcn_%d' % layer]
-            bi = torch.matmul(torch.mul(ego, side), self.weight_dict['W_bi_%d' % layer]) + self.weight_dict['b_bi_%d' % layer]
-            ego = nn.LeakyReLU(negative_slope=0.2)(s + bi)
+            p = float(self.mess_dropout[layer])
             if keep_masks is not None:
-                ego = ego * keep_masks[layer] / (1.0 - self.mess_dropout[layer])
-            else:
-                ego = nn.Dropout(self.mess_dropout[layer])(ego)
-            outs.append(nn.functional.normalize(ego, p=2, dim=1))
+                keep = keep_masks[layer]
+            else:  # the draw nn.Dropout(p) makes (Bernoulli(1-p) per element, torch device generator), always on
+                keep = (torch.rand_like(ego.detach()) >= p).float()
+            # SpMM + fused dense epilogue (two 64x64 products, biases, E*side, LeakyReLU, dropout, row-normalise)
+            ego, norm = ops.ngcf_layer(ego, wd['W_gcn_%d' % layer], wd['b_gcn_%d' % layer], wd['W_bi_%d' % layer], wd['b_bi_%d' % layer],
+                                       self.Graph, keep, p)
+            outs.append(norm)
         final = torch.cat(outs, dim=1)
         return self._split(final)
 

@@ -193,6 +193,22 @@ int idg_infonce_fwd_bwd_dev(const float* d_V1, const float* d_V2, const int64_t*
                             int32_t d, float temperature, float loss_scale, float* d_loss, float* d_gV1, float* d_gV2,
                             void* d_ws, void* stream);
 
+/* ---- a8: models/NGCF.py:87-106, dense part of one layer (side = A_hat.E comes from idg_spmm_layer) ----------
+ * forward:  S = side W_gcn + b_gcn + (E*side) W_bi + b_bi;  D = LeakyReLU_0.2(S) * keep/(1-p);  out = D/max(|D|,1e-12)
+ *           d_keep: [N,64] 0/1 dropout draws or NULL (no dropout); out rows have stride out_stride floats (a 64-column
+ *           block of the [N,256] concat or a plain [N,64] tensor).  S and D are kept for the backward.
+ * backward: given dO (stride dO_stride) and dD_ext (gradient reaching D from the next layer, may be NULL):
+ *           dside, dE_direct [N,64] (the caller finishes dE = dE_direct + A_hat.dside with idg_spmm_layer),
+ *           dW_gcn, dW_bi [64,64], db [64] (same for both biases).  d_ws: idg_ngcf_workspace_bytes() bytes. */
+int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
+                       const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D,
+                       float* d_out, int32_t out_stride, void* stream);
+int64_t idg_ngcf_workspace_bytes(void);
+int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep,
+                       float drop_p, const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride,
+                       const float* d_dD_ext, int32_t N, float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb,
+                       float* d_db, void* d_ws, void* stream);
+
 /* ---- a13/a14: get_rating_for_test + Test (models/LightGCN.py:74-80,
  * utility_train/batch_test.py:52-68) fused: score = <Fu[user], Fi[item]>, train
  * positives removed, top-K by (score desc, item id asc).  No [b, I] matrix is

@@ -102,6 +102,26 @@ def main():
         ftc = FusedTrainer(kind, G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=Bc, use_cuda_graph=False, **kw)
         out["step_%s_B2048_eager_ms" % kind], _ = timed(lambda: ftc.step(uc, pc, nc), iters=10, warm=2)
         del ftc
+    # NGCF: one autograd step (3 x (SpMM + fused dense kernel) fwd/bwd, 256-d BPR) on the with-self graph
+    if os.environ.get("IDG_BENCH_NGCF", "1") == "1":
+        csr_s = build_norm_adjacency(g.train_user, g.train_item, U, I, add_self=True, device=dev)
+        Gs = Graph(csr_s)
+        Eng = X.clone().requires_grad_(True)
+        Ws = [[torch.nn.init.xavier_uniform_(torch.empty(64, 64, device=dev)).requires_grad_(True), torch.zeros(1, 64, device=dev, requires_grad=True),
+               torch.nn.init.xavier_uniform_(torch.empty(64, 64, device=dev)).requires_grad_(True), torch.zeros(1, 64, device=dev, requires_grad=True)] for _ in range(3)]
+        ub, pb, nb_ = torch.randint(0, U, (1024,), device=dev), torch.randint(0, I, (1024,), device=dev), torch.randint(0, I, (1024,), device=dev)
+
+        def ngcf_step():
+            ego, outs = Eng, [Eng]
+            for Wg, bg, Wb, bb in Ws:
+                keep = (torch.rand_like(ego.detach()) >= 0.1).float()
+                ego, o = ops.ngcf_layer(ego, Wg, bg, Wb, bb, Gs, keep, 0.1)
+                outs.append(o)
+            fin = torch.cat(outs, dim=1)
+            loss = ops.bpr_reg_loss(fin, fin, ub, pb, nb_, U, 0.0, 0)[0]
+            loss.backward()
+        out["step_NGCF_B1024_autograd_ms"], _ = timed(ngcf_step, iters=10, warm=2)
+        del Gs, csr_s
     # eval
     import scipy.sparse as sp
     net = sp.csr_matrix((np.ones(len(g.train_user)), (g.train_user, g.train_item)), shape=(U, I))
