@@ -364,9 +364,48 @@ __global__ void __launch_bounds__(1024) ordered_sum_kernel(const double* __restr
     }
 }
 
+// models/LightGCN.py:74-80 as written: rating[b, i] = sigmoid(<Fu[users[b]], Fi[i]>) materialised as a dense matrix.
+// Only for API completeness (Test() never calls it); 32x32 tiles, fp32 FMA in the reference's k order.
+__global__ void __launch_bounds__(256) rating_matrix_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, const int64_t* __restrict__ users,
+                                                            int nu, int I, int d, float* __restrict__ out) {
+    __shared__ float su[32][33], si[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 4 rows each
+    const int b0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < d; k0 += 32) {
+        for (int r = ty; r < 32; r += 8) {
+            const int b = b0 + r, i = i0 + r;
+            su[r][tx] = (b < nu && k0 + tx < d) ? Fu[(size_t)users[b] * d + k0 + tx] : 0.f;
+            si[r][tx] = (i < I && k0 + tx < d) ? Fi[(size_t)i * d + k0 + tx] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float iv = si[tx][k];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a] = fmaf(su[ty * 4 + a][k], iv, acc[a]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int b = b0 + ty * 4 + a, i = i0 + tx;
+        if (b < nu && i < I) out[(size_t)b * I + i] = 1.f / (1.f + expf(-acc[a]));
+    }
+}
+
 }  // namespace idg
 
 using namespace idg;
+
+extern "C" int idg_rating_matrix(const float* d_Fu, const float* d_Fi, const int64_t* d_users, int32_t nu, int32_t I, int32_t d, float* d_out,
+                                 void* stream) {
+    if (!d_Fu || !d_Fi || !d_users || !d_out || nu <= 0 || I <= 0 || d <= 0) return fail(-1, "idg_rating_matrix: bad argument%s");
+    const dim3 grid((I + 31) / 32, (nu + 31) / 32);
+    rating_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_Fu, d_Fi, d_users, nu, I, d, d_out);
+    IDG_LAUNCH_CHECK("rating_matrix_kernel");
+    return 0;
+}
 
 extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, int32_t K) {
     if (nu <= 0 || I <= 0) return 0;

@@ -9,12 +9,15 @@
 //            fp32 operands are read as tf32 (low 13 mantissa bits ignored):
 //            |s~ - s| <= (2^-9 + small) * |u||i|  -> candidate margin 2*delta_u.
 //   roles:   warp 0      MMA issuer (one elected thread) + TMEM alloc/dealloc
-//            warps 2-3   operand loaders: cp.async 16-byte chunks into the 128B-swizzled K-major
-//                        UMMA layout, 3-stage ring, mbarrier full/empty
+//            warps 2-3   operand loaders: the user tile (gathered rows) by cp.async into the 128B-swizzled K-major
+//                        UMMA layout; item tiles by TMA (cp.async.bulk.tensor.2d, 128B-swizzle tensor map, one
+//                        elected thread, mbarrier expect_tx), 3-stage ring
 //            warps 4-7   epilogue: thread <-> user row (TMEM lane), tcgen05.ld 32 columns at a time,
 //                        train-mask by a per-row cursor over the sorted positives, threshold filter
 //                        in registers, per-row candidate lists in shared memory, warp-cooperative prune
 //   bound:   TMEM drain (64 B/clk/SM = 16 scores/clk/SM), not the MMA rate.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <math.h>
 
 #include "tc_common.cuh"
@@ -74,7 +77,8 @@ __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2
 
 __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
                                                                     const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
-                                                                    const int64_t* __restrict__ users, int nu, int K, EvalWsTc w) {
+                                                                    const int64_t* __restrict__ users, int nu, int K, EvalWsTc w,
+                                                                    const __grid_constant__ CUtensorMap tmap_items) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                        // 32 KB
     unsigned char* sB = smem + 2 * kSubTile;                         // kTcStages x 32 KB
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
     const int ntiles = (I + kTcN - 1) / kTcN;
 
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, kTcLoaders); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }  // full: one arrive.expect_tx + TMA bytes
         for (int b = 0; b < kTcBufs; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
         mbar_init(afull, kTcLoaders);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,27 +145,19 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(afull);
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t % kTcStages;
-            mbar_wait(empty + s, ((t / kTcStages) & 1) ^ 1);
-            const uint32_t dst = smem_u32(sB + (size_t)s * 2 * kSubTile);
-            const int i0 = t * kTcN;
-#pragma unroll 4
-            for (int c = lt; c < kTcN * 16; c += kTcLoaders) {
-                const int r = c >> 4, kc = c & 15;
-                const int i = i0 + r;
-                cp_async16(dst + sw128_offset(r, kc), Fi + (size_t)min(i, I - 1) * kTcD + kc * 4, (i < I) ? 16 : 0);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (t > 0) {  // keep two tiles in flight: publish the previous one
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(full + (t - 1) % kTcStages);
+        // B: item tiles by TMA -- the tensor map (box 32 floats x 128 rows, 128B swizzle) lands each [128 x 32] column block
+        // directly in the UMMA K-major layout; rows past I are zero-filled by the hardware.  One elected thread.
+        if (lt == 0) {
+            tma_prefetch_desc(&tmap_items);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kTcStages;
+                mbar_wait(empty + s, ((t / kTcStages) & 1) ^ 1);
+                const uint32_t dst = smem_u32(sB + (size_t)s * 2 * kSubTile);
+                mbar_arrive_expect_tx(full + s, 2 * kSubTile);
+                tma_load_2d(dst, &tmap_items, 0, t * kTcN, full + s);
+                tma_load_2d(dst + kSubTile, &tmap_items, 32, t * kTcN, full + s);
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full + (ntiles - 1) % kTcStages);
     } else if (warp >= 4) {
         // ===================== epilogue: one thread per user row =====================
         const int q = warp & 3;
@@ -278,10 +274,27 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
                               cudaStream_t stream) {
     EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids};
+    // tensor map of the item table [I rows x 64 fp32]: driver entry point fetched through the runtime (no libcuda link)
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        IDG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(-1, "cuTensorMapEncodeTiled is not available%s");
+        encode = (PFN_cuTensorMapEncodeTiled)fn;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)kTcD, (cuuint64_t)I};
+    const cuuint64_t gstride[1] = {(cuuint64_t)kTcD * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kTcN};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Fi), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(-1, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)cr);
     const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + sizeof(float) * kTcM * kTcCap + sizeof(int) * kTcM * kTcCap +
                         sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
     IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w);
+    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap);
     IDG_LAUNCH_CHECK("eval_candidates_tc_kernel");
     return 0;
 }

@@ -113,4 +113,4 @@ class PropagationModel(nn.Module):
         completeness; Test() ranks through the fused top-K kernel and never materialises it."""
         with torch.no_grad():
             users_emb, items_emb = self.aggregate()[:2]
-            return self.activation(torch.matmul(users_emb[user.long()], items_emb.t()))
+            return ops.rating_matrix(users_emb, items_emb, user)

@@ -187,6 +187,15 @@ def eval_topk(Fu, Fi, users, mask_indptr, mask_indices, K, want_scores=False, ws
     return (ids, sc) if want_scores else ids
 
 
+def rating_matrix(Fu, Fi, users):
+    """sigmoid(Fu[users] . Fi^T) as a dense [b, I] tensor (LightGCN.py:74-80); API completeness only."""
+    Fu, Fi = _f32c(Fu), _f32c(Fi)
+    users = users.long().contiguous()
+    out = torch.empty((users.numel(), Fi.shape[0]), dtype=torch.float32, device=Fu.device)
+    check(_lib.lib().idg_rating_matrix(ptr(Fu), ptr(Fi), ptr(users), users.numel(), Fi.shape[0], Fu.shape[1], ptr(out), cur_stream()), "idg_rating_matrix")
+    return out
+
+
 def eval_metric_sums(topk_ids, users, test_indptr, test_indices, ks, ws=None):
     """float64 [len(ks), 3] sums over users of (recall, precision, ndcg) at each k (metrics.py:4-36)."""
     l = _lib.lib()

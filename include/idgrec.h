@@ -223,6 +223,11 @@ int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, in
                   const int32_t* d_mask_indptr, const int32_t* d_mask_indices, const int64_t* d_users,
                   int32_t nu, int32_t K, int64_t* d_out_ids, float* d_out_scores, void* d_ws, void* stream);
 
+/* get_rating_for_test as the reference writes it (models/LightGCN.py:74-80): d_out [nu, I] = sigmoid(Fu[users] . Fi^T).
+ * API completeness only: the evaluator ranks through idg_eval_topk and never materialises this matrix. */
+int idg_rating_matrix(const float* d_Fu, const float* d_Fi, const int64_t* d_users, int32_t nu, int32_t I, int32_t d,
+                      float* d_out, void* stream);
+
 /* metrics.py:4-58 + batch_test.py:80-91 on device: sums over users of
  * recall/precision/ndcg at each k in h_ks (nk <= 8) -> d_sums[3*nk] (float64).
  * test CSR = test_dict rows (int32, sorted inside a row, duplicates kept: metrics.py:27 uses

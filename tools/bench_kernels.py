@@ -102,6 +102,9 @@ def main():
         ftc = FusedTrainer(kind, G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=Bc, use_cuda_graph=False, **kw)
         out["step_%s_B2048_eager_ms" % kind], _ = timed(lambda: ftc.step(uc, pc, nc), iters=10, warm=2)
         del ftc
+        ftg = FusedTrainer(kind, G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=Bc, use_cuda_graph=True, **kw)
+        out["step_%s_B2048_graph_ms" % kind], _ = timed(lambda: ftg.step(uc, pc, nc), iters=20, warm=3)
+        del ftg
     # NGCF: one autograd step (3 x (SpMM + fused dense kernel) fwd/bwd, 256-d BPR) on the with-self graph
     if os.environ.get("IDG_BENCH_NGCF", "1") == "1":
         csr_s = build_norm_adjacency(g.train_user, g.train_item, U, I, add_self=True, device=dev)
