@@ -24,7 +24,8 @@ namespace idg {
 // csrc/eval_tc.cu: the same candidate pass on tcgen05 tensor cores (d = 64)
 int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
-                              cudaStream_t stream);
+                              float* list_s, int* list_i, cudaStream_t stream);
+constexpr int kTcListCap = 80;  // == kTcCap in eval_tc.cu
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
 constexpr int kFallbackCtas = 148;  // one per SM; scratch = 148 x I doubles
@@ -35,6 +36,8 @@ struct EvalWs {
     int* flag_list;    // [nu] positions (into d_users) that need the exhaustive pass
     int* cand_cnt;     // [nu]
     int* cand_ids;     // [nu, kCandOut]
+    float* tc_ls;      // [ceil(nu/128)*128, kTcListCap] tensor-core pass: per-row candidate lists
+    int* tc_li;
     double* scratch;   // [kFallbackCtas, I]
 };
 
@@ -48,6 +51,9 @@ __host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
     w.flag_list = (int*)p; p += ev_align(sizeof(int) * (size_t)nu);
     w.cand_cnt = (int*)p; p += ev_align(sizeof(int) * (size_t)nu);
     w.cand_ids = (int*)p; p += ev_align(sizeof(int) * (size_t)nu * kCandOut);
+    const size_t nup = ((size_t)nu + 127) / 128 * 128;
+    w.tc_ls = (float*)p; p += ev_align(sizeof(float) * nup * kTcListCap);
+    w.tc_li = (int*)p; p += ev_align(sizeof(int) * nup * kTcListCap);
     w.scratch = (double*)p;
     return w;
 }
@@ -410,7 +416,9 @@ extern "C" int idg_rating_matrix(const float* d_Fu, const float* d_Fi, const int
 extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, int32_t K) {
     if (nu <= 0 || I <= 0) return 0;
     const size_t metrics = ev_align(sizeof(double) * (size_t)nu * 3 * 8);
+    const size_t nup = ((size_t)nu + 127) / 128 * 128;
     const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
+                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) +
                        ev_align(sizeof(double) * (size_t)kFallbackCtas * I);
     return (int64_t)(sel > metrics ? sel : metrics);
 }
@@ -433,7 +441,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
     if (d == 64 && use_tc) {
         if (int rc = launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
-                                               w.flag_list, w.cand_cnt, w.cand_ids, stream))
+                                               w.flag_list, w.cand_cnt, w.cand_ids, w.tc_ls, w.tc_li, stream))
             return rc;
     } else if (d == 64) {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -25,7 +25,8 @@
 namespace idg {
 
 constexpr int kTcM = 128, kTcN = 128, kTcD = 64;
-constexpr int kTcStages = 3, kTcBufs = 4;
+constexpr int kTcStages = 2, kTcBufs = 2;   // per CTA; two CTAs share an SM (2 x 97 KB smem, 2 x 256 TMEM columns)
+constexpr uint32_t kTcTmemCols = kTcBufs * 128;
 constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
@@ -36,11 +37,24 @@ struct EvalWsTc {
     int* flag_list;
     int* cand_cnt;
     int* cand_ids;
+    float* list_s;  // [ceil(nu/128)*128, kTcCap] per-row candidate scores in L2 (rare appends): frees shared memory for 2 CTAs/SM
+    int* list_i;
 };
 
 // smem byte offset of the 16-byte chunk kc (0..15) of row r inside an operand tile [128 rows x 64 fp32]
 __device__ __forceinline__ uint32_t sw128_offset(int r, int kc) {
     return (uint32_t)(kc >> 3) * kSubTile + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((kc & 7) ^ (r & 7)) << 4);
+}
+
+// Out-of-line append of the survivors of one 4-column group (columns j0, j0+8, j0+16, j0+24 of the chunk).  Kept
+// out of the epilogue's hot loop on purpose: ncu showed the loop stalled on instruction fetch (no_instruction) when
+// the 32 append sites were inlined.
+__device__ __noinline__ int tc_group_append(float v0, float v1, float v2, float v3, float tau, int id0, int I, float* ls, int* li, int cnt) {
+    if (v0 >= tau && id0 < I) { ls[cnt] = v0; li[cnt] = id0; ++cnt; }
+    if (v1 >= tau && id0 + 8 < I) { ls[cnt] = v1; li[cnt] = id0 + 8; ++cnt; }
+    if (v2 >= tau && id0 + 16 < I) { ls[cnt] = v2; li[cnt] = id0 + 16; ++cnt; }
+    if (v3 >= tau && id0 + 24 < I) { ls[cnt] = v3; li[cnt] = id0 + 24; ++cnt; }
+    return cnt;
 }
 
 // warp-cooperative prune of one row's candidate list: tau = (K-th largest) - 2*delta, keep >= tau
@@ -49,12 +63,18 @@ __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int idx = lane + 32 * q;
-        s[q] = (idx < m) ? ls[idx] : -INFINITY; id[q] = (idx < m) ? li[idx] : 0; rank[q] = 0;
+        s[q] = (idx < m) ? __ldcg(ls + idx) : -INFINITY; id[q] = (idx < m) ? __ldcg(li + idx) : 0; rank[q] = 0;
     }
-    for (int j = 0; j < m; ++j) {
-        const float sj = ls[j];
+    // rank counting over the list held in registers (3 entries per lane), broadcast by shuffle
 #pragma unroll
-        for (int q = 0; q < 3; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && j < lane + 32 * q);
+    for (int qq = 0; qq < 3; ++qq) {
+        for (int l = 0; l < 32; ++l) {
+            const int j = l + 32 * qq;
+            if (j >= m) break;
+            const float sj = __shfl_sync(0xffffffffu, s[qq], l);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && j < lane + 32 * q);
+        }
     }
     float vk = -INFINITY;
 #pragma unroll
@@ -75,16 +95,14 @@ __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2
     new_cnt = kept; new_tau = tau;
 }
 
-__global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
+__global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
                                                                     const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
                                                                     const int64_t* __restrict__ users, int nu, int K, EvalWsTc w,
                                                                     const __grid_constant__ CUtensorMap tmap_items) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                        // 32 KB
     unsigned char* sB = smem + 2 * kSubTile;                         // kTcStages x 32 KB
-    float* ls = reinterpret_cast<float*>(sB + kTcStages * 2 * kSubTile);  // [128][kTcCap]
-    int* li = reinterpret_cast<int*>(ls + kTcM * kTcCap);            // [128][kTcCap]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li + kTcM * kTcCap);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * 2 * kSubTile);
     uint64_t* full = bars;                   // [kTcStages] loaders -> MMA
     uint64_t* empty = bars + kTcStages;      // [kTcStages] MMA -> loaders
     uint64_t* tfull = empty + kTcStages;     // [kTcBufs]   MMA -> epilogue
@@ -94,6 +112,8 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u0 = blockIdx.x * kTcM;
+    float* ls = w.list_s + (size_t)u0 * kTcCap;  // this CTA's 128 rows
+    int* li = w.list_i + (size_t)u0 * kTcCap;
     const int ntiles = (I + kTcN - 1) / kTcN;
 
     if (tid == 0) {
@@ -103,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTcTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -210,18 +230,10 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
                 for (int j = 0; j < 8; ++j) m8[j] = fmaxf(fmaxf(v[j], v[j + 8]), fmaxf(v[j + 16], v[j + 24]));
                 const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
                 if (m >= tau) {
-                    // usually one or two survivors per warp-chunk: descend only into the 4-element groups whose
-                    // maximum passes (the epilogue is instruction-issue bound, ncu: ~450 instr per warp-chunk before)
+                    // usually one or two survivors per warp-chunk: descend only into the 4-column groups whose maximum passes
 #pragma unroll
-                    for (int g8 = 0; g8 < 8; ++g8) {
-                        if (m8[g8] >= tau) {
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) {
-                                const int j = g8 + 8 * q4;
-                                if (v[j] >= tau && c0 + j < I) { my_ls[cnt] = v[j]; my_li[cnt] = c0 + j; ++cnt; }
-                            }
-                        }
-                    }
+                    for (int g8 = 0; g8 < 8; ++g8)
+                        if (m8[g8] >= tau) cnt = tc_group_append(v[g8], v[g8 + 8], v[g8 + 16], v[g8 + 24], tau, c0 + g8, I, my_ls, my_li, cnt);
                 }
                 unsigned need = __ballot_sync(0xffffffffu, cnt > kTcTrig);
                 while (need) {
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
                 w.flag_list[atomicAdd(w.flag_cnt, 1)] = p;
             } else {
                 w.cand_cnt[p] = cnt;
-                for (int j = 0; j < cnt; ++j) w.cand_ids[(size_t)p * kTcCandOut + j] = my_li[j];
+                for (int j = 0; j < cnt; ++j) w.cand_ids[(size_t)p * kTcCandOut + j] = __ldcg(my_li + j);
             }
         }
     }
@@ -266,14 +278,14 @@ __global__ void __launch_bounds__(256, 1) eval_candidates_tc_kernel(const float*
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
     }
 }
 
 int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
-                              cudaStream_t stream) {
-    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids};
+                              float* list_s, int* list_i, cudaStream_t stream) {
+    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids, list_s, list_i};
     // tensor map of the item table [I rows x 64 fp32]: driver entry point fetched through the runtime (no libcuda link)
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -291,8 +303,7 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Fi), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(-1, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)cr);
-    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + sizeof(float) * kTcM * kTcCap + sizeof(int) * kTcM * kTcCap +
-                        sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
+    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
     IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap);
     IDG_LAUNCH_CHECK("eval_candidates_tc_kernel");
