@@ -129,6 +129,11 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            try:  # a fresh checkout: compile the extension (nvcc, sm_100a) -- this is a build, not a fallback
+                build()
+            except Exception:  # noqa: BLE001
+                pass
+        if not os.path.exists(LIB_PATH):
             raise IdgError(
                 "libidgrec_sm100.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "at the repo root; there is no CPU fallback for the ID-GRec hot path." % LIB_PATH)
