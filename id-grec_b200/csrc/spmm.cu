@@ -67,6 +67,7 @@ struct SpmmArgs {
     float adam_b1, adam_b2, adam_eps;
     float* adam_peer_p[7]; float* adam_mc_p;
     int skip_zero_rows;       // SPARSE kernels: rows that come out exactly zero are not stored (outputs pre-zeroed by the caller)
+    const unsigned* rowmask;  // ROWMASK kernels: rows whose bit is clear are skipped (outputs untouched)
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
 };
 
@@ -74,6 +75,7 @@ struct SpmmArgs {
 
 struct idg_graph {
     const idg_peers* peers = nullptr;
+    const unsigned* closure = nullptr;  // optional: batch rows + their neighbours (idg_graph_set_closure)
     int32_t n_rows = 0, n_cols = 0, row_offset = 0;
     int64_t nnz = 0;
     int n_items = 0, n_heavy = 0, n_parts = 0;
@@ -163,7 +165,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -180,6 +182,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
         return;
     }
     const int4 it = __ldg(a.items + item);
+    if (ROWMASK) {  // neighbourhood-restricted layer: only rows the next (batch-restricted) layer will read
+        const int grow = a.row_offset + ((it.w < 0) ? it.x : a.heavy[it.x].row);
+        if (!((__ldg(a.rowmask + (grow >> 5)) >> (grow & 31)) & 1u)) return;
+    }
     const float* __restrict__ X = a.X + sub * 4;
     const int2* __restrict__ cvp = a.colval;
 
@@ -350,6 +356,7 @@ struct SpmmExtra {
     const int* d_wl_count = nullptr;
     int max_wl = 0;
     const unsigned* bitmap = nullptr;  // sparse-input launch
+    const unsigned* rowmask = nullptr; // row-masked launch
     int skip_zero_rows = 0;
     const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
@@ -369,6 +376,7 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.X = d_X; a.Y = d_Y; a.addend = d_addend; a.addend2 = d_addend2; a.scale2 = scale2; a.noise = d_noise; a.eps = eps;
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap; a.skip_zero_rows = ex.skip_zero_rows;
+    a.rowmask = ex.rowmask;
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
     a.adam_p = nullptr; a.adam_m = a.adam_v = nullptr; a.adam_regc = a.adam_scalars = nullptr; a.adam_mc_p = nullptr;
     a.adam_b1 = a.adam_b2 = a.adam_eps = 0.f;
@@ -419,6 +427,10 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
         if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
         else spmm_kernel<32, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.rowmask) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
     } else if (ex.worklist) {
         // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
         if (d == 64) spmm_kernel<16, 8, false, 1><<<grid, T, 0, stream>>>(a);
@@ -495,6 +507,36 @@ __global__ void __launch_bounds__(256) batch_unique_kernel(const int64_t* __rest
     }
 }
 
+// closure[r] = 1 iff row r has a column flagged in `batch` (r is a neighbour of a batch row); one lane group per work
+// item of the schedule (heavy rows are already chunked), early exit on the first hit.  The batch rows themselves are
+// OR-ed in by closure_or_kernel.
+template <int LPR>
+__global__ void __launch_bounds__(256) closure_kernel(const int4* __restrict__ items, int n_items, const int2* __restrict__ colval,
+                                                      const HeavyRow* __restrict__ heavy, int row_offset, const unsigned* __restrict__ batch,
+                                                      unsigned* __restrict__ closure) {
+    const int lane = threadIdx.x & 31;
+    const int group = lane / LPR, sub = lane % LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (group * LPR));
+    const int item = (blockIdx.x * 8 + (threadIdx.x >> 5)) * (32 / LPR) + group;
+    if (item >= n_items) return;
+    const int4 it = __ldg(items + item);
+    bool any = false;
+    for (int base = it.y; base < it.z && !any; base += LPR) {
+        const int k = base + sub;
+        bool hit = false;
+        if (k < it.z) { const int c = __ldg(colval + k).x; hit = (__ldg(batch + (c >> 5)) >> (c & 31)) & 1u; }
+        any = __any_sync(gmask, hit);
+    }
+    if (any && sub == 0) {
+        const int grow = row_offset + ((it.w < 0) ? it.x : heavy[it.x].row);
+        atomicOr(closure + (grow >> 5), 1u << (grow & 31));
+    }
+}
+__global__ void closure_or_kernel(const unsigned* __restrict__ batch, unsigned* __restrict__ closure, int w0, int w1) {
+    const int i = w0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w1) { const unsigned b = batch[i]; if (b) atomicOr(closure + i, b); }
+}
+
 __global__ void batch_rows_clear_kernel(const int* __restrict__ rowlist, const int* __restrict__ count, unsigned* __restrict__ bitmap) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < *count) bitmap[rowlist[i] >> 5] = 0u;  // every set bit belongs to a listed row
@@ -548,6 +590,36 @@ extern "C" int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_c
     batch_rows_clear_kernel<<<(max_rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_rowlist, d_count, d_bitmap);
     IDG_LAUNCH_CHECK("batch_rows_clear_kernel");
     return 0;
+}
+
+// closure |= {rows of this handle with a neighbour in the batch} | {batch rows of this handle's row range}
+extern "C" int idg_closure_bitmap(const idg_graph* g, const uint32_t* d_batch_bitmap, uint32_t* d_closure, void* stream_) {
+    if (!g || !d_batch_bitmap || !d_closure) return fail(-1, "idg_closure_bitmap: null argument%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (g->n_items > 0) {
+        closure_kernel<16><<<(g->n_items + 15) / 16, 256, 0, stream>>>(g->items, g->n_items, g->colval, g->heavy, g->row_offset, d_batch_bitmap, d_closure);
+        IDG_LAUNCH_CHECK("closure_kernel");
+    }
+    const int w0 = g->row_offset >> 5, w1 = (g->row_offset + g->n_rows + 31) >> 5;
+    if (w1 > w0) {
+        closure_or_kernel<<<(w1 - w0 + 255) / 256, 256, 0, stream>>>(d_batch_bitmap, d_closure, w0, w1);
+        IDG_LAUNCH_CHECK("closure_or_kernel");
+    }
+    return 0;
+}
+
+extern "C" int idg_graph_set_closure(idg_graph* g, const uint32_t* d_closure) {
+    if (!g) return fail(-1, "idg_graph_set_closure: null graph%s");
+    g->closure = d_closure;
+    return 0;
+}
+
+extern "C" int idg_spmm_layer_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps, const float* d_acc_in,
+                                     float* d_acc_out, float acc_div, int32_t d, const uint32_t* d_rowmask, void* stream) {
+    if (!d_rowmask) return fail(-1, "idg_spmm_layer_masked: null row mask%s");
+    SpmmExtra ex;
+    ex.rowmask = d_rowmask;
+    return spmm_launch(g, d_X, d_Y, nullptr, nullptr, 0.f, d_noise, eps, d_acc_in, d_acc_out, acc_div, d, stream, ex);
 }
 
 extern "C" int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows) {
@@ -624,7 +696,12 @@ extern "C" int idg_propagate_fwd_ex(const idg_graph* g, const float* d_X0, int32
         int rc;
         if (last && d_rowlist)
             rc = spmm_rows(g, x, need_y ? y : nullptr, nz, eps, acc_in, d_out_mean, cnt, d, d_rowlist, d_count, max_rows, d_worklist, stream);
-        else
+        else if (l == K - 1 && d_rowlist && g->closure) {
+            // the batch-restricted last layer only reads this layer at the batch rows and their neighbours
+            SpmmExtra ex;
+            ex.rowmask = g->closure;
+            rc = spmm_launch(g, x, y, nullptr, nullptr, 0.f, nz, eps, acc_in, d_out_mean, 1.0f, d, stream, ex);
+        } else
             rc = idg_spmm_layer(g, x, need_y ? y : nullptr, nullptr, nz, eps, acc_in, d_out_mean, last ? cnt : 1.0f, d, stream);
         if (rc) return rc;
         x = y;
@@ -664,6 +741,8 @@ static int propagate_bwd_impl(const idg_graph* g, const float* d_G, const float*
         const int layer = K - s;  // index of the H being produced; 0 => gX0
         SpmmExtra ex;
         if (s == 1) ex.bitmap = d_bitmap;
+        // H_{K-1} = G + A G is non-zero only on the batch rows and their neighbours: the next product gathers just those
+        if (s == 2 && layer > 0 && d_bitmap && g->closure) ex.bitmap = g->closure;
         if (layer > 0) {
             float* y = buf[pb]; pb ^= 1;
             rc = spmm_launch(g, h, y, d_G, (d_Gcl && cl_layer == layer) ? d_Gcl : nullptr, cnt, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);

@@ -24,14 +24,15 @@ from .graph import BatchRows, Graph
 
 def partition_rows(indptr, world: int):
     """Contiguous row ranges balanced by nonzeros (+ one unit per row for the epilogue traffic).
-    Returns world+1 boundaries; boundaries are multiples of 4 rows so every range is 16-byte aligned."""
+    Returns world+1 boundaries; inner boundaries are multiples of 128 rows (16-byte aligned row ranges, and each
+    rank's slice of a row bitmap is a whole number of 16-byte groups of words)."""
     indptr = np.asarray(indptr, dtype=np.int64)
     n = len(indptr) - 1
     cost = indptr + 8 * np.arange(n + 1, dtype=np.int64)      # cumulative work up to each row boundary
     bounds = [0]
     for r in range(1, world):
         b = int(np.searchsorted(cost, cost[-1] * r / world))
-        b = min(n, max(bounds[-1], (b + 3) // 4 * 4))
+        b = min(n, max(bounds[-1], (b + 127) // 128 * 128))
         bounds.append(b)
     bounds.append(n)
     return bounds
@@ -139,7 +140,7 @@ class DistFusedTrainer:
     """LightGCN training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer)."""
 
     def __init__(self, kind, csr, table, num_users, K, reg_lambda, lr, rank, world, group=None, max_batch=1024,
-                 betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None):
+                 betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None, closure_restrict="auto"):
         if kind != "LightGCN":
             raise NotImplementedError("multi-GPU training is implemented for LightGCN (BASELINE.json configs 2 and 5)")
         if not 2 <= K <= 3:
@@ -166,6 +167,16 @@ class DistFusedTrainer:
         self.gE0, self.m, self.v, self.G, self.F = z(), z(), z(), z(), z()
         self.rows = BatchRows(N, max_batch, dev)
         self.rows.worklist(self.full)
+        # batch-neighbourhood restriction of forward layer K-1 and of the second backward product (see engine.py);
+        # every rank computes the closure bits of its own rows and publishes its words to the peers
+        if closure_restrict == "auto":
+            from .graph import expected_closure_fraction
+            closure_restrict = K >= 3 and expected_closure_fraction(csr, num_users, max_batch) < 0.4
+        self.use_closure = bool(closure_restrict) and K >= 3
+        self.closure = self.slab.carve(((N + 127) // 128 * 4 + 4,), torch.int32)
+        self.closure.zero_()
+        if self.use_closure:
+            self.rows.closure = self.closure
         self.max_batch, self.step_count = max_batch, 0
         self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
         self.n_loss = 2
@@ -205,11 +216,21 @@ class DistFusedTrainer:
             # the first backward product only publishes non-zero rows: clear this rank's copy of its output now; every
             # peer passes two barriers (after this point in stream order) before it writes into it
             self.H[0].zero_()
+        if self.use_closure:
+            check(l.idg_closure_bitmap(loc._h, ptr(rows.bitmap), ptr(self.closure), s), "idg_closure_bitmap")
+            w0, w1 = self.b0 // 32, (self.b1 + 31) // 32
+            if w1 > w0:
+                slab.push(self.closure[w0:(w1 + 3) // 4 * 4])  # whole 16-byte groups: inner bounds are multiples of 128 rows
+            slab.barrier()
         self._mark('batch_rows')
         # forward: layers 1..K-1 on the local rows, rows pushed to every peer by the epilogue
         x = self.E0
         for k in range(K - 1):
-            loc.spmm_layer(x, Y=self.W[k])
+            if self.use_closure and k == K - 2:
+                # layer K-1 only on the batch rows and their neighbours: the restricted last layer reads nothing else
+                check(l.idg_spmm_layer_masked(loc._h, ptr(x), ptr(self.W[k]), None, 0.0, None, None, 1.0, d, ptr(self.closure), s), "idg_spmm_layer_masked")
+            else:
+                loc.spmm_layer(x, Y=self.W[k])
             self._mark('fwd_layer%d' % (k + 1))
             slab.barrier()
             self._mark('barrier')
@@ -237,7 +258,10 @@ class DistFusedTrainer:
         self._mark('barrier')
         h = self.H[0]
         for k in range(1, K - 1):
-            loc.spmm_layer(h, Y=self.H[k], addend=self.G)
+            if self.use_closure and k == 1:  # H_{K-1} is zero outside the closure: gather only those columns
+                check(l.idg_spmm_layer_sparse_in(loc._h, ptr(h), ptr(self.H[k]), ptr(self.G), None, None, 1.0, d, ptr(self.closure), 0, s), "idg_spmm_layer_sparse_in")
+            else:
+                loc.spmm_layer(h, Y=self.H[k], addend=self.G)
             self._mark('bwd_layer')
             slab.barrier()
             self._mark('barrier')
@@ -245,7 +269,7 @@ class DistFusedTrainer:
         check(l.idg_spmm_layer_adam(loc._h, ptr(h), ptr(self.G), float(K + 1), d, adam, s), "idg_spmm_layer_adam")
         self._mark('bwd_last_adam_push')
         check(l.idg_bpr_finish(ptr(self.E0), None, ptr(self.G), B, d, self.reg_lambda, None, ptr(self.regc), ptr(self.ws), s), "idg_bpr_finish")
-        rows.clear()
+        rows.clear()   # also zeroes the closure words (before the final barrier: peers publish theirs after it)
         self._mark('finish')
         slab.barrier()
         self._mark('barrier')

@@ -20,7 +20,7 @@ from ._lib import check, cur_stream, ptr
 class FusedTrainer:
     def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
                  eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8,
-                 restrict_rows=True, fuse_adam=True):
+                 restrict_rows=True, fuse_adam=True, closure_restrict="auto"):
         assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR")
         self.l = _lib.lib()
         self.kind, self.graph, self.E0 = kind, graph, table
@@ -53,12 +53,21 @@ class FusedTrainer:
         # identical-result work skipping (SURVEY.md 8 d): last forward layer only on the batch rows, first
         # backward product only over the batch columns
         self.rows = None
+        self.use_closure = False
         if kind != "MFBPR":
             graph.work(self.d)  # allocate the layer ping-pong buffers before any graph capture
             if restrict_rows:
                 from .graph import BatchRows
                 self.rows = BatchRows(self.N, max_batch, dev)
                 self.rows.worklist(graph)
+                # layer K-1 / second backward product restricted to the batch neighbourhood when that is a small
+                # part of the graph (scale-up graphs; ~76 % of the nodes at the amazon-book shape -> off)
+                if closure_restrict == "auto":
+                    from .graph import expected_closure_fraction
+                    closure_restrict = K >= 2 and expected_closure_fraction(graph.csr, num_users, max_batch) < 0.4
+                self.use_closure = bool(closure_restrict) and K >= 2
+                if self.use_closure:
+                    self.rows.enable_closure(graph)
         # Adam applied in the epilogue of the last backward layer (no gradient pass through memory)
         self.fuse_adam = fuse_adam and kind != "MFBPR"
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -107,6 +116,8 @@ class FusedTrainer:
             rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
         elif rows is not None:
             rows.build(u, p, n, B, self.U)
+        if self.use_closure:
+            rows.build_closure(g)
         if self.kind == "LightGCN":
             g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
             self._bpr(B, u, p, n, fused)

@@ -151,6 +151,16 @@ class Graph:
         return out
 
 
+def expected_closure_fraction(csr, num_users, batch):
+    """Rough size of {batch rows + neighbours} / N for one mini-batch of `batch` (user, pos, neg) samples: users are
+    drawn per train edge (degree-biased), positives are degree-biased items, negatives uniform items."""
+    deg = (csr.indptr[1:] - csr.indptr[:-1]).double()
+    du, di = deg[:num_users], deg[num_users:]
+    biased = lambda x: float((x * x).sum() / x.sum().clamp(min=1.0))
+    est = batch * (biased(du) + biased(di) + float(di.mean()))
+    return min(1.0, est / float(deg.numel()))
+
+
 class BatchRows:
     """Unique rows {user, U+pos, U+neg} of a mini-batch on the device: list + count + bitmap."""
 
@@ -160,6 +170,7 @@ class BatchRows:
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
         self.bitmap = torch.zeros((N + 31) // 32 + 1, dtype=torch.int32, device=device)
         self.lead = torch.zeros(3 * max_batch, dtype=torch.uint8, device=device)
+        self.closure = None  # optional bitmap: batch rows + their neighbours (enable_closure)
         self._wl = {}
 
     def worklist(self, graph):
@@ -173,6 +184,14 @@ class BatchRows:
         check(_lib.lib().idg_batch_rows(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),
                                         cur_stream()), "idg_batch_rows")
 
+    def enable_closure(self, graph, buffer=None):
+        """Allocate (or adopt) the closure bitmap and register it with the propagation handle."""
+        self.closure = buffer if buffer is not None else torch.zeros_like(self.bitmap)
+        check(_lib.lib().idg_graph_set_closure(graph._h, ptr(self.closure)), "idg_graph_set_closure")
+
+    def build_closure(self, graph):
+        check(_lib.lib().idg_closure_bitmap(graph._h, ptr(self.bitmap), ptr(self.closure), cur_stream()), "idg_closure_bitmap")
+
     def build_unique(self, users_ptr, pos_ptr, neg_ptr, B, num_users, uidx, ucnt, iidx, icnt):
         check(_lib.lib().idg_batch_rows_unique(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),
                                                ptr(self.lead), ptr(uidx), ptr(ucnt), ptr(iidx), ptr(icnt), cur_stream()), "idg_batch_rows_unique")
@@ -180,3 +199,5 @@ class BatchRows:
     def clear(self):
         check(_lib.lib().idg_batch_rows_clear(ptr(self.rowlist), ptr(self.count), self.max_rows, ptr(self.bitmap), cur_stream()),
               "idg_batch_rows_clear")
+        if self.closure is not None:
+            self.closure.zero_()

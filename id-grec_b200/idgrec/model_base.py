@@ -87,7 +87,8 @@ class PropagationModel(nn.Module):
                 from .dist import DistFusedTrainer
                 ft = DistFusedTrainer(self.kind, self.Graph.csr, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda,
                                       lr, dist.get_rank(), world, max_batch=max_batch, full_graph=self.Graph,
-                                      use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'))
+                                      use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
+                                      closure_restrict={'0': False, '1': True}.get(str(cfg.get('closure_restrict', 'auto')), 'auto'))
                 U = self.dataset.num_users
                 self._table = ft.E0
                 self.user_embedding.weight.data, self.item_embedding.weight.data = ft.E0[:U], ft.E0[U:]
@@ -99,7 +100,8 @@ class PropagationModel(nn.Module):
                 eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)), max_batch=max_batch,
                 use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
                 restrict_rows=str(cfg.get('restrict_rows', '1')) not in ('0', 'False', 'false'),
-                fuse_adam=str(cfg.get('fuse_adam', '1')) not in ('0', 'False', 'false'))
+                fuse_adam=str(cfg.get('fuse_adam', '1')) not in ('0', 'False', 'false'),
+                closure_restrict={'0': False, '1': True}.get(str(cfg.get('closure_restrict', 'auto')), 'auto'))
         return self._fused
 
     # -- evaluation ------------------------------------------------------------------------------

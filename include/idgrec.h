@@ -117,6 +117,17 @@ int idg_batch_rows_unique(const int64_t* d_user, const int64_t* d_pos, const int
                           int64_t* d_uidx, int32_t* d_ucnt, int64_t* d_iidx, int32_t* d_icnt, void* stream);
 int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows, uint32_t* d_bitmap,
                          void* stream);
+/* Neighbourhood of the batch ("closure" = batch rows + rows with a batch neighbour) as a bitmap, all-zero on entry;
+ * computed for the rows of the handle (a row-partitioned rank computes its slice).  Once registered with
+ * idg_graph_set_closure (NULL to clear), idg_propagate_fwd_ex evaluates layer K-1 only on closure rows (the batch-
+ * restricted last layer reads nothing else) and idg_propagate_bwd_ex/_adam gather only closure columns in the
+ * second backward product (H_{K-1} = G + A.G is zero elsewhere).  Pays off when the closure is a small part of the
+ * graph (1M x 1M scale-up: ~20 %); identical results.  idg_spmm_layer_masked is the masked layer alone. */
+int idg_closure_bitmap(const idg_graph* g, const uint32_t* d_batch_bitmap, uint32_t* d_closure, void* stream);
+int idg_graph_set_closure(idg_graph* g, const uint32_t* d_closure);
+int idg_spmm_layer_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
+                          const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
+                          const uint32_t* d_rowmask, void* stream);
 /* scratch ints needed by the row-restricted entry points for up to max_rows listed rows */
 int64_t idg_graph_worklist_ints(const idg_graph* g, int32_t max_rows);
 /* idg_spmm_layer evaluated only on the listed rows (other rows of the outputs are left untouched);

@@ -17,9 +17,9 @@ def test_partition_rows_balanced_and_aligned():
     for world in (1, 2, 4, 8):
         b = partition_rows(indptr, world)
         assert b[0] == 0 and b[-1] == 20000 and len(b) == world + 1
-        assert all(b[i] <= b[i + 1] for i in range(world)) and all(x % 4 == 0 for x in b[:-1])
+        assert all(b[i] <= b[i + 1] for i in range(world)) and all(x % 128 == 0 for x in b[:-1])
         work = [indptr[b[i + 1]] - indptr[b[i]] + 8 * (b[i + 1] - b[i]) for i in range(world)]
-        assert max(work) <= 1.15 * (sum(work) / world) + 5000 + 64
+        assert max(work) <= 1.15 * (sum(work) / world) + 128 * 5000
     # degenerate: fewer rows than ranks
     b = partition_rows(np.array([0, 3, 5]), 4)
     assert b[0] == 0 and b[-1] == 2 and all(b[i] <= b[i + 1] for i in range(4))

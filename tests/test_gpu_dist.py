@@ -11,11 +11,11 @@ from conftest import REPO
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("graph", ["1", "0"])
-def test_two_gpu_training_bit_identical(graph):
+@pytest.mark.parametrize("graph,closure", [("1", "auto"), ("0", "auto"), ("1", "1")])
+def test_two_gpu_training_bit_identical(graph, closure):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, IDG_GRAPH=graph)
+    env = dict(os.environ, IDG_GRAPH=graph, IDG_CLOSURE=closure)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29731", os.path.join(REPO, "tools", "dist_check.py"), "small", "4"],
                        capture_output=True, text=True, timeout=600, env=env)

@@ -174,8 +174,25 @@ def test_row_restricted_and_sparse_input_layers(dev):
     for _ in range(K):
         h = ref + torch.sparse.mm(A, h)
     _assert_close(sparse.cpu().numpy(), (h / (K + 1)).numpy())
+    # neighbourhood ("closure") restriction: layer K-1 only on batch rows + neighbours, second backward product over them
+    rows.enable_closure(G)
+    rows.build_closure(G)
+    import scipy.sparse as sp
+    Acsr = G.csr.to_scipy()
+    nb = np.zeros(U + I, bool)
+    nb[want] = True
+    nb[np.unique(Acsr[want].indices)] = True   # A_hat is symmetric: neighbours of the batch rows
+    cbits = rows.closure.cpu().numpy().view(np.uint32)
+    got_c = np.flatnonzero(np.unpackbits(cbits.view(np.uint8), bitorder="little"))
+    np.testing.assert_array_equal(got_c, np.flatnonzero(nb))
+    part2 = G.propagate_fwd(X0, K, True, rows=rows)
+    assert torch.equal(full[w], part2[w])
+    sparse2 = G.propagate_bwd(Gd, K, True, rows=rows)
+    _assert_close(sparse2.cpu().numpy(), dense.cpu().numpy(), rtol=1e-6)
+    from idgrec import _lib
+    _lib.check(_lib.lib().idg_graph_set_closure(G._h, None))
     rows.clear()
-    assert int(rows.bitmap.abs().sum().item()) == 0
+    assert int(rows.bitmap.abs().sum().item()) == 0 and int(rows.closure.abs().sum().item()) == 0
 
 
 # ---------------------------------------------------------------- a9: BPR + reg

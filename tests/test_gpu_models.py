@@ -56,7 +56,7 @@ def test_model_init_matches_reference_rng_order(dev, golden_dirs, golden_tiny):
     np.testing.assert_array_equal(m.item_embedding.weight.detach().numpy(), golden_tiny["lg_item_w0"])
 
 
-@pytest.mark.parametrize("path", ["autograd", "fused", "fused_graph", "fused_dense"])
+@pytest.mark.parametrize("path", ["autograd", "fused", "fused_graph", "fused_dense", "fused_closure"])
 def test_lightgcn_two_steps_vs_reference(dev, golden_dirs, golden_tiny, path):
     """Reference trainer loop (trainer.py:40-56) for two batches of 256: losses, gradients and the
     Adam-updated tables equal the unmodified reference's."""
@@ -65,7 +65,7 @@ def test_lightgcn_two_steps_vs_reference(dev, golden_dirs, golden_tiny, path):
     # "fused": Adam-fused epilogue, eager; "fused_graph": same, replayed from a CUDA graph; "fused_dense": no row
     # restriction and a separate Adam kernel (so the gradient table can be compared as well)
     cfg = _cfg("LightGCN", batch_size=256, cuda_graph=int(path == "fused_graph"), restrict_rows=int(path != "fused_dense"),
-               fuse_adam=int(path != "fused_dense"))
+               fuse_adam=int(path != "fused_dense"), closure_restrict=int(path == "fused_closure"))
     d = _data(golden_dirs, cfg)
     m = LightGCN(cfg, d, dev)
     _load_weights(m, g["lg_user_w0"], g["lg_item_w0"])

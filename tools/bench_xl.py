@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--eval-users", type=int, default=16384, help="test users ranked per rank")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--closure", default="auto", choices=["auto", "0", "1"])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -54,7 +55,8 @@ def main():
     gen.manual_seed(7)
     bound = (6.0 / (U + d)) ** 0.5
     table = (torch.rand(N, d, generator=gen, device=dev) * 2 - 1) * bound
-    ft = DistFusedTrainer("LightGCN", csr, table, U, K, 1e-4, 1e-3, rank, world, max_batch=B, use_cuda_graph=not args.no_graph)
+    ft = DistFusedTrainer("LightGCN", csr, table, U, K, 1e-4, 1e-3, rank, world, max_batch=B, use_cuda_graph=not args.no_graph,
+                           closure_restrict={"0": False, "1": True}.get(args.closure, "auto"))
     del table
     nb = args.steps + args.warmup
     sel = torch.randint(0, E, (nb, B), generator=gen, device=dev)
@@ -123,7 +125,7 @@ def main():
                           "layer_ms_local_rows": layer_ms, "layer_alg_GBs_per_gpu": alg / layer_ms / 1e6, "layer_gather_GBs_per_gpu": gat / layer_ms / 1e6,
                           "layer_gather_frac_of_hbm": gat / layer_ms / 1e6 / hbm, "hbm_peak_GBs": hbm,
                           "eval_users_per_s_total": nu * world / eval_ms * 1e3, "eval_ms": eval_ms, "eval_users_per_rank": nu,
-                          "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": not args.no_graph, "breakdown_ms": breakdown, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}))
+                          "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": not args.no_graph, "breakdown_ms": breakdown, "closure_restrict": ft.use_closure, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}))
     if world > 1:
         dist.destroy_process_group()
 

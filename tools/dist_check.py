@@ -27,7 +27,8 @@ def main():
     shape = sys.argv[1] if len(sys.argv) > 1 else "small"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     cfg = {"embedding_size": "64", "batch_size": "1024", "test_batch_size": "1024", "learn_rate": "0.001", "reg_lambda": "0.0001",
-           "GCN_layer": "3", "top_K": "[10, 20]", "sparsity_test": "0", "dataset": "synthetic", "cuda_graph": os.environ.get("IDG_GRAPH", "1")}
+           "GCN_layer": "3", "top_K": "[10, 20]", "sparsity_test": "0", "dataset": "synthetic", "cuda_graph": os.environ.get("IDG_GRAPH", "1"),
+           "closure_restrict": os.environ.get("IDG_CLOSURE", "auto")}
     g = datagen.gen_graph(shape)
     data = Data.from_arrays(g.num_users, g.num_items, g.train_user, g.train_item, g.test_user, g.test_item, cfg)
     tools.set_seed(2024)
@@ -69,7 +70,7 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("recall@20", res["recall"][1], "ndcg@20", res["ndcg"][1], "bounds", ft.bounds, "slab", ft.slab.backend, "multicast", ft.slab.multicast)
+        print("closure", ft.use_closure, "recall@20", res["recall"][1], "ndcg@20", res["ndcg"][1], "bounds", ft.bounds, "slab", ft.slab.backend, "multicast", ft.slab.multicast)
         print("DIST_CHECK", "PASS" if int(flag.item()) == 1 else "FAIL")
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
