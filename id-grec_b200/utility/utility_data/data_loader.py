@@ -30,7 +30,7 @@ class Data(object):
             self.split_test_dict = None
             self.split_state = None
             if "sparsity_test" in config.keys() and int(config["sparsity_test"]) == 1:
-                raise NotImplementedError("sparsity_test = 1 is outside the accelerated hot path (SURVEY.md section 8 f)")
+                self.split_test_dict, self.split_state = self.create_sparsity_split()
 
     # -- construction ------------------------------------------------------------------------
     @classmethod
@@ -48,6 +48,8 @@ class Data(object):
         self.pos_length = None
         self.split_test_dict = self.split_state = None
         self._finish()
+        if config and int(config.get("sparsity_test", 0)) == 1:
+            self.split_test_dict, self.split_state = self.create_sparsity_split()
         return self
 
     def load_data(self):
@@ -155,6 +157,41 @@ class Data(object):
         for u, (_, items) in sorted(first_seen.items(), key=lambda kv: kv[1][0]):
             test_data[u] = items
         return test_data
+
+    def create_sparsity_split(self):
+        """data_loader.py:161-204: test users bucketed by activity (train + test interactions), cut
+        every time a bucket sequence accumulates a quarter of all interactions (the reference never
+        advances its ``count``, so the threshold stays at 25 %), remainder appended at the end (an
+        EMPTY remainder is appended too when the last activity level itself closes a group -- kept,
+        see batch_test.sparsity_test).  Users inside a group keep test_dict order within each level."""
+        users = np.fromiter(self.test_dict.keys(), dtype=np.int64, count=len(self.test_dict))
+        ip = self.user_item_net.indptr
+        n_test = np.fromiter((len(v) for v in self.test_dict.values()), dtype=np.int64, count=len(users))
+        activity = (ip[users + 1] - ip[users]).astype(np.int64) + n_test
+        order = np.argsort(activity, kind="stable")          # level ascending, test_dict order inside a level
+        levels, first = np.unique(activity[order], return_index=True)
+        bounds = np.append(first, len(order))
+        total = self.num_train + self.num_test
+        split_uids, split_state = [], []
+        temp, n_rates, n_count = [], 0, total
+
+        def close(level):
+            split_uids.append(temp)
+            state = '\t #inter per user<=[%d], #users=[%d], #all rates=[%d]' % (level, len(temp), n_rates)
+            split_state.append(state)
+            print(state)
+
+        for idx, level in enumerate(levels.tolist()):
+            members = users[order[bounds[idx]:bounds[idx + 1]]].tolist()
+            temp = temp + members
+            n_rates += level * len(members)
+            n_count -= level * len(members)
+            if n_rates >= 0.25 * total:
+                close(level)
+                temp, n_rates = [], 0
+            if idx == len(levels) - 1 or n_count == 0:
+                close(level)
+        return split_uids, split_state
 
     # -- device-side copies for the CUDA evaluator ------------------------------------------
     def device_cache(self, device):
