@@ -1,0 +1,440 @@
+// Batch x batch losses of the LightGCN-backbone models (SURVEY.md section 8 f, rank 4), forward + backward.
+//
+// Every one of these reference losses gathers the batch rows of the propagated tables, L2-normalises them
+// (F.normalize, eps 1e-12) and reduces an element-wise function of one or two n x n similarity matrices:
+//   kind 0  LightCCF  neighbourhood-aggregation loss         models/LightCCF.py:81-94
+//   kind 1  LightCSCF margin variant of the same             models/LightCSCF.py:93-104
+//   kind 2  SCCF  "down" term  log mean(psi(S) * counts)      models/SCCF.py:72-79
+//   kind 3  SCCF  "up"   term  -mean log psi(<a_i,b_i>)       models/SCCF.py:64-70
+//   kind 4  DirectAU alignment  mean |a_i - b_i|^2            utility_function/losses.py:61-64
+//   kind 5  DirectAU uniformity log mean_{i<j} exp(-2 d_ij^2) utility_function/losses.py:67-69
+// a_i = X_i/|X_i|, b_j = Y_j/|Y_j|, S = a b^T, R = a a^T.  With per-row statistics T_i the gradients all have the form
+//   dL/dS = H + diag(w),  dL/dR = H   =>   dL/da = H b + (H + H^T) a + w*b,   dL/db = H^T a + w*a
+// so the path is: row normalise -> fp32 GEMMs (S, R) -> one row kernel that turns S into H in place (deterministic
+// block reductions, fixed order) -> three GEMMs against the [n,d] operands -> normalisation backward.
+// n is a mini-batch (<= 4096): the n x n fp32 matrices (<= 64 MB) stay in L2; nothing here touches the [N,d] tables.
+// Duplicate ids in the batch are handled by idg_gather_rows / idg_scatter_add_rows (first occurrence sums all of its
+// duplicates in entry order: no float atomics, bit-reproducible).
+#include <math.h>
+
+#include "idg_common.cuh"
+
+namespace idg {
+
+// ------------------------------------------------------------------------------------------------------------
+// C[M,N] = alpha * op(A) op(B) + beta * C,  row-major, fp32 FMA, k ascending (fixed summation order)
+//   op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k];   op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n]
+// ------------------------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) pl_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                       float* __restrict__ C, int ldc, float alpha, float beta) {
+    __shared__ float As[16][68];
+    __shared__ float Bs[16][68];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 256;
+            {
+                const int mm = TA ? (e & 63) : (e >> 4), kk = TA ? (e >> 6) : (e & 15);
+                const int m = m0 + mm, k = k0 + kk;
+                float v = 0.f;
+                if (m < M && k < K) v = TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+                As[kk][mm] = v;
+            }
+            {
+                const int nn = TB ? (e >> 4) : (e & 63), kk = TB ? (e & 15) : (e >> 6);
+                const int n = n0 + nn, k = k0 + kk;
+                float v = 0.f;
+                if (n < N && k < K) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+                Bs[kk][nn] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) av[a] = As[kk][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int m = m0 + ty * 4 + a;
+        if (m >= M) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int n = n0 + tx * 4 + b;
+            if (n >= N) continue;
+            float* c = C + (size_t)m * ldc + n;
+            *c = (beta != 0.f) ? fmaf(alpha, acc[a][b], beta * *c) : alpha * acc[a][b];
+        }
+    }
+}
+
+static int pl_sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float alpha,
+                    float beta, cudaStream_t st) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    if (!ta && !tb) pl_sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else if (!ta && tb) pl_sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else if (ta && !tb) pl_sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else pl_sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    IDG_LAUNCH_CHECK("pl_sgemm_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// sum over a 256-thread block in a fixed order; every thread gets the result
+__device__ __forceinline__ float block_sum256(float v, float* sm) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    return t;
+}
+
+// F.normalize(x, dim=-1): x / max(|x|, 1e-12); one warp per row
+__global__ void __launch_bounds__(256) pl_rownorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ Xn, float* __restrict__ nrm) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* x = X + (size_t)i * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s = fmaf(x[c], x[c], s);
+    s = warp_sum(s);
+    const float nr = fmaxf(sqrtf(s), 1e-12f);
+    for (int c = lane; c < d; c += 32) Xn[(size_t)i * d + c] = x[c] / nr;
+    if (lane == 0) nrm[i] = nr;
+}
+
+__global__ void pl_diag_kernel(const float* __restrict__ R, int n, float* __restrict__ diag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) diag[i] = R[(size_t)i * n + i];
+}
+
+struct PhiVal { float f, df; };
+// kinds 0/1: phi(t) = exp(t/tau) [+ exp(relu(t - m)/tau)]
+__device__ __forceinline__ PhiVal phi_ccf(float t, float tau, float margin, int use_margin) {
+    const float e = expf(t / tau);
+    PhiVal r{e, e / tau};
+    if (use_margin) {
+        const float z = t - margin;
+        const float e2 = expf(fmaxf(z, 0.f) / tau);
+        r.f += e2;
+        if (z > 0.f) r.df += e2 / tau;
+    }
+    return r;
+}
+// kinds 2/3: psi(s) = exp(s/tau) + exp(s^2/tau)
+__device__ __forceinline__ PhiVal psi_sccf(float s, float tau) {
+    const float e1 = expf(s / tau), e2 = expf(s * s / tau);
+    return PhiVal{e1 + e2, e1 / tau + 2.f * s * e2 / tau};
+}
+
+// kinds 0/1, one CTA per row i:  T_i, loss_i, w_i and S[i,:] <- H[i,:]
+__global__ void __launch_bounds__(256) pl_rows_ccf_kernel(float* __restrict__ S, const float* __restrict__ R, int n, float tau, float margin, int use_margin,
+                                                         float* __restrict__ w, float* __restrict__ lossi) {
+    __shared__ float sm[8];
+    const int i = blockIdx.x;
+    float* s = S + (size_t)i * n;
+    const float* r = R + (size_t)i * n;
+    const float sii = s[i];
+    float part = 0.f;
+    for (int j = threadIdx.x; j < n; j += 256) part += phi_ccf(s[j] + r[j], tau, margin, use_margin).f;
+    const float T = block_sum256(part, sm);
+    const PhiVal pp = phi_ccf(sii, tau, margin, use_margin);
+    const float ratio = pp.f / T;
+    const float q = -1.f / ((float)n * (ratio + 1e-5f));          // 10e-6 == 1e-5
+    const float hcoef = -q * ratio / T;
+    __syncthreads();                                               // every thread holds sii before the row is overwritten
+    for (int j = threadIdx.x; j < n; j += 256) s[j] = hcoef * phi_ccf(s[j] + r[j], tau, margin, use_margin).df;
+    if (threadIdx.x == 0) {
+        w[i] = q * pp.df / T;
+        lossi[i] = -logf(ratio + 1e-5f);
+    }
+}
+
+// kind 2 pass 1: rowT_i = sum_j psi(S_ij)
+__global__ void __launch_bounds__(256) pl_rows_sccf_sum_kernel(const float* __restrict__ S, int n, int m, float tau, float* __restrict__ rowT) {
+    __shared__ float sm[8];
+    const int i = blockIdx.x;
+    const float* s = S + (size_t)i * m;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < m; j += 256) part += psi_sccf(s[j], tau).f;
+    const float T = block_sum256(part, sm);
+    if (threadIdx.x == 0) rowT[i] = T;
+}
+// kind 2 pass 2: S_ij <- psi'(S_ij) / total
+__global__ void __launch_bounds__(256) pl_rows_sccf_grad_kernel(float* __restrict__ S, int64_t total_elems, float tau, const float* __restrict__ scal) {
+    const float inv = 1.f / scal[0];
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total_elems; e += (int64_t)gridDim.x * 256) S[e] = psi_sccf(S[e], tau).df * inv;
+}
+
+// kind 5: R[i,:] <- E[i,:] = exp(-2 d_ij^2) (0 on the diagonal), rowT_i = sum_j E_ij
+__global__ void __launch_bounds__(256) pl_rows_uniform_kernel(float* __restrict__ R, const float* __restrict__ diag, int n, float* __restrict__ rowT) {
+    __shared__ float sm[8];
+    const int i = blockIdx.x;
+    float* r = R + (size_t)i * n;
+    const float dii = diag[i];
+    float part = 0.f;
+    for (int j = threadIdx.x; j < n; j += 256) {
+        const float d2 = fmaxf(dii + diag[j] - 2.f * r[j], 0.f);
+        const float e = (j == i) ? 0.f : expf(-2.f * d2);
+        r[j] = e;
+        part += e;
+    }
+    const float T = block_sum256(part, sm);
+    if (threadIdx.x == 0) rowT[i] = T;
+}
+
+// kinds 3/4 (element-wise over matching rows), one warp per row
+__global__ void __launch_bounds__(256) pl_rows_pairwise_kernel(int kind, const float* __restrict__ Xn, const float* __restrict__ Yn, int n, int d, float tau,
+                                                              float* __restrict__ w, float* __restrict__ lossi) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* a = Xn + (size_t)i * d;
+    const float* b = Yn + (size_t)i * d;
+    float s = 0.f;
+    if (kind == 3) {
+        for (int c = lane; c < d; c += 32) s = fmaf(a[c], b[c], s);
+        s = warp_sum(s);
+        const PhiVal p = psi_sccf(s, tau);
+        if (lane == 0) { lossi[i] = logf(p.f); w[i] = -(p.df / p.f) / (float)n; }
+    } else {
+        for (int c = lane; c < d; c += 32) { const float t = a[c] - b[c]; s = fmaf(t, t, s); }
+        s = warp_sum(s);
+        if (lane == 0) { lossi[i] = s; w[i] = 0.f; }
+    }
+}
+
+// ordered sum of v[0..n) (single CTA) and the scalar epilogue of each kind
+__global__ void __launch_bounds__(1024) pl_reduce_kernel(int kind, const float* __restrict__ v, int n, float denom, float* __restrict__ scal, float* __restrict__ d_loss) {
+    __shared__ float sm[32];
+    float part = 0.f;
+    for (int j = threadIdx.x; j < n; j += 1024) part += v[j];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int q = 0; q < 32; ++q) t += sm[q];
+        scal[0] = t;
+        float out;
+        if (kind == 0 || kind == 1 || kind == 4) out = t / (float)n;
+        else if (kind == 3) out = -t / (float)n;
+        else out = logf(t / denom);       // kind 2: denom = n_unique_users * n_unique_items; kind 5: n (n - 1)
+        *d_loss = out;
+    }
+}
+
+// gradients w.r.t. the normalised rows assembled per kind, then F.normalize backward; one warp per row
+__global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Xn,
+                                                       const float* __restrict__ Yn, const float* __restrict__ nx, const float* __restrict__ ny,
+                                                       const float* __restrict__ w, const float* __restrict__ rowT, const float* __restrict__ scal,
+                                                       const float* __restrict__ tA, const float* __restrict__ tB, int n, int d,
+                                                       float* __restrict__ gX, float* __restrict__ gY) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const size_t o = (size_t)i * d;
+    const float wi = w ? w[i] : 0.f;
+    const float cu = (kind == 5) ? -8.f / scal[0] : 0.f;
+    const float ri = (kind == 5) ? rowT[i] : 0.f;
+    float da = 0.f, db = 0.f;
+    // pass 1: <a, ga>, <b, gb>
+    for (int c = lane; c < d; c += 32) {
+        const float a = Xn[o + c], b = Yn ? Yn[o + c] : 0.f;
+        float ga, gb = 0.f;
+        if (kind <= 1) { ga = tA[o + c] + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
+        else if (kind == 2) { ga = tA[o + c]; gb = tB[o + c]; }
+        else if (kind == 3) { ga = wi * b; gb = wi * a; }
+        else if (kind == 4) { ga = 2.f * (a - b) / (float)n; gb = -ga; }
+        else { ga = cu * (ri * a - tA[o + c]); }
+        da = fmaf(a, ga, da);
+        db = fmaf(b, gb, db);
+    }
+    da = warp_sum(da);
+    db = warp_sum(db);
+    const float na = nx[i], nb = ny ? ny[i] : 1.f;
+    for (int c = lane; c < d; c += 32) {
+        const float a = Xn[o + c], b = Yn ? Yn[o + c] : 0.f;
+        float ga, gb = 0.f;
+        if (kind <= 1) { ga = tA[o + c] + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
+        else if (kind == 2) { ga = tA[o + c]; gb = tB[o + c]; }
+        else if (kind == 3) { ga = wi * b; gb = wi * a; }
+        else if (kind == 4) { ga = 2.f * (a - b) / (float)n; gb = -ga; }
+        else { ga = cu * (ri * a - tA[o + c]); }
+        // d/dx of x / max(|x|, eps): (g - a <a,g>) / |x| above the clamp, g / eps below it
+        gX[o + c] = (na > 1e-12f) ? (ga - a * da) / na : ga / 1e-12f;
+        if (gY) gY[o + c] = (nb > 1e-12f) ? (gb - b * db) / nb : gb / 1e-12f;
+    }
+    (void)X; (void)Y;
+}
+
+// rows of a table into a dense [n,d] block / deterministic scatter-add of a dense block back into table rows
+__global__ void __launch_bounds__(256) pl_gather_kernel(const float* __restrict__ T, const int64_t* __restrict__ idx, int n, int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const float* src = T + (size_t)idx[i] * d;
+    for (int c = lane; c < d; c += 32) out[(size_t)i * d + c] = src[c];
+}
+
+__global__ void __launch_bounds__(256) pl_scatter_add_kernel(const float* __restrict__ G, const int64_t* __restrict__ idx, int n, int d, float* __restrict__ T) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int64_t me = idx[i];
+    // an earlier entry with the same id owns the row
+    for (int j0 = 0; j0 < i; j0 += 32) {
+        const int j = j0 + lane;
+        const bool hit = (j < i) && (idx[j] == me);
+        if (__ballot_sync(0xffffffffu, hit)) return;
+    }
+    float* dst = T + (size_t)me * d;
+    for (int c0 = 0; c0 < d; c0 += 32) {
+        const int c = c0 + lane;
+        float acc = 0.f;
+        for (int j0 = i; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, (j < n) && (idx[j] == me));
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if (c < d) acc += G[(size_t)(j0 + b) * d + c];
+            }
+        }
+        if (c < d) dst[c] += acc;
+    }
+}
+
+struct PlWs {
+    float *Xn, *Yn, *nx, *ny, *S, *R, *w, *rowT, *lossi, *diag, *tA, *tB, *scal;
+};
+__host__ inline size_t pl_align(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ inline size_t pl_carve(void* ws, int n, int d, PlWs* w) {
+    char* p = (char*)ws;
+    auto take = [&](size_t bytes) { char* q = p; p += pl_align(bytes); return (float*)q; };
+    const size_t nd = sizeof(float) * (size_t)n * d, nn = sizeof(float) * (size_t)n * n, n1 = sizeof(float) * (size_t)n;
+    PlWs t;
+    t.Xn = take(nd); t.Yn = take(nd); t.tA = take(nd); t.tB = take(nd);
+    t.nx = take(n1); t.ny = take(n1); t.w = take(n1); t.rowT = take(n1); t.lossi = take(n1); t.diag = take(n1);
+    t.scal = take(256);
+    t.S = take(nn); t.R = take(nn);
+    if (w) *w = t;
+    return (size_t)(p - (char*)ws);
+}
+
+}  // namespace idg
+
+using namespace idg;
+
+extern "C" int64_t idg_pair_loss_workspace_bytes(int32_t n, int32_t d) {
+    if (n <= 0 || d <= 0) return 0;
+    return (int64_t)pl_carve(nullptr, n, d, nullptr) + 256;
+}
+
+extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float* d_loss,
+                             float* d_gX, float* d_gY, void* d_ws, void* stream_) {
+    if (kind < 0 || kind > 5) return fail(-1, "idg_pair_loss: kind must be 0..5%s");
+    if (!d_X || !d_loss || !d_ws || n <= 0 || d <= 0 || n > 8192) return fail(-1, "idg_pair_loss: bad argument (n in 1..8192)%s");
+    if (kind != 5 && !d_Y) return fail(-1, "idg_pair_loss: kind %s needs both operands", "0..4");
+    if (kind == 5 && n < 2) return fail(-1, "idg_pair_loss: uniformity needs n >= 2%s");
+    if (kind <= 3 && !(p0 > 0.f)) return fail(-1, "idg_pair_loss: temperature must be > 0%s");
+    if (kind == 2 && !(p1 > 0.f)) return fail(-1, "idg_pair_loss: SCCF down term needs p1 = n_unique_users * n_unique_items > 0%s");
+    cudaStream_t st = (cudaStream_t)stream_;
+    PlWs w;
+    pl_carve((void*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255), n, d, &w);
+    const bool want_grad = d_gX != nullptr;
+    const int rb = (n + 7) / 8;
+    pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_X, n, d, w.Xn, w.nx);
+    IDG_LAUNCH_CHECK("pl_rownorm_kernel");
+    if (kind != 5) {
+        pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_Y, n, d, w.Yn, w.ny);
+        IDG_LAUNCH_CHECK("pl_rownorm_kernel");
+    }
+    int rc;
+    if (kind <= 1) {
+        if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Yn, d, w.S, n, 1.f, 0.f, st))) return rc;
+        if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Xn, d, w.R, n, 1.f, 0.f, st))) return rc;
+        pl_rows_ccf_kernel<<<n, 256, 0, st>>>(w.S, w.R, n, p0, p1, kind == 1, w.w, w.lossi);
+        IDG_LAUNCH_CHECK("pl_rows_ccf_kernel");
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+        IDG_LAUNCH_CHECK("pl_reduce_kernel");
+        if (want_grad) {
+            // tA = H b + H a,  tB = H^T a
+            if ((rc = pl_sgemm(false, false, n, d, n, w.S, n, w.Yn, d, w.tA, d, 1.f, 0.f, st))) return rc;
+            if ((rc = pl_sgemm(false, false, n, d, n, w.S, n, w.Xn, d, w.tA, d, 1.f, 1.f, st))) return rc;
+            if ((rc = pl_sgemm(true, false, n, d, n, w.S, n, w.Xn, d, w.tB, d, 1.f, 0.f, st))) return rc;
+        }
+    } else if (kind == 2) {
+        if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Yn, d, w.S, n, 1.f, 0.f, st))) return rc;
+        pl_rows_sccf_sum_kernel<<<n, 256, 0, st>>>(w.S, n, n, p0, w.rowT);
+        IDG_LAUNCH_CHECK("pl_rows_sccf_sum_kernel");
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss);
+        IDG_LAUNCH_CHECK("pl_reduce_kernel");
+        if (want_grad) {
+            pl_rows_sccf_grad_kernel<<<kNumSMs * 4, 256, 0, st>>>(w.S, (int64_t)n * n, p0, w.scal);
+            IDG_LAUNCH_CHECK("pl_rows_sccf_grad_kernel");
+            if ((rc = pl_sgemm(false, false, n, d, n, w.S, n, w.Yn, d, w.tA, d, 1.f, 0.f, st))) return rc;
+            if ((rc = pl_sgemm(true, false, n, d, n, w.S, n, w.Xn, d, w.tB, d, 1.f, 0.f, st))) return rc;
+        }
+    } else if (kind == 3 || kind == 4) {
+        pl_rows_pairwise_kernel<<<rb, 256, 0, st>>>(kind, w.Xn, w.Yn, n, d, p0, w.w, w.lossi);
+        IDG_LAUNCH_CHECK("pl_rows_pairwise_kernel");
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+        IDG_LAUNCH_CHECK("pl_reduce_kernel");
+    } else {
+        if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Xn, d, w.R, n, 1.f, 0.f, st))) return rc;
+        pl_diag_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.R, n, w.diag);
+        IDG_LAUNCH_CHECK("pl_diag_kernel");
+        pl_rows_uniform_kernel<<<n, 256, 0, st>>>(w.R, w.diag, n, w.rowT);
+        IDG_LAUNCH_CHECK("pl_rows_uniform_kernel");
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss);
+        IDG_LAUNCH_CHECK("pl_reduce_kernel");
+        if (want_grad) {
+            if ((rc = pl_sgemm(false, false, n, d, n, w.R, n, w.Xn, d, w.tA, d, 1.f, 0.f, st))) return rc;
+        }
+    }
+    if (want_grad) {
+        if (kind != 5 && !d_gY) return fail(-1, "idg_pair_loss: d_gY is required with d_gX for kind %s", "0..4");
+        pl_finish_kernel<<<rb, 256, 0, st>>>(kind, d_X, d_Y, w.Xn, kind == 5 ? nullptr : w.Yn, w.nx, kind == 5 ? nullptr : w.ny,
+                                            (kind <= 1 || kind == 3) ? w.w : nullptr, w.rowT, w.scal, w.tA, w.tB, n, d, d_gX, kind == 5 ? nullptr : d_gY);
+        IDG_LAUNCH_CHECK("pl_finish_kernel");
+    }
+    return 0;
+}
+
+extern "C" int idg_gather_rows(const float* d_T, const int64_t* d_idx, int32_t n, int32_t d, float* d_out, void* stream) {
+    if (!d_T || !d_idx || !d_out || n <= 0 || d <= 0) return fail(-1, "idg_gather_rows: bad argument%s");
+    pl_gather_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_T, d_idx, n, d, d_out);
+    IDG_LAUNCH_CHECK("pl_gather_kernel");
+    return 0;
+}
+
+extern "C" int idg_scatter_add_rows(const float* d_G, const int64_t* d_idx, int32_t n, int32_t d, float* d_T, void* stream) {
+    if (!d_G || !d_idx || !d_T || n <= 0 || d <= 0) return fail(-1, "idg_scatter_add_rows: bad argument%s");
+    pl_scatter_add_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_G, d_idx, n, d, d_T);
+    IDG_LAUNCH_CHECK("pl_scatter_add_kernel");
+    return 0;
+}

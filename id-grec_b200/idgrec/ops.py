@@ -168,6 +168,71 @@ def infonce_rows(V1, V2, idx, temperature):
     return InfoNCEFn.apply(V1, V2, idx, temperature)
 
 
+class GatherRowsFn(torch.autograd.Function):
+    """``table[idx]`` (e.g. all_user_embeddings[user.long()], models/LightCCF.py:66) as a dense [n,d] block; the
+    backward scatters with duplicates summed in entry order by their first occurrence (no float atomics)."""
+
+    @staticmethod
+    def forward(ctx, T, idx):
+        T = _f32c(T)
+        idx = idx.long().contiguous()
+        n, d = int(idx.numel()), T.shape[1]
+        out = torch.empty((n, d), dtype=torch.float32, device=T.device)
+        check(_lib.lib().idg_gather_rows(ptr(T), ptr(idx), n, d, ptr(out), cur_stream()), "idg_gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.shape = T.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = _f32c(g)
+        gT = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        check(_lib.lib().idg_scatter_add_rows(ptr(g), ptr(idx), int(idx.numel()), g.shape[1], ptr(gT), cur_stream()), "idg_scatter_add_rows")
+        return gT, None
+
+
+def gather_rows(T, idx):
+    return GatherRowsFn.apply(T, idx)
+
+
+PAIR_KINDS = {"lightccf": 0, "lightcscf": 1, "sccf_down": 2, "sccf_up": 3, "align": 4, "uniform": 5}
+
+
+class PairLossFn(torch.autograd.Function):
+    """One batch x batch loss of the LightGCN-backbone models (idg_pair_loss; include/idgrec.h) on dense [n,d]
+    blocks: forward and both gradients come out of one call, the backward only scales them."""
+
+    @staticmethod
+    def forward(ctx, X, Y, kind, p0, p1):
+        l = _lib.lib()
+        X = _f32c(X)
+        Y = _f32c(Y) if Y is not None else None
+        n, d = X.shape
+        ws = torch.empty(int(l.idg_pair_loss_workspace_bytes(n, d)), dtype=torch.uint8, device=X.device)
+        loss = torch.empty(1, dtype=torch.float32, device=X.device)
+        need = X.requires_grad or (Y is not None and Y.requires_grad)
+        gX = torch.empty_like(X) if need else None
+        gY = torch.empty_like(Y) if (need and Y is not None) else None
+        check(l.idg_pair_loss(int(kind), ptr(X), ptr(Y), n, d, float(p0), float(p1), ptr(loss), ptr(gX), ptr(gY), ptr(ws), cur_stream()),
+              "idg_pair_loss")
+        ctx.has_y = Y is not None
+        ctx.save_for_backward(*[t for t in (gX, gY) if t is not None])
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        saved = ctx.saved_tensors
+        gX = saved[0] * gl
+        gY = saved[1] * gl if (ctx.has_y and len(saved) > 1) else None
+        return gX, gY, None, None, None
+
+
+def pair_loss(kind, X, Y=None, p0=0.0, p1=0.0):
+    """kind: one of PAIR_KINDS.  X, Y: [n,d] (un-normalised) rows; returns a scalar tensor."""
+    return PairLossFn.apply(X, Y, PAIR_KINDS[kind], p0, p1)
+
+
 # ---------------------------------------------------------------------------------------
 # evaluation
 # ---------------------------------------------------------------------------------------
@@ -230,3 +295,18 @@ def neg_sample_replay(train_user, pos_indptr, pos_indices, cand):
         return None, int(used.value)
     check(rc, "idg_neg_sample_replay")
     return neg, int(used.value)
+
+
+def parse_ratings(path):
+    """data_loader.py:48-70 on the host in one pass (idg_parse_ratings): (line_user, line_len, users, items,
+    max_user, max_item); users/items in file order, one entry per interaction."""
+    l = _lib.lib()
+    n_pairs, n_lines, mu, mi = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    bp = str(path).encode()
+    check(l.idg_parse_ratings(bp, None, None, 0, C.byref(n_pairs), None, None, 0, C.byref(n_lines), C.byref(mu), C.byref(mi)), "idg_parse_ratings")
+    users, items = np.empty(n_pairs.value, dtype=np.int64), np.empty(n_pairs.value, dtype=np.int64)
+    line_user, line_len = np.empty(n_lines.value, dtype=np.int64), np.empty(n_lines.value, dtype=np.int64)
+    if n_pairs.value or n_lines.value:
+        check(l.idg_parse_ratings(bp, users.ctypes.data, items.ctypes.data, max(len(users), 1), C.byref(n_pairs), line_user.ctypes.data,
+                                  line_len.ctypes.data, max(len(line_user), 1), C.byref(n_lines), C.byref(mu), C.byref(mi)), "idg_parse_ratings")
+    return line_user, line_len, users, items, int(mu.value), int(mi.value)

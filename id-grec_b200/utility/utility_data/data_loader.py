@@ -74,28 +74,14 @@ class Data(object):
         self.test_dict = self.build_test()
 
     def read_ratings(self, file_name):
-        """data_loader.py:48-70: ``user item item ...`` per line; max ids tracked over both files."""
-        unique_users, pos_length, chunks_u, chunks_i = [], [], [], []
-        with open(file_name, "r") as f:
-            for line in f:
-                tok = line.split()
-                if not tok:
-                    if line == "":
-                        break
-                    continue
-                arr = np.array(tok, dtype=np.int64)
-                user_id, pos_id = int(arr[0]), arr[1:]
-                unique_users.append(user_id)
-                if len(pos_id) < 1:
-                    continue
-                self.num_users = max(self.num_users, user_id)
-                self.num_items = max(self.num_items, int(pos_id.max()))
-                chunks_u.append(np.full(len(pos_id), user_id, dtype=np.int64))
-                chunks_i.append(pos_id)
-                pos_length.append(len(pos_id))
-        users = np.concatenate(chunks_u) if chunks_u else np.zeros(0, np.int64)
-        items = np.concatenate(chunks_i) if chunks_i else np.zeros(0, np.int64)
-        return np.array(unique_users), users, items, len(items), pos_length
+        """data_loader.py:48-70: ``user item item ...`` per line; max ids tracked over both files.  One pass over
+        the file image by the C entry point idg_parse_ratings instead of a Python loop over the lines."""
+        from idgrec import ops
+        line_user, line_len, users, items, max_user, max_item = ops.parse_ratings(file_name)
+        if len(items):
+            self.num_users = max(self.num_users, max_user)
+            self.num_items = max(self.num_items, max_item)
+        return line_user, users, items, len(items), line_len[line_len > 0].tolist()
 
     def data_statistics(self):
         print("\t num_users:", self.num_users)

@@ -300,6 +300,38 @@ int idg_neg_sample_replay(const int64_t* h_train_user, int64_t E, const int32_t*
                           const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand,
                           int64_t* h_neg, int64_t* h_consumed);
 
+/* ---- a1: data_loader.py:48-70, the dataset text format ("user item item ..." per line) parsed on the HOST in one
+ * pass.  Two-call protocol: pair_cap = line_cap = 0 counts (*n_pairs, *n_lines); the second call fills
+ * h_user/h_item [n_pairs] (file order = inter_users/inter_items), h_line_user/h_line_len [n_lines] (unique_users and
+ * the per-line item counts, 0 for a user with an empty line).  *max_user/*max_item follow data_loader.py:62-63
+ * (lines with at least one item only; -1 when there is none).  -3: cannot open, -4: not an integer token. */
+int idg_parse_ratings(const char* path, int64_t* h_user, int64_t* h_item, int64_t pair_cap, int64_t* n_pairs,
+                      int64_t* h_line_user, int64_t* h_line_len, int64_t line_cap, int64_t* n_lines,
+                      int64_t* max_user, int64_t* max_item);
+
+/* ---- section 8 f (rank 4): batch x batch losses of the LightGCN-backbone models, forward + backward ----------
+ * X, Y: dense [n,d] blocks (batch rows of the propagated tables, see idg_gather_rows); both are L2-normalised inside
+ * (F.normalize, eps 1e-12) and the gradients are returned w.r.t. the UN-normalised X / Y for an upstream gradient of 1.
+ *   kind 0  LightCCF neighbourhood-aggregation loss (models/LightCCF.py:81-94)            p0 = temperature
+ *   kind 1  LightCSCF margin loss (models/LightCSCF.py:93-104)                            p0 = temperature, p1 = margin
+ *   kind 2  SCCF "down" = log(sum_ij psi(S_ij) / p1) over ALL batch pairs (models/SCCF.py:72-79; summing over batch
+ *           pairs equals the reference's count-weighted sum over unique users x unique items)  p0 = temperature,
+ *           p1 = n_unique_users * n_unique_items
+ *   kind 3  SCCF "-up" = -mean_i log psi(<a_i,b_i>) (models/SCCF.py:64-70)                 p0 = temperature
+ *   kind 4  DirectAU alignment  mean_i |a_i - b_i|^2 (utility_function/losses.py:61-64)
+ *   kind 5  DirectAU uniformity log mean_{i<j} exp(-2 |a_i - a_j|^2) (losses.py:67-69); Y, gY unused (may be NULL)
+ * d_loss: one float.  d_gX/d_gY [n,d] may both be NULL (forward only).  n <= 8192.  Deterministic (fixed-order
+ * reductions, no float atomics).  Workspace: idg_pair_loss_workspace_bytes(n, d) (two n x n fp32 matrices). */
+int64_t idg_pair_loss_workspace_bytes(int32_t n, int32_t d);
+int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1,
+                  float* d_loss, float* d_gX, float* d_gY, void* d_ws, void* stream);
+
+/* out[i,:] = T[idx[i],:]  (all_user_embeddings[user.long()], models/LightCCF.py:66) and its backward:
+ * T[idx[i],:] += G[i,:] with duplicates summed in entry order by the first occurrence (index_put(accumulate) without
+ * float atomics; bit-reproducible). */
+int idg_gather_rows(const float* d_T, const int64_t* d_idx, int32_t n, int32_t d, float* d_out, void* stream);
+int idg_scatter_add_rows(const float* d_G, const int64_t* d_idx, int32_t n, int32_t d, float* d_T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

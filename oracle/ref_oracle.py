@@ -492,6 +492,155 @@ def evaluate(Fu, Fi, data: OracleData, top_K: Sequence[int], test_batch_size: in
 
 
 # --------------------------------------------------------------------------
+# section 8 f rows: activity split, sparsity test, SGL sub-graphs, loss-only models
+# --------------------------------------------------------------------------
+
+
+def sparsity_split(data: OracleData):
+    """data_loader.py:161-204, statement by statement (``count`` is never advanced there, so every
+    group closes at 25 % of all interactions; the remainder -- possibly empty -- closes at the end)."""
+    by_level: Dict[int, List[int]] = {}
+    for uid in data.test_dict.keys():
+        by_level.setdefault(len(data.all_positive[uid]) + len(data.test_dict[uid]), []).append(uid)
+    total = data.num_train + data.num_test
+    groups, temp, n_rates, n_count = [], [], 0, total
+    levels = sorted(by_level)
+    for idx, level in enumerate(levels):
+        temp = temp + by_level[level]
+        n_rates += level * len(by_level[level])
+        n_count -= level * len(by_level[level])
+        if n_rates >= 0.25 * total:
+            groups.append(temp)
+            temp, n_rates = [], 0
+        if idx == len(levels) - 1 or n_count == 0:
+            groups.append(temp)
+    return groups
+
+
+def evaluate_groups(Fu, Fi, data: OracleData, groups, top_K: Sequence[int], mode: str = "exact"):
+    """batch_test.py:110-170: Test()'s metrics per activity group, each divided by the group size."""
+    indptr, indices = data.user_item_net.indptr, data.user_item_net.indices
+    fn = topk_exact if mode == "exact" else topk_reference_faithful
+    out = []
+    for users in groups:
+        ids, _ = fn(Fu, Fi, list(users), indptr, indices, max(top_K))
+        truth = [data.test_dict[u] for u in users]
+        r = hit_matrix(ids, truth)
+        tl = np.array([len(t) for t in truth], dtype=np.float64)
+        res = {k: np.zeros(len(top_K)) for k in ("precision", "recall", "hit", "ndcg")}
+        for j, k in enumerate(top_K):
+            rc, pr, nd = metric_sums(r, tl, k)
+            res["recall"][j], res["precision"][j], res["ndcg"][j] = rc / len(users), pr / len(users), nd / len(users)
+        out.append(res)
+    return out
+
+
+def subgraph_adjacency(user_item_net: sp.csr_matrix, keep_index: np.ndarray):
+    """tools.py:67-92 (``ed``/``rw``) for a given list of kept edges (the reference draws it with the
+    unseeded python ``random.sample``): float32 ones, A = G + G^T, d = rowsum^-1/2 (inf -> 0) in
+    float32, D A D.  Canonical CSR (indptr, indices, data fp32)."""
+    U, I = user_item_net.shape
+    N = U + I
+    ui, ii = user_item_net.nonzero()
+    ui, ii = np.array(ui)[keep_index], np.array(ii)[keep_index]
+    g = sp.csr_matrix((np.ones_like(ui, dtype=np.float32), (ui, ii + U)), shape=(N, N))
+    adj = g + g.T
+    with np.errstate(divide="ignore"):
+        d_inv = np.power(np.array(adj.sum(axis=1)), -0.5).flatten()
+    d_inv[np.isinf(d_inv)] = 0.0
+    dm = sp.diags(d_inv)
+    out = dm.dot(adj).dot(dm).tocsr()
+    out.sort_indices()
+    return out.indptr, out.indices, out.data
+
+
+def lightccf_na_loss(e1, e2, tau):
+    """models/LightCCF.py:81-94 (10e-6 == 1e-5)."""
+    e1, e2 = torch.nn.functional.normalize(e1), torch.nn.functional.normalize(e2)
+    pos = torch.exp((e1 * e2).sum(dim=-1) / tau)
+    ttl = torch.exp((torch.matmul(e1, e2.t()) + torch.matmul(e1, e1.t())) / tau).sum(dim=1)
+    return torch.mean(-torch.log(pos / ttl + 10e-6))
+
+
+def lightcscf_loss(e1, e2, tau, margin):
+    """models/LightCSCF.py:93-104."""
+    e1, e2 = torch.nn.functional.normalize(e1, dim=1), torch.nn.functional.normalize(e2, dim=1)
+    sim = (e1 * e2).sum(dim=-1)
+    pos = torch.exp(sim / tau) + torch.exp(torch.relu(sim - margin) / tau)
+    t = torch.matmul(e1, e2.t()) + torch.matmul(e1, e1.t())
+    ttl = (torch.exp(t / tau) + torch.exp(torch.relu(t - margin) / tau)).sum(dim=1)
+    return torch.mean(-torch.log(pos / ttl + 10e-6))
+
+
+def sccf_losses(fu, fi, user, pos, tau):
+    """models/SCCF.py:59-81 -> [-up, down]."""
+    u_idx, u_counts = torch.unique(user, return_counts=True)
+    i_idx, i_counts = torch.unique(pos, return_counts=True)
+    u_counts, i_counts = u_counts.reshape(-1, 1).float(), i_counts.reshape(-1, 1).float()
+    a, b = torch.nn.functional.normalize(fu[user], dim=-1), torch.nn.functional.normalize(fi[pos], dim=-1)
+    ip = (a * b).sum(dim=1)
+    up = ((ip / tau).exp() + (ip ** 2 / tau).exp()).log().mean()
+    a, b = torch.nn.functional.normalize(fu[u_idx], dim=-1), torch.nn.functional.normalize(fi[i_idx], dim=-1)
+    sim = a @ b.t()
+    score = (sim / tau).exp() + (sim ** 2 / tau).exp()
+    down = (score * (u_counts @ i_counts.t())).mean().log()
+    return [-up, down]
+
+
+def align_loss(e1, e2):
+    """losses.py:61-64."""
+    e1, e2 = torch.nn.functional.normalize(e1, dim=-1), torch.nn.functional.normalize(e2, dim=-1)
+    return torch.mean((e1 - e2).norm(p=2, dim=1).pow(2))
+
+
+def uniform_loss(e):
+    """losses.py:67-69."""
+    e = torch.nn.functional.normalize(e, dim=-1)
+    return torch.pdist(e, p=2).pow(2).mul(-2).exp().mean().log()
+
+
+def next_model_step(kind: str, A, user_w, item_w, user, pos, neg, cfg: dict, encoder: str = "LightGCN", sub_graphs=None, K: int = 3):
+    """forward + backward of LightCCF / LightCSCF / SCCF / DirectAU / SGL on one batch
+    (models/LightCCF.py:58-79, LightCSCF.py:58-91, SCCF.py:54-81, DirectAU.py:59-79, SGL.py:60-89)."""
+    uw = torch.nn.Parameter(torch.from_numpy(np.array(user_w, dtype=np.float32)))
+    iw = torch.nn.Parameter(torch.from_numpy(np.array(item_w, dtype=np.float32)))
+    U, I = uw.shape[0], iw.shape[0]
+    user, pos, neg = (torch.as_tensor(t, dtype=torch.long) for t in (user, pos, neg))
+
+    def agg(graph):
+        return torch.split(propagate(graph, torch.cat([uw, iw]), K, True), [U, I])
+
+    fu, fi = (uw, iw) if encoder == "MF" else agg(A)
+    ue, pe, ne = fu[user], fi[pos], fi[neg]
+    reg3 = reg_loss(uw[user], iw[pos], iw[neg])
+    if kind == "LightCCF":
+        losses = [bpr_loss(ue, pe, ne), float(cfg["reg_lambda"]) * reg3,
+                  float(cfg["ssl_lambda"]) * lightccf_na_loss(ue, pe, float(cfg["temperature"]))]
+    elif kind == "LightCSCF":
+        na = float(cfg["lambda_gamma"]) * lightcscf_loss(ue, pe, float(cfg["temperature"]), float(cfg["lambda_margin"]))
+        reg = float(cfg["lambda_reg"]) * reg3
+        losses = [bpr_loss(ue, pe, ne), reg, na] if encoder == "MF" else [reg, na]
+    elif kind == "SCCF":
+        losses = sccf_losses(fu, fi, user, pos, float(cfg["temperature"]))
+    elif kind == "DirectAU":
+        losses = [align_loss(ue, pe), float(cfg["gamma"]) * (uniform_loss(ue) + uniform_loss(pe)) / 2,
+                  float(cfg["reg_lambda"]) * reg_loss(uw[user], iw[pos])]
+    elif kind == "SGL":
+        u1, i1 = agg(sub_graphs[0])
+        u2, i2 = agg(sub_graphs[1])
+        tau = float(cfg["temperature"])
+        ssl = infonce_loss(u1[user], u2[user], tau) + infonce_loss(i1[pos], i2[pos], tau)
+        losses = [bpr_loss(ue, pe, ne), float(cfg["reg_lambda"]) * reg3, float(cfg["ssl_lambda"]) * ssl]
+    else:
+        raise ValueError(kind)
+    total = 0.0
+    for l in losses:
+        total = total + l
+    total.backward()
+    return StepResult([float(l.item()) for l in losses], uw.grad.numpy().copy(), iw.grad.numpy().copy())
+
+
+# --------------------------------------------------------------------------
 # timing helper for bench.py's cpu_baseline / --impl reference legs
 # --------------------------------------------------------------------------
 
