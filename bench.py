@@ -244,7 +244,7 @@ def main():
     tot, t_train, t_eval, wall = (float(x) / args.steps for x in t.tolist())
 
     # ---------------- e2e: through the public trainer API with host buffers ----------------
-    h2d = 3 * E * 8
+    h2d = 2 * E * 8                                           # negatives + permutation; the train edges are resident
     d2h = 4 * 4 + 3 * 2 * 8
     barrier()
     e0 = time.perf_counter()

@@ -164,3 +164,51 @@ extern "C" int idg_neg_sample_replay(const int64_t* h_train_user, int64_t E, con
     *h_consumed = j;
     return 0;
 }
+
+// Resumable form of the same walk: edges [e_begin, E) against one chunk of the candidate stream.  Running out of
+// candidates is a normal outcome (the caller draws the next chunk from the numpy generator and resumes at
+// *h_edges_done), so a first chunk of exactly E candidates plus small follow-up chunks replaces the over-provisioned
+// bulk draw and the second full-length draw that re-positions the generator.
+extern "C" int idg_neg_sample_walk(const int64_t* h_train_user, int64_t e_begin, int64_t E, const int32_t* h_pos_indptr,
+                                   const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand, int64_t* h_neg,
+                                   int64_t* h_edges_done, int64_t* h_consumed) {
+    if (!h_train_user || !h_pos_indptr || !h_pos_indices || !h_cand || !h_neg || !h_edges_done || !h_consumed || e_begin < 0 || E < e_begin)
+        return fail(-1, "idg_neg_sample_walk: bad argument%s");
+    int64_t j = 0, e = e_begin;
+    for (; e < E; ++e) {
+        const int64_t u = h_train_user[e];
+        const int32_t* lo = h_pos_indices + h_pos_indptr[u];
+        const int32_t* hi = h_pos_indices + h_pos_indptr[u + 1];
+        bool placed = false;
+        while (j < n_cand) {
+            const int64_t c = h_cand[j++];
+            const int32_t* a = lo; const int32_t* b = hi;
+            while (a < b) { const int32_t* m = a + (b - a) / 2; if (*m < c) a = m + 1; else b = m; }
+            if (a < hi && *a == c) continue;      // `neg in all_positive[user]` (data_loader.py:121): draw again
+            h_neg[e] = c;
+            placed = true;
+            break;
+        }
+        if (!placed) break;                        // chunk exhausted while edge e was still rejecting
+    }
+    *h_edges_done = e; *h_consumed = j;
+    return 0;
+}
+
+// tools.shuffle applied on the device (tools.py:35-52): out[0..3)[k] = (user, pos, neg)[perm[k]]
+__global__ void permute3_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ b, const int64_t* __restrict__ c,
+                                const int64_t* __restrict__ perm, int64_t n, int64_t* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t p = perm[k];
+    out[k] = a[p]; out[n + k] = b[p]; out[2 * n + k] = c[p];
+}
+
+extern "C" int idg_permute3(const int64_t* d_a, const int64_t* d_b, const int64_t* d_c, const int64_t* d_perm, int64_t n, int64_t* d_out,
+                            void* stream) {
+    if (!d_a || !d_b || !d_c || !d_perm || !d_out || n < 0) return fail(-1, "idg_permute3: bad argument%s");
+    if (n == 0) return 0;
+    permute3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, d_c, d_perm, n, d_out);
+    IDG_LAUNCH_CHECK("permute3_kernel");
+    return 0;
+}

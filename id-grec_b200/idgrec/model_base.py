@@ -21,7 +21,7 @@ class PropagationModel(nn.Module):
     def __init__(self, config, dataset, device, graph_fn=None):
         super().__init__()
         self.config, self.dataset, self.device = config, dataset, device
-        self.reg_lambda = float(config['reg_lambda'])
+        self.reg_lambda = float(config.get('reg_lambda', config.get('lambda_reg', 0.0)))
         dim = int(config['embedding_size'])
         self.user_embedding = nn.Embedding(num_embeddings=dataset.num_users, embedding_dim=dim)
         self.item_embedding = nn.Embedding(num_embeddings=dataset.num_items, embedding_dim=dim)
@@ -103,6 +103,18 @@ class PropagationModel(nn.Module):
                 fuse_adam=str(cfg.get('fuse_adam', '1')) not in ('0', 'False', 'false'),
                 closure_restrict={'0': False, '1': True}.get(str(cfg.get('closure_restrict', 'auto')), 'auto'))
         return self._fused
+
+    # -- LightGCN-or-MF encoder of the loss-only models (LightCCF.py:59-62, DirectAU.py:60-66, ...) -----------
+    def encode(self, E0=None):
+        """[N,d] final table: K-layer propagation with the layer-0 mean, or the ego table itself for ``encoder = MF``."""
+        E0 = self.table() if E0 is None else E0
+        if str(self.config.get('encoder', 'LightGCN')) == 'MF':
+            return E0
+        return ops.propagate(E0, self.Graph, self.num_layers, include_layer0=True)
+
+    def batch_rows(self, final, user, positive):
+        """(F_u[user], F_i[positive]) as dense [B,d] blocks whose backward scatters deterministically."""
+        return ops.gather_rows(final, user.long()), ops.gather_rows(final, positive.long() + self.dataset.num_users)
 
     # -- evaluation ------------------------------------------------------------------------------
     def final_embeddings(self):

@@ -211,7 +211,7 @@ class PairLossFn(torch.autograd.Function):
         n, d = X.shape
         ws = torch.empty(int(l.idg_pair_loss_workspace_bytes(n, d)), dtype=torch.uint8, device=X.device)
         loss = torch.empty(1, dtype=torch.float32, device=X.device)
-        need = X.requires_grad or (Y is not None and Y.requires_grad)
+        need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         gX = torch.empty_like(X) if need else None
         gY = torch.empty_like(Y) if (need and Y is not None) else None
         check(l.idg_pair_loss(int(kind), ptr(X), ptr(Y), n, d, float(p0), float(p1), ptr(loss), ptr(gX), ptr(gY), ptr(ws), cur_stream()),

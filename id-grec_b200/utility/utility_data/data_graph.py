@@ -40,6 +40,19 @@ class NormAdjacency:
         return self.tocsr(device).tocoo()
 
 
+class EdgeListAdjacency(NormAdjacency):
+    """D^-1/2 A D^-1/2 of an explicit (user, item) edge list -- the edge-dropped sub-graphs of SGL
+    (utility_function/tools.py:67-92) go through the same device CSR builder as the full graph."""
+
+    def __init__(self, user_index, item_index, num_users, num_items):
+        class _Edges:
+            pass
+        d = _Edges()
+        d.train_user, d.train_item = user_index, item_index
+        d.num_users, d.num_items, d.num_nodes = int(num_users), int(num_items), int(num_users) + int(num_items)
+        super().__init__(d, add_self=False)
+
+
 def sparse_adjacency_matrix_with_self(data):
     """D^-1/2 (A + I) D^-1/2, float64 arithmetic rounded to fp32 once (data_graph.py:7-30; NGCF)."""
     return NormAdjacency(data, add_self=True)

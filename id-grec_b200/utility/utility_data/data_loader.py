@@ -99,29 +99,48 @@ class Data(object):
         return strs
 
     # -- sampling ----------------------------------------------------------------------------
-    def sample_data_to_train_all(self):
-        """data_loader.py:108-127, exact.  The reference draws np.random.randint(0, num_items) once
-        per attempt; scalar draws equal one bulk draw (same values, same final generator state), so a
-        bulk candidate stream is replayed against the sorted positives of each edge's user by the C
-        entry point idg_neg_sample_replay and the global numpy generator is then advanced by exactly the
-        number of candidates the reference would have consumed (tools.shuffle reads it next)."""
-        from idgrec import ops
+    def sample_negatives(self):
+        """The negatives of data_loader.py:108-127, exact, as one int64 array (edge order = file order).
+
+        The reference draws np.random.randint(0, num_items) once per attempt; scalar draws equal a bulk draw of the
+        same length (same values, same final generator state), and a bulk draw equals consecutive smaller ones.  So
+        the candidate stream is taken from the global numpy generator in chunks -- the first exactly E long (every edge
+        consumes at least one candidate), then short ones for the edges still rejecting -- and replayed against the
+        sorted positives of each edge's user by the C entry point idg_neg_sample_walk.  The last chunk is re-drawn at
+        exactly the consumed length, so the generator ends where the reference's would (tools.shuffle reads it next)."""
+        import ctypes as C
+        from idgrec import _lib
+        l = _lib.lib()
         E = len(self.train_user)
+        neg = np.empty(E, dtype=np.int64)
         if E == 0:
+            return neg
+        if getattr(self, "_walk_csr", None) is None:
+            net = self.user_item_net
+            self._walk_csr = (np.ascontiguousarray(self.train_user, dtype=np.int64), np.ascontiguousarray(net.indptr, dtype=np.int32),
+                              np.ascontiguousarray(net.indices, dtype=np.int32))
+        tu, ip, ix = self._walk_csr
+        e, chunk = 0, E
+        done, used = C.c_int64(0), C.c_int64(0)
+        while e < E:
+            state = np.random.get_state()
+            cand = np.random.randint(0, self.num_items, size=chunk)
+            if cand.dtype != np.int64:
+                cand = cand.astype(np.int64)
+            _lib.check(l.idg_neg_sample_walk(tu.ctypes.data, e, E, ip.ctypes.data, ix.ctypes.data, cand.ctypes.data, len(cand),
+                                             neg.ctypes.data, C.byref(done), C.byref(used)), "idg_neg_sample_walk")
+            e = int(done.value)
+            if e >= E and int(used.value) < len(cand):
+                np.random.set_state(state)                      # finished inside this chunk: consume exactly `used` draws
+                np.random.randint(0, self.num_items, size=int(used.value))
+            chunk = max(1024, 2 * (E - e))
+        return neg
+
+    def sample_data_to_train_all(self):
+        """data_loader.py:108-127 -> int64 [E, 3] (user, positive, negative); see sample_negatives."""
+        if len(self.train_user) == 0:
             return np.zeros((0, 3), dtype=np.int64)
-        net = self.user_item_net
-        state = np.random.get_state()
-        slack = max(4096, E // 16)
-        while True:
-            np.random.set_state(state)
-            cand = np.random.randint(0, self.num_items, size=E + slack)
-            neg, used = ops.neg_sample_replay(self.train_user, net.indptr, net.indices, cand)
-            if neg is not None:
-                break
-            slack *= 4
-        np.random.set_state(state)
-        np.random.randint(0, self.num_items, size=used)
-        return np.stack([self.train_user, self.train_item, neg], axis=1)
+        return np.stack([self.train_user, self.train_item, self.sample_negatives()], axis=1)
 
     def get_user_pos_items(self, users):
         """data_loader.py:129-133: sorted train items of each user (views into the CSR)."""
@@ -198,5 +217,7 @@ class Data(object):
                 "test_indptr": torch.from_numpy(tptr.astype(np.int32)).to(device),
                 "test_indices": torch.from_numpy(ti[order].astype(np.int32)).to(device),
                 "test_users": torch.from_numpy(users).to(device),
+                "train_user": torch.from_numpy(np.ascontiguousarray(self.train_user, dtype=np.int64)).to(device),
+                "train_item": torch.from_numpy(np.ascontiguousarray(self.train_item, dtype=np.int64)).to(device),
             }
         return self._dev[key]

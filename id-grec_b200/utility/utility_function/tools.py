@@ -4,6 +4,7 @@ Same names and argument meaning.  ``shuffle``/``mini_batch``/``set_seed`` keep t
 global-RNG stream the reference consumes so epochs >= 1 see bit-identical batches.
 """
 import os
+import random
 
 import numpy as np
 import torch
@@ -61,6 +62,25 @@ def mini_batch(*tensors, **kwargs):
     else:
         for i in range(0, len(tensors[0]), batch_size):
             yield tuple(x[i:i + batch_size] for x in tensors)
+
+
+def create_adj_mat(inter_graph, aug_type, ssl_rate):
+    """tools.py:67-92: the edge-dropped graph of SGL.  The kept edges are drawn exactly like the reference does
+    (python ``random.sample`` over the row-major nonzeros of user_item_net -- a stream set_seed() does not seed);
+    the symmetric normalisation of the kept edges runs in the device CSR builder (float32 degrees, ``inf -> 0``)."""
+    from utility.utility_data.data_graph import EdgeListAdjacency
+    num_users, num_items = inter_graph.get_shape()
+    user_index, item_index = inter_graph.nonzero()
+    if aug_type == 'nd':
+        raise NotImplementedError("The method does not implemented.")
+    elif aug_type in ['ed', 'rw']:
+        edge_number = inter_graph.count_nonzero()
+        keep_index = random.sample(range(edge_number), k=int((1 - ssl_rate) * edge_number))
+        user_index = np.array(user_index)[keep_index]
+        item_index = np.array(item_index)[keep_index]
+    else:
+        raise ValueError("unknown aug_type %r" % (aug_type,))
+    return EdgeListAdjacency(user_index, item_index, num_users, num_items)
 
 
 def convert_sp_mat_to_sp_tensor(sp_mat):

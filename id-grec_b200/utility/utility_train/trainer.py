@@ -15,24 +15,33 @@ import utility.utility_train.batch_test as batch_test
 
 def sample_epoch(dataset, device):
     """trainer.py:26-35: sample, move to the device, shuffle with the numpy global stream.
-    ids stay int64 end to end (the reference's float32 round-trip is exact below 2^24)."""
-    sample_data = dataset.sample_data_to_train_all()
-    perm = np.arange(len(sample_data))
-    np.random.shuffle(perm)                       # tools.shuffle (tools.py:41-42), same stream position
-    E = len(sample_data)
+    ids stay int64 end to end (the reference's float32 round-trip is exact below 2^24).  On CUDA only the
+    negatives and the permutation cross PCIe (one pinned [2, E] int64 block): the train edges are resident on the
+    device and tools.shuffle's fancy indexing runs there (idg_permute3)."""
+    device = torch.device(device)
     if device.type != "cuda":
+        sample_data = dataset.sample_data_to_train_all()
+        perm = np.arange(len(sample_data))
+        np.random.shuffle(perm)                   # tools.shuffle (tools.py:41-42), same stream position
         t = torch.from_numpy(np.ascontiguousarray(sample_data[perm].T))
         return t[0], t[1], t[2]
-    # gather straight into a reused pinned staging buffer, one async H2D copy of [3, E] int64
+    from idgrec import _lib
+    E = len(dataset.train_user)
     stage = _PINNED.get(E)
     if stage is None:
-        stage = _PINNED[E] = torch.empty((3, E), dtype=torch.int64).pin_memory()
+        stage = _PINNED[E] = torch.empty((2, max(E, 1)), dtype=torch.int64).pin_memory()
     host = stage.numpy()
-    for c in range(3):
-        np.take(sample_data[:, c], perm, out=host[c])
+    host[0, :E] = dataset.sample_negatives()
+    perm = host[1, :E]
+    perm[:] = np.arange(E)
+    np.random.shuffle(perm)                       # same generator position as the reference: right after the sampler
+    cache = dataset.device_cache(device)
     t = stage.to(device, non_blocking=True)
+    out = torch.empty((3, E), dtype=torch.int64, device=device)
+    _lib.check(_lib.lib().idg_permute3(_lib.ptr(cache["train_user"]), _lib.ptr(cache["train_item"]), _lib.ptr(t[0]), _lib.ptr(t[1]), E,
+                                       _lib.ptr(out), _lib.cur_stream()), "idg_permute3")
     torch.cuda.current_stream().synchronize()      # the staging buffer is reused by the next epoch's prefetch
-    return t[0], t[1], t[2]
+    return out[0], out[1], out[2]
 
 
 _PINNED = {}
@@ -72,19 +81,18 @@ def universal_trainer(model, args, config, dataset, device, logger):
                 prefetched = sample_epoch(dataset, device)
             total_loss_list = fused.pop_epoch_losses()    # one device read per epoch
         else:
-            total_loss_list = []
-            for batch_i, (bu, bp, bn) in enumerate(tools.mini_batch(users, pos_items, neg_items, batch_size=batch_size)):
+            acc = None
+            for bu, bp, bn in tools.mini_batch(users, pos_items, neg_items, batch_size=batch_size):
                 loss_list = model(bu, bp, bn)
-                if batch_i == 0:
-                    assert len(loss_list) >= 1
-                    total_loss_list = [0.] * len(loss_list)
-                total_loss = 0.
-                for i in range(len(loss_list)):
-                    total_loss += loss_list[i]
-                    total_loss_list[i] += loss_list[i].item()
+                assert len(loss_list) >= 1
+                stacked = torch.stack([l.reshape(()) for l in loss_list])
                 Optim.zero_grad()
-                total_loss.backward()
+                stacked.sum().backward()
                 Optim.step()
+                # per-loss epoch sums stay on the device: one read per epoch instead of len(loss_list) .item() syncs
+                # per batch (trainer.py:52)
+                acc = stacked.detach() if acc is None else acc + stacked.detach()
+            total_loss_list = acc.cpu().tolist() if acc is not None else []
 
         end_time = time()
         loss_strs = str(round(sum(total_loss_list) / num_batch, 6)) \
@@ -92,7 +100,7 @@ def universal_trainer(model, args, config, dataset, device, logger):
         print("Training time: %.3f | training loss: %s" % (end_time - start_time, loss_strs))
         logger.info("Epoch: %4d | Training time: %.3f | training loss: %s" % (epoch + 1, end_time - start_time, loss_strs))
 
-        if epoch % int(config['interval']) == 0:
+        if epoch % int(config.get('interval', 1)) == 0:   # configure/DirectAU.txt has no interval line
             result, best_results = batch_test.general_test(dataset, model, device, config, epoch, best_results)
             logger.info("Epoch: %4d | Test recall: %s | Test NDCG: %s" % (epoch + 1, result['recall'], result['ndcg']))
             if best_results['stop'] > 0:

@@ -300,6 +300,18 @@ int idg_neg_sample_replay(const int64_t* h_train_user, int64_t E, const int32_t*
                           const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand,
                           int64_t* h_neg, int64_t* h_consumed);
 
+/* Resumable form: edges [e_begin, E) against ONE CHUNK of the candidate stream; *h_edges_done = first edge not yet
+ * placed (== E when finished), *h_consumed = candidates of this chunk that were used.  A candidate rejected for the
+ * edge at which the chunk ran out stays consumed, exactly as in the reference's while-loop. */
+int idg_neg_sample_walk(const int64_t* h_train_user, int64_t e_begin, int64_t E, const int32_t* h_pos_indptr,
+                        const int32_t* h_pos_indices, const int64_t* h_cand, int64_t n_cand, int64_t* h_neg,
+                        int64_t* h_edges_done, int64_t* h_consumed);
+
+/* a5: tools.shuffle (tools.py:35-52) applied on the device: d_out[3,n] = (a, b, c)[perm] (users, positives, negatives
+ * of one epoch; only the permutation and the negatives cross PCIe, the train edges are resident). */
+int idg_permute3(const int64_t* d_a, const int64_t* d_b, const int64_t* d_c, const int64_t* d_perm, int64_t n,
+                 int64_t* d_out, void* stream);
+
 /* ---- a1: data_loader.py:48-70, the dataset text format ("user item item ..." per line) parsed on the HOST in one
  * pass.  Two-call protocol: pair_cap = line_cap = 0 counts (*n_pairs, *n_lines); the second call fills
  * h_user/h_item [n_pairs] (file order = inter_users/inter_items), h_line_user/h_line_len [n_lines] (unique_users and

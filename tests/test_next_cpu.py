@@ -220,3 +220,37 @@ def test_pair_loss_closed_forms_equal_autograd(kind):
     np.testing.assert_allclose(gX, tx.grad.numpy(), rtol=1e-7, atol=1e-11)
     if gY is not None:
         np.testing.assert_allclose(gY, ty.grad.numpy(), rtol=1e-7, atol=1e-11)
+
+
+# ------------------------------------------------------------------------------------------------
+# host parser of the dataset text format (idg_parse_ratings)
+# ------------------------------------------------------------------------------------------------
+def test_parse_ratings_matches_reference_semantics(tmp_path, golden_dirs, golden_quirks):
+    from idgrec import _lib, ops
+    from oracle import ref_oracle as O
+    # the quirks file: duplicate pairs, a user with an empty line, an item id that only occurs in test
+    path = os.path.join(golden_dirs["quirks"], "train.txt")
+    line_user, line_len, users, items, mu, mi = ops.parse_ratings(path)
+    np.testing.assert_array_equal(users, golden_quirks["train_user"])
+    np.testing.assert_array_equal(items, golden_quirks["train_item"])
+    ref = O.read_ratings(path)
+    np.testing.assert_array_equal(line_user, np.asarray(ref[0]))
+    assert line_len.sum() == len(items) and (line_len == 0).sum() == 1
+    assert mu == users.max() and mi == items.max()
+    # tabs / CRLF / several blanks / no trailing newline / blank lines are tolerated, ids may be large
+    p = tmp_path / "a.txt"
+    p.write_bytes(b"3 1  2\t5\r\n\n7\n0 16777217 4")
+    line_user, line_len, users, items, mu, mi = ops.parse_ratings(str(p))
+    assert line_user.tolist() == [3, 7, 0] and line_len.tolist() == [3, 0, 2]
+    assert users.tolist() == [3, 3, 3, 0, 0] and items.tolist() == [1, 2, 5, 16777217, 4]
+    assert (mu, mi) == (3, 16777217)
+    # empty file, missing file, junk
+    e = tmp_path / "e.txt"
+    e.write_bytes(b"")
+    assert [len(x) for x in ops.parse_ratings(str(e))[:4]] == [0, 0, 0, 0]
+    with pytest.raises(_lib.IdgError):
+        ops.parse_ratings(str(tmp_path / "missing.txt"))
+    j = tmp_path / "j.txt"
+    j.write_bytes(b"1 2 x3\n")
+    with pytest.raises(_lib.IdgError):
+        ops.parse_ratings(str(j))
