@@ -100,9 +100,12 @@ def test_pair_loss_kernels_vs_closed_form(dev, kind, n, d):
     loss.backward()
     ref, gX, gY = pair_loss_closed_form(k, X.astype(np.float64), None if kind == "uniform" else Y.astype(np.float64), p0, p1)
     assert abs(loss.item() - ref) <= 2e-5 * max(1.0, abs(ref)), (loss.item(), ref)
-    _close(tx.grad.cpu().numpy(), gX, rtol=2e-5)
+    # the gradient is a difference of O(1/(n tau)) terms; for a 2-row batch they cancel to ~1e-4, so the fp32 rounding
+    # of the terms (1e-7 absolute) is the floor of the comparison there
+    floor = 1e-7 if n <= 2 else 0.0
+    np.testing.assert_allclose(tx.grad.cpu().numpy(), gX, rtol=2e-5, atol=max(floor, 2e-5 * np.abs(gX).max()))
     if gY is not None:
-        _close(ty.grad.cpu().numpy(), gY, rtol=2e-5)
+        np.testing.assert_allclose(ty.grad.cpu().numpy(), gY, rtol=2e-5, atol=max(floor, 2e-5 * np.abs(gY).max()))
     # forward-only call (no gradient buffers) gives the same loss, and the result is bit-reproducible
     with torch.no_grad():
         l2 = ops.pair_loss(kind, tx.detach(), None if kind == "uniform" else ty.detach(), p0, p1)
