@@ -25,55 +25,58 @@ namespace idg {
 // C[M,N] = alpha * op(A) op(B) + beta * C,  row-major, fp32 FMA, k ascending (fixed summation order)
 //   op(A)[m,k] = TA ? A[k*lda+m] : A[m*lda+k];   op(B)[k,n] = TB ? B[n*ldb+k] : B[k*ldb+n]
 // ------------------------------------------------------------------------------------------------------------
-template <bool TA, bool TB>
+template <bool TA, bool TB, int BM>
 __global__ void __launch_bounds__(256) pl_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                        float* __restrict__ C, int ldc, float alpha, float beta) {
-    __shared__ float As[16][68];
+    // BM x 64 output tile per CTA (BM = 64, or 32 for the skinny [n,n] x [n,d] products so that the grid covers the SMs),
+    // 16-deep k steps, (BM/16) x 4 micro-tile per thread
+    constexpr int RM = BM / 16;
+    __shared__ float As[16][BM + 4];
     __shared__ float Bs[16][68];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * 64;
+    float acc[RM][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RM; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     for (int k0 = 0; k0 < K; k0 += 16) {
 #pragma unroll
+        for (int q = 0; q < BM / 16; ++q) {
+            const int e = tid + q * 256;
+            const int mm = TA ? (e % BM) : (e >> 4), kk = TA ? (e / BM) : (e & 15);
+            const int m = m0 + mm, k = k0 + kk;
+            float v = 0.f;
+            if (m < M && k < K) v = TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
+            As[kk][mm] = v;
+        }
+#pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int e = tid + q * 256;
-            {
-                const int mm = TA ? (e & 63) : (e >> 4), kk = TA ? (e >> 6) : (e & 15);
-                const int m = m0 + mm, k = k0 + kk;
-                float v = 0.f;
-                if (m < M && k < K) v = TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k];
-                As[kk][mm] = v;
-            }
-            {
-                const int nn = TB ? (e >> 4) : (e & 63), kk = TB ? (e & 15) : (e >> 6);
-                const int n = n0 + nn, k = k0 + kk;
-                float v = 0.f;
-                if (n < N && k < K) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
-                Bs[kk][nn] = v;
-            }
+            const int nn = TB ? (e >> 4) : (e & 63), kk = TB ? (e & 15) : (e >> 6);
+            const int n = n0 + nn, k = k0 + kk;
+            float v = 0.f;
+            if (n < N && k < K) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+            Bs[kk][nn] = v;
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float av[4], bv[4];
+            float av[RM], bv[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = As[kk][ty * 4 + a];
+            for (int a = 0; a < RM; ++a) av[a] = As[kk][ty * RM + a];
 #pragma unroll
             for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx * 4 + b];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < RM; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int m = m0 + ty * 4 + a;
+    for (int a = 0; a < RM; ++a) {
+        const int m = m0 + ty * RM + a;
         if (m >= M) continue;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -85,13 +88,21 @@ __global__ void __launch_bounds__(256) pl_sgemm_kernel(int M, int N, int K, cons
     }
 }
 
+template <int BM>
+static void pl_sgemm_launch(bool ta, bool tb, dim3 grid, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                            float alpha, float beta, cudaStream_t st) {
+    if (!ta && !tb) pl_sgemm_kernel<false, false, BM><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else if (!ta && tb) pl_sgemm_kernel<false, true, BM><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else if (ta && !tb) pl_sgemm_kernel<true, false, BM><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    else pl_sgemm_kernel<true, true, BM><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+}
+
 static int pl_sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, float alpha,
                     float beta, cudaStream_t st) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
-    if (!ta && !tb) pl_sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
-    else if (!ta && tb) pl_sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
-    else if (ta && !tb) pl_sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
-    else pl_sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta);
+    // 64-row tiles unless that leaves most of the 148 SMs idle (the [n,n] x [n,d] gradient products: N = d or 2d)
+    const int tiles64 = ((N + 63) / 64) * ((M + 63) / 64);
+    if (tiles64 >= 2 * kNumSMs) pl_sgemm_launch<64>(ta, tb, dim3((N + 63) / 64, (M + 63) / 64), M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, st);
+    else pl_sgemm_launch<32>(ta, tb, dim3((N + 63) / 64, (M + 31) / 32), M, N, K, A, lda, B, ldb, C, ldc, alpha, beta, st);
     IDG_LAUNCH_CHECK("pl_sgemm_kernel");
     return 0;
 }
@@ -118,7 +129,10 @@ __device__ __forceinline__ float block_sum256(float v, float* sm) {
 }
 
 // F.normalize(x, dim=-1): x / max(|x|, 1e-12); one warp per row
-__global__ void __launch_bounds__(256) pl_rownorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ Xn, float* __restrict__ nrm) {
+// (copy, ld_copy): optional second destination with its own leading dimension -- the [Yn | Xn] operand of the merged
+// gradient product
+__global__ void __launch_bounds__(256) pl_rownorm_kernel(const float* __restrict__ X, int n, int d, float* __restrict__ Xn, float* __restrict__ nrm,
+                                                        float* __restrict__ copy, int ld_copy) {
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
     const float* x = X + (size_t)i * d;
@@ -126,7 +140,11 @@ __global__ void __launch_bounds__(256) pl_rownorm_kernel(const float* __restrict
     for (int c = lane; c < d; c += 32) s = fmaf(x[c], x[c], s);
     s = warp_sum(s);
     const float nr = fmaxf(sqrtf(s), 1e-12f);
-    for (int c = lane; c < d; c += 32) Xn[(size_t)i * d + c] = x[c] / nr;
+    for (int c = lane; c < d; c += 32) {
+        const float v = x[c] / nr;
+        Xn[(size_t)i * d + c] = v;
+        if (copy) copy[(size_t)i * ld_copy + c] = v;
+    }
     if (lane == 0) nrm[i] = nr;
 }
 
@@ -254,11 +272,14 @@ __global__ void __launch_bounds__(1024) pl_reduce_kernel(int kind, const float* 
 __global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Xn,
                                                        const float* __restrict__ Yn, const float* __restrict__ nx, const float* __restrict__ ny,
                                                        const float* __restrict__ w, const float* __restrict__ rowT, const float* __restrict__ scal,
-                                                       const float* __restrict__ tA, const float* __restrict__ tB, int n, int d,
+                                                       const float* __restrict__ tA, int fold_tA, const float* __restrict__ tB, int n, int d,
                                                        float* __restrict__ gX, float* __restrict__ gY) {
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
     const size_t o = (size_t)i * d;
+    // fold_tA: tA is [n, 2d] = H [Yn | Xn]; the two halves are summed here (H b + H a)
+    const size_t oa = fold_tA ? (size_t)i * 2 * d : o;
+    const int hi = fold_tA ? d : 0;
     const float wi = w ? w[i] : 0.f;
     const float cu = (kind == 5) ? -8.f / scal[0] : 0.f;
     const float ri = (kind == 5) ? rowT[i] : 0.f;
@@ -267,7 +288,7 @@ __global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* _
     for (int c = lane; c < d; c += 32) {
         const float a = Xn[o + c], b = Yn ? Yn[o + c] : 0.f;
         float ga, gb = 0.f;
-        if (kind <= 1) { ga = tA[o + c] + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
+        if (kind <= 1) { ga = (tA[oa + c] + (fold_tA ? tA[oa + hi + c] : 0.f)) + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
         else if (kind == 2) { ga = tA[o + c]; gb = tB[o + c]; }
         else if (kind == 3) { ga = wi * b; gb = wi * a; }
         else if (kind == 4) { ga = 2.f * (a - b) / (float)n; gb = -ga; }
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* _
     for (int c = lane; c < d; c += 32) {
         const float a = Xn[o + c], b = Yn ? Yn[o + c] : 0.f;
         float ga, gb = 0.f;
-        if (kind <= 1) { ga = tA[o + c] + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
+        if (kind <= 1) { ga = (tA[oa + c] + (fold_tA ? tA[oa + hi + c] : 0.f)) + tB[o + c] + wi * b; gb = tB[o + c] + wi * a; }
         else if (kind == 2) { ga = tA[o + c]; gb = tB[o + c]; }
         else if (kind == 3) { ga = wi * b; gb = wi * a; }
         else if (kind == 4) { ga = 2.f * (a - b) / (float)n; gb = -ga; }
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(256) pl_scatter_add_kernel(const float* __rest
 }
 
 struct PlWs {
-    float *Xn, *Yn, *nx, *ny, *S, *R, *w, *rowT, *lossi, *diag, *tA, *tB, *scal;
+    float *Xn, *Yn, *YX, *nx, *ny, *S, *R, *w, *rowT, *lossi, *diag, *tA, *tB, *scal;
 };
 __host__ inline size_t pl_align(size_t x) { return (x + 255) & ~(size_t)255; }
 __host__ inline size_t pl_carve(void* ws, int n, int d, PlWs* w) {
@@ -337,7 +358,7 @@ __host__ inline size_t pl_carve(void* ws, int n, int d, PlWs* w) {
     auto take = [&](size_t bytes) { char* q = p; p += pl_align(bytes); return (float*)q; };
     const size_t nd = sizeof(float) * (size_t)n * d, nn = sizeof(float) * (size_t)n * n, n1 = sizeof(float) * (size_t)n;
     PlWs t;
-    t.Xn = take(nd); t.Yn = take(nd); t.tA = take(nd); t.tB = take(nd);
+    t.Xn = take(nd); t.Yn = take(nd); t.YX = take(2 * nd); t.tA = take(2 * nd); t.tB = take(nd);
     t.nx = take(n1); t.ny = take(n1); t.w = take(n1); t.rowT = take(n1); t.lossi = take(n1); t.diag = take(n1);
     t.scal = take(256);
     t.S = take(nn); t.R = take(nn);
@@ -367,10 +388,11 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
     pl_carve((void*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255), n, d, &w);
     const bool want_grad = d_gX != nullptr;
     const int rb = (n + 7) / 8;
-    pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_X, n, d, w.Xn, w.nx);
+    const bool merged = want_grad && kind <= 1;       // gradient product against [Yn | Xn] in one pass over H
+    pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_X, n, d, w.Xn, w.nx, merged ? w.YX + d : nullptr, 2 * d);
     IDG_LAUNCH_CHECK("pl_rownorm_kernel");
     if (kind != 5) {
-        pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_Y, n, d, w.Yn, w.ny);
+        pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_Y, n, d, w.Yn, w.ny, merged ? w.YX : nullptr, 2 * d);
         IDG_LAUNCH_CHECK("pl_rownorm_kernel");
     }
     int rc;
@@ -382,9 +404,8 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
         pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
         IDG_LAUNCH_CHECK("pl_reduce_kernel");
         if (want_grad) {
-            // tA = H b + H a,  tB = H^T a
-            if ((rc = pl_sgemm(false, false, n, d, n, w.S, n, w.Yn, d, w.tA, d, 1.f, 0.f, st))) return rc;
-            if ((rc = pl_sgemm(false, false, n, d, n, w.S, n, w.Xn, d, w.tA, d, 1.f, 1.f, st))) return rc;
+            // tA [n,2d] = H [b | a] (folded to H b + H a by the finish kernel),  tB = H^T a
+            if ((rc = pl_sgemm(false, false, n, 2 * d, n, w.S, n, w.YX, 2 * d, w.tA, 2 * d, 1.f, 0.f, st))) return rc;
             if ((rc = pl_sgemm(true, false, n, d, n, w.S, n, w.Xn, d, w.tB, d, 1.f, 0.f, st))) return rc;
         }
     } else if (kind == 2) {
@@ -419,7 +440,8 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
     if (want_grad) {
         if (kind != 5 && !d_gY) return fail(-1, "idg_pair_loss: d_gY is required with d_gX for kind %s", "0..4");
         pl_finish_kernel<<<rb, 256, 0, st>>>(kind, d_X, d_Y, w.Xn, kind == 5 ? nullptr : w.Yn, w.nx, kind == 5 ? nullptr : w.ny,
-                                            (kind <= 1 || kind == 3) ? w.w : nullptr, w.rowT, w.scal, w.tA, w.tB, n, d, d_gX, kind == 5 ? nullptr : d_gY);
+                                            (kind <= 1 || kind == 3) ? w.w : nullptr, w.rowT, w.scal, w.tA, merged ? 1 : 0, w.tB, n, d, d_gX,
+                                            kind == 5 ? nullptr : d_gY);
         IDG_LAUNCH_CHECK("pl_finish_kernel");
     }
     return 0;

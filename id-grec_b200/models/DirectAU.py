@@ -8,6 +8,7 @@ from idgrec.model_base import PropagationModel
 
 class DirectAU(PropagationModel):
     kind = "DirectAU"
+    graph_capturable = True   # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
     fused_trainer = None  # autograd ops over the CUDA kernels + torch.optim.Adam, reference loop trainer.py:40-56
 
     def __init__(self, config, dataset, device):

@@ -14,6 +14,7 @@ from idgrec.model_base import PropagationModel
 
 class NGCF(PropagationModel):
     kind = "NGCF"
+    graph_capturable = True   # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
     fused_trainer = None  # trained through autograd + torch.optim.Adam (dense weights), reference loop trainer.py:40-56
 
     def __init__(self, config, dataset, device):

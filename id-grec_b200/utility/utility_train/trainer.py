@@ -52,6 +52,12 @@ def universal_trainer(model, args, config, dataset, device, logger):
     lr = float(config['learn_rate'])
     batch_size = int(config['batch_size'])
     fused = model.fused_trainer(lr, batch_size) if getattr(model, "fused_trainer", None) is not None else None
+    if (fused is None and getattr(model, "graph_capturable", False) and torch.device(device).type == "cuda"
+            and str(config.get('cuda_graph', '1')) not in ('0', 'False', 'false')):
+        # autograd-path models without host syncs in forward(): the whole step (forward, backward, Adam) replays from
+        # a CUDA graph; same kernels, same order, same results as the eager loop below
+        from idgrec.graphed import GraphedStep
+        fused = GraphedStep(model, lr, batch_size)
     Optim = None if fused is not None else torch.optim.Adam(model.parameters(), lr=lr)
 
     best_results = dict()

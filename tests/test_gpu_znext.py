@@ -292,3 +292,50 @@ def test_sparsity_test_and_top40_vs_reference(dev, golden_dirs, golden_tiny, gol
     od = O.load_dataset(golden_dirs["tiny"])
     ref_ids, _ = O.topk_exact(fu.cpu().numpy(), fi.cpu().numpy(), users, od.user_item_net.indptr, od.user_item_net.indices, 40)
     np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-step CUDA-graph replay of the autograd-path models
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["LightCCF", "DirectAU", "NGCF"])
+def test_graphed_step_equals_eager_loop(dev, golden_dirs, golden_tiny, kind):
+    """GraphedStep (forward -> backward -> capturable Adam replayed from a CUDA graph, captured per batch size, warm-up
+    undone) follows the same trajectory as the reference's eager loop (trainer.py:40-56) over 5 batches incl. a short one."""
+    from idgrec.graphed import GraphedStep
+    over = dict(NEXT_CFG.get(kind, {}))
+    if kind == "NGCF":
+        over = {"mess_drop_prob": "[0.0, 0.0, 0.0]"}      # dropout off: both runs must be deterministic
+    else:
+        over["encoder"] = "LightGCN"
+    cfg = _cfg(kind, batch_size=256, **over)
+    d = _data(golden_dirs, cfg)
+    s0 = golden_tiny["sample_ep0"][golden_tiny["perm_ep0"]]
+    batches = [torch.from_numpy(s0[a:b].copy()).to(dev) for a, b in ((0, 256), (256, 512), (512, 768), (768, 868), (868, 1124))]
+    finals, sums = [], []
+    for mode in ("eager", "graph"):
+        import utility.utility_function.tools as tools
+        tools.set_seed(2024)
+        m = getattr(importlib.import_module("models." + kind), kind)(cfg, d, dev)
+        m.to(dev)
+        if mode == "eager":
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+            acc = None
+            for b in batches:
+                ll = m(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+                st = torch.stack([l.reshape(()) for l in ll])
+                opt.zero_grad()
+                st.sum().backward()
+                opt.step()
+                acc = st.detach() if acc is None else acc + st.detach()
+            sums.append(acc.cpu().numpy())
+        else:
+            gs = GraphedStep(m, 1e-3, 256)
+            for b in batches:
+                gs.step(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+            assert sorted(gs.graphs) == [100, 256] and gs.replays == 5
+            sums.append(np.asarray(gs.pop_epoch_losses()))
+            assert gs.pop_epoch_losses() == [0.0] * len(sums[-1])
+        finals.append([p.detach().cpu().numpy().copy() for p in m.parameters()])
+    np.testing.assert_allclose(sums[1], sums[0], rtol=2e-5)
+    for a, b in zip(finals[1], finals[0]):
+        _close(a, b, rtol=2e-5)

@@ -52,8 +52,8 @@ def main():
         out["scatter_add_n%d_ms" % n] = timed(lambda: _lib.check(_lib.lib().idg_scatter_add_rows(_lib.ptr(G), _lib.ptr(idx), n, 64, _lib.ptr(gT), _lib.cur_stream())))
     # ---- one autograd train step of the added models
     graphs = {}
-    for shape, kind, over in (("amazon-book", "LightCCF", {}), ("amazon-book", "LightCSCF", {}), ("yelp2018", "DirectAU", {}),
-                              ("yelp2018", "SCCF", {"encoder": "LightGCN"}), ("yelp2018", "SGL", {})):
+    for shape, kind, over in (("amazon-book", "LightCCF", {}), ("amazon-book", "LightCSCF", {}), ("amazon-book", "NGCF", {}),
+                              ("yelp2018", "DirectAU", {}), ("yelp2018", "SCCF", {"encoder": "LightGCN"}), ("yelp2018", "SGL", {})):
         g = graphs.get(shape) or graphs.setdefault(shape, datagen.gen_graph(shape))
         cfg = tools.read_configuration(os.path.join(REPO, "id-grec_b200", "configure", kind + ".txt"), kind)
         cfg.update(over)
@@ -77,6 +77,11 @@ def main():
             torch.stack([l.reshape(()) for l in ll]).sum().backward()
             opt.step()
         out["step_%s_%s_B%d_ms" % (kind, shape, B)] = timed(step, iters=10, warm=3)
+        if getattr(m, "graph_capturable", False):
+            from idgrec.graphed import GraphedStep
+            gs = GraphedStep(m, 1e-3, B)
+            out["step_graph_%s_%s_B%d_ms" % (kind, shape, B)] = timed(lambda: gs.step(bu, bp, bn), iters=20, warm=3)
+            del gs
         if kind == "LightCCF":
             # host legs of one epoch at the amazon-book shape
             t0 = time.perf_counter()
