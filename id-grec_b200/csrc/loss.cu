@@ -11,6 +11,8 @@
 // Deterministic scatter without float atomics or a sort: the 3B (node) keys are
 // scanned by one warp per entry; the first occurrence of a node ("leader") sums the
 // contributions of all its occurrences in ascending entry order and writes the row.
+#include <math.h>
+
 #include "idg_common.cuh"
 
 namespace idg {
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(256) bpr_fwd_kernel(const float* __restrict__ 
 }
 
 // fixed-order block reduction of the per-sample terms -> loss[0] = bpr, loss[1] = lambda*reg
-__global__ void __launch_bounds__(1024) bpr_reduce_kernel(BprWs w, int B, float reg_lambda, float* __restrict__ loss) {
+// ``tail`` (optional): per-step scalar work that would otherwise be two more single-thread launches in the captured
+// step -- the epoch loss sums and the bias-corrected Adam scalars of this step (adam_prepare_kernel's job).
+__global__ void __launch_bounds__(1024) bpr_reduce_kernel(BprWs w, int B, float reg_lambda, float* __restrict__ loss, idg_step_tail tail) {
     __shared__ float sl[1024], sr[1024];
     float a = 0.f, r = 0.f;
     for (int i = threadIdx.x; i < B; i += 1024) { a += w.loss_b[i]; r += w.reg_b[i]; }
@@ -87,25 +91,38 @@ __global__ void __launch_bounds__(1024) bpr_reduce_kernel(BprWs w, int B, float 
         if (threadIdx.x < s) { sl[threadIdx.x] += sl[threadIdx.x + s]; sr[threadIdx.x] += sr[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { loss[0] = sl[0] / (float)B; loss[1] = reg_lambda * (sr[0] / (float)B); }
+    if (threadIdx.x == 0) {
+        const float l0 = sl[0] / (float)B, l1 = reg_lambda * (sr[0] / (float)B);
+        loss[0] = l0; loss[1] = l1;
+        if (tail.d_loss_acc) { tail.d_loss_acc[0] += l0; tail.d_loss_acc[1] += l1; }
+        if (tail.d_step) {
+            const double t = (double)(*tail.d_step + 1);
+            tail.d_scalars[0] = (float)((double)tail.lr / (1.0 - pow((double)tail.beta1, t)));
+            tail.d_scalars[1] = (float)sqrt(1.0 - pow((double)tail.beta2, t));
+            *tail.d_step += 1;
+        }
+    }
 }
 
 template <int VPL>
 __global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ F, int B, int reg_mask, const float* __restrict__ upstream, BprWs w, float* __restrict__ G,
                                                       float* __restrict__ regc, float reg_coef) {
     constexpr int d = 32 * VPL;
-    extern __shared__ int skeys[];  // [3B]
+    extern __shared__ __align__(16) int skeys[];  // [3B] padded with -1 to a multiple of 128 (4 keys per lane and step)
     const int n = 3 * B;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = w.keys[i];
+    const int npad = (n + 127) & ~127;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) skeys[i] = (i < n) ? w.keys[i] : -1;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (e >= n) return;
     const int node = skeys[e];
+    const int4* skeys4 = reinterpret_cast<const int4*>(skeys);
     // leader test: any earlier entry with the same row?
-    for (int base = 0; base < e; base += 32) {
-        const int i = base + lane;
-        const bool hit = (i < e) && (skeys[i] == node);
+    for (int base = 0; base < e; base += 128) {
+        const int i = base + lane * 4;
+        const int4 k = skeys4[i >> 2];
+        const bool hit = ((i < e) && (k.x == node)) || ((i + 1 < e) && (k.y == node)) || ((i + 2 < e) && (k.z == node)) || ((i + 3 < e) && (k.w == node));
         if (__any_sync(0xffffffffu, hit)) {
             if (lane == 0) { w.lead_node[e] = -1; w.lead_mult[e] = 0; }
             return;
@@ -116,25 +133,36 @@ __global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ 
     for (int v = 0; v < VPL; ++v) acc[v] = 0.f;
     int mult = 0;
     const float up = upstream ? upstream[0] : 1.f;
-    for (int base = e & ~31; base < n; base += 32) {
-        const int i = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, (i >= e) && (i < n) && (skeys[i] == node));
-        while (m) {
-            const int j = base + __ffs(m) - 1;
-            m &= m - 1;
-            const int role = j / B, b = j - role * B;
-            mult += (reg_mask >> role) & 1;
-            const float c = w.coef[b] * up;
-            if (role == 0) {
-                const float* p = F + (size_t)skeys[B + b] * d;
-                const float* q = F + (size_t)skeys[2 * B + b] * d;
+    for (int base = e & ~127; base < n; base += 128) {
+        const int i = base + lane * 4;
+        const int4 k = skeys4[i >> 2];
+        unsigned m[4];
+        m[0] = __ballot_sync(0xffffffffu, (i >= e) && (k.x == node));
+        m[1] = __ballot_sync(0xffffffffu, (i + 1 >= e) && (k.y == node));
+        m[2] = __ballot_sync(0xffffffffu, (i + 2 >= e) && (k.z == node));
+        m[3] = __ballot_sync(0xffffffffu, (i + 3 >= e) && (k.w == node));
+        unsigned any = m[0] | m[1] | m[2] | m[3];
+        while (any) {                       // ascending entry order: lane-major, then the 4 keys of that lane
+            const int L = __ffs(any) - 1;
+            any &= any - 1;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v] += c * (__ldg(p + lane * VPL + v) - __ldg(q + lane * VPL + v));
-            } else {
-                const float* u = F + (size_t)skeys[b] * d;
-                const float cc = (role == 1) ? c : -c;
+            for (int q = 0; q < 4; ++q) {
+                if (!((m[q] >> L) & 1u)) continue;
+                const int j = base + L * 4 + q;
+                const int role = j / B, b = j - role * B;
+                mult += (reg_mask >> role) & 1;
+                const float c = w.coef[b] * up;
+                if (role == 0) {
+                    const float* p = F + (size_t)skeys[B + b] * d;
+                    const float* q2 = F + (size_t)skeys[2 * B + b] * d;
 #pragma unroll
-                for (int v = 0; v < VPL; ++v) acc[v] += cc * __ldg(u + lane * VPL + v);
+                    for (int v = 0; v < VPL; ++v) acc[v] += c * (__ldg(p + lane * VPL + v) - __ldg(q2 + lane * VPL + v));
+                } else {
+                    const float* u = F + (size_t)skeys[b] * d;
+                    const float cc = (role == 1) ? c : -c;
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) acc[v] += cc * __ldg(u + lane * VPL + v);
+                }
             }
         }
     }
@@ -150,7 +178,7 @@ __global__ void __launch_bounds__(256) bpr_bwd_kernel(const float* __restrict__ 
 template <int VPL>
 __global__ void __launch_bounds__(256) bpr_finish_kernel(const float* __restrict__ E0, float* __restrict__ gE0, float* __restrict__ G,
                                                          int n, float coef, const float* __restrict__ upstream, BprWs w,
-                                                         float* __restrict__ regc) {
+                                                         float* __restrict__ regc, unsigned* __restrict__ bitmap) {
     constexpr int d = 32 * VPL;
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -165,6 +193,8 @@ __global__ void __launch_bounds__(256) bpr_finish_kernel(const float* __restrict
         if (G) G[o] = 0.f;
     }
     if (regc && lane == 0) regc[node] = 0.f;
+    // batch row bitmap of the step (idg_batch_rows): the leaders are exactly its rows; racing leaders of one word all store 0
+    if (bitmap && lane == 0) bitmap[node >> 5] = 0u;
 }
 
 }  // namespace idg
@@ -185,9 +215,9 @@ extern "C" int64_t idg_bpr_workspace_bytes(int32_t B) {
         default: return fail(-1, "d must be 32, 64, 128 or 256 (%s%lld)", "", (long long)d); \
     }
 
-extern "C" int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
-                               const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda, int reg_mask,
-                               float* d_loss, void* d_ws, void* stream_) {
+static int bpr_forward_impl(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
+                            const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda, int reg_mask,
+                            float* d_loss, const idg_step_tail* tail_in, void* d_ws, void* stream_) {
     if (!d_F || !d_E0 || !d_user || !d_pos || !d_neg || !d_loss || !d_ws) return fail(-1, "idg_bpr_forward: null argument%s");
     if (B <= 0 || U <= 0 || N <= U) return fail(-1, "idg_bpr_forward: bad sizes%s");
     if (3 * (size_t)B * sizeof(int) > 200 * 1024) return fail(-1, "idg_bpr_forward: batch too large for the shared-memory key table (B=%s%lld)", "", B);
@@ -195,9 +225,24 @@ extern "C" int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_
     BprWs w = bpr_carve(d_ws, B);
     IDG_DISPATCH_D(d, (bpr_fwd_kernel<VPL><<<(B + 7) / 8, 256, 0, stream>>>(d_F, d_E0, d_user, d_pos, d_neg, B, U, reg_mask, w)));
     IDG_LAUNCH_CHECK("bpr_fwd_kernel");
-    bpr_reduce_kernel<<<1, 1024, 0, stream>>>(w, B, reg_lambda, d_loss);
+    idg_step_tail tail = {nullptr, nullptr, nullptr, 0.f, 0.f, 0.f};
+    if (tail_in) tail = *tail_in;
+    if (tail.d_step && !tail.d_scalars) return fail(-1, "idg_bpr_forward_tail: d_scalars is required with d_step%s");
+    bpr_reduce_kernel<<<1, 1024, 0, stream>>>(w, B, reg_lambda, d_loss, tail);
     IDG_LAUNCH_CHECK("bpr_reduce_kernel");
     return 0;
+}
+
+extern "C" int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
+                               const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda, int reg_mask,
+                               float* d_loss, void* d_ws, void* stream) {
+    return bpr_forward_impl(d_F, d_E0, d_user, d_pos, d_neg, B, U, N, d, reg_lambda, reg_mask, d_loss, nullptr, d_ws, stream);
+}
+
+extern "C" int idg_bpr_forward_tail(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
+                                    const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda, int reg_mask,
+                                    float* d_loss, const idg_step_tail* tail, void* d_ws, void* stream) {
+    return bpr_forward_impl(d_F, d_E0, d_user, d_pos, d_neg, B, U, N, d, reg_lambda, reg_mask, d_loss, tail, d_ws, stream);
 }
 
 extern "C" int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_mask, const float* d_upstream, float* d_G,
@@ -205,7 +250,7 @@ extern "C" int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_
     if (!d_F || !d_G || !d_ws || B <= 0) return fail(-1, "idg_bpr_backward: bad argument%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     BprWs w = bpr_carve(d_ws, B);
-    const size_t smem = sizeof(int) * 3 * (size_t)B;
+    const size_t smem = sizeof(int) * (((3 * (size_t)B) + 127) & ~(size_t)127);
     IDG_DISPATCH_D(d, {
         if (smem > 48 * 1024) IDG_CUDA(cudaFuncSetAttribute(bpr_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bpr_bwd_kernel<VPL><<<(3 * B + 7) / 8, 256, smem, stream>>>(d_F, B, reg_mask, d_upstream, w, d_G, d_regc, reg_lambda / (float)B);
@@ -214,14 +259,24 @@ extern "C" int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_
     return 0;
 }
 
-extern "C" int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
-                              const float* d_upstream, float* d_regc, void* d_ws, void* stream_) {
+static int bpr_finish_impl(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
+                           const float* d_upstream, float* d_regc, uint32_t* d_bitmap, void* d_ws, void* stream_) {
     if (!d_ws || B <= 0 || (d_gE0 && !d_E0)) return fail(-1, "idg_bpr_finish: bad argument%s");
-    if (!d_gE0 && !d_G && !d_regc) return 0;
+    if (!d_gE0 && !d_G && !d_regc && !d_bitmap) return 0;
     cudaStream_t stream = (cudaStream_t)stream_;
     BprWs w = bpr_carve(d_ws, B);
     const float coef = reg_lambda / (float)B;
-    IDG_DISPATCH_D(d, (bpr_finish_kernel<VPL><<<(3 * B + 7) / 8, 256, 0, stream>>>(d_E0, d_gE0, d_G, 3 * B, coef, d_upstream, w, d_regc)));
+    IDG_DISPATCH_D(d, (bpr_finish_kernel<VPL><<<(3 * B + 7) / 8, 256, 0, stream>>>(d_E0, d_gE0, d_G, 3 * B, coef, d_upstream, w, d_regc, d_bitmap)));
     IDG_LAUNCH_CHECK("bpr_finish_kernel");
     return 0;
+}
+
+extern "C" int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
+                              const float* d_upstream, float* d_regc, void* d_ws, void* stream) {
+    return bpr_finish_impl(d_E0, d_gE0, d_G, B, d, reg_lambda, d_upstream, d_regc, nullptr, d_ws, stream);
+}
+
+extern "C" int idg_bpr_finish_clear(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
+                                    const float* d_upstream, float* d_regc, uint32_t* d_bitmap, void* d_ws, void* stream) {
+    return bpr_finish_impl(d_E0, d_gE0, d_G, B, d, reg_lambda, d_upstream, d_regc, d_bitmap, d_ws, stream);
 }

@@ -457,20 +457,24 @@ __global__ void __launch_bounds__(256) batch_rows_kernel(const int64_t* __restri
                                                          const int64_t* __restrict__ neg, int B, int U, int* __restrict__ rowlist,
                                                          int* __restrict__ count, unsigned* __restrict__ bitmap,
                                                          unsigned char* __restrict__ lead) {
-    extern __shared__ int skeys[];
+    extern __shared__ __align__(16) int skeys[];   // [3B] padded with -1 to a multiple of 128 (4 keys per lane and step)
     const int n = 3 * B;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int npad = (n + 127) & ~127;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
         const int role = i / B, b = i - role * B;
-        skeys[i] = role == 0 ? (int)user[b] : U + (int)(role == 1 ? pos[b] : neg[b]);
+        skeys[i] = (i >= n) ? -1 : (role == 0 ? (int)user[b] : U + (int)(role == 1 ? pos[b] : neg[b]));
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (e >= n) return;
     const int node = skeys[e];
-    for (int base = 0; base < e; base += 32) {
-        const int i = base + lane;
-        if (__any_sync(0xffffffffu, (i < e) && (skeys[i] == node))) {
+    const int4* skeys4 = reinterpret_cast<const int4*>(skeys);
+    for (int base = 0; base < e; base += 128) {
+        const int i = base + lane * 4;
+        const int4 k = skeys4[i >> 2];
+        const bool hit = ((i < e) && (k.x == node)) || ((i + 1 < e) && (k.y == node)) || ((i + 2 < e) && (k.z == node)) || ((i + 3 < e) && (k.w == node));
+        if (__any_sync(0xffffffffu, hit)) {
             if (lead && lane == 0) lead[e] = 0;
             return;
         }
@@ -558,7 +562,7 @@ __global__ void expand_rows_kernel(const int* __restrict__ rowlist, const int* _
 static int batch_rows_impl(const int64_t* d_user, const int64_t* d_pos, const int64_t* d_neg, int32_t B, int32_t U,
                            int32_t* d_rowlist, int32_t* d_count, uint32_t* d_bitmap, unsigned char* d_lead, void* stream_) {
     if (!d_user || !d_pos || !d_neg || !d_rowlist || !d_count || !d_bitmap || B <= 0) return fail(-1, "idg_batch_rows: bad argument%s");
-    const size_t smem = sizeof(int) * 3 * (size_t)B;
+    const size_t smem = sizeof(int) * (((3 * (size_t)B) + 127) & ~(size_t)127);
     if (smem > 200 * 1024) return fail(-1, "idg_batch_rows: batch too large (B=%s%lld)", "", B);
     cudaStream_t stream = (cudaStream_t)stream_;
     IDG_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), stream));

@@ -83,6 +83,8 @@ SIGNATURES = {
     "idg_propagate_bwd_ex": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
     "idg_bpr_workspace_bytes": (_i64, [_i32]),
     "idg_bpr_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, C.c_int, _p, _p, _p]),
+    "idg_bpr_forward_tail": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, C.c_int, _p, _p, _p, _p]),
+    "idg_bpr_finish_clear": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _p, _p, _p, _p, _p]),
     "idg_bpr_backward": (C.c_int, [_p, _i32, _i32, C.c_int, _p, _p, _f32, _p, _p, _p]),
     "idg_bpr_finish": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _p, _p, _p, _p]),
     "idg_axpby": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
@@ -129,6 +131,11 @@ SIGNATURES = {
 class AdamArgs(C.Structure):
     """idg_adam_args of include/idgrec.h."""
     _fields_ = [("p", _p), ("m", _p), ("v", _p), ("regc", _p), ("d_scalars", _p), ("beta1", _f32), ("beta2", _f32), ("eps", _f32)]
+
+
+class StepTail(C.Structure):
+    """idg_step_tail of include/idgrec.h."""
+    _fields_ = [("d_loss_acc", _p), ("d_step", _p), ("d_scalars", _p), ("lr", _f32), ("beta1", _f32), ("beta2", _f32)]
 
 
 _lib = None

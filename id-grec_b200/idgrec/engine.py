@@ -74,6 +74,13 @@ class FusedTrainer:
         self.regc = torch.zeros(self.N, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
+        # scalar tail of the BPR loss reduction: epoch loss sums (models whose loss list is complete after BPR) and the
+        # bias-corrected Adam scalars of the step -- two single-thread launches less per step
+        self._tail_acc = kind in ("LightGCN", "MFBPR")
+        self._tail = {}
+        for with_adam in (False, True):
+            self._tail[with_adam] = _lib.StepTail(ptr(self.loss_acc) if self._tail_acc else None, ptr(self.d_step) if with_adam else None,
+                                                  ptr(self.adam_scalars) if with_adam else None, lr, betas[0], betas[1])
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -87,16 +94,17 @@ class FusedTrainer:
 
     def _bpr(self, B, u, p, n, fused):
         l, s = self.l, cur_stream()
-        check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, 7,
-                                ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
+        import ctypes as C
+        check(l.idg_bpr_forward_tail(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, 7,
+                                     ptr(self.loss), C.byref(self._tail[bool(fused)]), ptr(self.ws), s), "idg_bpr_forward_tail")
         check(l.idg_bpr_backward(ptr(self.F), B, self.d, 7, None, ptr(self.G), self.reg_lambda, ptr(self.regc) if fused else None,
                                  ptr(self.ws), s), "idg_bpr_backward")
-        if fused:
-            check(l.idg_adam_prepare(ptr(self.d_step), ptr(self.adam_scalars), self.lr, self.betas[0], self.betas[1], s), "idg_adam_prepare")
 
     def _finish(self, B, fused):
-        check(self.l.idg_bpr_finish(ptr(self.E0), None if fused else ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None,
-                                    ptr(self.regc) if fused else None, ptr(self.ws), cur_stream()), "idg_bpr_finish")
+        # also clears the batch-row bitmap: the rows it visits are exactly the rows of this step's row set
+        check(self.l.idg_bpr_finish_clear(ptr(self.E0), None if fused else ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None,
+                                          ptr(self.regc) if fused else None, ptr(self.rows.bitmap) if self.rows is not None else None,
+                                          ptr(self.ws), cur_stream()), "idg_bpr_finish_clear")
 
     def _draw_noise(self, view):
         if self.injected_noise is not None:
@@ -159,8 +167,8 @@ class FusedTrainer:
                 for idx, _ in uniq:  # entries past the count are stale but valid rows of an all-zero table: harmless
                     check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), B, self.d, s), "idg_zero_rows")
         self._finish(B, fused)
-        if rows is not None:
-            rows.clear()
+        if rows is not None and rows.closure is not None:
+            rows.closure.zero_()
 
     # ------------------------------------------------------------------ public
     def step(self, users, pos, neg, apply_adam=True):
@@ -176,7 +184,8 @@ class FusedTrainer:
             if not fused:
                 self._adam()
             self.step_count += 1
-        self.loss_acc += self.loss
+        if not self._tail_acc:
+            self.loss_acc += self.loss
         return self.loss[:self.n_loss]
 
     def _step_graph(self, B, users, pos, neg):
@@ -197,7 +206,8 @@ class FusedTrainer:
             self._body(B, u, p, n, fused=self.fuse_adam)
             if not self.fuse_adam:
                 self._adam()
-            check(self.l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, cur_stream()), "idg_axpby")
+            if not self._tail_acc:
+                check(self.l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, cur_stream()), "idg_axpby")
 
         # warm-up outside capture would advance the model; capture directly (kernels are launched lazily at replay)
         torch.cuda.synchronize()

@@ -40,6 +40,16 @@ typedef struct idg_adam_args {
     float beta1, beta2, eps;
 } idg_adam_args;
 
+/* Scalar work of one captured train step folded into the single-thread epilogue of the BPR loss reduction
+ * (idg_bpr_forward_tail): d_loss_acc[0..1] += {bpr, reg} (epoch sums, read once per epoch instead of trainer.py:52's
+ * .item() per batch) and, when d_step is given, the job of idg_adam_prepare for this step.  Any pointer may be NULL. */
+typedef struct idg_step_tail {
+    float* d_loss_acc;
+    int32_t* d_step;
+    float* d_scalars;
+    float lr, beta1, beta2;
+} idg_step_tail;
+
 int idg_version(void);
 const char* idg_last_error(void);
 /* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
@@ -173,6 +183,9 @@ int idg_bpr_forward(const float* d_F, const float* d_E0, const int64_t* d_user, 
 /* backward: writes the touched rows of d_G = upstream[0] * d bpr / dF.  d_upstream: device float[2]
  * = (dL/d bpr, dL/d reg) handed down by autograd, or NULL for (1, 1).  d_regc (may be NULL): [N] floats, all
  * zero on entry; receives upstream[1]*reg_lambda/B*multiplicity for the touched rows (Adam-fused path). */
+int idg_bpr_forward_tail(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,
+                         const int64_t* d_neg, int32_t B, int32_t U, int32_t N, int32_t d, float reg_lambda, int reg_mask,
+                         float* d_loss, const idg_step_tail* tail, void* d_ws, void* stream);
 int idg_bpr_backward(const float* d_F, int32_t B, int32_t d, int reg_mask, const float* d_upstream,
                      float* d_G, float reg_lambda, float* d_regc, void* d_ws, void* stream);
 /* After the propagation backward has consumed G: adds the L2-reg gradient
@@ -182,6 +195,10 @@ int idg_bpr_finish(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32
                    const float* d_upstream, float* d_regc, void* d_ws, void* stream);
 
 /* small utilities used between the fused kernels */
+/* idg_bpr_finish that also clears the step's batch-row bitmap (the rows it visits are exactly the rows
+ * idg_batch_rows listed), replacing a separate idg_batch_rows_clear launch. */
+int idg_bpr_finish_clear(const float* d_E0, float* d_gE0, float* d_G, int32_t B, int32_t d, float reg_lambda,
+                         const float* d_upstream, float* d_regc, uint32_t* d_bitmap, void* d_ws, void* stream);
 int idg_axpby(float* d_out, float a, const float* d_x, float b, const float* d_y, int64_t n, void* stream);
 int idg_zero_rows(float* d_buf, const int64_t* d_idx, int32_t n, int32_t d, void* stream);
 
