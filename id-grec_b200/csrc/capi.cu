@@ -212,3 +212,29 @@ extern "C" int idg_permute3(const int64_t* d_a, const int64_t* d_b, const int64_
     IDG_LAUNCH_CHECK("permute3_kernel");
     return 0;
 }
+
+// nn.Tanh of EGCF's propagation (models/EGCF.py:42,52-53,71), forward and backward (gx = gy * (1 - y^2))
+__global__ void tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = tanhf(x[i]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gy, float* __restrict__ gx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float t = y[i]; gx[i] = gy[i] * (1.f - t * t); }
+}
+
+extern "C" int idg_tanh_fwd(const float* d_x, float* d_y, int64_t n, void* stream) {
+    if (!d_x || !d_y || n < 0) return fail(-1, "idg_tanh_fwd: bad argument%s");
+    if (n == 0) return 0;
+    tanh_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_y, n);
+    IDG_LAUNCH_CHECK("tanh_fwd_kernel");
+    return 0;
+}
+
+extern "C" int idg_tanh_bwd(const float* d_y, const float* d_gy, float* d_gx, int64_t n, void* stream) {
+    if (!d_y || !d_gy || !d_gx || n < 0) return fail(-1, "idg_tanh_bwd: bad argument%s");
+    if (n == 0) return 0;
+    tanh_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_y, d_gy, d_gx, n);
+    IDG_LAUNCH_CHECK("tanh_bwd_kernel");
+    return 0;
+}

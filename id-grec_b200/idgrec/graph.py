@@ -34,8 +34,12 @@ class DeviceCSR:
 
 
 def build_norm_adjacency(train_user, train_item, num_users: int, num_items: int, add_self: bool = False,
-                         device="cuda") -> DeviceCSR:
-    """data_graph.py:33-55 (``add_self=False``) / :7-30 (``add_self=True``) on the device."""
+                         device="cuda", f64_degrees: bool | None = None) -> DeviceCSR:
+    """data_graph.py:33-55 (``add_self=False``) / :7-30 (``add_self=True``) on the device.
+    ``f64_degrees`` (default: same as add_self): d = deg^-1/2 and the products in float64, rounded to fp32 once --
+    the arithmetic of sparse_adjacency_matrix_with_self and of sparse_adjacency_matrix_R (data_graph.py:56-77, whose
+    D_u^-1/2 R D_i^-1/2 is the upper-right block of this symmetric matrix and its transpose the lower-left one)."""
+    f64 = add_self if f64_degrees is None else bool(f64_degrees)
     l = _lib.lib()
     dev = torch.device(device)
     if torch.is_tensor(train_user):
@@ -57,7 +61,7 @@ def build_norm_adjacency(train_user, train_item, num_users: int, num_items: int,
         nnz = int(nnz.value)
         deg_h = deg.cpu().numpy()
         with np.errstate(divide="ignore"):
-            if add_self:  # dok_f32 + sp.eye promotes to float64 (data_graph.py:19-24)
+            if f64:  # dok_f32 + sp.eye promotes to float64 (data_graph.py:19-24); user_item_net is float64 (:62-70)
                 d = np.power(deg_h, -0.5)
             else:         # float32 throughout (data_graph.py:44-48)
                 d = np.power(deg_h.astype(np.float32), np.float32(-0.5)).astype(np.float32)
@@ -65,7 +69,7 @@ def build_norm_adjacency(train_user, train_item, num_users: int, num_items: int,
         d_dev = torch.from_numpy(d).to(dev)
         data = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
         check(l.idg_csr_normalise(ptr(indptr), ptr(indices), ptr(mult), N, nnz,
-                                  None if add_self else ptr(d_dev), ptr(d_dev) if add_self else None, ptr(data), cur_stream()),
+                                  None if f64 else ptr(d_dev), ptr(d_dev) if f64 else None, ptr(data), cur_stream()),
               "idg_csr_normalise")
         indices = indices[:nnz].clone()
         data = data[:nnz].clone()

@@ -66,6 +66,55 @@ def spmm(X, graph):
     return SpmmFn.apply(X, graph)
 
 
+class RowRangeSpmmFn(torch.autograd.Function):
+    """Y[rows of g_out] = A_hat[those rows, :] . X, zero elsewhere -- e.g. torch.sparse.mm(R, item_embedding) of
+    models/EGCF.py:52 with R the user rows of the symmetric bipartite matrix and X = [0; item_embedding].  Backward for a
+    symmetric bipartite A_hat: the rows that can receive gradient are g_in's (the other side), gX = A_hat[g_in rows, :] . gY."""
+
+    @staticmethod
+    def forward(ctx, X, g_out, g_in):
+        X = _f32c(X)
+        ctx.g_in = g_in
+        Y = torch.zeros_like(X)
+        g_out.spmm_layer(X, Y=Y)
+        return Y
+
+    @staticmethod
+    def backward(ctx, gY):
+        gY = _f32c(gY)
+        gX = torch.zeros_like(gY)
+        ctx.g_in.spmm_layer(gY, Y=gX)
+        return gX, None, None
+
+
+def spmm_rows(X, g_out, g_in):
+    return RowRangeSpmmFn.apply(X, g_out, g_in)
+
+
+class TanhFn(torch.autograd.Function):
+    """nn.Tanh (models/EGCF.py:42) on the CUDA library's element-wise kernels."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        check(_lib.lib().idg_tanh_fwd(ptr(x), ptr(y), x.numel(), cur_stream()), "idg_tanh_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = _f32c(gy)
+        gx = torch.empty_like(gy)
+        check(_lib.lib().idg_tanh_bwd(ptr(y), ptr(gy), ptr(gx), y.numel(), cur_stream()), "idg_tanh_bwd")
+        return gx
+
+
+def tanh(x):
+    return TanhFn.apply(x)
+
+
 class NgcfLayerFn(torch.autograd.Function):
     """One NGCF layer (NGCF.py:85-106): SpMM + fused dense epilogue kernels, forward and backward.
     Returns (D, O): the next layer's input and the row-normalised block of the final concat."""

@@ -14,7 +14,7 @@ import Parser
 import utility.utility_data.data_loader as data_loader
 import utility.utility_function.tools as tools
 
-MODELS = ("LightGCN", "SimGCL", "XSimGCL", "NGCF", "MFBPR", "SGL", "LightCCF", "LightCSCF", "SCCF", "DirectAU")
+MODELS = ("LightGCN", "SimGCL", "XSimGCL", "NGCF", "MFBPR", "SGL", "LightCCF", "LightCSCF", "SCCF", "DirectAU", "EGCF")
 
 
 def main(argv=None):

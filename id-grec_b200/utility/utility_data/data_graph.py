@@ -53,6 +53,46 @@ class EdgeListAdjacency(NormAdjacency):
         super().__init__(d, add_self=False)
 
 
+class BipartiteAdjacency(NormAdjacency):
+    """What sparse_adjacency_matrix_R returns: D_u^-1/2 R D_i^-1/2 (float64 arithmetic, rounded to fp32 once by
+    tools.py:101).  On the device it is kept as the symmetric [[0, R_hat], [R_hat^T, 0]] CSR; ``.to(device)`` yields a
+    handle with the user-row half (R_hat . x) and the item-row half (R_hat^T . x) as two propagation graphs."""
+
+    class Handle:
+        def __init__(self, csr, num_users):
+            self.csr = csr
+            self.users = Graph(csr, 0, num_users)                 # rows of R_hat:   user_emb = R_hat . item_emb
+            self.items = Graph(csr, num_users, csr.shape[0])      # rows of R_hat^T: item_emb = R_hat^T . user_emb
+            self.num_users = num_users
+
+    def __init__(self, data):
+        super().__init__(data, add_self=False)
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("ID-GRec B200 hot path needs a CUDA device (got %s); there is no CPU fallback" % device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = str(device)
+        if key not in self._graphs:
+            d = self.data
+            csr = build_norm_adjacency(d.train_user, d.train_item, d.num_users, d.num_items, add_self=False, device=device, f64_degrees=True)
+            self._graphs[key] = BipartiteAdjacency.Handle(csr, d.num_users)
+        return self._graphs[key]
+
+    def tocsr(self, device="cuda"):
+        """The [U, I] matrix itself (scipy), e.g. for comparison with the reference's pre_R.npz."""
+        h = self.to(device)
+        full = h.csr.to_scipy()
+        return full[:h.num_users, h.num_users:].tocsr()
+
+
+def sparse_adjacency_matrix_R(data):
+    """D_u^-1/2 R D_i^-1/2 (data_graph.py:56-77; EGCF).  No pre_R.npz cache is written or trusted."""
+    return BipartiteAdjacency(data)
+
+
 def sparse_adjacency_matrix_with_self(data):
     """D^-1/2 (A + I) D^-1/2, float64 arithmetic rounded to fp32 once (data_graph.py:7-30; NGCF)."""
     return NormAdjacency(data, add_self=True)

@@ -329,6 +329,10 @@ int idg_neg_sample_walk(const int64_t* h_train_user, int64_t e_begin, int64_t E,
 int idg_permute3(const int64_t* d_a, const int64_t* d_b, const int64_t* d_c, const int64_t* d_perm, int64_t n,
                  int64_t* d_out, void* stream);
 
+/* nn.Tanh between the propagation layers of EGCF (models/EGCF.py:42,52-53,71): y = tanh(x); gx = gy (1 - y^2). */
+int idg_tanh_fwd(const float* d_x, float* d_y, int64_t n, void* stream);
+int idg_tanh_bwd(const float* d_y, const float* d_gy, float* d_gx, int64_t n, void* stream);
+
 /* ---- a1: data_loader.py:48-70, the dataset text format ("user item item ..." per line) parsed on the HOST in one
  * pass.  Two-call protocol: pair_cap = line_cap = 0 counts (*n_pairs, *n_lines); the second call fills
  * h_user/h_item [n_pairs] (file order = inter_users/inter_items), h_line_user/h_line_len [n_lines] (unique_users and

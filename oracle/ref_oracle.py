@@ -640,6 +640,57 @@ def next_model_step(kind: str, A, user_w, item_w, user, pos, neg, cfg: dict, enc
     return StepResult([float(l.item()) for l in losses], uw.grad.numpy().copy(), iw.grad.numpy().copy())
 
 
+def bipartite_adjacency(user_item_net: sp.csr_matrix):
+    """data_graph.py:56-77: D_u^-1/2 R D_i^-1/2 in float64 (user_item_net holds float64 ones), as the fp32 torch COO
+    tensor the model holds after tools.py:95-109 + ``.coalesce()`` (models/EGCF.py:33-35)."""
+    R = user_item_net
+    with np.errstate(divide="ignore"):
+        rd = np.power(np.array(R.sum(axis=1)), -0.5).flatten()
+        cd = np.power(np.array(R.sum(axis=0)), -0.5).flatten()
+    rd[np.isinf(rd)] = 0.0
+    cd[np.isinf(cd)] = 0.0
+    M = sp.diags(rd).dot(R).dot(sp.diags(cd)).tocoo().astype(np.float32)
+    idx = torch.from_numpy(np.stack([M.row, M.col]).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(M.data), M.shape).coalesce()
+
+
+def egcf_aggregate(Rt: torch.Tensor, A: Optional[torch.Tensor], item_w: torch.Tensor, K: int, mode: str):
+    """models/EGCF.py:45-84: users = tanh(R items); 'parallel': K x tanh(A_hat .) on [users; items], summed;
+    'alternating': users <- tanh(R items), items <- tanh(R^T users), each side summed over the layers."""
+    U, I = Rt.shape
+    if mode == "parallel":
+        users = torch.tanh(torch.sparse.mm(Rt, item_w))
+        x = torch.cat([users, item_w])
+        outs = []
+        for _ in range(K):
+            x = torch.tanh(torch.sparse.mm(A, x))
+            outs.append(x)
+        return torch.split(torch.sum(torch.stack(outs, dim=1), dim=1), [U, I])
+    items, us, its = item_w, [], []
+    for _ in range(K):
+        users = torch.tanh(torch.sparse.mm(Rt, items))
+        items = torch.tanh(torch.sparse.mm(Rt.transpose(0, 1), users))
+        us.append(users)
+        its.append(items)
+    return torch.sum(torch.stack(us, dim=1), dim=1), torch.sum(torch.stack(its, dim=1), dim=1)
+
+
+def egcf_step(Rt, A, item_w, user, pos, neg, cfg: dict, mode: str, K: int = 3):
+    """models/EGCF.py:86-112 forward + backward -> (losses, grad_item, final_users, final_items)."""
+    iw = torch.nn.Parameter(torch.from_numpy(np.array(item_w, dtype=np.float32)))
+    user, pos, neg = (torch.as_tensor(t, dtype=torch.long) for t in (user, pos, neg))
+    fu, fi = egcf_aggregate(Rt, A, iw, K, mode)
+    ue, pe, ne = fu[user], fi[pos], fi[neg]
+    tau = float(cfg["temperature"])
+    losses = [bpr_loss(ue, pe, ne), float(cfg["reg_lambda"]) * reg_loss(iw[pos], iw[neg]),
+              float(cfg["ssl_lambda"]) * (infonce_loss(ue, ue, tau) + infonce_loss(pe, pe, tau) + infonce_loss(ue, pe, tau))]
+    total = 0.0
+    for l in losses:
+        total = total + l
+    total.backward()
+    return [float(l.item()) for l in losses], iw.grad.numpy().copy(), fu.detach().numpy().copy(), fi.detach().numpy().copy()
+
+
 # --------------------------------------------------------------------------
 # timing helper for bench.py's cpu_baseline / --impl reference legs
 # --------------------------------------------------------------------------

@@ -159,6 +159,27 @@ def main():
         out["sgl_loss"] = np.array([l.item() for l in ll])
         out["sgl_gu"], out["sgl_gi"] = grads(mm)
 
+        # ---------------- EGCF (item-only embeddings, R graph, tanh layers, three InfoNCE terms), both aggregate modes
+        from models.EGCF import EGCF
+        import utility.utility_data.data_graph as ref_graph
+        Rm = ref_graph.sparse_adjacency_matrix_R(data).tocsr().copy()
+        Rm.sort_indices()
+        out["egcf_R_dtype"] = np.array(str(Rm.dtype))
+        Rt = ref_tools.convert_sp_mat_to_sp_tensor(Rm).coalesce()     # what the model holds: fp32 values (tools.py:101)
+        out["egcf_R_index"], out["egcf_R_value"] = Rt.indices().numpy(), Rt.values().numpy()
+        for mode in ("parallel", "alternating"):
+            c2 = dict(cfg, ssl_lambda="0.1", temperature="0.1", mode=mode)
+            ref_tools.set_seed(2024)
+            mm = EGCF(c2, data, dev)
+            out["egcf_item_w0"] = mm.item_embedding.weight.detach().numpy().copy()
+            with torch.no_grad():
+                fu, fi = mm.parallel_aggregate() if mode == "parallel" else mm.alternating_aggregate()
+            out["egcf_%s_fu" % mode], out["egcf_%s_fi" % mode] = fu.numpy().copy(), fi.numpy().copy()
+            ll = mm(bu, bp, bn)
+            sum(ll).backward()
+            out["egcf_%s_loss" % mode] = np.array([l.item() for l in ll])
+            out["egcf_%s_gi" % mode] = mm.item_embedding.weight.grad.numpy().copy()
+
         # ---------------- functional known answers for the added losses
         g = torch.Generator().manual_seed(11)
         a, b = (torch.randn(37, 64, generator=g) for _ in range(2))

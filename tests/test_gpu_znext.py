@@ -230,17 +230,48 @@ def test_sgl_vs_reference(dev, golden_dirs, golden_tiny, golden_next, monkeypatc
     assert Trainer is not None
 
 
-@pytest.mark.parametrize("kind", ["LightCCF", "DirectAU", "SGL"])
+@pytest.mark.parametrize("mode", ["parallel", "alternating"])
+def test_egcf_vs_reference(dev, golden_dirs, golden_next, mode):
+    """EGCF.py:45-112: the R graph equals the reference's bit for bit (float64 degrees, rounded to fp32 once), final
+    embeddings, losses and the item-table gradient equal the reference's in both aggregate modes."""
+    import utility.utility_function.tools as tools
+    from models.EGCF import EGCF
+    cfg = _cfg("EGCF", batch_size=256, mode=mode, ssl_lambda=0.1, temperature=0.1)
+    d = _data(golden_dirs, cfg)
+    tools.set_seed(2024)
+    m = EGCF(cfg, d, dev)
+    # same torch-generator draws as the reference: nn.Embedding's own init, then xavier on the item table only
+    np.testing.assert_array_equal(m.item_embedding.weight.detach().numpy(), golden_next["egcf_item_w0"])
+    R = m.user_Graph.csr.to_scipy()[:d.num_users, d.num_users:].tocoo()
+    order = np.lexsort((R.col, R.row))
+    np.testing.assert_array_equal(np.stack([R.row[order], R.col[order]]), golden_next["egcf_R_index"])
+    np.testing.assert_array_equal(R.data[order].view(np.uint32), golden_next["egcf_R_value"].view(np.uint32))
+    m.to(dev)
+    fu, fi = m.final_embeddings()
+    _close(fu.cpu().numpy(), golden_next["egcf_%s_fu" % mode]); _close(fi.cpu().numpy(), golden_next["egcf_%s_fi" % mode])
+    b = torch.from_numpy(golden_next["batch"].copy()).to(dev)
+    losses = m(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+    (losses[0] + losses[1] + losses[2]).backward()
+    np.testing.assert_allclose([l.item() for l in losses], golden_next["egcf_%s_loss" % mode], rtol=RTOL)
+    _close(m.item_embedding.weight.grad.cpu().numpy(), golden_next["egcf_%s_gi" % mode], rtol=1e-4)
+    r = m.get_rating_for_test(torch.arange(7, device=dev))
+    want = 1.0 / (1.0 + np.exp(-(golden_next["egcf_%s_fu" % mode][:7].astype(np.float64) @ golden_next["egcf_%s_fi" % mode].astype(np.float64).T)))
+    np.testing.assert_allclose(r.cpu().numpy(), want, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["LightCCF", "DirectAU", "SGL", "EGCF"])
 def test_trainers_run_end_to_end(dev, golden_dirs, kind, capsys):
     """Trainer(...).train() for two epochs on the tiny dataset: finite decreasing-or-equal losses, metrics in range,
     the same log lines as the reference."""
     import logging
     import utility.utility_function.tools as tools
-    cfg = _cfg(kind, batch_size=256, training_epochs=2, interval=1, test_batch_size=37, **NEXT_CFG[kind])
-    if kind != "SGL":
-        cfg["encoder"] = "LightGCN"
-    else:
+    cfg = _cfg(kind, batch_size=256, training_epochs=2, interval=1, test_batch_size=37, **NEXT_CFG.get(kind, {}))
+    if kind == "SGL":
         cfg.update(aug_type="ed", ssl_ratio="0.1")
+    elif kind == "EGCF":
+        cfg.update(mode="alternating", top_K="[10, 20]")
+    else:
+        cfg["encoder"] = "LightGCN"
     tools.set_seed(2024)
     d = _data(golden_dirs, cfg)
     logger = logging.getLogger("idgrec-test-" + kind)
@@ -252,10 +283,10 @@ def test_trainers_run_end_to_end(dev, golden_dirs, kind, capsys):
     logger.addHandler(H())
     logger.setLevel(logging.INFO)
     tr = importlib.import_module("models." + kind).Trainer(None, cfg, d, dev, logger)
-    w0 = tr.model.user_embedding.weight.detach().clone()
+    w0 = tr.model.item_embedding.weight.detach().clone()
     tr.train()
     assert any("training loss" in r for r in records) and any("Test recall" in r for r in records)
-    w1 = tr.model.user_embedding.weight.detach().cpu()
+    w1 = tr.model.item_embedding.weight.detach().cpu()
     assert torch.isfinite(w1).all() and not torch.equal(w1, w0.cpu())
 
 
@@ -297,7 +328,7 @@ def test_sparsity_test_and_top40_vs_reference(dev, golden_dirs, golden_tiny, gol
 # ------------------------------------------------------------------------------------------------
 # whole-step CUDA-graph replay of the autograd-path models
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind", ["LightCCF", "DirectAU", "NGCF"])
+@pytest.mark.parametrize("kind", ["LightCCF", "DirectAU", "NGCF", "EGCF"])
 def test_graphed_step_equals_eager_loop(dev, golden_dirs, golden_tiny, kind):
     """GraphedStep (forward -> backward -> capturable Adam replayed from a CUDA graph, captured per batch size, warm-up
     undone) follows the same trajectory as the reference's eager loop (trainer.py:40-56) over 5 batches incl. a short one."""
@@ -305,6 +336,8 @@ def test_graphed_step_equals_eager_loop(dev, golden_dirs, golden_tiny, kind):
     over = dict(NEXT_CFG.get(kind, {}))
     if kind == "NGCF":
         over = {"mess_drop_prob": "[0.0, 0.0, 0.0]"}      # dropout off: both runs must be deterministic
+    elif kind == "EGCF":
+        over = {"mode": "parallel"}
     else:
         over["encoder"] = "LightGCN"
     cfg = _cfg(kind, batch_size=256, **over)

@@ -103,6 +103,23 @@ def test_oracle_sparsity_groups_match_reference(golden_dirs, golden_tiny, golden
         np.testing.assert_allclose(full[k], golden_next["test2040_" + k], atol=5e-5)
 
 
+@pytest.mark.parametrize("mode", ["parallel", "alternating"])
+def test_oracle_egcf_matches_reference(golden_dirs, golden_next, mode):
+    from oracle import ref_oracle as O
+    d, A = _tiny_graph(golden_dirs)
+    Rt = O.bipartite_adjacency(d.user_item_net)
+    assert str(golden_next["egcf_R_dtype"]) == "float64"
+    np.testing.assert_array_equal(Rt.indices().numpy(), golden_next["egcf_R_index"])
+    np.testing.assert_array_equal(Rt.values().numpy().view(np.uint32), golden_next["egcf_R_value"].view(np.uint32))
+    b = golden_next["batch"]
+    cfg = dict(reg_lambda=1e-4, ssl_lambda=0.1, temperature=0.1)
+    losses, gi, fu, fi = O.egcf_step(Rt, A, golden_next["egcf_item_w0"], b[:, 0], b[:, 1], b[:, 2], cfg, mode)
+    np.testing.assert_allclose(losses, golden_next["egcf_%s_loss" % mode], rtol=2e-6)
+    _close(gi, golden_next["egcf_%s_gi" % mode], 1e-5)
+    _close(fu, golden_next["egcf_%s_fu" % mode], 1e-6)
+    _close(fi, golden_next["egcf_%s_fi" % mode], 1e-6)
+
+
 def test_functional_known_answers(golden_next):
     from oracle import ref_oracle as O
     a, b = torch.from_numpy(golden_next["fn_a"]), torch.from_numpy(golden_next["fn_b"])

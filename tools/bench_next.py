@@ -53,7 +53,7 @@ def main():
     # ---- one autograd train step of the added models
     graphs = {}
     for shape, kind, over in (("amazon-book", "LightCCF", {}), ("amazon-book", "LightCSCF", {}), ("amazon-book", "NGCF", {}),
-                              ("yelp2018", "DirectAU", {}), ("yelp2018", "SCCF", {"encoder": "LightGCN"}), ("yelp2018", "SGL", {})):
+                              ("yelp2018", "DirectAU", {}), ("yelp2018", "SCCF", {"encoder": "LightGCN"}), ("yelp2018", "SGL", {}), ("yelp2018", "EGCF", {})):
         g = graphs.get(shape) or graphs.setdefault(shape, datagen.gen_graph(shape))
         cfg = tools.read_configuration(os.path.join(REPO, "id-grec_b200", "configure", kind + ".txt"), kind)
         cfg.update(over)
