@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(256) nce_tc_transpose_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------------
 // scores: E[r][c] = exp(<x_r, y_c>/tau) for r, c < n (0 elsewhere) as (hi, lo); optional row-sum partials.
 // grid (n_pad/128, kNtSplits); 256 threads.  smem: X hi/lo 64 KB + 2 stages x (Y hi/lo 64 KB) = 192 KB.
+// EPI 0: E = exp(S / tau) as (hi, lo) + row-sum partials (InfoNCE).  EPI 1: raw S into EH (one fp32 matrix, ld n_pad, 0 outside
+// n x n).  EPI 2: EH += S (the S + R sum of the neighbourhood-aggregation losses, csrc/pairloss.cu).
+template <int EPI>
 __global__ void __launch_bounds__(256, 1) nce_tc_scores_kernel(const float* __restrict__ XH, const float* __restrict__ XL,
                                                                const float* __restrict__ YH, const float* __restrict__ YL,
                                                                const int* __restrict__ d_n, int n_in, int n_pad, float inv_tau,
@@ -189,16 +192,28 @@ __global__ void __launch_bounds__(256, 1) nce_tc_scores_kernel(const float* __re
                 float4* el = reinterpret_cast<float4*>(EL + (size_t)r * n_pad + c0);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    float h[4], l[4];
+                    if (EPI == 0) {
+                        float h[4], l[4];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 * 4 + jj;
-                        const float e = (rvalid && c0 + j < n) ? expf(__uint_as_float(raw[j]) * inv_tau) : 0.f;
-                        rowsum += e;
-                        split_tf32(e, h[jj], l[jj]);
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            const float e = (rvalid && c0 + j < n) ? expf(__uint_as_float(raw[j]) * inv_tau) : 0.f;
+                            rowsum += e;
+                            split_tf32(e, h[jj], l[jj]);
+                        }
+                        eh[j4] = make_float4(h[0], h[1], h[2], h[3]);
+                        el[j4] = make_float4(l[0], l[1], l[2], l[3]);
+                    } else {
+                        float v[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            v[jj] = (rvalid && c0 + j < n) ? __uint_as_float(raw[j]) : 0.f;
+                        }
+                        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+                        if (EPI == 2) { const float4 old = eh[j4]; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                        eh[j4] = o;
                     }
-                    eh[j4] = make_float4(h[0], h[1], h[2], h[3]);
-                    el[j4] = make_float4(l[0], l[1], l[2], l[3]);
                 }
             }
         }
@@ -352,12 +367,12 @@ int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, 
     if (stage == 0) {
         nce_tc_split_kernel<<<(np + 7) / 8, 256, 0, stream>>>(A, Bm, d_n, n_max, np, AH, AL, BH, BL);
         IDG_LAUNCH_CHECK("nce_tc_split_kernel");
-        IDG_CUDA(cudaFuncSetAttribute(nce_tc_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-        nce_tc_scores_kernel<<<grid, 256, smem_s, stream>>>(AH, AL, BH, BL, d_n, n_max, np, inv_tau, E1H, E1L, part_sum);
+        IDG_CUDA(cudaFuncSetAttribute(nce_tc_scores_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        nce_tc_scores_kernel<0><<<grid, 256, smem_s, stream>>>(AH, AL, BH, BL, d_n, n_max, np, inv_tau, E1H, E1L, part_sum);
         IDG_LAUNCH_CHECK("nce_tc_scores_kernel");
         return 0;
     }
-    nce_tc_scores_kernel<<<grid, 256, smem_s, stream>>>(BH, BL, AH, AL, d_n, n_max, np, inv_tau, E2H, E2L, nullptr);
+    nce_tc_scores_kernel<0><<<grid, 256, smem_s, stream>>>(BH, BL, AH, AL, d_n, n_max, np, inv_tau, E2H, E2L, nullptr);
     IDG_LAUNCH_CHECK("nce_tc_scores_kernel");
     nce_tc_transpose_kernel<<<np / 32, 256, 0, stream>>>(Bm, nullptr, d_n, n_max, np, BtH, BtL);
     IDG_LAUNCH_CHECK("nce_tc_transpose_kernel");
@@ -367,6 +382,38 @@ int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, 
     nce_tc_gemm_kernel<<<grid, 256, smem_g, stream>>>(E1H, E1L, BtH, BtL, d_n, n_max, np, part_pb);
     IDG_LAUNCH_CHECK("nce_tc_gemm_kernel");
     nce_tc_gemm_kernel<<<grid, 256, smem_g, stream>>>(E2H, E2L, AtH, AtL, d_n, n_max, np, part_qa);
+    IDG_LAUNCH_CHECK("nce_tc_gemm_kernel");
+    return 0;
+}
+
+// ---- entry points for csrc/pairloss.cu (same kernels, plain n x n x 64 contractions) ------------------------------------------
+// (hi, lo) splits of two [n,64] operands, rows >= n zero (n_pad rows each)
+int tc_split_rows(const float* A, const float* B, int n, int np, float* AH, float* AL, float* BH, float* BL, cudaStream_t stream) {
+    nce_tc_split_kernel<<<(np + 7) / 8, 256, 0, stream>>>(A, B, nullptr, n, np, AH, AL, BH, BL);
+    IDG_LAUNCH_CHECK("nce_tc_split_kernel");
+    return 0;
+}
+
+// out[n_pad, n_pad] (=|+=) X Y^T on the n x n block, 0 (or unchanged + 0) outside; X, Y given as splits
+int tc_scores_raw(const float* XH, const float* XL, const float* YH, const float* YL, int n, int np, float* out, int accumulate, cudaStream_t stream) {
+    const size_t smem_s = 4 * kAtom128 + 2 * 4 * kAtom128 + 128;
+    const dim3 grid(np / 128, kNtSplits);
+    if (accumulate) {
+        IDG_CUDA(cudaFuncSetAttribute(nce_tc_scores_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        nce_tc_scores_kernel<2><<<grid, 256, smem_s, stream>>>(XH, XL, YH, YL, nullptr, n, np, 1.f, out, nullptr, nullptr);
+    } else {
+        IDG_CUDA(cudaFuncSetAttribute(nce_tc_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        nce_tc_scores_kernel<1><<<grid, 256, smem_s, stream>>>(XH, XL, YH, YL, nullptr, n, np, 1.f, out, nullptr, nullptr);
+    }
+    IDG_LAUNCH_CHECK("nce_tc_scores_kernel");
+    return 0;
+}
+
+// part[kNtSplits][n_pad][64]: split-wise partial sums of E . Yt^T  (E [n_pad,n_pad] and Yt [64,n_pad] as splits, zero outside n)
+int tc_gemm64(const float* EH, const float* EL, const float* TH, const float* TL, int n, int np, float* part, cudaStream_t stream) {
+    const size_t smem_g = 4 * (2 * kAtom128 + 2 * kAtom64) + 128;
+    IDG_CUDA(cudaFuncSetAttribute(nce_tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    nce_tc_gemm_kernel<<<dim3(np / 128, kNtSplits), 256, smem_g, stream>>>(EH, EL, TH, TL, nullptr, n, np, part);
     IDG_LAUNCH_CHECK("nce_tc_gemm_kernel");
     return 0;
 }

@@ -13,6 +13,10 @@
 // so the path is: row normalise -> fp32 GEMMs (S, R) -> one row kernel that turns S into H in place (deterministic
 // block reductions, fixed order) -> three GEMMs against the [n,d] operands -> normalisation backward.
 // n is a mini-batch (<= 4096): the n x n fp32 matrices (<= 64 MB) stay in L2; nothing here touches the [N,d] tables.
+// For d = 64 and n >= 256 every contraction runs on the tcgen05 tensor cores as a 3xTF32 split product (the kernels of
+// csrc/infonce_tc.cu: TMEM accumulators, error ~2^-21, inside the 1e-5 parity bar): S (+ R) by the scores kernel with a raw
+// epilogue, the row kernels write dL/dS directly as (hi, lo) pairs, H (a + b) and H^T a by the [n,n] x [n,64] kernel.
+// Other shapes (d != 64, tiny batches) take the fp32 CUDA-core tiles below.
 // Duplicate ids in the batch are handled by idg_gather_rows / idg_scatter_add_rows (first occurrence sums all of its
 // duplicates in entry order: no float atomics, bit-reproducible).
 #include <math.h>
@@ -20,6 +24,11 @@
 #include "idg_common.cuh"
 
 namespace idg {
+
+// csrc/infonce_tc.cu: 3xTF32 contractions on tcgen05 (n_pad = n rounded up to 128)
+int tc_split_rows(const float* A, const float* B, int n, int np, float* AH, float* AL, float* BH, float* BL, cudaStream_t stream);
+int tc_scores_raw(const float* XH, const float* XL, const float* YH, const float* YL, int n, int np, float* out, int accumulate, cudaStream_t stream);
+int tc_gemm64(const float* EH, const float* EL, const float* TH, const float* TL, int n, int np, float* part, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------------------
 // C[M,N] = alpha * op(A) op(B) + beta * C,  row-major, fp32 FMA, k ascending (fixed summation order)
@@ -196,10 +205,10 @@ __global__ void __launch_bounds__(256) pl_rows_ccf_kernel(float* __restrict__ S,
 }
 
 // kind 2 pass 1: rowT_i = sum_j psi(S_ij)
-__global__ void __launch_bounds__(256) pl_rows_sccf_sum_kernel(const float* __restrict__ S, int n, int m, float tau, float* __restrict__ rowT) {
+__global__ void __launch_bounds__(256) pl_rows_sccf_sum_kernel(const float* __restrict__ S, int m, int ld, float tau, float* __restrict__ rowT) {
     __shared__ float sm[8];
     const int i = blockIdx.x;
-    const float* s = S + (size_t)i * m;
+    const float* s = S + (size_t)i * ld;
     float part = 0.f;
     for (int j = threadIdx.x; j < m; j += 256) part += psi_sccf(s[j], tau).f;
     const float T = block_sum256(part, sm);
@@ -349,8 +358,144 @@ __global__ void __launch_bounds__(256) pl_scatter_add_kernel(const float* __rest
     }
 }
 
+// ---- tensor-core path helpers (d = 64) -------------------------------------------------------------------------------
+__device__ __forceinline__ void pl_split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
+}
+
+// diag[i] = <a_i, b_i> in fp32 (the positive score S_ii / the squared norm R_ii); one warp per row
+__global__ void __launch_bounds__(256) pl_diag_dot_kernel(const float* __restrict__ Xn, const float* __restrict__ Yn, int n, int d, float* __restrict__ diag) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s = fmaf(Xn[(size_t)i * d + c], Yn[(size_t)i * d + c], s);
+    s = warp_sum(s);
+    if (lane == 0) diag[i] = s;
+}
+
+// kinds 0/1, one CTA per row i < n of T = S + R (ld np): statistics as pl_rows_ccf_kernel, then T[i,:] <- hi(H[i,:]),
+// HL[i,:] <- lo(H[i,:]) with zeros in the padded columns [n, np)
+__global__ void __launch_bounds__(256) pl_rows_ccf_tc_kernel(float* __restrict__ T, float* __restrict__ HL, const float* __restrict__ sdiag, int n, int np,
+                                                            float tau, float margin, int use_margin, float* __restrict__ w, float* __restrict__ lossi) {
+    __shared__ float sm[8];
+    const int i = blockIdx.x;
+    float* t = T + (size_t)i * np;
+    float* hl = HL + (size_t)i * np;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < n; j += 256) part += phi_ccf(t[j], tau, margin, use_margin).f;
+    const float Tsum = block_sum256(part, sm);
+    const PhiVal pp = phi_ccf(sdiag[i], tau, margin, use_margin);
+    const float ratio = pp.f / Tsum;
+    const float q = -1.f / ((float)n * (ratio + 1e-5f));
+    const float hcoef = -q * ratio / Tsum;
+    for (int j = threadIdx.x; j < np; j += 256) {
+        float hi = 0.f, lo = 0.f;
+        if (j < n) pl_split_tf32(hcoef * phi_ccf(t[j], tau, margin, use_margin).df, hi, lo);
+        t[j] = hi; hl[j] = lo;
+    }
+    if (threadIdx.x == 0) {
+        w[i] = q * pp.df / Tsum;
+        lossi[i] = -logf(ratio + 1e-5f);
+    }
+}
+
+// kind 2 pass 2 on the padded matrix: S[i,:] <- hi(psi'(S_ij)/total), HL <- lo, zeros in the padding; one CTA per row
+__global__ void __launch_bounds__(256) pl_rows_sccf_grad_tc_kernel(float* __restrict__ S, float* __restrict__ HL, int n, int np, float tau,
+                                                                  const float* __restrict__ scal) {
+    const int i = blockIdx.x;
+    const float inv = 1.f / scal[0];
+    float* s = S + (size_t)i * np;
+    float* hl = HL + (size_t)i * np;
+    for (int j = threadIdx.x; j < np; j += 256) {
+        float hi = 0.f, lo = 0.f;
+        if (j < n) pl_split_tf32(psi_sccf(s[j], tau).df * inv, hi, lo);
+        s[j] = hi; hl[j] = lo;
+    }
+}
+
+// kind 5 on the padded matrix: R[i,:] <- hi(E[i,:]), HL <- lo, rowT_i = sum_j E_ij (E_ij = exp(-2 d_ij^2), 0 on the diagonal)
+__global__ void __launch_bounds__(256) pl_rows_uniform_tc_kernel(float* __restrict__ R, float* __restrict__ HL, const float* __restrict__ diag, int n, int np,
+                                                                float* __restrict__ rowT) {
+    __shared__ float sm[8];
+    const int i = blockIdx.x;
+    float* r = R + (size_t)i * np;
+    float* hl = HL + (size_t)i * np;
+    const float dii = diag[i];
+    float part = 0.f;
+    for (int j = threadIdx.x; j < np; j += 256) {
+        float e = 0.f;
+        if (j < n && j != i) e = expf(-2.f * fmaxf(dii + diag[j] - 2.f * r[j], 0.f));
+        float hi, lo;
+        pl_split_tf32(e, hi, lo);
+        r[j] = hi; hl[j] = lo;
+        part += e;
+    }
+    const float Tsum = block_sum256(part, sm);
+    if (threadIdx.x == 0) rowT[i] = Tsum;
+}
+
+// (OH, OL)[c][r] = (IH, IL)[r][c] on the n x n block, zero elsewhere in [np, np]; 32 x 32 tiles
+__global__ void __launch_bounds__(256) pl_transpose_split_kernel(const float* __restrict__ IH, const float* __restrict__ IL, int n, int np,
+                                                                float* __restrict__ OH, float* __restrict__ OL) {
+    __shared__ float th[32][33], tl[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int q = ty; q < 32; q += 8) {
+        const int r = r0 + q, c = c0 + tx;
+        const bool ok = r < n && c < n;
+        th[q][tx] = ok ? IH[(size_t)r * np + c] : 0.f;
+        tl[q][tx] = ok ? IL[(size_t)r * np + c] : 0.f;
+    }
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8) {
+        const int c = c0 + q, r = r0 + tx;
+        OH[(size_t)c * np + r] = th[tx][q];
+        OL[(size_t)c * np + r] = tl[tx][q];
+    }
+}
+
+// K-major right operand of the [n,n] x [n,64] product: (TH, TL)[k][c] = split(Y[c][k] (+ Y2[c][k])) for c < n, 0 beyond
+__global__ void __launch_bounds__(256) pl_operand_t_kernel(const float* __restrict__ Y, const float* __restrict__ Y2, int n, int np,
+                                                          float* __restrict__ TH, float* __restrict__ TL) {
+    __shared__ float tile[32][65];
+    const int c0 = blockIdx.x * 32;
+    for (int q = threadIdx.x; q < 32 * 64; q += 256) {
+        const int c = q >> 6, k = q & 63;
+        float v = 0.f;
+        if (c0 + c < n) { v = Y[(size_t)(c0 + c) * 64 + k]; if (Y2) v += Y2[(size_t)(c0 + c) * 64 + k]; }
+        tile[c][k] = v;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 32 * 64; q += 256) {
+        const int k = q >> 5, c = q & 31;
+        float hi, lo;
+        pl_split_tf32(tile[c][k], hi, lo);
+        TH[(size_t)k * np + c0 + c] = hi;
+        TL[(size_t)k * np + c0 + c] = lo;
+    }
+}
+
+// out[i][0..63] = sum over the 4 column splits (in split order) of part[s][i][0..63]
+__global__ void __launch_bounds__(256) pl_fold_parts_kernel(const float* __restrict__ part, int n, int np, float* __restrict__ out) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= n * 64) return;
+    const int i = e >> 6, c = e & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += part[((size_t)q * np + i) * 64 + c];
+    out[e] = s;
+}
+
+constexpr int kTcMinRows = 256;
+__host__ inline bool pl_use_tc(int n, int d) { return d == 64 && n >= kTcMinRows; }
+__host__ inline int pl_np(int n) { return (n + 127) / 128 * 128; }
+
 struct PlWs {
     float *Xn, *Yn, *YX, *nx, *ny, *S, *R, *w, *rowT, *lossi, *diag, *tA, *tB, *scal;
+    // tensor-core path (d = 64, n >= 256): operand splits [np,64] x 4, K-major operands [64,np] x 4, H^T splits [np,np] x 2 (S and R
+    // above are [np,np] there and end up holding hi(H) / lo(H)), split-wise partial products [4,np,64] x 2
+    float *XH, *XL, *YH, *YL, *T1H, *T1L, *T2H, *T2L, *HtH, *HtL, *partA, *partB;
 };
 __host__ inline size_t pl_align(size_t x) { return (x + 255) & ~(size_t)255; }
 __host__ inline size_t pl_carve(void* ws, int n, int d, PlWs* w) {
@@ -361,7 +506,18 @@ __host__ inline size_t pl_carve(void* ws, int n, int d, PlWs* w) {
     t.Xn = take(nd); t.Yn = take(nd); t.YX = take(2 * nd); t.tA = take(2 * nd); t.tB = take(nd);
     t.nx = take(n1); t.ny = take(n1); t.w = take(n1); t.rowT = take(n1); t.lossi = take(n1); t.diag = take(n1);
     t.scal = take(256);
-    t.S = take(nn); t.R = take(nn);
+    if (pl_use_tc(n, d)) {
+        const size_t np = (size_t)pl_np(n), pd = sizeof(float) * np * 64, pp = sizeof(float) * np * np;
+        t.XH = take(pd); t.XL = take(pd); t.YH = take(pd); t.YL = take(pd);
+        t.T1H = take(pd); t.T1L = take(pd); t.T2H = take(pd); t.T2L = take(pd);
+        t.partA = take(4 * pd); t.partB = take(4 * pd);
+        t.S = take(pp + 4096); t.R = take(pp + 4096); t.HtH = take(pp + 4096); t.HtL = take(pp + 4096);
+        t.S = (float*)(((uintptr_t)t.S + 1023) & ~(uintptr_t)1023); t.R = (float*)(((uintptr_t)t.R + 1023) & ~(uintptr_t)1023);
+        t.HtH = (float*)(((uintptr_t)t.HtH + 1023) & ~(uintptr_t)1023); t.HtL = (float*)(((uintptr_t)t.HtL + 1023) & ~(uintptr_t)1023);
+    } else {
+        t.XH = t.XL = t.YH = t.YL = t.T1H = t.T1L = t.T2H = t.T2L = t.HtH = t.HtL = t.partA = t.partB = nullptr;
+        t.S = take(nn); t.R = take(nn);
+    }
     if (w) *w = t;
     return (size_t)(p - (char*)ws);
 }
@@ -388,7 +544,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
     pl_carve((void*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255), n, d, &w);
     const bool want_grad = d_gX != nullptr;
     const int rb = (n + 7) / 8;
-    const bool merged = want_grad && kind <= 1;       // gradient product against [Yn | Xn] in one pass over H
+    const bool merged = want_grad && kind <= 1 && !pl_use_tc(n, d);   // fp32 path: gradient product against [Yn | Xn] in one pass over H
     pl_rownorm_kernel<<<rb, 256, 0, st>>>(d_X, n, d, w.Xn, w.nx, merged ? w.YX + d : nullptr, 2 * d);
     IDG_LAUNCH_CHECK("pl_rownorm_kernel");
     if (kind != 5) {
@@ -396,6 +552,62 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
         IDG_LAUNCH_CHECK("pl_rownorm_kernel");
     }
     int rc;
+    if (pl_use_tc(n, d) && kind != 3 && kind != 4) {
+        // ---- tcgen05 path: every n x n x 64 contraction as a 3xTF32 split product --------------------------------------
+        const int np = pl_np(n);
+        const dim3 tgrid(np / 32, np / 32);
+        if ((rc = tc_split_rows(w.Xn, kind == 5 ? w.Xn : w.Yn, n, np, w.XH, w.XL, w.YH, w.YL, st))) return rc;
+        if (kind <= 1) {
+            if ((rc = tc_scores_raw(w.XH, w.XL, w.YH, w.YL, n, np, w.S, 0, st))) return rc;       // S = a b^T
+            if ((rc = tc_scores_raw(w.XH, w.XL, w.XH, w.XL, n, np, w.S, 1, st))) return rc;       // S += a a^T
+            pl_diag_dot_kernel<<<rb, 256, 0, st>>>(w.Xn, w.Yn, n, d, w.diag);
+            IDG_LAUNCH_CHECK("pl_diag_dot_kernel");
+            pl_rows_ccf_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, w.diag, n, np, p0, p1, kind == 1, w.w, w.lossi);
+            IDG_LAUNCH_CHECK("pl_rows_ccf_tc_kernel");
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+            IDG_LAUNCH_CHECK("pl_reduce_kernel");
+        } else if (kind == 2) {
+            if ((rc = tc_scores_raw(w.XH, w.XL, w.YH, w.YL, n, np, w.S, 0, st))) return rc;
+            pl_rows_sccf_sum_kernel<<<n, 256, 0, st>>>(w.S, n, np, p0, w.rowT);   // n columns, row stride np
+            IDG_LAUNCH_CHECK("pl_rows_sccf_sum_kernel");
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss);
+            IDG_LAUNCH_CHECK("pl_reduce_kernel");
+            if (want_grad) {
+                pl_rows_sccf_grad_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, n, np, p0, w.scal);
+                IDG_LAUNCH_CHECK("pl_rows_sccf_grad_tc_kernel");
+            }
+        } else {
+            if ((rc = tc_scores_raw(w.XH, w.XL, w.XH, w.XL, n, np, w.S, 0, st))) return rc;       // R = a a^T
+            pl_diag_dot_kernel<<<rb, 256, 0, st>>>(w.Xn, w.Xn, n, d, w.diag);
+            IDG_LAUNCH_CHECK("pl_diag_dot_kernel");
+            pl_rows_uniform_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, w.diag, n, np, w.rowT);
+            IDG_LAUNCH_CHECK("pl_rows_uniform_tc_kernel");
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss);
+            IDG_LAUNCH_CHECK("pl_reduce_kernel");
+        }
+        if (want_grad) {
+            if (kind != 5 && !d_gY) return fail(-1, "idg_pair_loss: d_gY is required with d_gX for kind %s", "0..4");
+            // (w.S, w.R) now hold (hi, lo) of H.  tA = H (a + b) [kinds 0/1], H b [kind 2], E a [kind 5];  tB = H^T a
+            pl_operand_t_kernel<<<np / 32, 256, 0, st>>>(kind == 5 ? w.Xn : w.Yn, kind <= 1 ? w.Xn : nullptr, n, np, w.T1H, w.T1L);
+            IDG_LAUNCH_CHECK("pl_operand_t_kernel");
+            if ((rc = tc_gemm64(w.S, w.R, w.T1H, w.T1L, n, np, w.partA, st))) return rc;
+            pl_fold_parts_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(w.partA, n, np, w.tA);
+            IDG_LAUNCH_CHECK("pl_fold_parts_kernel");
+            if (kind != 5) {
+                pl_transpose_split_kernel<<<tgrid, 256, 0, st>>>(w.S, w.R, n, np, w.HtH, w.HtL);
+                IDG_LAUNCH_CHECK("pl_transpose_split_kernel");
+                pl_operand_t_kernel<<<np / 32, 256, 0, st>>>(w.Xn, nullptr, n, np, w.T2H, w.T2L);
+                IDG_LAUNCH_CHECK("pl_operand_t_kernel");
+                if ((rc = tc_gemm64(w.HtH, w.HtL, w.T2H, w.T2L, n, np, w.partB, st))) return rc;
+                pl_fold_parts_kernel<<<(n * 64 + 255) / 256, 256, 0, st>>>(w.partB, n, np, w.tB);
+                IDG_LAUNCH_CHECK("pl_fold_parts_kernel");
+            }
+            pl_finish_kernel<<<rb, 256, 0, st>>>(kind, d_X, d_Y, w.Xn, kind == 5 ? nullptr : w.Yn, w.nx, kind == 5 ? nullptr : w.ny,
+                                                kind <= 1 ? w.w : nullptr, w.rowT, w.scal, w.tA, 0, w.tB, n, d, d_gX, kind == 5 ? nullptr : d_gY);
+            IDG_LAUNCH_CHECK("pl_finish_kernel");
+        }
+        return 0;
+    }
     if (kind <= 1) {
         if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Yn, d, w.S, n, 1.f, 0.f, st))) return rc;
         if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Xn, d, w.R, n, 1.f, 0.f, st))) return rc;

@@ -78,7 +78,7 @@ def test_gather_scatter_rows_with_duplicates(dev, n, d, N):
 
 
 @pytest.mark.parametrize("kind", ["lightccf", "lightcscf", "sccf_down", "sccf_up", "align", "uniform"])
-@pytest.mark.parametrize("n,d", [(2, 64), (48, 64), (257, 64), (1000, 32)])
+@pytest.mark.parametrize("n,d", [(2, 64), (48, 64), (257, 64), (1000, 32), (1000, 64)])
 def test_pair_loss_kernels_vs_closed_form(dev, kind, n, d):
     """Loss and both gradients of every kind against the float64 closed form (itself checked against autograd of
     the oracle in tests/test_next_cpu.py); sizes off the 64-tile grid, duplicate rows, both margin branches."""
