@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(256) pl_rows_pairwise_kernel(int kind, const f
 }
 
 // ordered sum of v[0..n) (single CTA) and the scalar epilogue of each kind
-__global__ void __launch_bounds__(1024) pl_reduce_kernel(int kind, const float* __restrict__ v, int n, float denom, float* __restrict__ scal, float* __restrict__ d_loss) {
+// *d_loss += scale * loss (callers zero it first); cnt_a/cnt_b (optional, kind 2): the denominator is read from the device
+__global__ void __launch_bounds__(1024) pl_reduce_kernel(int kind, const float* __restrict__ v, int n, float denom, float* __restrict__ scal, float* __restrict__ d_loss,
+                                                        float scale, const int* __restrict__ cnt_a, const int* __restrict__ cnt_b) {
     __shared__ float sm[32];
     float part = 0.f;
     for (int j = threadIdx.x; j < n; j += 1024) part += v[j];
@@ -272,8 +274,11 @@ __global__ void __launch_bounds__(1024) pl_reduce_kernel(int kind, const float* 
         float out;
         if (kind == 0 || kind == 1 || kind == 4) out = t / (float)n;
         else if (kind == 3) out = -t / (float)n;
-        else out = logf(t / denom);       // kind 2: denom = n_unique_users * n_unique_items; kind 5: n (n - 1)
-        *d_loss = out;
+        else {                            // kind 2: denom = n_unique_users * n_unique_items; kind 5: n (n - 1)
+            if (kind == 2 && cnt_a && cnt_b) denom = (float)(*cnt_a) * (float)(*cnt_b);
+            out = logf(t / denom);
+        }
+        *d_loss += scale * out;
     }
 }
 
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* _
                                                        const float* __restrict__ Yn, const float* __restrict__ nx, const float* __restrict__ ny,
                                                        const float* __restrict__ w, const float* __restrict__ rowT, const float* __restrict__ scal,
                                                        const float* __restrict__ tA, int fold_tA, const float* __restrict__ tB, int n, int d,
-                                                       float* __restrict__ gX, float* __restrict__ gY) {
+                                                       float scale, float* __restrict__ gX, float* __restrict__ gY) {
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
     const size_t o = (size_t)i * d;
@@ -317,8 +322,8 @@ __global__ void __launch_bounds__(256) pl_finish_kernel(int kind, const float* _
         else if (kind == 4) { ga = 2.f * (a - b) / (float)n; gb = -ga; }
         else { ga = cu * (ri * a - tA[o + c]); }
         // d/dx of x / max(|x|, eps): (g - a <a,g>) / |x| above the clamp, g / eps below it
-        gX[o + c] = (na > 1e-12f) ? (ga - a * da) / na : ga / 1e-12f;
-        if (gY) gY[o + c] = (nb > 1e-12f) ? (gb - b * db) / nb : gb / 1e-12f;
+        gX[o + c] = scale * ((na > 1e-12f) ? (ga - a * da) / na : ga / 1e-12f);
+        if (gY) gY[o + c] = scale * ((nb > 1e-12f) ? (gb - b * db) / nb : gb / 1e-12f);
     }
     (void)X; (void)Y;
 }
@@ -331,31 +336,51 @@ __global__ void __launch_bounds__(256) pl_gather_kernel(const float* __restrict_
     for (int c = lane; c < d; c += 32) out[(size_t)i * d + c] = src[c];
 }
 
+// One warp per entry i; the ids sit in shared memory as int32 (padded with -1 to a multiple of 128) and are scanned 4 per lane
+// and step.  An entry with an earlier duplicate returns; the first occurrence sums all of its duplicates in ascending entry
+// order (d <= 256: up to 8 floats per lane) and adds the row to the table.
 __global__ void __launch_bounds__(256) pl_scatter_add_kernel(const float* __restrict__ G, const int64_t* __restrict__ idx, int n, int d, float* __restrict__ T) {
+    extern __shared__ __align__(16) int pl_skeys[];
+    const int npad = (n + 127) & ~127;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) pl_skeys[i] = (i < n) ? (int)idx[i] : -1;
+    __syncthreads();
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= n) return;
-    const int64_t me = idx[i];
-    // an earlier entry with the same id owns the row
-    for (int j0 = 0; j0 < i; j0 += 32) {
-        const int j = j0 + lane;
-        const bool hit = (j < i) && (idx[j] == me);
-        if (__ballot_sync(0xffffffffu, hit)) return;
+    const int me = pl_skeys[i];
+    const int4* k4 = reinterpret_cast<const int4*>(pl_skeys);
+    for (int base = 0; base < i; base += 128) {
+        const int j = base + lane * 4;
+        const int4 k = k4[j >> 2];
+        const bool hit = ((j < i) && (k.x == me)) || ((j + 1 < i) && (k.y == me)) || ((j + 2 < i) && (k.z == me)) || ((j + 3 < i) && (k.w == me));
+        if (__any_sync(0xffffffffu, hit)) return;
     }
-    float* dst = T + (size_t)me * d;
-    for (int c0 = 0; c0 < d; c0 += 32) {
-        const int c = c0 + lane;
-        float acc = 0.f;
-        for (int j0 = i; j0 < n; j0 += 32) {
-            const int j = j0 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, (j < n) && (idx[j] == me));
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                if (c < d) acc += G[(size_t)(j0 + b) * d + c];
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int base = i & ~127; base < n; base += 128) {
+        const int j = base + lane * 4;
+        const int4 k = k4[j >> 2];
+        unsigned m[4];
+        m[0] = __ballot_sync(0xffffffffu, (j >= i) && (k.x == me));
+        m[1] = __ballot_sync(0xffffffffu, (j + 1 >= i) && (k.y == me));
+        m[2] = __ballot_sync(0xffffffffu, (j + 2 >= i) && (k.z == me));
+        m[3] = __ballot_sync(0xffffffffu, (j + 3 >= i) && (k.w == me));
+        unsigned any = m[0] | m[1] | m[2] | m[3];
+        while (any) {
+            const int L = __ffs(any) - 1;
+            any &= any - 1;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                if (!((m[q4] >> L) & 1u)) continue;
+                const float* g = G + (size_t)(base + L * 4 + q4) * d;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const int c = q * 32 + lane; if (c < d) acc[q] += g[c]; }
             }
         }
-        if (c < d) dst[c] += acc;
     }
+    float* dst = T + (size_t)(long long)me * d;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int c = q * 32 + lane; if (c < d) dst[c] += acc[q]; }
 }
 
 // ---- tensor-core path helpers (d = 64) -------------------------------------------------------------------------------
@@ -531,14 +556,15 @@ extern "C" int64_t idg_pair_loss_workspace_bytes(int32_t n, int32_t d) {
     return (int64_t)pl_carve(nullptr, n, d, nullptr) + 256;
 }
 
-extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float* d_loss,
-                             float* d_gX, float* d_gY, void* d_ws, void* stream_) {
+static int pair_loss_impl(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float scale,
+                          const int32_t* d_cnt_a, const int32_t* d_cnt_b, float* d_loss, float* d_gX, float* d_gY, void* d_ws, void* stream_) {
     if (kind < 0 || kind > 5) return fail(-1, "idg_pair_loss: kind must be 0..5%s");
     if (!d_X || !d_loss || !d_ws || n <= 0 || d <= 0 || n > 8192) return fail(-1, "idg_pair_loss: bad argument (n in 1..8192)%s");
     if (kind != 5 && !d_Y) return fail(-1, "idg_pair_loss: kind %s needs both operands", "0..4");
     if (kind == 5 && n < 2) return fail(-1, "idg_pair_loss: uniformity needs n >= 2%s");
     if (kind <= 3 && !(p0 > 0.f)) return fail(-1, "idg_pair_loss: temperature must be > 0%s");
-    if (kind == 2 && !(p1 > 0.f)) return fail(-1, "idg_pair_loss: SCCF down term needs p1 = n_unique_users * n_unique_items > 0%s");
+    if (kind == 2 && !(p1 > 0.f) && !(d_cnt_a && d_cnt_b))
+        return fail(-1, "idg_pair_loss: SCCF down term needs p1 = n_unique_users * n_unique_items > 0 (or the two device counts)%s");
     cudaStream_t st = (cudaStream_t)stream_;
     PlWs w;
     pl_carve((void*)(((uintptr_t)d_ws + 255) & ~(uintptr_t)255), n, d, &w);
@@ -564,13 +590,13 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
             IDG_LAUNCH_CHECK("pl_diag_dot_kernel");
             pl_rows_ccf_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, w.diag, n, np, p0, p1, kind == 1, w.w, w.lossi);
             IDG_LAUNCH_CHECK("pl_rows_ccf_tc_kernel");
-            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
             IDG_LAUNCH_CHECK("pl_reduce_kernel");
         } else if (kind == 2) {
             if ((rc = tc_scores_raw(w.XH, w.XL, w.YH, w.YL, n, np, w.S, 0, st))) return rc;
             pl_rows_sccf_sum_kernel<<<n, 256, 0, st>>>(w.S, n, np, p0, w.rowT);   // n columns, row stride np
             IDG_LAUNCH_CHECK("pl_rows_sccf_sum_kernel");
-            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss);
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
             IDG_LAUNCH_CHECK("pl_reduce_kernel");
             if (want_grad) {
                 pl_rows_sccf_grad_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, n, np, p0, w.scal);
@@ -582,7 +608,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
             IDG_LAUNCH_CHECK("pl_diag_dot_kernel");
             pl_rows_uniform_tc_kernel<<<n, 256, 0, st>>>(w.S, w.R, w.diag, n, np, w.rowT);
             IDG_LAUNCH_CHECK("pl_rows_uniform_tc_kernel");
-            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss);
+            pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
             IDG_LAUNCH_CHECK("pl_reduce_kernel");
         }
         if (want_grad) {
@@ -603,7 +629,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
                 IDG_LAUNCH_CHECK("pl_fold_parts_kernel");
             }
             pl_finish_kernel<<<rb, 256, 0, st>>>(kind, d_X, d_Y, w.Xn, kind == 5 ? nullptr : w.Yn, w.nx, kind == 5 ? nullptr : w.ny,
-                                                kind <= 1 ? w.w : nullptr, w.rowT, w.scal, w.tA, 0, w.tB, n, d, d_gX, kind == 5 ? nullptr : d_gY);
+                                                kind <= 1 ? w.w : nullptr, w.rowT, w.scal, w.tA, 0, w.tB, n, d, scale, d_gX, kind == 5 ? nullptr : d_gY);
             IDG_LAUNCH_CHECK("pl_finish_kernel");
         }
         return 0;
@@ -613,7 +639,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
         if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Xn, d, w.R, n, 1.f, 0.f, st))) return rc;
         pl_rows_ccf_kernel<<<n, 256, 0, st>>>(w.S, w.R, n, p0, p1, kind == 1, w.w, w.lossi);
         IDG_LAUNCH_CHECK("pl_rows_ccf_kernel");
-        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
         IDG_LAUNCH_CHECK("pl_reduce_kernel");
         if (want_grad) {
             // tA [n,2d] = H [b | a] (folded to H b + H a by the finish kernel),  tB = H^T a
@@ -624,7 +650,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
         if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Yn, d, w.S, n, 1.f, 0.f, st))) return rc;
         pl_rows_sccf_sum_kernel<<<n, 256, 0, st>>>(w.S, n, n, p0, w.rowT);
         IDG_LAUNCH_CHECK("pl_rows_sccf_sum_kernel");
-        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss);
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, p1, w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
         IDG_LAUNCH_CHECK("pl_reduce_kernel");
         if (want_grad) {
             pl_rows_sccf_grad_kernel<<<kNumSMs * 4, 256, 0, st>>>(w.S, (int64_t)n * n, p0, w.scal);
@@ -635,7 +661,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
     } else if (kind == 3 || kind == 4) {
         pl_rows_pairwise_kernel<<<rb, 256, 0, st>>>(kind, w.Xn, w.Yn, n, d, p0, w.w, w.lossi);
         IDG_LAUNCH_CHECK("pl_rows_pairwise_kernel");
-        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss);
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.lossi, n, 1.f, w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
         IDG_LAUNCH_CHECK("pl_reduce_kernel");
     } else {
         if ((rc = pl_sgemm(false, true, n, n, d, w.Xn, d, w.Xn, d, w.R, n, 1.f, 0.f, st))) return rc;
@@ -643,7 +669,7 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
         IDG_LAUNCH_CHECK("pl_diag_kernel");
         pl_rows_uniform_kernel<<<n, 256, 0, st>>>(w.R, w.diag, n, w.rowT);
         IDG_LAUNCH_CHECK("pl_rows_uniform_kernel");
-        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss);
+        pl_reduce_kernel<<<1, 1024, 0, st>>>(kind, w.rowT, n, (float)n * (float)(n - 1), w.scal, d_loss, scale, d_cnt_a, d_cnt_b);
         IDG_LAUNCH_CHECK("pl_reduce_kernel");
         if (want_grad) {
             if ((rc = pl_sgemm(false, false, n, d, n, w.R, n, w.Xn, d, w.tA, d, 1.f, 0.f, st))) return rc;
@@ -652,11 +678,24 @@ extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, i
     if (want_grad) {
         if (kind != 5 && !d_gY) return fail(-1, "idg_pair_loss: d_gY is required with d_gX for kind %s", "0..4");
         pl_finish_kernel<<<rb, 256, 0, st>>>(kind, d_X, d_Y, w.Xn, kind == 5 ? nullptr : w.Yn, w.nx, kind == 5 ? nullptr : w.ny,
-                                            (kind <= 1 || kind == 3) ? w.w : nullptr, w.rowT, w.scal, w.tA, merged ? 1 : 0, w.tB, n, d, d_gX,
+                                            (kind <= 1 || kind == 3) ? w.w : nullptr, w.rowT, w.scal, w.tA, merged ? 1 : 0, w.tB, n, d, scale, d_gX,
                                             kind == 5 ? nullptr : d_gY);
         IDG_LAUNCH_CHECK("pl_finish_kernel");
     }
     return 0;
+}
+
+extern "C" int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float* d_loss,
+                             float* d_gX, float* d_gY, void* d_ws, void* stream) {
+    if (!d_loss) return fail(-1, "idg_pair_loss: null d_loss%s");
+    IDG_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(float), (cudaStream_t)stream));
+    return pair_loss_impl(kind, d_X, d_Y, n, d, p0, p1, 1.f, nullptr, nullptr, d_loss, d_gX, d_gY, d_ws, stream);
+}
+
+extern "C" int idg_pair_loss_ex(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float scale,
+                                const int32_t* d_cnt_a, const int32_t* d_cnt_b, float* d_loss, float* d_gX, float* d_gY, void* d_ws,
+                                void* stream) {
+    return pair_loss_impl(kind, d_X, d_Y, n, d, p0, p1, scale, d_cnt_a, d_cnt_b, d_loss, d_gX, d_gY, d_ws, stream);
 }
 
 extern "C" int idg_gather_rows(const float* d_T, const int64_t* d_idx, int32_t n, int32_t d, float* d_out, void* stream) {
@@ -667,8 +706,9 @@ extern "C" int idg_gather_rows(const float* d_T, const int64_t* d_idx, int32_t n
 }
 
 extern "C" int idg_scatter_add_rows(const float* d_G, const int64_t* d_idx, int32_t n, int32_t d, float* d_T, void* stream) {
-    if (!d_G || !d_idx || !d_T || n <= 0 || d <= 0) return fail(-1, "idg_scatter_add_rows: bad argument%s");
-    pl_scatter_add_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_G, d_idx, n, d, d_T);
+    if (!d_G || !d_idx || !d_T || n <= 0 || d <= 0 || d > 256 || n > 8192) return fail(-1, "idg_scatter_add_rows: bad argument (d <= 256, n <= 8192)%s");
+    const size_t smem = sizeof(int) * (size_t)((n + 127) & ~127);
+    pl_scatter_add_kernel<<<(n + 7) / 8, 256, smem, (cudaStream_t)stream>>>(d_G, d_idx, n, d, d_T);
     IDG_LAUNCH_CHECK("pl_scatter_add_kernel");
     return 0;
 }

@@ -124,6 +124,7 @@ SIGNATURES = {
     "idg_parse_ratings": (C.c_int, [C.c_char_p, _p, _p, _i64, C.POINTER(_i64), _p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "idg_pair_loss_workspace_bytes": (_i64, [_i32, _i32]),
     "idg_pair_loss": (C.c_int, [_i32, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
+    "idg_pair_loss_ex": (C.c_int, [_i32, _p, _p, _i32, _i32, _f32, _f32, _f32, _p, _p, _p, _p, _p, _p, _p]),
     "idg_gather_rows": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "idg_scatter_add_rows": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
 }

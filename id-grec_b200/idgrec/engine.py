@@ -17,11 +17,22 @@ from . import _lib
 from ._lib import check, cur_stream, ptr
 
 
+# LightGCN-backbone models whose extra loss is a batch x batch term on (F_u[user], F_i[positive]) (SURVEY 8 f rank 4):
+#   kind -> (loss slots reported, in the reference's order; BPR upstream weight; reg upstream weight; reg mask)
+# raw slots of self.loss: 0 = bpr, 1 = reg, 2 / 3 = pair terms
+PAIR_MODELS = {
+    "LightCCF": ((0, 1, 2), 1.0, 1.0, 7),    # [bpr, reg, ssl_lambda * na]            models/LightCCF.py:73-77
+    "LightCSCF": ((1, 2), 0.0, 1.0, 7),      # [reg, lambda_gamma * na]               models/LightCSCF.py:84-89 (LightGCN encoder)
+    "SCCF": ((2, 3), 0.0, 0.0, 0),           # [-up, down]                            models/SCCF.py:80
+    "DirectAU": ((2, 3, 1), 0.0, 1.0, 3),    # [align, gamma * uniform, reg(u, pos)]  models/DirectAU.py:69-78
+}
+
+
 class FusedTrainer:
     def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
                  eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8,
-                 restrict_rows=True, fuse_adam=True, closure_restrict="auto"):
-        assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR")
+                 restrict_rows=True, fuse_adam=True, closure_restrict="auto", margin=0.0, gamma=0.0):
+        assert kind in ("LightGCN", "SimGCL", "XSimGCL", "MFBPR") or kind in PAIR_MODELS
         self.l = _lib.lib()
         self.kind, self.graph, self.E0 = kind, graph, table
         self.U, (self.N, self.d), self.K = num_users, table.shape, K
@@ -36,6 +47,20 @@ class FusedTrainer:
         self.max_batch = max_batch
         self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
         self.n_loss = 3 if kind in ("SimGCL", "XSimGCL") else 2
+        self.loss_order = None
+        if kind in PAIR_MODELS:
+            order, w_bpr, w_reg, self.reg_mask = PAIR_MODELS[kind]
+            self.loss_order = torch.tensor(order, dtype=torch.long, device=dev)
+            self.n_loss = len(order)
+            self.up_w = torch.tensor([w_bpr, w_reg], dtype=torch.float32, device=dev)
+            self.margin, self.gamma = margin, gamma
+            self.pA, self.pP = (torch.empty(max_batch, self.d, dtype=torch.float32, device=dev) for _ in range(2))
+            self.gA, self.gP, self.gA2, self.gP2 = (torch.empty(max_batch, self.d, dtype=torch.float32, device=dev) for _ in range(4))
+            self.pair_ws = torch.empty(int(self.l.idg_pair_loss_workspace_bytes(max_batch, self.d)), dtype=torch.uint8, device=dev)
+            self.ucnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.icnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.uidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
+            self.iidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
         self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
         self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
@@ -95,16 +120,55 @@ class FusedTrainer:
     def _bpr(self, B, u, p, n, fused):
         l, s = self.l, cur_stream()
         import ctypes as C
-        check(l.idg_bpr_forward_tail(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, 7,
+        mask = getattr(self, "reg_mask", 7)
+        up = ptr(self.up_w) if self.loss_order is not None else None     # which of (bpr, reg) enter the objective
+        check(l.idg_bpr_forward_tail(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, mask,
                                      ptr(self.loss), C.byref(self._tail[bool(fused)]), ptr(self.ws), s), "idg_bpr_forward_tail")
-        check(l.idg_bpr_backward(ptr(self.F), B, self.d, 7, None, ptr(self.G), self.reg_lambda, ptr(self.regc) if fused else None,
+        check(l.idg_bpr_backward(ptr(self.F), B, self.d, mask, up, ptr(self.G), self.reg_lambda, ptr(self.regc) if fused else None,
                                  ptr(self.ws), s), "idg_bpr_backward")
 
     def _finish(self, B, fused):
         # also clears the batch-row bitmap: the rows it visits are exactly the rows of this step's row set
-        check(self.l.idg_bpr_finish_clear(ptr(self.E0), None if fused else ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, None,
+        up = ptr(self.up_w) if self.loss_order is not None else None
+        check(self.l.idg_bpr_finish_clear(ptr(self.E0), None if fused else ptr(self.gE0), ptr(self.G), B, self.d, self.reg_lambda, up,
                                           ptr(self.regc) if fused else None, ptr(self.rows.bitmap) if self.rows is not None else None,
                                           ptr(self.ws), cur_stream()), "idg_bpr_finish_clear")
+
+    def _pair(self, B, u, p):
+        """Batch x batch term(s) of the LightGCN-backbone models on (F[user], F[U + positive]): gather -> idg_pair_loss_ex
+        (tcgen05 contractions) -> deterministic scatter-add of the row gradients into G, which the shared backward
+        propagation then carries to the parameters together with the BPR gradient."""
+        l, s, d = self.l, cur_stream(), self.d
+        item_off = self.U * d * 4
+        check(l.idg_gather_rows(ptr(self.F), u, B, d, ptr(self.pA), s), "idg_gather_rows")
+        check(l.idg_gather_rows(ptr(self.F) + item_off, p, B, d, ptr(self.pP), s), "idg_gather_rows")
+        self.loss[2:4].zero_()
+        L2, L3 = ptr(self.loss[2:]), ptr(self.loss[3:])
+
+        def pair(kind, X, Y, p0, p1, scale, out, gX, gY, ca=None, cb=None):
+            check(l.idg_pair_loss_ex(kind, ptr(X), ptr(Y) if Y is not None else None, B, d, p0, p1, scale, ca, cb, out, ptr(gX),
+                                     ptr(gY) if gY is not None else None, ptr(self.pair_ws), s), "idg_pair_loss_ex")
+
+        def scatter(gX, idx, off):
+            check(l.idg_scatter_add_rows(ptr(gX), idx, B, d, ptr(self.G) + off, s), "idg_scatter_add_rows")
+
+        if self.kind == "LightCCF":
+            pair(0, self.pA, self.pP, self.temperature, 0.0, self.ssl_lambda, L2, self.gA, self.gP)
+        elif self.kind == "LightCSCF":
+            pair(1, self.pA, self.pP, self.temperature, self.margin, self.ssl_lambda, L2, self.gA, self.gP)
+        elif self.kind == "SCCF":
+            pair(3, self.pA, self.pP, self.temperature, 0.0, 1.0, L2, self.gA, self.gP)
+            pair(2, self.pA, self.pP, self.temperature, 0.0, 1.0, L3, self.gA2, self.gP2, ptr(self.ucnt), ptr(self.icnt))
+            check(l.idg_axpby(ptr(self.gA), 1.0, ptr(self.gA), 1.0, ptr(self.gA2), B * d, s), "idg_axpby")
+            check(l.idg_axpby(ptr(self.gP), 1.0, ptr(self.gP), 1.0, ptr(self.gP2), B * d, s), "idg_axpby")
+        else:  # DirectAU: align + gamma * (uniform(users) + uniform(items)) / 2
+            pair(4, self.pA, self.pP, 0.0, 0.0, 1.0, L2, self.gA, self.gP)
+            pair(5, self.pA, None, 0.0, 0.0, 0.5 * self.gamma, L3, self.gA2, None)
+            pair(5, self.pP, None, 0.0, 0.0, 0.5 * self.gamma, L3, self.gP2, None)
+            check(l.idg_axpby(ptr(self.gA), 1.0, ptr(self.gA), 1.0, ptr(self.gA2), B * d, s), "idg_axpby")
+            check(l.idg_axpby(ptr(self.gP), 1.0, ptr(self.gP), 1.0, ptr(self.gP2), B * d, s), "idg_axpby")
+        scatter(self.gA, u, 0)
+        scatter(self.gP, p, item_off)
 
     def _draw_noise(self, view):
         if self.injected_noise is not None:
@@ -119,7 +183,7 @@ class FusedTrainer:
         adam = self.adam_args if fused else None
         out = None if fused else self.gE0
         rows = self.rows
-        contrastive = self.kind in ("SimGCL", "XSimGCL")
+        contrastive = self.kind in ("SimGCL", "XSimGCL") or self.kind == "SCCF"   # SCCF needs the two unique counts
         if rows is not None and contrastive:
             rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
         elif rows is not None:
@@ -129,6 +193,14 @@ class FusedTrainer:
         if self.kind == "LightGCN":
             g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
             self._bpr(B, u, p, n, fused)
+            g.propagate_bwd(self.G, K, True, out=out, rows=rows, adam=adam)
+        elif self.kind in PAIR_MODELS:
+            if rows is None and self.kind == "SCCF":
+                check(self.l.idg_unique_rows(u, B, 0, ptr(self.uidx), ptr(self.ucnt), cur_stream()), "idg_unique_rows")
+                check(self.l.idg_unique_rows(p, B, self.U, ptr(self.iidx), ptr(self.icnt), cur_stream()), "idg_unique_rows")
+            g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
+            self._bpr(B, u, p, n, fused)
+            self._pair(B, u, p)
             g.propagate_bwd(self.G, K, True, out=out, rows=rows, adam=adam)
         elif self.kind == "MFBPR":
             self._bpr(B, u, p, n, False)
@@ -186,7 +258,7 @@ class FusedTrainer:
             self.step_count += 1
         if not self._tail_acc:
             self.loss_acc += self.loss
-        return self.loss[:self.n_loss]
+        return self._report(self.loss)
 
     def _step_graph(self, B, users, pos, neg):
         """CUDA-graph replay: the step's kernels (incl. the device-side Adam step counter) are captured
@@ -197,7 +269,11 @@ class FusedTrainer:
         self._graphs[B].replay()
         self.replayed_launches += self._graph_launches[B]
         self.step_count += 1
-        return self.loss[:self.n_loss]
+        return self._report(self.loss)
+
+    def _report(self, raw):
+        """Losses in the order of the model's loss list (raw slots: bpr, reg, pair terms)."""
+        return raw[:self.n_loss] if self.loss_order is None else raw[self.loss_order]
 
     def _capture(self, B):
         u, p, n = (self.batch[k].data_ptr() for k in range(3))
@@ -219,6 +295,6 @@ class FusedTrainer:
         self._graphs[B] = gr
 
     def pop_epoch_losses(self):
-        out = self.loss_acc[:self.n_loss].tolist()
+        out = self._report(self.loss_acc).tolist()
         self.loss_acc.zero_()
         return out

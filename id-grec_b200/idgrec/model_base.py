@@ -82,7 +82,7 @@ class PropagationModel(nn.Module):
             cfg = self.config
             import torch.distributed as dist
             world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-            if world > 1 and int(cfg.get('num_gpus', world)) > 1:
+            if world > 1 and int(cfg.get('num_gpus', world)) > 1 and self.kind == "LightGCN":
                 # row-partitioned over the process group: the parameter table moves into the peer slab
                 from .dist import DistFusedTrainer
                 ft = DistFusedTrainer(self.kind, self.Graph.csr, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda,
@@ -96,7 +96,8 @@ class PropagationModel(nn.Module):
                 return ft
             self._fused = FusedTrainer(
                 self.kind, self.Graph, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda, lr,
-                ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),
+                ssl_lambda=float(cfg.get('ssl_lambda', cfg.get('lambda_gamma', 0.0))), temperature=float(cfg.get('temperature', 0.2)),
+                margin=float(cfg.get('lambda_margin', 0.0)), gamma=float(cfg.get('gamma', 0.0)),
                 eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)), max_batch=max_batch,
                 use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
                 restrict_rows=str(cfg.get('restrict_rows', '1')) not in ('0', 'False', 'false'),

@@ -9,12 +9,18 @@ from idgrec.model_base import PropagationModel
 class LightCCF(PropagationModel):
     kind = "LightCCF"
     graph_capturable = True   # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
-    fused_trainer = None  # autograd ops over the CUDA kernels + torch.optim.Adam, reference loop trainer.py:40-56
 
     def __init__(self, config, dataset, device):
         super(LightCCF, self).__init__(config, dataset, device, utility.utility_data.data_graph.sparse_adjacency_matrix)
         self.ssl_lambda = float(config['ssl_lambda'])
         self.temperature = float(config['temperature'])
+
+    def fused_trainer(self, lr, max_batch):
+        """LightGCN encoder: the fused CUDA-graph step of idgrec.engine (row-restricted propagation, batch x batch loss on
+        tensor cores, Adam in the last backward epilogue).  MF encoder: autograd ops + torch.optim.Adam."""
+        if self.config['encoder'] == 'MF':
+            return None
+        return super(LightCCF, self).fused_trainer(lr, max_batch)
 
     def aggregate(self):
         """LightCCF.py:44-62 (the MF encoder returns the ego tables, :59-60)."""

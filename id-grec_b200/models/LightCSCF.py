@@ -9,7 +9,6 @@ from idgrec.model_base import PropagationModel
 class LightCSCF(PropagationModel):
     kind = "LightCSCF"
     graph_capturable = True   # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
-    fused_trainer = None  # autograd ops over the CUDA kernels + torch.optim.Adam, reference loop trainer.py:40-56
 
     def __init__(self, config, dataset, device):
         super(LightCSCF, self).__init__(config, dataset, device, utility.utility_data.data_graph.sparse_adjacency_matrix)
@@ -17,6 +16,13 @@ class LightCSCF(PropagationModel):
         self.lambda_gamma = float(config['lambda_gamma'])
         self.lambda_reg = float(config['lambda_reg'])
         self.lambda_margin = float(config['lambda_margin'])
+
+    def fused_trainer(self, lr, max_batch):
+        """LightGCN encoder: the fused CUDA-graph step of idgrec.engine (row-restricted propagation, batch x batch loss on
+        tensor cores, Adam in the last backward epilogue).  MF encoder: autograd ops + torch.optim.Adam."""
+        if self.config['encoder'] == 'MF':
+            return None
+        return super(LightCSCF, self).fused_trainer(lr, max_batch)
 
     def aggregate(self):
         return self._split(self.encode())

@@ -359,6 +359,13 @@ int64_t idg_pair_loss_workspace_bytes(int32_t n, int32_t d);
 int idg_pair_loss(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1,
                   float* d_loss, float* d_gX, float* d_gY, void* d_ws, void* stream);
 
+/* Same, for the fused train step: *d_loss += scale * loss and the gradients are multiplied by scale (ssl_lambda, gamma / 2,
+ * ...); kind 2 may take its denominator from two device counts (n_unique_users, n_unique_items written by
+ * idg_batch_rows_unique) instead of p1, so the whole step stays free of host syncs. */
+int idg_pair_loss_ex(int32_t kind, const float* d_X, const float* d_Y, int32_t n, int32_t d, float p0, float p1, float scale,
+                     const int32_t* d_cnt_a, const int32_t* d_cnt_b, float* d_loss, float* d_gX, float* d_gY, void* d_ws,
+                     void* stream);
+
 /* out[i,:] = T[idx[i],:]  (all_user_embeddings[user.long()], models/LightCCF.py:66) and its backward:
  * T[idx[i],:] += G[i,:] with duplicates summed in entry order by the first occurrence (index_put(accumulate) without
  * float atomics; bit-reproducible). */

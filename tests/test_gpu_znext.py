@@ -372,3 +372,67 @@ def test_graphed_step_equals_eager_loop(dev, golden_dirs, golden_tiny, kind):
     np.testing.assert_allclose(sums[1], sums[0], rtol=2e-5)
     for a, b in zip(finals[1], finals[0]):
         _close(a, b, rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# the same models on the fused CUDA-graph step (idgrec.engine.FusedTrainer)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["LightCCF", "LightCSCF", "SCCF", "DirectAU"])
+def test_pair_models_fused_step_vs_reference(dev, golden_dirs, golden_tiny, golden_next, kind):
+    """One fused step (row-restricted propagation, BPR / reg selected by upstream weights, batch x batch loss on tensor cores,
+    deterministic scatter into the shared backward propagation): losses and the full gradient equal the reference's."""
+    for restrict in (1, 0):
+        cfg = _cfg(kind, batch_size=256, encoder="LightGCN", cuda_graph=0, restrict_rows=restrict, fuse_adam=0, **NEXT_CFG[kind])
+        d = _data(golden_dirs, cfg)
+        m = getattr(importlib.import_module("models." + kind), kind)(cfg, d, dev)
+        _load_weights(m, golden_tiny["lg_user_w0"], golden_tiny["lg_item_w0"])
+        m.to(dev)
+        ft = m.fused_trainer(1e-3, 256)
+        assert ft is not None and ft.kind == kind
+        b = torch.from_numpy(golden_next["batch"].copy()).to(dev)
+        loss = ft.step(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous(), apply_adam=False)
+        p = "%s_lightgcn" % kind.lower()
+        np.testing.assert_allclose(loss.cpu().numpy(), golden_next[p + "_loss"], rtol=RTOL)
+        _close(ft.gE0[:d.num_users].cpu().numpy(), golden_next[p + "_gu"], rtol=1e-4)
+        _close(ft.gE0[d.num_users:].cpu().numpy(), golden_next[p + "_gi"], rtol=1e-4)
+        assert float(ft.G.abs().max()) == 0.0        # the gradient scratch table is clean again after the step
+    # MF encoder keeps the autograd path
+    cfg = _cfg(kind, batch_size=256, encoder="MF", **NEXT_CFG[kind])
+    m = getattr(importlib.import_module("models." + kind), kind)(cfg, _data(golden_dirs, cfg), dev)
+    m.to(dev)
+    assert m.fused_trainer(1e-3, 256) is None
+
+
+@pytest.mark.parametrize("kind", ["LightCCF", "SCCF", "DirectAU"])
+def test_pair_models_fused_graph_trajectory(dev, golden_dirs, golden_tiny, kind):
+    """Five batches (one short) through the captured fused step with Adam in the last backward epilogue follow the eager
+    autograd + torch.optim.Adam loop of the reference (trainer.py:40-56)."""
+    s0 = golden_tiny["sample_ep0"][golden_tiny["perm_ep0"]]
+    batches = [torch.from_numpy(s0[a:b].copy()).to(dev) for a, b in ((0, 256), (256, 512), (512, 768), (768, 868), (868, 1124))]
+    finals, sums = [], []
+    for mode in ("eager", "fused"):
+        cfg = _cfg(kind, batch_size=256, encoder="LightGCN", **NEXT_CFG[kind])
+        d = _data(golden_dirs, cfg)
+        m = getattr(importlib.import_module("models." + kind), kind)(cfg, d, dev)
+        _load_weights(m, golden_tiny["lg_user_w0"], golden_tiny["lg_item_w0"])
+        m.to(dev)
+        if mode == "eager":
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+            acc = None
+            for b in batches:
+                ll = m(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+                st = torch.stack([l.reshape(()) for l in ll])
+                opt.zero_grad()
+                st.sum().backward()
+                opt.step()
+                acc = st.detach() if acc is None else acc + st.detach()
+            sums.append(acc.cpu().numpy())
+        else:
+            ft = m.fused_trainer(1e-3, 256)
+            for b in batches:
+                ft.step(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+            sums.append(np.asarray(ft.pop_epoch_losses()))
+        finals.append([m.user_embedding.weight.detach().cpu().numpy().copy(), m.item_embedding.weight.detach().cpu().numpy().copy()])
+    np.testing.assert_allclose(sums[1], sums[0], rtol=2e-5)
+    for a, b in zip(finals[1], finals[0]):
+        _close(a, b, rtol=2e-5)

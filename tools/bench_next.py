@@ -77,7 +77,10 @@ def main():
             torch.stack([l.reshape(()) for l in ll]).sum().backward()
             opt.step()
         out["step_%s_%s_B%d_ms" % (kind, shape, B)] = timed(step, iters=10, warm=3)
-        if getattr(m, "graph_capturable", False):
+        ft = m.fused_trainer(1e-3, B) if callable(getattr(m, "fused_trainer", None)) else None
+        if ft is not None:
+            out["step_fused_%s_%s_B%d_ms" % (kind, shape, B)] = timed(lambda: ft.step(bu, bp, bn), iters=20, warm=3)
+        elif getattr(m, "graph_capturable", False):
             from idgrec.graphed import GraphedStep
             gs = GraphedStep(m, 1e-3, B)
             out["step_graph_%s_%s_B%d_ms" % (kind, shape, B)] = timed(lambda: gs.step(bu, bp, bn), iters=20, warm=3)
