@@ -15,7 +15,16 @@ from idgrec.model_base import PropagationModel
 class NGCF(PropagationModel):
     kind = "NGCF"
     graph_capturable = True   # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
-    fused_trainer = None  # trained through autograd + torch.optim.Adam (dense weights), reference loop trainer.py:40-56
+
+    def fused_trainer(self, lr, max_batch):
+        """The whole step (propagation, dense layers, BPR, both backward chains, Adam) without autograd, replayed from a
+        CUDA graph (idgrec/engine_ngcf.py).  ``fused_step = 0`` in the config keeps the autograd ops + torch.optim.Adam."""
+        if str(self.config.get('fused_step', '1')) in ('0', 'False', 'false'):
+            return None
+        if self._fused is None or self._fused.lr != lr or self._fused.max_batch < max_batch:
+            from idgrec.engine_ngcf import NgcfFusedTrainer
+            self._fused = NgcfFusedTrainer(self, lr, max_batch, use_cuda_graph=str(self.config.get('cuda_graph', '1')) not in ('0', 'False', 'false'))
+        return self._fused
 
     def __init__(self, config, dataset, device):
         super(NGCF, self).__init__(config, dataset, device, None)

@@ -436,3 +436,73 @@ def test_pair_models_fused_graph_trajectory(dev, golden_dirs, golden_tiny, kind)
     np.testing.assert_allclose(sums[1], sums[0], rtol=2e-5)
     for a, b in zip(finals[1], finals[0]):
         _close(a, b, rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# NGCF on its fused step (idgrec.engine_ngcf.NgcfFusedTrainer)
+# ------------------------------------------------------------------------------------------------
+def _ngcf(dev, golden_dirs, golden_tiny, **over):
+    from models.NGCF import NGCF
+    g = golden_tiny
+    cfg = _cfg("NGCF", **over)
+    d = _data(golden_dirs, cfg)
+    m = NGCF(cfg, d, dev)
+    _load_weights(m, g["ngcf_user_w0"], g["ngcf_item_w0"])
+    with torch.no_grad():
+        for l in range(3):
+            for k in ("W_gcn", "b_gcn", "W_bi", "b_bi"):
+                m.weight_dict["%s_%d" % (k, l)].copy_(torch.from_numpy(g["ngcf_%s_%d" % (k, l)]))
+    m.to(dev)
+    return m, d
+
+
+def test_ngcf_fused_step_vs_reference(dev, golden_dirs, golden_tiny):
+    """One fused NGCF step with the reference's dropout masks injected: losses, table gradients and all 12 dense-weight
+    gradients equal the unmodified reference's (ngcf_* in tiny.npz)."""
+    g = golden_tiny
+    m, d = _ngcf(dev, golden_dirs, g)
+    ft = m.fused_trainer(1e-4, 256)
+    ft.injected_keep = [torch.from_numpy(x).to(dev) for x in g["ngcf_masks"]]
+    b = torch.from_numpy(g["batch"].copy()).to(dev)
+    loss = ft.step(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous(), apply_adam=False)
+    np.testing.assert_allclose(loss.cpu().numpy(), g["ngcf_loss"], rtol=RTOL)
+    _close(ft.gE0[:d.num_users].cpu().numpy(), g["ngcf_gu"], rtol=1e-4)
+    _close(ft.gE0[d.num_users:].cpu().numpy(), g["ngcf_gi"], rtol=1e-4)
+    for l in range(3):
+        for k in ("W_gcn", "b_gcn", "W_bi", "b_bi"):
+            name = "%s_%d" % (k, l)
+            _close(ft.gw[name].cpu().numpy().reshape(g["ngcf_g_" + name].shape), g["ngcf_g_" + name], rtol=1e-4)
+    assert float(ft.G.abs().max()) == 0.0 and float(ft.G64.abs().max()) == 0.0
+    # the parameters are views of the flat buffer: evaluation sees what Adam updates
+    assert m.weight_dict["W_bi_2"].data_ptr() == ft.w["W_bi_2"].data_ptr()
+
+
+def test_ngcf_fused_step_equals_eager_loop(dev, golden_dirs, golden_tiny):
+    """Five batches (one short) through the captured fused step follow the autograd ops + torch.optim.Adam loop (dropout off)."""
+    s0 = golden_tiny["sample_ep0"][golden_tiny["perm_ep0"]]
+    batches = [torch.from_numpy(s0[a:b].copy()).to(dev) for a, b in ((0, 256), (256, 512), (512, 768), (768, 868), (868, 1124))]
+    finals, sums = [], []
+    for mode in ("eager", "fused"):
+        m, d = _ngcf(dev, golden_dirs, golden_tiny, mess_drop_prob="[0.0, 0.0, 0.0]", fused_step=int(mode == "fused"))
+        if mode == "eager":
+            assert m.fused_trainer(1e-3, 256) is None
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+            acc = None
+            for b in batches:
+                ll = m(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+                st = torch.stack([l.reshape(()) for l in ll])
+                opt.zero_grad()
+                st.sum().backward()
+                opt.step()
+                acc = st.detach() if acc is None else acc + st.detach()
+            sums.append(acc.cpu().numpy())
+        else:
+            ft = m.fused_trainer(1e-3, 256)
+            for b in batches:
+                ft.step(b[:, 0].contiguous(), b[:, 1].contiguous(), b[:, 2].contiguous())
+            assert sorted(ft._graphs) == [100, 256]
+            sums.append(np.asarray(ft.pop_epoch_losses()))
+        finals.append([p.detach().cpu().numpy().copy() for p in m.parameters()])
+    np.testing.assert_allclose(sums[1], sums[0], rtol=2e-5)
+    for a, b in zip(finals[1], finals[0]):
+        _close(a, b, rtol=2e-5)
