@@ -10,8 +10,10 @@
 //   dD   = dD_ext + (dO - O <O,dO>)/|D| ;  dS = dD (*) keep/(1-p) (*) (S>0 ? 1 : 0.2)
 //   dZ   = dS . [W_gcn ; W_bi]^T ;  dside = dZ1 + dZ2 (*) E ;  dE_direct = dZ2 (*) side
 //   dW   = Z^T . dS ,  db = colsum(dS)                per-CTA partials, summed in CTA order (deterministic)
-// fp32 CUDA-core tiles: the 1e-5 parity bar needs fp32 products and these GEMMs (1.2 GFLOP per layer at the
-// amazon-book shape) are a small fraction of the layer's SpMM time.
+// fp32 CUDA-core tiles (16-18 TFLOP/s).  A 3xTF32 version of the forward product on mma.sync.m16n8k8 was written and measured
+// this round (parity green, 149 us per layer against 130 us for these tiles at the amazon-book shape): the
+// warp-level tf32 MMA of sm_100a issues at about twice the fp32 FMA rate, so three split passes lose to plain fp32.  The
+// tcgen05 route (as csrc/infonce_tc.cu) is what would make these 64-wide products stream-bound.
 #include <math.h>
 
 #include "idg_common.cuh"
@@ -212,19 +214,23 @@ __global__ void __launch_bounds__(256) ngcf_dense_bwd_kernel(const float* __rest
     if (tid < 64) db_part[(size_t)blockIdx.x * 64 + tid] = dbv;
 }
 
-// ordered sum of the per-CTA partials: dWg, dWb [64,64], db [64] (shared by b_gcn and b_bi)
-__global__ void ngcf_reduce_kernel(const float* __restrict__ dW_part, const float* __restrict__ db_part, int n_parts, float* __restrict__ dWg,
-                                   float* __restrict__ dWb, float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 128 * 64) {
-        float a = 0.f;
-        for (int p = 0; p < n_parts; ++p) a += dW_part[(size_t)p * 128 * 64 + i];
-        if (i < 64 * 64) dWg[i] = a; else dWb[i - 64 * 64] = a;
-    } else if (i < 128 * 64 + 64) {
-        const int c = i - 128 * 64;
-        float a = 0.f;
-        for (int p = 0; p < n_parts; ++p) a += db_part[(size_t)p * 64 + c];
-        db[c] = a;
+// ordered sum of the per-CTA partials: dWg, dWb [64,64], db [64] (shared by b_gcn and b_bi).  64 consecutive outputs per CTA
+// (coalesced rows of the partial tables), 4 interleaved slices of the partials per output, folded in slice order.
+__global__ void __launch_bounds__(256) ngcf_reduce_kernel(const float* __restrict__ dW_part, const float* __restrict__ db_part, int n_parts,
+                                                         float* __restrict__ dWg, float* __restrict__ dWb, float* __restrict__ db) {
+    __shared__ float sm[4][64];
+    const int ix = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + ix;
+    float a = 0.f;
+    if (i < 128 * 64) { for (int p = sl; p < n_parts; p += 4) a += dW_part[(size_t)p * 128 * 64 + i]; }
+    else if (i < 128 * 64 + 64) { const int c = i - 128 * 64; for (int p = sl; p < n_parts; p += 4) a += db_part[(size_t)p * 64 + c]; }
+    sm[sl][ix] = a;
+    __syncthreads();
+    if (sl == 0 && i < 128 * 64 + 64) {
+        a = (sm[0][ix] + sm[1][ix]) + (sm[2][ix] + sm[3][ix]);
+        if (i < 64 * 64) dWg[i] = a;
+        else if (i < 128 * 64) dWb[i - 64 * 64] = a;
+        else db[i - 128 * 64] = a;
     }
 }
 
@@ -261,7 +267,7 @@ extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const f
     ngcf_dense_bwd_kernel<<<kNgCtas, 256, smem, stream>>>(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside,
                                                           d_dE_direct, dW_part, db_part);
     IDG_LAUNCH_CHECK("ngcf_dense_bwd_kernel");
-    ngcf_reduce_kernel<<<(128 * 64 + 64 + 255) / 256, 256, 0, stream>>>(dW_part, db_part, kNgCtas, d_dWg, d_dWb, d_db);
+    ngcf_reduce_kernel<<<(128 * 64 + 64 + 63) / 64, 256, 0, stream>>>(dW_part, db_part, kNgCtas, d_dWg, d_dWb, d_db);
     IDG_LAUNCH_CHECK("ngcf_reduce_kernel");
     return 0;
 }

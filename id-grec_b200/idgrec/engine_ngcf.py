@@ -53,7 +53,7 @@ class NgcfFusedTrainer:
         N, d, K = self.N, self.d, self.K
         self.final = z(N, (K + 1) * d)
         self.side, self.S, self.D = ([z(N, d) for _ in range(K)] for _ in range(3))
-        self.rnd, self.keep = ([z(N, d) for _ in range(K)] for _ in range(2))
+        self.keep = [z(N, d) for _ in range(K)]
         self.G = z(N, (K + 1) * d)                       # dL/dfinal: non-zero on the batch rows only, re-zeroed by bpr_finish
         self.G64 = z(N, d)                               # scratch for the reg-only BPR call (stays zero)
         self.dside, self.dEd = z(N, d), z(N, d)
@@ -85,8 +85,7 @@ class NgcfFusedTrainer:
             if self.injected_keep is not None:
                 self.keep[layer].copy_(self.injected_keep[layer])
             else:  # nn.Dropout(p)'s draw (NGCF.py:99-100: always active): Bernoulli(1 - p) per element from the device generator
-                self.rnd[layer].uniform_()
-                self.keep[layer].copy_(self.rnd[layer] >= pr)
+                self.keep[layer].bernoulli_(1.0 - pr)
             g.spmm_layer(E, Y=self.side[layer])
             check(l.idg_ngcf_dense_fwd(ptr(E), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['b_gcn_%d' % layer]),
                                        ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]), ptr(self.keep[layer]), pr, N, ptr(self.S[layer]),

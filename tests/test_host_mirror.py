@@ -131,3 +131,35 @@ def test_models_fail_loudly_without_cuda(golden_dirs):
     d = Data(golden_dirs["tiny"], dict(_cfg(), dataset="tiny"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         LightGCN(dict(_cfg(), dataset="tiny"), d, torch.device("cpu"))
+
+
+@pytest.mark.parametrize("kind,extra", [
+    ("LightCCF", dict(ssl_lambda=5.0, temperature=0.22, encoder="LightGCN")),
+    ("LightCSCF", dict(lambda_reg=1e-4, lambda_gamma=1.0, lambda_margin=0.7, temperature=0.2, encoder="LightGCN")),
+    ("SCCF", dict(temperature=0.1, encoder="LightGCN")),
+    ("DirectAU", dict(gamma=2.0, encoder="LightGCN")),
+    ("SGL", dict(ssl_lambda=0.1, ssl_ratio=0.1, aug_type="ed", temperature=0.2)),
+    ("EGCF", dict(ssl_lambda=0.1, temperature=0.1, mode="parallel")),
+])
+def test_next_row_models_fail_loudly_without_cuda(golden_dirs, kind, extra):
+    """The section-8(f) models have no CPU path either: building their graph on a CPU device raises."""
+    import importlib
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from utility.utility_data.data_loader import Data
+    cfg = dict(_cfg(), dataset="tiny", **{k: str(v) for k, v in extra.items()})
+    d = Data(golden_dirs["tiny"], cfg)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        getattr(importlib.import_module("models." + kind), kind)(cfg, d, torch.device("cpu"))
+
+
+def test_loss_ops_fail_loudly_without_cuda():
+    """ops.pair_loss / gather_rows go straight to the CUDA library: CPU tensors are refused, not silently computed."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from idgrec import ops
+    x = torch.zeros(4, 64)
+    with pytest.raises(Exception):
+        ops.pair_loss("align", x, x)

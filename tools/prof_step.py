@@ -17,6 +17,7 @@ kind, shape = sys.argv[1], sys.argv[2]
 dev = torch.device("cuda:0")
 g = datagen.gen_graph(shape)
 cfg = tools.read_configuration(os.path.join(REPO, "id-grec_b200", "configure", kind + ".txt"), kind)
+cfg["cuda_graph"] = "0"          # eager launches so that the profiler sees every kernel
 data = Data.from_arrays(g.num_users, g.num_items, g.train_user, g.train_item, g.test_user, g.test_item, cfg)
 tools.set_seed(2024)
 m = getattr(importlib.import_module("models." + kind), kind)(cfg, data, dev)
@@ -27,12 +28,20 @@ rng = np.random.default_rng(0)
 e = rng.integers(0, len(g.train_user), B)
 bu, bp = (torch.from_numpy(a[e]).to(dev) for a in (g.train_user, g.train_item))
 bn = torch.from_numpy(rng.integers(0, g.num_items, B)).to(dev)
+ft = m.fused_trainer(1e-3, B) if callable(getattr(m, "fused_trainer", None)) else None
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_push("steps")
-for _ in range(2):
-    ll = m(bu, bp, bn)
-    opt.zero_grad()
-    torch.stack([l.reshape(()) for l in ll]).sum().backward()
-    opt.step()
+if ft is not None:
+    ft.step(bu, bp, bn)            # allocations, first-use attribute calls
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("steps")
+    for _ in range(2):
+        ft.step(bu, bp, bn)
+else:
+    torch.cuda.nvtx.range_push("steps")
+    for _ in range(2):
+        ll = m(bu, bp, bn)
+        opt.zero_grad()
+        torch.stack([l.reshape(()) for l in ll]).sum().backward()
+        opt.step()
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
