@@ -10,87 +10,23 @@
 //   dD   = dD_ext + (dO - O <O,dO>)/|D| ;  dS = dD (*) keep/(1-p) (*) (S>0 ? 1 : 0.2)
 //   dZ   = dS . [W_gcn ; W_bi]^T ;  dside = dZ1 + dZ2 (*) E ;  dE_direct = dZ2 (*) side
 //   dW   = Z^T . dS ,  db = colsum(dS)                per-CTA partials, summed in CTA order (deterministic)
-// fp32 CUDA-core tiles (16-18 TFLOP/s).  A 3xTF32 version of the forward product on mma.sync.m16n8k8 was written and measured
-// this round (parity green, 149 us per layer against 130 us for these tiles at the amazon-book shape): the
-// warp-level tf32 MMA of sm_100a issues at about twice the fp32 FMA rate, so three split passes lose to plain fp32.  The
-// tcgen05 route (as csrc/infonce_tc.cu) is what would make these 64-wide products stream-bound.
+// The forward product runs on tcgen05 (csrc/ngcf_tc.cu, 3xTF32 split, TMEM accumulator); this file keeps the backward on fp32
+// CUDA-core tiles (16-18 TFLOP/s) and the entry points.  Measured per layer at the amazon-book shape: fp32 tiles 130 us, a
+// 3xTF32 mma.sync.m16n8k8 forward 149 us (the warp-level tf32 MMA of sm_100a issues at ~2x the fp32 FMA rate, so three split
+// passes lose), tcgen05 with 2 loader warps 220 us, with 7 operand-builder warps and batched loads ~122 us (now bound by the
+// one-tile-per-CTA pipeline and the row-per-thread epilogue stores, not by the MMA).
 #include <math.h>
 
 #include "idg_common.cuh"
 
 namespace idg {
 
+// csrc/ngcf_tc.cu: the forward product on tcgen05 (3xTF32 split, TMEM accumulators)
+int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const float* bg, const float* Wb, const float* bb, const float* keep,
+                      float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream);
+
 constexpr int kNgTile = 64;     // rows per tile
 constexpr int kNgCtas = 296;    // persistent grid of the backward kernel (2 per SM)
-
-// ---- forward: one CTA per 64-row tile, 256 threads, thread (ty,tx) -> rows ty*4.., columns tx*4..
-__global__ void __launch_bounds__(256) ngcf_dense_fwd_kernel(const float* __restrict__ E, const float* __restrict__ side,
-                                                             const float* __restrict__ Wg, const float* __restrict__ bg,
-                                                             const float* __restrict__ Wb, const float* __restrict__ bb,
-                                                             const float* __restrict__ keep, float inv_keep, int N,
-                                                             float* __restrict__ S_pre, float* __restrict__ D, float* __restrict__ out,
-                                                             int out_stride) {
-    extern __shared__ __align__(16) float sm[];
-    float* Zt = sm;                  // [128 k][64 rows]
-    float* W = Zt + 128 * kNgTile;   // [128 k][64 cols]
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    // persistent CTAs: the 32 KB weight tile is staged once per CTA, not once per 64-row tile
-    for (int q = tid; q < 64 * 64; q += 256) { W[q] = Wg[q]; W[64 * 64 + q] = Wb[q]; }
-    const float4 b1 = ldg4(bg + tx * 4), b2 = ldg4(bb + tx * 4);
-    const float bias[4] = {b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w};
-    const int ntiles = (N + kNgTile - 1) / kNgTile;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int r0 = t * kNgTile;
-        __syncthreads();   // the previous tile's Zt has been consumed (and W is in place on the first pass)
-        for (int q = tid; q < kNgTile * 16; q += 256) {
-            const int r = q & 63, c4 = q >> 6;  // lane <-> row: conflict-free transposed stores
-            float4 s = f4zero(), e = f4zero();
-            if (r0 + r < N) { s = ldg4(side + (size_t)(r0 + r) * 64 + c4 * 4); e = ldg4(E + (size_t)(r0 + r) * 64 + c4 * 4); }
-            const float sv[4] = {s.x, s.y, s.z, s.w}, ev[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { Zt[(c4 * 4 + j) * kNgTile + r] = sv[j]; Zt[(64 + c4 * 4 + j) * kNgTile + r] = ev[j] * sv[j]; }
-        }
-        __syncthreads();
-        float acc[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < 128; ++k) {
-            const float4 z = *reinterpret_cast<const float4*>(Zt + k * kNgTile + ty * 4);
-            const float4 w = *reinterpret_cast<const float4*>(W + k * 64 + tx * 4);
-            const float za[4] = {z.x, z.y, z.z, z.w}, wb[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(za[a], wb[b], acc[a][b]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int r = r0 + ty * 4 + a;
-            float s[4], dv[4], ss = 0.f;
-            float4 kp = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (keep && r < N) kp = ldg4(keep + (size_t)r * 64 + tx * 4);
-            const float kv[4] = {kp.x, kp.y, kp.z, kp.w};
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                s[b] = acc[a][b] + bias[b];
-                const float act = s[b] > 0.f ? s[b] : 0.2f * s[b];
-                dv[b] = keep ? act * kv[b] * inv_keep : act;
-                ss = fmaf(dv[b], dv[b], ss);
-            }
-#pragma unroll
-            for (int m = 8; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);  // 16 lanes share a row
-            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-            if (r < N) {
-                st4(S_pre + (size_t)r * 64 + tx * 4, make_float4(s[0], s[1], s[2], s[3]));
-                st4(D + (size_t)r * 64 + tx * 4, make_float4(dv[0], dv[1], dv[2], dv[3]));
-                st4(out + (size_t)r * out_stride + tx * 4, make_float4(dv[0] / nrm, dv[1] / nrm, dv[2] / nrm, dv[3] / nrm));
-            }
-        }
-    }
-}
 
 // ---- backward: persistent CTAs loop over 64-row tiles, accumulating dW/db partials in registers
 __global__ void __launch_bounds__(256) ngcf_dense_bwd_kernel(const float* __restrict__ E, const float* __restrict__ side,
@@ -243,13 +179,8 @@ extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const f
                                   int32_t out_stride, void* stream) {
     if (!d_E || !d_side || !d_Wg || !d_bg || !d_Wb || !d_bb || !d_S || !d_D || !d_out || N <= 0) return fail(-1, "idg_ngcf_dense_fwd: bad argument%s");
     if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "idg_ngcf_dense_fwd: drop_p must be in [0,1)%s");
-    const size_t smem = sizeof(float) * (128 * kNgTile + 128 * 64);
-    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ntiles = (N + kNgTile - 1) / kNgTile;
-    ngcf_dense_fwd_kernel<<<ntiles < 3 * kNumSMs ? ntiles : 3 * kNumSMs, 256, smem, (cudaStream_t)stream>>>(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, 1.f / (1.f - drop_p), N, d_S,
-                                                                                          d_D, d_out, out_stride);
-    IDG_LAUNCH_CHECK("ngcf_dense_fwd_kernel");
-    return 0;
+    if (out_stride & 3) return fail(-1, "idg_ngcf_dense_fwd: out_stride must be a multiple of 4%s");
+    return ngcf_dense_fwd_tc(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, 1.f / (1.f - drop_p), N, d_S, d_D, d_out, out_stride, (cudaStream_t)stream);
 }
 
 extern "C" int64_t idg_ngcf_workspace_bytes(void) { return (int64_t)sizeof(float) * kNgCtas * (128 * 64 + 64); }
