@@ -74,5 +74,6 @@ if __name__ == "__main__":
     launches(tag)
     for rep, name in (("prof_spmm_ab_v2.ncu-rep", "spmm_amazon-book_%s_ncu_full.json" % tag), ("prof_eval_ab.ncu-rep", "eval_amazon-book_%s_ncu_full.json" % tag),
                       ("prof_spmm_ab.ncu-rep", "spmm_amazon-book_%s_first_kernel_ncu_full.json" % tag),
-                      ("prof_pair.ncu-rep", "pairloss_lightccf_B4096_%s_ncu_full.json" % tag)):
+                      ("prof_pair.ncu-rep", "pairloss_lightccf_B4096_%s_ncu_full.json" % tag),
+                      ("prof_pair_tc.ncu-rep", "pairloss_tc_lightccf_B4096_%s_ncu_full.json" % tag)):
         report(rep, name)
