@@ -147,7 +147,7 @@ def run_reference(args):
             "config": workload_config(args, g),
             "cpu_baseline": {"value": v, "unit": "s/epoch", "cores": est["cores"], "kind": "port", "sample": "per step: " + est["sample"]},
             "e2e": {"value": v, "unit": "s/epoch", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, g):
@@ -158,8 +158,24 @@ def workload_config(args, g):
 
 
 # --------------------------------------------------------------------------------------------
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library prints there during the run
+    (NCCL's version banner, torch warnings) has been diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    sys.stdout.flush()
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # stdout of this process (and of the native libraries it loads) -> stderr until emit()
     if args.impl == "reference":
         return run_reference(args)
     rank = int(os.environ.get("RANK", "0"))
@@ -312,7 +328,7 @@ def main():
         est = cpu_epoch_estimate(g, n_train_batches=3, n_eval_batches=2)
         line["cpu_baseline"] = {"value": est["epoch_s"], "unit": "s/epoch", "cores": est["cores"], "kind": "port", "sample": est["sample"],
                                 "t_train_batch_s": est["t_train_batch_s"], "t_eval_batch_s": est["t_eval_batch_s"]}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
