@@ -142,6 +142,44 @@ class Data(object):
             return np.zeros((0, 3), dtype=np.int64)
         return np.stack([self.train_user, self.train_item, self.sample_negatives()], axis=1)
 
+    def sample_data_to_train_random(self):
+        """data_loader.py:86-106 (uniform user sampling of the official LightGCN code; no model of the reference calls
+        it).  The same numpy calls in the same order, so the global generator stream and the result are the reference's."""
+        users = np.random.randint(0, self.num_users, len(self.train_user))
+        sample_list = []
+        ip, ix = self.user_item_net.indptr, self.user_item_net.indices
+        for user in users:
+            lo, hi = ip[user], ip[user + 1]
+            if hi == lo:
+                continue
+            positive_item = ix[lo + np.random.randint(0, hi - lo)]
+            while True:
+                negative_item = np.random.randint(0, self.num_items)
+                k = lo + np.searchsorted(ix[lo:hi], negative_item)
+                if k < hi and ix[k] == negative_item:
+                    continue
+                break
+            sample_list.append([user, positive_item, negative_item])
+        return np.array(sample_list)
+
+    def get_user_n_neg_items(self, users, n):
+        """data_loader.py:135-149: n negatives per user, rejection against the user's train positives."""
+        ip, ix = self.user_item_net.indptr, self.user_item_net.indices
+        negative_items = []
+        for user in users:
+            lo, hi = ip[user], ip[user + 1]
+            negative_list = []
+            for _ in range(n):
+                while True:
+                    negative_item = np.random.randint(0, self.num_items)
+                    k = lo + np.searchsorted(ix[lo:hi], negative_item)
+                    if k < hi and ix[k] == negative_item:
+                        continue
+                    negative_list.append(negative_item)
+                    break
+            negative_items.append(negative_list)
+        return negative_items
+
     def get_user_pos_items(self, users):
         """data_loader.py:129-133: sorted train items of each user (views into the CSR)."""
         ip, ix = self.user_item_net.indptr, self.user_item_net.indices

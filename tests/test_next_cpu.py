@@ -271,3 +271,20 @@ def test_parse_ratings_matches_reference_semantics(tmp_path, golden_dirs, golden
     j.write_bytes(b"1 2 x3\n")
     with pytest.raises(_lib.IdgError):
         ops.parse_ratings(str(j))
+
+
+@pytest.mark.parametrize("name", ["tiny", "quirks"])
+def test_remaining_data_samplers_match_reference(golden_dirs, name):
+    """Data.sample_data_to_train_random / get_user_n_neg_items (data_loader.py:86-106,135-149): values and the numpy
+    generator state they leave equal the unmodified reference's (tests/golden/samplers.npz)."""
+    from utility.utility_data.data_loader import Data
+    g = np.load(os.path.join(GOLDEN, "samplers.npz"), allow_pickle=False)
+    d = Data(golden_dirs[name], {})
+    np.random.seed(77)
+    a = d.sample_data_to_train_random()
+    b = d.get_user_n_neg_items(list(range(0, d.num_users, 3)), 4)
+    st = np.random.get_state()
+    np.testing.assert_array_equal(a, g["rand_" + name])
+    np.testing.assert_array_equal(np.array(b, dtype=np.int64), g["nneg_" + name])
+    np.testing.assert_array_equal(st[1], g["rng_key_" + name])
+    assert st[2] == int(g["rng_pos_" + name])
