@@ -11,6 +11,8 @@ path in the model classes computes the same values for the reference's own train
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -119,7 +121,6 @@ class FusedTrainer:
 
     def _bpr(self, B, u, p, n, fused):
         l, s = self.l, cur_stream()
-        import ctypes as C
         mask = getattr(self, "reg_mask", 7)
         up = ptr(self.up_w) if self.loss_order is not None else None     # which of (bpr, reg) enter the objective
         check(l.idg_bpr_forward_tail(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, self.d, self.reg_lambda, mask,
