@@ -29,6 +29,8 @@ def read_configuration(filename, model):
         for line in f:
             if line == "":
                 break
+            if line.lstrip().startswith("#") or not line.strip():
+                continue          # comment / blank lines (the shipped files carry a provenance header)
             try:
                 name, value = line.strip().split("=")
                 config[name.strip()] = value.strip()
