@@ -336,7 +336,7 @@ int idg_tanh_bwd(const float* d_y, const float* d_gy, float* d_gx, int64_t n, vo
 /* ---- a1: data_loader.py:48-70, the dataset text format ("user item item ..." per line) parsed on the HOST in one
  * pass.  Two-call protocol: pair_cap = line_cap = 0 counts (*n_pairs, *n_lines); the second call fills
  * h_user/h_item [n_pairs] (file order = inter_users/inter_items), h_line_user/h_line_len [n_lines] (unique_users and
- * the per-line item counts, 0 for a user with an empty line).  *max_user/*max_item follow data_loader.py:62-63
+ * the per-line item counts, 0 for a user with an empty line).  *max_user and *max_item follow data_loader.py:62-63
  * (lines with at least one item only; -1 when there is none).  -3: cannot open, -4: not an integer token. */
 int idg_parse_ratings(const char* path, int64_t* h_user, int64_t* h_item, int64_t pair_cap, int64_t* n_pairs,
                       int64_t* h_line_user, int64_t* h_line_len, int64_t line_cap, int64_t* n_lines,
