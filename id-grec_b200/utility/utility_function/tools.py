@@ -11,59 +11,68 @@ import torch
 
 
 def set_seed(seed):
-    """tools.py:8-14."""
+    """tools.py:8-14: seeds the three generators the path draws from -- numpy's legacy global stream (negative
+    sampler + epoch shuffle), torch's CPU generator (xavier init) and every CUDA generator (SimGCL noise, dropout)."""
+    seed = int(seed)
     np.random.seed(seed)
+    torch.manual_seed(seed)           # CPU generator; torch also forwards the seed to the CUDA generators
     if torch.cuda.is_available():
-        torch.cuda.manual_seed(seed)
         torch.cuda.manual_seed_all(seed)
-    torch.manual_seed(seed)
+
+
+def _parse_config_line(text):
+    """``key = value`` -> (key, value); None for blank / comment lines; ValueError for anything else."""
+    body = text.strip()
+    if not body or body.startswith("#"):
+        return None
+    key, sep, value = body.partition("=")
+    if not sep or "=" in value:        # the reference's ``a, b = line.split("=")`` accepts exactly one '='
+        raise ValueError(body)
+    return key.strip(), value.strip()
 
 
 def read_configuration(filename, model):
-    """tools.py:17-32: ``key = value`` lines into a dict of strings."""
-    if not os.path.exists(filename):
-        print("\tThe path does not have a configuration file for " + model + ".")
-        raise IOError
-    config = dict()
-    with open(filename, "r") as f:
-        for line in f:
-            if line == "":
-                break
-            if line.lstrip().startswith("#") or not line.strip():
-                continue          # comment / blank lines (the shipped files carry a provenance header)
+    """tools.py:17-32: the ``key = value`` file of a model as a dict of strings.  A missing file raises IOError;
+    malformed lines are reported and skipped, like the reference does."""
+    if not os.path.isfile(filename):
+        print("\tNo configuration file for model %s at %s." % (model, filename))
+        raise IOError(filename)
+    config = {}
+    with open(filename, "r") as handle:
+        for number, text in enumerate(handle, 1):
             try:
-                name, value = line.strip().split("=")
-                config[name.strip()] = value.strip()
+                item = _parse_config_line(text)
             except ValueError:
-                print("\tConfiguration file format error.")
+                print("\tConfiguration file format error (line %d of %s)." % (number, filename))
+                continue
+            if item is not None:
+                config[item[0]] = item[1]
     return config
 
 
 def shuffle(*arrays, **kwargs):
-    """tools.py:35-52: one np.random.shuffle of arange(n), applied to every array."""
-    require_indices = kwargs.get('indices', False)
-    if len(set(len(x) for x in arrays)) != 1:
-        raise ValueError('Inputs to shuffle must have the same length.')
-    shuffle_indices = np.arange(len(arrays[0]))
-    np.random.shuffle(shuffle_indices)
-    if torch.is_tensor(arrays[0]) and arrays[0].is_cuda:
-        sel = torch.from_numpy(shuffle_indices).to(arrays[0].device)
-    else:
-        sel = shuffle_indices
-    result = arrays[0][sel] if len(arrays) == 1 else tuple(x[sel] for x in arrays)
-    return (result, shuffle_indices) if require_indices else result
+    """tools.py:35-52: ONE ``np.random.shuffle`` of ``arange(n)`` (the numpy global stream, right after the sampler)
+    applied to every input; ``indices=True`` also returns the permutation.  Device tensors are permuted on the
+    device."""
+    lengths = {len(a) for a in arrays}
+    if len(lengths) != 1:
+        raise ValueError("shuffle: all inputs need the same length, got %s" % sorted(lengths))
+    perm = np.arange(lengths.pop())
+    np.random.shuffle(perm)
+    first = arrays[0]
+    sel = torch.from_numpy(perm).to(first.device) if (torch.is_tensor(first) and first.is_cuda) else perm
+    out = tuple(a[sel] for a in arrays)
+    out = out[0] if len(out) == 1 else out
+    return (out, perm) if kwargs.get('indices', False) else out
 
 
 def mini_batch(*tensors, **kwargs):
-    """tools.py:55-64: consecutive slices, last one short."""
-    batch_size = kwargs.get('batch_size', 1024)
-    if len(tensors) == 1:
-        tensor = tensors[0]
-        for i in range(0, len(tensor), batch_size):
-            yield tensor[i:i + batch_size]
-    else:
-        for i in range(0, len(tensors[0]), batch_size):
-            yield tuple(x[i:i + batch_size] for x in tensors)
+    """tools.py:55-64: consecutive ``batch_size`` slices of the inputs (default 1024), the last one short; one input
+    yields slices, several yield tuples."""
+    step = int(kwargs.get('batch_size', 1024))
+    for lo in range(0, len(tensors[0]), step):
+        piece = tuple(t[lo:lo + step] for t in tensors)
+        yield piece[0] if len(piece) == 1 else piece
 
 
 def create_adj_mat(inter_graph, aug_type, ssl_rate):

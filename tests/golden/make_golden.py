@@ -20,9 +20,14 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = "/root/reference"
 OUT = os.path.join(REPO, "tests", "golden")
-sys.path.insert(0, os.path.join(REPO, "id-grec_b200"))
+PKG = os.path.join(REPO, "id-grec_b200")
+sys.path.insert(0, PKG)
 from idgrec import datagen  # noqa: E402  (only the dataset writer; no product compute)
 
+# the product package mirrors the reference's module names (utility.*, models.*, Parser) and the reference's
+# directories are namespace packages (no __init__.py), so a regular package of the same name anywhere on sys.path
+# would shadow them: take the product directory off the path again before importing the reference
+sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") not in (PKG, REPO)]
 for m in [k for k in sys.modules if k.split(".")[0] in ("utility", "models", "Parser")]:
     del sys.modules[m]
 sys.path.insert(0, REF)
