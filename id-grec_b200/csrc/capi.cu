@@ -97,6 +97,18 @@ extern "C" int idg_axpby(float* d_out, float a, const float* d_x, float b, const
     return 0;
 }
 
+__global__ void accumulate_f64_kernel(double* __restrict__ acc, const float* __restrict__ x, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += (double)x[i];
+}
+extern "C" int idg_accumulate_f64(double* d_acc, const float* d_x, int32_t n, void* stream) {
+    if (!d_acc || !d_x || n < 0) return fail(-1, "idg_accumulate_f64: bad argument%s");
+    if (n == 0) return 0;
+    accumulate_f64_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_acc, d_x, n);
+    IDG_LAUNCH_CHECK("accumulate_f64_kernel");
+    return 0;
+}
+
 extern "C" int idg_zero_rows(float* d_buf, const int64_t* d_idx, int32_t n, int32_t d, void* stream) {
     if (!d_buf || !d_idx || n < 0 || d <= 0 || (d & 3)) return fail(-1, "idg_zero_rows: bad argument%s");
     if (n == 0) return 0;

@@ -315,6 +315,13 @@ __global__ void __launch_bounds__(256) eval_exhaustive_kernel(const float* __res
     }
 }
 
+// Shapes outside the fast kernels (d not in {32, 64, 128, 256}, K > 48): every user takes pass C.
+__global__ void eval_flag_all_kernel(int nu, EvalWs w) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nu) { w.flag_list[p] = p; w.cand_cnt[p] = 0; }
+    if (p == 0) *w.flag_cnt = nu;
+}
+
 // metrics.py:4-58 + batch_test.py:80-107: per-user recall/precision/ndcg terms, then an ordered sum.
 __global__ void __launch_bounds__(256) eval_metrics_kernel(const int64_t* __restrict__ topk, const int64_t* __restrict__ users, int nu,
                                                            int K, const int32_t* __restrict__ tptr, const int32_t* __restrict__ tind,
@@ -326,10 +333,12 @@ __global__ void __launch_bounds__(256) eval_metrics_kernel(const int64_t* __rest
     const int ks[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
     const int u = (int)users[p];
     const int lo = tptr[u], hi = tptr[u + 1], nt = hi - lo;
-    // hit bits over the K positions (K <= 64): lane handles positions lane, lane+32
-    unsigned long long hits = 0;
-    for (int q = 0; q < 2; ++q) {
-        const int j = lane + 32 * q;
+    // hit bits of 32 positions at a time (lane <-> position); lane 0 folds them into the running sums in position order
+    double nh[8], dcg[8], idcg[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { nh[t] = 0.0; dcg[t] = 0.0; idcg[t] = 0.0; }
+    for (int j0 = 0; j0 < K; j0 += 32) {
+        const int j = j0 + lane;
         bool h = false;
         if (j < K) {
             const int item = (int)topk[(size_t)p * K + j];
@@ -338,21 +347,29 @@ __global__ void __launch_bounds__(256) eval_metrics_kernel(const int64_t* __rest
             h = (a < hi && tind[a] == item);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, h);
-        hits |= (unsigned long long)bal << (32 * q);
+        if (lane == 0) {
+            const int jn = min(K, j0 + 32);
+            for (int jj = j0; jj < jn; ++jj) {
+                const double disc = 1.0 / log2((double)(jj + 2));
+                const bool hit = (bal >> (jj - j0)) & 1u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (t < nk && jj < ks[t]) {
+                        if (hit) { nh[t] += 1.0; dcg[t] += disc; }
+                        if (jj < nt) idcg[t] += disc;
+                    }
+                }
+            }
+        }
     }
     if (lane == 0) {
-        for (int t = 0; t < nk; ++t) {
-            const int k = ks[t];
-            double nh = 0, dcg = 0, idcg = 0;
-            for (int j = 0; j < k; ++j) {
-                const double disc = 1.0 / log2((double)(j + 2));
-                if ((hits >> j) & 1ull) { nh += 1.0; dcg += disc; }
-                if (j < nt) idcg += disc;
-            }
-            if (idcg == 0.0) idcg = 1.0;
-            per_user[(size_t)p * 3 * nk + 3 * t + 0] = (nt > 0) ? nh / (double)nt : 0.0;  // recall term
-            per_user[(size_t)p * 3 * nk + 3 * t + 1] = nh / (double)k;                      // precision term
-            per_user[(size_t)p * 3 * nk + 3 * t + 2] = dcg / idcg;                          // ndcg term
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (t >= nk) break;
+            const double id = (idcg[t] == 0.0) ? 1.0 : idcg[t];
+            per_user[(size_t)p * 3 * nk + 3 * t + 0] = (nt > 0) ? nh[t] / (double)nt : 0.0;  // recall term
+            per_user[(size_t)p * 3 * nk + 3 * t + 1] = nh[t] / (double)ks[t];                 // precision term
+            per_user[(size_t)p * 3 * nk + 3 * t + 2] = dcg[t] / id;                           // ndcg term
         }
     }
 }
@@ -428,11 +445,20 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
                              float* d_out_scores, void* d_ws, void* stream_) {
     if (!d_Fu || !d_Fi || !d_mask_indptr || !d_users || !d_out_ids || !d_ws) return fail(-1, "idg_eval_topk: null argument%s");
     if (nu <= 0 || I <= 0 || U <= 0) return fail(-1, "idg_eval_topk: bad sizes%s");
-    if (K < 1 || K > 48 || K > I) return fail(-1, "idg_eval_topk: K must be in [1, min(48, I)] (%s%lld)", "", K);
-    if (d != 64 && d != 256) return fail(-1, "idg_eval_topk: d must be 64 or 256 (%s%lld)", "", d);
+    if (K < 1 || K > I) return fail(-1, "idg_eval_topk: K must be in [1, I] (%s%lld)", "", K);
+    if (d < 1) return fail(-1, "idg_eval_topk: d must be positive (%s%lld)", "", d);
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalWs w = eval_carve(d_ws, nu, I);
     IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
+    if (K > 48 || (d != 32 && d != 64 && d != 128 && d != 256)) {
+        // reference-legal but outside the tiled kernels (any embedding_size / top_K parses in the reference): exact
+        // exhaustive ranking for every user -- same ids, one fp64 score row per user instead of the candidate filter
+        eval_flag_all_kernel<<<(nu + 255) / 256, 256, 0, stream>>>(nu, w);
+        IDG_LAUNCH_CHECK("eval_flag_all_kernel");
+        eval_exhaustive_kernel<<<kFallbackCtas, 256, 0, stream>>>(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w, d_out_ids, d_out_scores);
+        IDG_LAUNCH_CHECK("eval_exhaustive_kernel");
+        return 0;
+    }
     item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm);
     IDG_LAUNCH_CHECK("item_norm_kernel");
     const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
@@ -446,6 +472,12 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     } else if (d == 64) {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_candidates_kernel<64><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
+    } else if (d == 32) {
+        IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_candidates_kernel<32><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
+    } else if (d == 128) {
+        IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        eval_candidates_kernel<128><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
     } else {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_candidates_kernel<256><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
@@ -461,7 +493,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
 extern "C" int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t nu, int32_t K, const int32_t* d_test_indptr,
                                 const int32_t* d_test_indices, const int32_t* h_ks, int32_t nk, double* d_sums, void* d_ws, void* stream_) {
     if (!d_topk_ids || !d_users || !d_test_indptr || !d_test_indices || !h_ks || !d_sums || !d_ws) return fail(-1, "idg_eval_metrics: null argument%s");
-    if (nu <= 0 || K < 1 || K > 64 || nk < 1 || nk > 8) return fail(-1, "idg_eval_metrics: bad sizes%s");
+    if (nu <= 0 || K < 1 || nk < 1 || nk > 8) return fail(-1, "idg_eval_metrics: bad sizes (at most 8 cut-offs per call)%s");
     int ks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < nk; ++t) { if (h_ks[t] < 1 || h_ks[t] > K) return fail(-1, "idg_eval_metrics: k out of range%s"); ks[t] = h_ks[t]; }
     cudaStream_t stream = (cudaStream_t)stream_;

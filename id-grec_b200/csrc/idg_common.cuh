@@ -14,6 +14,7 @@ struct idg_peers {
     int rank = 0, world = 1;
     char* bases[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     char* mc_base = nullptr;  // NVSwitch multicast mapping of the same slab (NVLS): one store reaches every GPU
+    unsigned long long timeout_ns = 20000000000ull;  // bound of one flag-barrier wait (idg_peers_set_timeout_ms)
 };
 
 namespace idg {

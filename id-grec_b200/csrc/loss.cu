@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(1024) bpr_reduce_kernel(BprWs w, int B, float 
     if (threadIdx.x == 0) {
         const float l0 = sl[0] / (float)B, l1 = reg_lambda * (sr[0] / (float)B);
         loss[0] = l0; loss[1] = l1;
-        if (tail.d_loss_acc) { tail.d_loss_acc[0] += l0; tail.d_loss_acc[1] += l1; }
+        if (tail.d_loss_acc) { tail.d_loss_acc[0] += (double)l0; tail.d_loss_acc[1] += (double)l1; }
         if (tail.d_step) {
             const double t = (double)(*tail.d_step + 1);
             tail.d_scalars[0] = (float)((double)tail.lr / (1.0 - pow((double)tail.beta1, t)));
@@ -211,8 +211,10 @@ extern "C" int64_t idg_bpr_workspace_bytes(int32_t B) {
         case 32: { constexpr int VPL = 1; __VA_ARGS__; break; }                                    \
         case 64: { constexpr int VPL = 2; __VA_ARGS__; break; }                                    \
         case 128: { constexpr int VPL = 4; __VA_ARGS__; break; }                                   \
+        case 192: { constexpr int VPL = 6; __VA_ARGS__; break; } /* NGCF concat, GCN_layer = 2 */   \
         case 256: { constexpr int VPL = 8; __VA_ARGS__; break; }                                   \
-        default: return fail(-1, "d must be 32, 64, 128 or 256 (%s%lld)", "", (long long)d); \
+        case 320: { constexpr int VPL = 10; __VA_ARGS__; break; } /* NGCF concat, GCN_layer = 4 */  \
+        default: return fail(-1, "d must be 32, 64, 128, 192, 256 or 320 (%s%lld)", "", (long long)d); \
     }
 
 static int bpr_forward_impl(const float* d_F, const float* d_E0, const int64_t* d_user, const int64_t* d_pos,

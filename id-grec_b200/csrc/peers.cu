@@ -25,8 +25,18 @@ __global__ void mc_push_kernel(const float4* __restrict__ src, float* mc_dst, in
     multimem_st4(mc_dst + 4 * i, src[i]);
 }
 
-// state layout (ints, inside the slab): [0] = epoch counter (local), [8 + r] = last epoch announced by rank r
-__global__ void peer_barrier_kernel(int* state, PeerPtrs peer_states, int rank, int world) {
+// state layout (ints, inside the slab): [0] = epoch counter (local), [1] = error word (0 = healthy, else
+// 1 + index of the first peer that did not arrive within the time limit), [8 + r] = last epoch announced by rank r.
+// The wait is bounded (a dead peer must surface as an error, not as a hung stream): after
+// timeout_ns without the peer's flag the thread records the peer in state[1] and returns; every later barrier of a
+// failed slab returns immediately, so a captured train step drains instead of spinning, and the host reads the
+// error word with idg_peers_status at its next synchronisation point.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void peer_barrier_kernel(int* state, PeerPtrs peer_states, int rank, int world, unsigned long long timeout_ns) {
     __shared__ int s_epoch;
     if (threadIdx.x == 0) { s_epoch = state[0] + 1; state[0] = s_epoch; }
     __syncthreads();
@@ -38,8 +48,17 @@ __global__ void peer_barrier_kernel(int* state, PeerPtrs peer_states, int rank, 
     }
     __threadfence_system();
     if (threadIdx.x < world) {
-        volatile int* mine = reinterpret_cast<volatile int*>(state) + 8;
-        while (mine[threadIdx.x] < e) { }
+        volatile int* st = reinterpret_cast<volatile int*>(state);
+        if (st[1] == 0) {
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (st[8 + threadIdx.x] < e) {
+                if ((++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
+                    atomicCAS(state + 1, 0, 1 + (int)threadIdx.x);
+                    break;
+                }
+            }
+        }
     }
     __threadfence_system();
 }
@@ -116,6 +135,12 @@ extern "C" int idg_peers_push(const idg_peers* p, const void* d_src, int64_t byt
     return 0;
 }
 
+extern "C" int idg_peers_set_timeout_ms(idg_peers* p, int64_t ms) {
+    if (!p || ms <= 0) return fail(-1, "idg_peers_set_timeout_ms: bad argument%s");
+    p->timeout_ns = (unsigned long long)ms * 1000000ull;
+    return 0;
+}
+
 extern "C" int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* stream) {
     if (!p || !d_state) return fail(-1, "idg_peers_barrier: null argument%s");
     if (p->world == 1) return 0;
@@ -123,7 +148,19 @@ extern "C" int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* str
     if (int rc = slab_offset(p, d_state, 64 * (int64_t)sizeof(int), &off)) return rc;
     PeerPtrs st;
     for (int q = 0; q < 8; ++q) st.p[q] = (q < p->world) ? p->bases[q] + off : nullptr;
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_state, st, p->rank, p->world);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_state, st, p->rank, p->world, p->timeout_ns);
     IDG_LAUNCH_CHECK("peer_barrier_kernel");
     return 0;
+}
+
+// Synchronises the stream and reads the barrier's error word: 0 = every barrier so far completed,
+// IDG_ERR_PEER_TIMEOUT + r = rank r did not reach a barrier within the time limit (idg_last_error names it).
+extern "C" int idg_peers_status(const idg_peers* p, const int32_t* d_state, void* stream) {
+    if (!p || !d_state) return fail(-1, "idg_peers_status: null argument%s");
+    int word = 0;
+    IDG_CUDA(cudaMemcpyAsync(&word, d_state + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    IDG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (word == 0) return 0;
+    return fail(IDG_ERR_PEER_TIMEOUT + (word - 1), "idg_peers_barrier: rank %s%lld did not arrive within %lld ms", "", word - 1,
+                (long long)(p->timeout_ns / 1000000ull));
 }

@@ -61,6 +61,7 @@ SIGNATURES = {
     "idg_version": (C.c_int, []),
     "idg_last_error": (C.c_char_p, []),
     "idg_launch_count": (_i64, []),
+    "idg_accumulate_f64": (C.c_int, [_p, _p, _i32, _p]),
     "idg_csr_structure": (C.c_int, [_p, _p, _i64, _i32, _i32, C.c_int, _p, _p, _p, _p, C.POINTER(_i64), _p]),
     "idg_csr_normalise": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _p, _p]),
     "idg_graph_create": (C.c_int, [_p, _p, _p, _i32, _i32, _i64, _i32, C.POINTER(_p), _p]),
@@ -116,6 +117,8 @@ SIGNATURES = {
     "idg_graph_set_peers": (C.c_int, [_p, _p]),
     "idg_peers_push": (C.c_int, [_p, _p, _i64, _p]),
     "idg_peers_barrier": (C.c_int, [_p, _p, _p]),
+    "idg_peers_set_timeout_ms": (C.c_int, [_p, _i64]),
+    "idg_peers_status": (C.c_int, [_p, _p, _p]),
     "idg_neg_sample_replay": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64)]),
     "idg_neg_sample_walk": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64), C.POINTER(_i64)]),
     "idg_permute3": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),

@@ -115,6 +115,8 @@ class PeerSlab:
         if mc:
             check(self.l.idg_peers_set_multicast(h, mc), "idg_peers_set_multicast")
             self.multicast = True
+        if os.environ.get("IDG_PEER_TIMEOUT_MS"):
+            check(self.l.idg_peers_set_timeout_ms(h, int(os.environ["IDG_PEER_TIMEOUT_MS"])), "idg_peers_set_timeout_ms")
         self._off = 0
         self.state = self.carve((64,), torch.int32)
         torch.cuda.synchronize()
@@ -135,6 +137,10 @@ class PeerSlab:
     def push(self, t):
         check(self.l.idg_peers_push(self.handle, ptr(t), t.numel() * t.element_size(), cur_stream()), "idg_peers_push")
 
+    def status(self):
+        """Synchronises the stream; raises IdgError (rc = IDG_ERR_PEER_TIMEOUT + rank) if a peer missed a barrier."""
+        check(self.l.idg_peers_status(self.handle, ptr(self.state), cur_stream()), "idg_peers_status")
+
 
 class DistFusedTrainer:
     """LightGCN training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer)."""
@@ -144,7 +150,7 @@ class DistFusedTrainer:
         if kind != "LightGCN":
             raise NotImplementedError("multi-GPU training is implemented for LightGCN (BASELINE.json configs 2 and 5)")
         if not 2 <= K <= 3:
-            raise NotImplementedError("row-restricted distributed forward supports 1..3 layers")
+            raise NotImplementedError("the row-partitioned step supports GCN_layer = 2 or 3 (got %d)" % K)
         self.l = _lib.lib()
         self.kind, self.rank, self.world = kind, rank, world
         self.U, (self.N, self.d), self.K = num_users, table.shape, K
@@ -181,7 +187,7 @@ class DistFusedTrainer:
         self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
         self.n_loss = 2
         self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.regc = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -273,7 +279,7 @@ class DistFusedTrainer:
         self._mark('finish')
         slab.barrier()
         self._mark('barrier')
-        check(l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, s), "idg_axpby")
+        check(l.idg_accumulate_f64(ptr(self.loss_acc), ptr(self.loss), 4, s), "idg_accumulate_f64")
 
     def step(self, users, pos, neg, apply_adam=True):
         assert apply_adam, "the distributed step always applies Adam"
@@ -297,6 +303,7 @@ class DistFusedTrainer:
         return self.loss[:2]
 
     def pop_epoch_losses(self):
+        self.slab.status()   # a peer that missed a flag barrier invalidates the epoch: surface it here, not as a hang
         out = self.loss_acc[:2].tolist()
         self.loss_acc.zero_()
         return out

@@ -64,7 +64,7 @@ class FusedTrainer:
             self.uidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
             self.iidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
         self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.loss_acc = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)   # epoch sums in float64 (trainer.py:52-53)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         if kind in ("SimGCL", "XSimGCL"):
             self.noise = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev)
@@ -284,7 +284,7 @@ class FusedTrainer:
             if not self.fuse_adam:
                 self._adam()
             if not self._tail_acc:
-                check(self.l.idg_axpby(ptr(self.loss_acc), 1.0, ptr(self.loss_acc), 1.0, ptr(self.loss), 4, cur_stream()), "idg_axpby")
+                check(self.l.idg_accumulate_f64(ptr(self.loss_acc), ptr(self.loss), 4, cur_stream()), "idg_accumulate_f64")
 
         # warm-up outside capture would advance the model; capture directly (kernels are launched lazily at replay)
         torch.cuda.synchronize()

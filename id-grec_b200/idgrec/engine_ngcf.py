@@ -67,7 +67,7 @@ class NgcfFusedTrainer:
         self.ngws = torch.empty(int(self.l.idg_ngcf_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.up_reg = torch.tensor([0.0, 1.0], dtype=torch.float32, device=dev)   # the d = 64 BPR call contributes the reg term only
         self.loss_a, self.loss_b = z(4), z(4)
-        self.loss_acc = z(2)
+        self.loss_acc = torch.zeros(2, dtype=torch.float64, device=dev)   # epoch sums in float64 (trainer.py:52-53)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         self.graph.work(d)
         self._graphs, self.replays, self.step_count = {}, 0, 0

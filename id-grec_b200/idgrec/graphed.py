@@ -34,7 +34,7 @@ class GraphedStep:
         stacked.sum().backward()
         self.opt.step()
         if self.loss_acc is None:
-            self.loss_acc = torch.zeros_like(stacked.detach())
+            self.loss_acc = torch.zeros_like(stacked.detach(), dtype=torch.float64)   # Python-float sums in the reference (trainer.py:52-53)
         self.loss_acc.add_(stacked.detach())
 
     def _snapshot(self):

@@ -9,6 +9,45 @@ from . import ops
 from .engine import FusedTrainer
 
 
+def validate_config(kind, config, dataset):
+    """Checks a configuration against the limits of the CUDA kernels BEFORE training starts (the reference accepts any
+    embedding_size / GCN_layer / top_K; a value outside the kernels must not surface as an error inside the first
+    Test() after a whole epoch).  Evaluation itself takes any embedding width and any top_K (idg_eval_topk ranks
+    exhaustively outside its tiled shapes)."""
+    problems = []
+    d = int(config['embedding_size'])
+    mf = kind == "MFBPR" or str(config.get('encoder', 'LightGCN')) == 'MF'
+    if not mf and d not in (32, 64, 128):
+        problems.append("embedding_size = %d: the propagation kernel handles 32, 64 or 128" % d)
+    if mf and d not in (32, 64, 128, 192, 256, 320):
+        problems.append("embedding_size = %d: the BPR kernels handle 32, 64, 128, 192, 256 or 320" % d)
+    if kind in ("SimGCL", "XSimGCL", "SGL", "EGCF") and d != 64:
+        problems.append("embedding_size = %d: the InfoNCE kernels of %s handle 64" % (d, kind))
+    if kind == "NGCF":
+        layers = eval(config['layer_size'])
+        K = int(config['GCN_layer'])
+        if d != 64 or any(int(x) != 64 for x in layers[:K]):
+            problems.append("NGCF: embedding_size and every used layer_size must be 64 (dense-layer kernels are 64 x 64)")
+        if K not in (1, 2, 3, 4):
+            problems.append("NGCF: GCN_layer = %d (the concatenated width 64 (K+1) must be 128, 192, 256 or 320)" % K)
+        if len(layers) < K or len(eval(config.get('mess_drop_prob', '[]'))) < (K if eval(config.get('mess_dropout', 'False')) else 0):
+            problems.append("NGCF: layer_size / mess_drop_prob shorter than GCN_layer")
+    elif not mf and int(config.get('GCN_layer', 1)) < 1:
+        problems.append("GCN_layer must be >= 1")
+    try:
+        topk = [int(k) for k in eval(config['top_K'])]
+    except Exception:  # noqa: BLE001
+        topk = None
+    if not topk or any(k < 1 for k in topk):
+        problems.append("top_K = %r: a non-empty list of positive cut-offs is needed" % (config.get('top_K'),))
+    elif len(topk) > 8:
+        problems.append("top_K has %d cut-offs: the metric kernel takes at most 8 per evaluation" % len(topk))
+    elif max(topk) > dataset.num_items:
+        problems.append("top_K = %s exceeds the number of items (%d)" % (topk, dataset.num_items))
+    if problems:
+        raise ValueError("configuration outside the accelerated path of %s:\n  - %s" % (kind, "\n  - ".join(problems)))
+
+
 class PropagationModel(nn.Module):
     """nn.Module with the reference's duck-typed model contract:
     ``forward(user, pos, neg) -> [losses]``, ``aggregate(...) -> (users_emb, items_emb)``,
@@ -20,6 +59,7 @@ class PropagationModel(nn.Module):
 
     def __init__(self, config, dataset, device, graph_fn=None):
         super().__init__()
+        validate_config(self.kind, config, dataset)
         self.config, self.dataset, self.device = config, dataset, device
         self.reg_lambda = float(config.get('reg_lambda', config.get('lambda_reg', 0.0)))
         dim = int(config['embedding_size'])
@@ -74,6 +114,8 @@ class PropagationModel(nn.Module):
 
     # -- fused trainer (used by utility_train.trainer.universal_trainer) -------------------------
     def fused_trainer(self, lr, max_batch):
+        if self.kind == "XSimGCL" and not 1 <= int(self.config.get('cl_layer', 1)) <= self.num_layers:
+            return None   # contrast view = ego table (XSimGCL.py:48): the autograd ops in forward() cover it
         if self._fused is None or self._fused.lr != lr or self._fused.max_batch < max_batch:
             if self._table is None:
                 self._fuse_tables()

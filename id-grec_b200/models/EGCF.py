@@ -16,6 +16,8 @@ class EGCF(nn.Module):
     graph_capturable = True    # forward() has no host sync: universal_trainer replays the whole step from a CUDA graph
 
     def __init__(self, config, dataset, device):
+        from idgrec.model_base import validate_config
+        validate_config("EGCF", config, dataset)
         super(EGCF, self).__init__()
         self.config, self.dataset, self.device = config, dataset, device
         self.reg_lambda = float(config['reg_lambda'])

@@ -40,7 +40,10 @@ class XSimGCL(PropagationModel):
         K = self.num_layers
         if noise is None:
             noise = torch.stack([torch.rand_like(E0.detach()) for _ in range(K)])
-        final, cl = ops.propagate(E0, self.Graph, K, include_layer0=False, noise=noise, eps=self.epsilon, cl_layer=self.cl_layer)
+        if 1 <= self.cl_layer <= K:
+            final, cl = ops.propagate(E0, self.Graph, K, include_layer0=False, noise=noise, eps=self.epsilon, cl_layer=self.cl_layer)
+        else:  # XSimGCL.py:48: no layer is captured, the contrast view stays the ego table
+            final, cl = ops.propagate(E0, self.Graph, K, include_layer0=False, noise=noise, eps=self.epsilon), E0
         loss = ops.bpr_reg_loss(final, E0, user, positive, negative, U, self.reg_lambda, 7)
         user_index = torch.unique(user)
         item_index = torch.unique(positive) + U

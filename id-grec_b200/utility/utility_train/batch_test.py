@@ -41,8 +41,28 @@ def rank_all(dataset, model, device, K, users=None):
     """ids [n_test_users, K] int64 on the device, ordered (score desc, item id asc), train positives removed."""
     cache = dataset.device_cache(device)
     users = cache["test_users"] if users is None else users
+    if not hasattr(model, "final_embeddings"):
+        return _rank_by_rating_matrix(dataset, model, device, K, users, cache), users
     users_emb, items_emb = model.final_embeddings()
     return ops.eval_topk(users_emb, items_emb, users, cache["mask_indptr"], cache["mask_indices"], K), users
+
+
+def _rank_by_rating_matrix(dataset, model, device, K, users, cache, test_batch_size=1024):
+    """Evaluation of a module that only offers the reference's ``get_rating_for_test(users) -> [b, I]`` (SURVEY 8 b: the
+    contract a foreign nn.Module has to meet): the reference's own per-batch flow (batch_test.py:52-68) with the Python
+    index lists replaced by device index arithmetic over the train CSR -- rating[train positives] = -1, torch.topk."""
+    ip, ix = cache["mask_indptr"].long(), cache["mask_indices"].long()
+    out = torch.empty((len(users), K), dtype=torch.int64, device=device)
+    for lo in range(0, len(users), test_batch_size):
+        bu = users[lo:lo + test_batch_size].long()
+        rating = model.get_rating_for_test(bu)
+        start, cnt = ip[bu], ip[bu + 1] - ip[bu]
+        rows = torch.repeat_interleave(torch.arange(len(bu), device=device), cnt)
+        first = torch.cumsum(cnt, 0) - cnt
+        cols = ix[torch.arange(int(cnt.sum()), device=device) - first[rows] + start[rows]]
+        rating[rows, cols] = -1
+        out[lo:lo + len(bu)] = torch.topk(rating, K).indices
+    return out
 
 
 def Test(dataset, model, device, config):
@@ -76,7 +96,9 @@ def sparsity_test(dataset, model, device, config):
     """batch_test.py:110-170: the same full-ranking metrics per activity group of
     ``dataset.split_test_dict``.  One propagation serves every group (the reference re-propagates per
     1024-user batch); each group is one launch of the ranking kernel over that group's users.  An empty
-    group trips the reference's batch-count assert (batch_test.py:152); so does it here."""
+    group (``create_sparsity_split`` appends one on purpose) and a group whose size is a multiple of test_batch_size
+    trip the reference's batch-count assert (batch_test.py:152); ``test_batch_size`` has no role here, so neither
+    aborts: an empty group reports zeros.  ``strict_reference_asserts = 1`` in the config restores the assert."""
     model = model.eval()
     topK = eval(config['top_K'])
     device = torch.device(device)
@@ -86,7 +108,12 @@ def sparsity_test(dataset, model, device, config):
     with torch.no_grad():
         users_emb, items_emb = model.final_embeddings()
         for users in dataset.split_test_dict:
-            assert len(users) // tb + 1 == (len(users) + tb - 1) // tb, "reference batch-count assert (batch_test.py:152)"
+            if str(config.get('strict_reference_asserts', '0')) not in ('0', 'False', 'false'):
+                assert len(users) // tb + 1 == (len(users) + tb - 1) // tb, "reference batch-count assert (batch_test.py:152)"
+            if len(users) == 0:
+                zero = np.zeros(len(topK))
+                sparsity_results.append({'precision': zero.copy(), 'recall': zero.copy(), 'hit': zero.copy(), 'ndcg': zero.copy()})
+                continue
             u = torch.as_tensor(np.asarray(users, dtype=np.int64), device=device)
             ids = ops.eval_topk(users_emb, items_emb, u, cache["mask_indptr"], cache["mask_indices"], max(topK))
             sums = ops.eval_metric_sums(ids, u, cache["test_indptr"], cache["test_indices"], topK).cpu().numpy()

@@ -37,6 +37,7 @@ def sample_epoch(dataset, device):
     np.random.shuffle(perm)                       # same generator position as the reference: right after the sampler
     cache = dataset.device_cache(device)
     t = stage.to(device, non_blocking=True)
+    _check_same_samples(t, E)
     out = torch.empty((3, E), dtype=torch.int64, device=device)
     _lib.check(_lib.lib().idg_permute3(_lib.ptr(cache["train_user"]), _lib.ptr(cache["train_item"]), _lib.ptr(t[0]), _lib.ptr(t[1]), E,
                                        _lib.ptr(out), _lib.cur_stream()), "idg_permute3")
@@ -45,6 +46,23 @@ def sample_epoch(dataset, device):
 
 
 _PINNED = {}
+
+
+def _check_same_samples(t, E):
+    """Row-partitioned training evaluates the loss redundantly on every rank and never reduces gradients: it is only
+    correct if all ranks drew the same negatives and the same permutation (same seed, same numpy stream position).
+    One int64 checksum per epoch, min/max all-reduced; a mismatch raises instead of silently corrupting the tables."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    w = torch.arange(1, E + 1, device=t.device, dtype=torch.int64)
+    c = ((t[0, :E] * 1000003 + t[1, :E]) * w).sum().reshape(1)
+    lo, hi = c.clone(), c.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if int(lo.item()) != int(hi.item()):
+        raise RuntimeError("ranks drew different epoch samples (negatives / shuffle differ): seed every rank identically "
+                           "(tools.set_seed) and keep other np.random calls off the global stream")
 
 
 def universal_trainer(model, args, config, dataset, device, logger):
@@ -83,9 +101,11 @@ def universal_trainer(model, args, config, dataset, device, logger):
                 fused.step(bu, bp, bn)
             # the steps are only enqueued: draw the next epoch's samples on the host while the GPU trains.  Nothing else
             # reads the numpy global generator in between, so the stream (and every batch) stays the reference's.
+            enqueue_time = time()
             if epoch + 1 < n_epochs:
                 prefetched = sample_epoch(dataset, device)
-            total_loss_list = fused.pop_epoch_losses()    # one device read per epoch
+            sampling_time = time() - enqueue_time         # host time of the NEXT epoch's sampler, hidden behind this epoch's kernels
+            total_loss_list = fused.pop_epoch_losses()    # one device read per epoch (waits for the epoch's last step)
         else:
             acc = None
             for bu, bp, bn in tools.mini_batch(users, pos_items, neg_items, batch_size=batch_size):
@@ -97,13 +117,17 @@ def universal_trainer(model, args, config, dataset, device, logger):
                 Optim.step()
                 # per-loss epoch sums stay on the device: one read per epoch instead of len(loss_list) .item() syncs
                 # per batch (trainer.py:52)
-                acc = stacked.detach() if acc is None else acc + stacked.detach()
+                acc = stacked.detach().double() if acc is None else acc + stacked.detach()
             total_loss_list = acc.cpu().tolist() if acc is not None else []
+            sampling_time = 0.0
 
+        # "Training time" = this epoch's steps: the overlapped sampling of the next epoch only counts where it outlasted them
         end_time = time()
         loss_strs = str(round(sum(total_loss_list) / num_batch, 6)) \
             + " = " + " + ".join([str(round(i / num_batch, 6)) for i in total_loss_list])
         print("Training time: %.3f | training loss: %s" % (end_time - start_time, loss_strs))
+        if sampling_time > 0.0:
+            print("\t(next epoch's host sampling: %.3f s, overlapped with this epoch's kernels)" % sampling_time)
         logger.info("Epoch: %4d | Training time: %.3f | training loss: %s" % (epoch + 1, end_time - start_time, loss_strs))
 
         if epoch % int(config.get('interval', 1)) == 0:   # configure/DirectAU.txt has no interval line

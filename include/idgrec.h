@@ -44,13 +44,16 @@ typedef struct idg_adam_args {
  * (idg_bpr_forward_tail): d_loss_acc[0..1] += {bpr, reg} (epoch sums, read once per epoch instead of trainer.py:52's
  * .item() per batch) and, when d_step is given, the job of idg_adam_prepare for this step.  Any pointer may be NULL. */
 typedef struct idg_step_tail {
-    float* d_loss_acc;
+    double* d_loss_acc; /* float64, like the reference's Python-float sums of .item() values (trainer.py:52-53) */
     int32_t* d_step;
     float* d_scalars;
     float lr, beta1, beta2;
 } idg_step_tail;
 
 int idg_version(void);
+/* d_acc[i] += (double)d_x[i], i < n: per-loss epoch sums kept on the device in float64 (the reference adds
+ * loss.item() values into Python floats, trainer.py:52-53), read once per epoch. */
+int idg_accumulate_f64(double* d_acc, const float* d_x, int32_t n, void* stream);
 const char* idg_last_error(void);
 /* number of kernels this library has launched so far in this process (bench.py "gpu_launches") */
 int64_t idg_launch_count(void);
@@ -245,7 +248,9 @@ int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg,
  * embeddings and every user whose candidate margin cannot be proven is recomputed
  * exhaustively, so ids equal the exact-rank oracle bit for bit.
  *   d_users [nu] int64 user ids; mask CSR = user_item_net (int32, U rows, sorted)
- *   d_out_ids [nu,K] int64, d_out_scores [nu,K] fp32 (may be NULL). K <= 64. */
+ *   d_out_ids [nu,K] int64, d_out_scores [nu,K] fp32 (may be NULL).  Any d >= 1 and any K <= I are accepted (the
+ *   reference takes any embedding_size / top_K): d in {32, 64, 128, 256} with K <= 48 run the tiled candidate
+ *   kernels (d = 64 on tcgen05); every other shape ranks each user exhaustively in fp64 -- same ids, slower. */
 int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, int32_t K);
 int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d,
                   const int32_t* d_mask_indptr, const int32_t* d_mask_indices, const int64_t* d_users,
@@ -306,6 +311,13 @@ int idg_peers_set_multicast(idg_peers* p, void* mc_base);
 int idg_graph_set_peers(idg_graph* g, const idg_peers* p);
 int idg_peers_push(const idg_peers* p, const void* d_src, int64_t bytes, void* stream);
 int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* stream);
+/* The barrier's wait is bounded (default 20 s per barrier, idg_peers_set_timeout_ms): a peer that never arrives is
+ * recorded in d_state[1] and the kernel returns instead of spinning; every later barrier on that slab returns at
+ * once.  idg_peers_status SYNCHRONISES the stream and returns 0, or IDG_ERR_PEER_TIMEOUT + r when rank r was missing
+ * (the results of the steps since the last healthy status are then invalid). */
+#define IDG_ERR_PEER_TIMEOUT 100000
+int idg_peers_set_timeout_ms(idg_peers* p, int64_t ms);
+int idg_peers_status(const idg_peers* p, const int32_t* d_state, void* stream);
 
 /* ---- a4: data_loader.py:108-127, exact replay on the HOST -------------------
  * h_cand: candidate stream = np.random.randint(0, I, size=n_cand) drawn from the
