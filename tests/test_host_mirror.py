@@ -163,3 +163,37 @@ def test_loss_ops_fail_loudly_without_cuda():
     x = torch.zeros(4, 64)
     with pytest.raises(Exception):
         ops.pair_loss("align", x, x)
+
+
+REF_ROOT = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_ROOT, "main.py")), reason="/root/reference is only present in the build container")
+def test_reference_main_py_text_drives_the_package_until_the_device_check(golden_dirs, tmp_path):
+    """Drop-in boundary (SURVEY 8 b): the UNMODIFIED text of the reference's main.py + Parser.py, placed over a copy of this
+    package, imports every module it names, reads the configuration, loads the dataset, logs the statistics line and
+    constructs models.LightGCN.Trainer -- and without a GPU stops exactly at the intended "no CPU fallback" error.  (The
+    GPU variant, tests/test_gpu_round2.py, lets it train.)  The two files are read from /root/reference at run time."""
+    import shutil
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: covered by the GPU variant")
+    work = tmp_path / "run"
+    shutil.copytree(os.path.join(REPO, "id-grec_b200"), work, ignore=shutil.ignore_patterns("__pycache__"))
+    for name in ("main.py", "Parser.py"):
+        shutil.copy(os.path.join(REF_ROOT, name), work / name)
+    ds = work / "dataset" / "tiny"
+    ds.mkdir(parents=True)
+    (work / "log").mkdir(exist_ok=True)
+    shutil.copy(os.path.join(golden_dirs["tiny"], "train.txt"), ds / "train.txt")
+    shutil.copy(os.path.join(golden_dirs["tiny"], "test.txt"), ds / "test.txt")
+    cfg_path = work / "configure" / "LightGCN.txt"
+    cfg_path.write_text(cfg_path.read_text().replace("dataset = yelp2018", "dataset = tiny"))
+    r = subprocess.run([sys.executable, "main.py", "--model=LightGCN"], cwd=work, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "Step 3.2: Loading dataset file..." in r.stdout and "Step 3.3: Init the Recommendation Model" in r.stdout
+    assert "no CPU fallback" in r.stderr, r.stderr[-1500:]
+    log = (work / "log" / "LightGCN" / "tiny.log").read_text()
+    assert "Run with LightGCN on tiny" in log

@@ -62,11 +62,34 @@ def main():
     t = ft.E0.clone()
     dist.broadcast(t, 0)
     ok &= bool(torch.equal(t, ft.E0))
+    # sharded evaluation == single-GPU evaluation: every rank ranks its user shard (what Test() does under world > 1);
+    # rank 0 also ranks ALL users from the single-GPU trainer's table.  ids must be bit-identical, metric sums equal to
+    # float64 summation order.
+    from idgrec import ops
+    from idgrec.dist import shard_range
+    cache = data.device_cache(dev)
+    all_users = cache["test_users"]
+    s0, s1 = shard_range(len(all_users), rank, world)
+    topK = eval(cfg["top_K"])
+    my_ids, _ = batch_test.rank_all(data, model, dev, max(topK), users=all_users[s0:s1].contiguous())
+    per = (len(all_users) + world - 1) // world
+    pad = torch.full((per, max(topK)), -1, dtype=torch.int64, device=dev)
+    pad[: s1 - s0] = my_ids
+    gathered = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad)
     if rank == 0:
-        # sharded evaluation == single-GPU evaluation
-        class M:  # minimal model view over the reference trainer's table
-            pass
-        import torch.distributed as d2
+        class SingleGpuView:   # the 1-GPU trainer's table behind the evaluator's model contract
+            def final_embeddings(self_inner):
+                F = model.Graph.propagate_fwd(ref.E0, 3, True)
+                return F[:data.num_users], F[data.num_users:]
+        ids1, users1 = batch_test.rank_all(data, SingleGpuView(), dev, max(topK))
+        sharded = torch.cat([gathered[r][: shard_range(len(all_users), r, world)[1] - shard_range(len(all_users), r, world)[0]] for r in range(world)])
+        ids_same = bool(torch.equal(sharded, ids1))
+        sums1 = ops.eval_metric_sums(ids1, users1, cache["test_indptr"], cache["test_indices"], topK).cpu().numpy() / float(len(all_users))
+        met_same = bool(np.allclose(sums1[:, 0], res["recall"], rtol=1e-12, atol=0) and np.allclose(sums1[:, 2], res["ndcg"], rtol=1e-12, atol=0)
+                        and np.allclose(sums1[:, 1], res["precision"], rtol=1e-12, atol=0))
+        print("sharded top-K ids == single-GPU ids:", ids_same, "| sharded Test() metrics == single-GPU metrics:", met_same)
+        ok &= ids_same and met_same
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
