@@ -12,7 +12,8 @@
 //           Per user, every unmasked item with s~ >= (running K-th largest s~) - 2*delta_u is
 //           kept; that set provably contains the exact top-K including all boundary ties.
 //   pass B  survivors are rescored exactly (fp64, k = 0..d-1) and ordered (score desc, id asc).
-//   pass C  users whose candidate list overflowed or came up short are recomputed exhaustively.
+//   pass C  users whose candidate list overflowed or came up short are ranked exactly over all items by the sliced
+//           pass of csrc/eval_exact.cu (the whole GPU cooperates on few users; nothing but top-K lists leaves the SM).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,7 +29,10 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
 constexpr int kTcListCap = 80;  // == kTcCap in eval_tc.cu
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
-constexpr int kFallbackCtas = 148;  // one per SM; scratch = 148 x I doubles
+// csrc/eval_exact.cu: pass C, exact sliced ranking of the flagged users (and of every user for shapes outside the tiles)
+size_t eval_exact_part_bytes(int nu, int K);
+int launch_eval_exact(const float* Fu, const float* Fi, int I, int d, const int32_t* mptr, const int32_t* mind, const int64_t* users, int K,
+                      const int* flag_cnt, const int* flag_list, void* part, int64_t* out_ids, float* out_scores, cudaStream_t stream);
 
 struct EvalWs {
     float* max_norm;   // [1] max_i |Fi[i]|_2 (as float bits, atomicMax on non-negative floats)
@@ -38,7 +42,7 @@ struct EvalWs {
     int* cand_ids;     // [nu, kCandOut]
     float* tc_ls;      // [ceil(nu/128)*128, kTcListCap] tensor-core pass: per-row candidate lists
     int* tc_li;
-    double* scratch;   // [kFallbackCtas, I]
+    void* part;        // per-slice top-K lists of the exact pass (eval_exact_part_bytes)
 };
 
 __host__ __device__ inline size_t ev_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -54,7 +58,7 @@ __host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     w.tc_ls = (float*)p; p += ev_align(sizeof(float) * nup * kTcListCap);
     w.tc_li = (int*)p; p += ev_align(sizeof(int) * nup * kTcListCap);
-    w.scratch = (double*)p;
+    w.part = (void*)p;
     return w;
 }
 
@@ -265,56 +269,6 @@ __global__ void __launch_bounds__(256) eval_rescore_kernel(const float* __restri
     }
 }
 
-// Pass C: exhaustive exact ranking for flagged users (rare: candidate overflow from massive ties,
-// or fewer than K unmasked items).  Masked items score -inf and stay eligible in id order, like
-// a stable sort of the reference's masked rating row.
-__global__ void __launch_bounds__(256) eval_exhaustive_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I, int d,
-                                                              const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
-                                                              const int64_t* __restrict__ users, int K, EvalWs w,
-                                                              int64_t* __restrict__ out_ids, float* __restrict__ out_scores) {
-    __shared__ double sb[8];
-    __shared__ int si[8];
-    __shared__ int s_best;
-    double* S = w.scratch + (size_t)blockIdx.x * I;
-    const int nflag = *w.flag_cnt;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int f = blockIdx.x; f < nflag; f += gridDim.x) {
-        const int p = w.flag_list[f];
-        const int u = (int)users[p];
-        const float* urow = Fu + (size_t)u * d;
-        for (int i = tid; i < I; i += 256) S[i] = exact_dot(urow, Fi + (size_t)i * d, d);
-        __syncthreads();
-        for (int j = mptr[u] + tid; j < mptr[u + 1]; j += 256) S[mind[j]] = -INFINITY;
-        __syncthreads();
-        for (int r = 0; r < K; ++r) {
-            double bs = 0.0; int bi = -1;
-            for (int i = tid; i < I; i += 256) {
-                const double v = S[i];
-                if (v != v) continue;  // taken
-                if (bi < 0 || v > bs) { bs = v; bi = i; }  // ascending i: first hit wins ties
-            }
-#pragma unroll
-            for (int mm = 16; mm >= 1; mm >>= 1) {
-                const double os = __shfl_xor_sync(0xffffffffu, bs, mm);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, mm);
-                if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
-            }
-            if (lane == 0) { sb[warp] = bs; si[warp] = bi; }
-            __syncthreads();
-            if (tid == 0) {
-                double b = sb[0]; int ii = si[0];
-                for (int q = 1; q < 8; ++q)
-                    if (si[q] >= 0 && (ii < 0 || sb[q] > b || (sb[q] == b && si[q] < ii))) { b = sb[q]; ii = si[q]; }
-                s_best = ii;
-                out_ids[(size_t)p * K + r] = (ii >= 0) ? ii : 0;
-                if (out_scores) out_scores[(size_t)p * K + r] = (ii >= 0) ? (float)b : -INFINITY;
-                if (ii >= 0) S[ii] = __longlong_as_double(0x7ff8000000000000ll);
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // Shapes outside the fast kernels (d not in {32, 64, 128, 256}, K > 48): every user takes pass C.
 __global__ void eval_flag_all_kernel(int nu, EvalWs w) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,7 +390,7 @@ extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, in
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
                        ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) +
-                       ev_align(sizeof(double) * (size_t)kFallbackCtas * I);
+                       ev_align(eval_exact_part_bytes(nu, K > 0 ? K : 1));
     return (int64_t)(sel > metrics ? sel : metrics);
 }
 
@@ -455,9 +409,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
         // exhaustive ranking for every user -- same ids, one fp64 score row per user instead of the candidate filter
         eval_flag_all_kernel<<<(nu + 255) / 256, 256, 0, stream>>>(nu, w);
         IDG_LAUNCH_CHECK("eval_flag_all_kernel");
-        eval_exhaustive_kernel<<<kFallbackCtas, 256, 0, stream>>>(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w, d_out_ids, d_out_scores);
-        IDG_LAUNCH_CHECK("eval_exhaustive_kernel");
-        return 0;
+        return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
     }
     item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm);
     IDG_LAUNCH_CHECK("item_norm_kernel");
@@ -485,9 +437,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     if (!(d == 64 && use_tc)) IDG_LAUNCH_CHECK("eval_candidates_kernel");
     eval_rescore_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_Fu, d_Fi, d, d_users, nu, K, w, d_out_ids, d_out_scores);
     IDG_LAUNCH_CHECK("eval_rescore_kernel");
-    eval_exhaustive_kernel<<<kFallbackCtas, 256, 0, stream>>>(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w, d_out_ids, d_out_scores);
-    IDG_LAUNCH_CHECK("eval_exhaustive_kernel");
-    return 0;
+    return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
 }
 
 extern "C" int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t nu, int32_t K, const int32_t* d_test_indptr,
