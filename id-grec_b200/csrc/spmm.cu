@@ -666,6 +666,17 @@ extern "C" int idg_spmm_layer_sparse_in(const idg_graph* g, const float* d_X, fl
     return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, d_acc_in, d_acc_out, acc_div, d, stream, ex);
 }
 
+// General backward-chain layer on the handle's rows: y = A h + addend + scale2 * addend2 (XSimGCL: the InfoNCE gradient of the
+// captured layer enters the Horner chain at that layer), optionally with the sparse-input gather (d_bitmap).
+extern "C" int idg_spmm_layer_add2(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
+                                   float scale2, int32_t d, const uint32_t* d_bitmap, int skip_zero_rows, void* stream) {
+    if (skip_zero_rows && d_addend2) return fail(-1, "idg_spmm_layer_add2: skip_zero_rows cannot be combined with a second addend%s");
+    SpmmExtra ex;
+    ex.bitmap = d_bitmap;
+    ex.skip_zero_rows = d_bitmap ? skip_zero_rows : 0;
+    return spmm_launch(g, d_X, d_Y, d_addend, d_addend2, scale2, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);
+}
+
 extern "C" int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
                                    const idg_adam_args* adam, void* stream) {
     if (!adam) return fail(-1, "idg_spmm_layer_adam: null adam%s");

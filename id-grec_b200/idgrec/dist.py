@@ -143,26 +143,44 @@ class PeerSlab:
 
 
 class DistFusedTrainer:
-    """LightGCN training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer)."""
+    """LightGCN / SimGCL / XSimGCL training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer).
+
+    The contrastive models run their extra propagations the same way (local rows, finished rows stored to all peers by the
+    SpMM epilogue, flag barrier per layer; sign-noise applied in the same epilogue from a noise tensor every rank draws
+    identically), evaluate BPR + InfoNCE redundantly on the complete batch rows, add all row gradients into ONE table
+    (the three propagations of SimGCL share their linear backward operator) and run one backward Horner chain whose
+    last product applies Adam.  XSimGCL's captured-layer gradient joins the chain at that layer (idg_spmm_layer_add2)."""
+
+    KINDS = ("LightGCN", "SimGCL", "XSimGCL")
 
     def __init__(self, kind, csr, table, num_users, K, reg_lambda, lr, rank, world, group=None, max_batch=1024,
-                 betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None, closure_restrict="auto"):
-        if kind != "LightGCN":
-            raise NotImplementedError("multi-GPU training is implemented for LightGCN (BASELINE.json configs 2 and 5)")
+                 betas=(0.9, 0.999), adam_eps=1e-8, use_cuda_graph=True, full_graph=None, closure_restrict="auto",
+                 ssl_lambda=0.0, temperature=0.2, eps=0.0, cl_layer=1):
+        if kind not in self.KINDS:
+            raise NotImplementedError("row-partitioned training covers %s (got %s)" % (", ".join(self.KINDS), kind))
         if not 2 <= K <= 3:
             raise NotImplementedError("the row-partitioned step supports GCN_layer = 2 or 3 (got %d)" % K)
+        if kind == "XSimGCL" and not 1 <= cl_layer <= K:
+            raise NotImplementedError("row-partitioned XSimGCL needs 1 <= cl_layer <= GCN_layer")
         self.l = _lib.lib()
         self.kind, self.rank, self.world = kind, rank, world
         self.U, (self.N, self.d), self.K = num_users, table.shape, K
         self.reg_lambda, self.lr, self.betas, self.adam_eps = reg_lambda, lr, betas, adam_eps
+        self.ssl_lambda, self.temperature, self.eps, self.cl_layer = ssl_lambda, temperature, eps, cl_layer
+        self.inc0 = kind == "LightGCN"                     # layer 0 in the mean (LightGCN.py:41 vs SimGCL.py:45)
+        self.cnt = float(K + (1 if self.inc0 else 0))
         dev = table.device
         self.dev = dev
         N, d = self.N, self.d
         nd = N * d * 4
-        self.slab = PeerSlab((1 + 2 * max(K - 1, 1)) * (nd + 4096) + (1 << 20), rank, world, group, dev)
+        n_views = {"LightGCN": 1, "SimGCL": 3, "XSimGCL": 1}[kind]
+        self.slab = PeerSlab((1 + (n_views + 1) * max(K - 1, 1)) * (nd + 4096) + (1 << 20), rank, world, group, dev)
         self.E0 = self.slab.carve((N, d))
         self.E0.copy_(table)
-        self.W = [self.slab.carve((N, d)) for _ in range(K - 1)]     # forward layer outputs X1..X_{K-1}
+        # forward layer outputs X1..X_{K-1}, one set per propagation of the step (a peer may already be writing the next
+        # propagation's layers while this rank still reads the previous one's in its batch-row layer)
+        self.Wv = [[self.slab.carve((N, d)) for _ in range(K - 1)] for _ in range(n_views)]
+        self.W = self.Wv[0]
         self.H = [self.slab.carve((N, d)) for _ in range(K - 1)]     # backward chain H_{K-1}..H_1
         self.bounds = partition_rows(csr.indptr.cpu().numpy(), world)
         self.b0, self.b1 = self.bounds[rank], self.bounds[rank + 1]
@@ -173,19 +191,20 @@ class DistFusedTrainer:
         self.gE0, self.m, self.v, self.G, self.F = z(), z(), z(), z(), z()
         self.rows = BatchRows(N, max_batch, dev)
         self.rows.worklist(self.full)
+        contrastive = kind != "LightGCN"
         # batch-neighbourhood restriction of forward layer K-1 and of the second backward product (see engine.py);
         # every rank computes the closure bits of its own rows and publishes its words to the peers
         if closure_restrict == "auto":
             from .graph import expected_closure_fraction
-            closure_restrict = K >= 3 and expected_closure_fraction(csr, num_users, max_batch) < 0.4
-        self.use_closure = bool(closure_restrict) and K >= 3
+            closure_restrict = K >= 3 and not contrastive and expected_closure_fraction(csr, num_users, max_batch) < 0.4
+        self.use_closure = bool(closure_restrict) and K >= 3 and not contrastive
         self.closure = self.slab.carve(((N + 127) // 128 * 4 + 4,), torch.int32)
         self.closure.zero_()
         if self.use_closure:
             self.rows.closure = self.closure
         self.max_batch, self.step_count = max_batch, 0
         self.ws = torch.empty(int(self.l.idg_bpr_workspace_bytes(max_batch)), dtype=torch.uint8, device=dev)
-        self.n_loss = 2
+        self.n_loss = 3 if contrastive else 2
         self.loss = torch.zeros(4, dtype=torch.float32, device=dev)
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
@@ -193,6 +212,18 @@ class DistFusedTrainer:
         self.regc = torch.zeros(N, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
+        if contrastive:
+            self.noise = torch.empty(K, N, d, dtype=torch.float32, device=dev)
+            self.nce_ws = torch.empty(int(self.l.idg_infonce_workspace_bytes(max_batch, d)), dtype=torch.uint8, device=dev)
+            self.V1 = z()
+            self.V2 = z() if kind == "SimGCL" else None
+            self.Gcl = z() if kind == "XSimGCL" else None
+            self.Hk = z() if (kind == "XSimGCL" and cl_layer == K) else None
+            self.uidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
+            self.iidx = torch.zeros(max_batch, dtype=torch.int64, device=dev)
+            self.ucnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.icnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.injected_noise = None   # parity tests: list of per-view [K,N,d] tensors
         self.use_cuda_graph = use_cuda_graph
         self._graphs, self._graph_launches, self.replayed_launches = {}, {}, 0
         self._prof = None
@@ -213,15 +244,52 @@ class DistFusedTrainer:
             e.record()
             self._prof.append((name, e))
 
+    def _draw_noise(self, view):
+        """Every rank draws the SAME full noise tensor (same device-generator state on all ranks after tools.set_seed), in the
+        reference's call pattern: one rand_like([N,d]) per layer, views in order (SimGCL.py:50)."""
+        if self.injected_noise is not None:
+            self.noise.copy_(self.injected_noise[view])
+        else:
+            for k in range(self.K):
+                self.noise[k].uniform_()
+
+    def _forward(self, W, out_mean, noise=False, out_cl=None):
+        """One propagation: layers 1..K-1 on the local rows (rows pushed to every peer by the epilogue), last layer + layer
+        mean on the batch rows only, every rank computing all of them (no exchange)."""
+        l, s, K, d, loc, rows, slab = self.l, cur_stream(), self.K, self.d, self.local, self.rows, self.slab
+        eps = self.eps if noise else 0.0
+        x = self.E0
+        for k in range(K - 1):
+            nz = self.noise[k] if noise else None
+            if self.use_closure and k == K - 2:
+                # layer K-1 only on the batch rows and their neighbours: the restricted last layer reads nothing else
+                check(l.idg_spmm_layer_masked(loc._h, ptr(x), ptr(W[k]), None, 0.0, None, None, 1.0, d, ptr(self.closure), s), "idg_spmm_layer_masked")
+            else:
+                loc.spmm_layer(x, Y=W[k], noise=nz, eps=eps)
+            self._mark('fwd_layer%d' % (k + 1))
+            slab.barrier()
+            self._mark('barrier')
+            x = W[k]
+        acc = ([self.E0] if self.inc0 else []) + list(W)
+        acc += [None] * (3 - len(acc))
+        y_cl = out_cl if (out_cl is not None and self.cl_layer == K) else None
+        check(l.idg_spmm_layer_rows(self.full._h, ptr(x), ptr(y_cl), ptr(self.noise[K - 1]) if noise else None, eps, ptr(acc[0]), ptr(acc[1]), ptr(acc[2]),
+                                    ptr(out_mean), self.cnt, d, ptr(rows.rowlist), ptr(rows.count), rows.max_rows, ptr(rows.worklist(self.full)), s),
+              "idg_spmm_layer_rows")
+        self._mark('fwd_last_rows')
+
     def _body(self, B, u, p, n):
         l, s, K, d = self.l, cur_stream(), self.K, self.d
         self._mark('start')
         loc, rows, slab = self.local, self.rows, self.slab
-        rows.build(u, p, n, B, self.U)
-        if K > 1:
-            # the first backward product only publishes non-zero rows: clear this rank's copy of its output now; every
-            # peer passes two barriers (after this point in stream order) before it writes into it
-            self.H[0].zero_()
+        contrastive = self.kind != "LightGCN"
+        if contrastive:
+            rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
+        else:
+            rows.build(u, p, n, B, self.U)
+        # the first backward product only publishes non-zero rows: clear this rank's copy of its output now; every
+        # peer passes two barriers (after this point in stream order) before it writes into it
+        self.H[0].zero_()
         if self.use_closure:
             check(l.idg_closure_bitmap(loc._h, ptr(rows.bitmap), ptr(self.closure), s), "idg_closure_bitmap")
             w0, w1 = self.b0 // 32, (self.b1 + 31) // 32
@@ -229,52 +297,71 @@ class DistFusedTrainer:
                 slab.push(self.closure[w0:(w1 + 3) // 4 * 4])  # whole 16-byte groups: inner bounds are multiples of 128 rows
             slab.barrier()
         self._mark('batch_rows')
-        # forward: layers 1..K-1 on the local rows, rows pushed to every peer by the epilogue
-        x = self.E0
-        for k in range(K - 1):
-            if self.use_closure and k == K - 2:
-                # layer K-1 only on the batch rows and their neighbours: the restricted last layer reads nothing else
-                check(l.idg_spmm_layer_masked(loc._h, ptr(x), ptr(self.W[k]), None, 0.0, None, None, 1.0, d, ptr(self.closure), s), "idg_spmm_layer_masked")
-            else:
-                loc.spmm_layer(x, Y=self.W[k])
-            self._mark('fwd_layer%d' % (k + 1))
-            slab.barrier()
-            self._mark('barrier')
-            x = self.W[k]
-        # last layer + mean only on the batch rows, every rank computes all of them (no exchange)
-        acc = [self.E0] + self.W
-        check(l.idg_spmm_layer_rows(self.full._h, ptr(x), None, None, 0.0, ptr(acc[0]), ptr(acc[1]) if K > 1 else None,
-                                    ptr(acc[2]) if K > 2 else None, ptr(self.F), float(K + 1), d, ptr(rows.rowlist), ptr(rows.count),
-                                    rows.max_rows, ptr(rows.worklist(self.full)), s), "idg_spmm_layer_rows")
-        self._mark('fwd_last_rows')
+        cl_view = None
+        if self.kind == "LightGCN":
+            self._forward(self.Wv[0], self.F)
+        elif self.kind == "SimGCL":
+            self._forward(self.Wv[0], self.F)
+            self._draw_noise(0)
+            self._forward(self.Wv[1], self.V1, noise=True)
+            self._draw_noise(1)
+            self._forward(self.Wv[2], self.V2, noise=True)
+        else:  # XSimGCL: one perturbed propagation, contrast view = post-noise output of layer cl_layer
+            self._draw_noise(0)
+            self._forward(self.Wv[0], self.F, noise=True, out_cl=self.V1)
+            cl_view = self.V1 if self.cl_layer == K else self.Wv[0][self.cl_layer - 1]
         check(l.idg_bpr_forward(ptr(self.F), ptr(self.E0), u, p, n, B, self.U, self.N, d, self.reg_lambda, 7, ptr(self.loss), ptr(self.ws), s), "idg_bpr_forward")
         check(l.idg_bpr_backward(ptr(self.F), B, d, 7, None, ptr(self.G), self.reg_lambda, ptr(self.regc), ptr(self.ws), s), "idg_bpr_backward")
         check(l.idg_adam_prepare(ptr(self.d_step), ptr(self.adam_scalars), self.lr, self.betas[0], self.betas[1], s), "idg_adam_prepare")
+        Gcl = None
+        if contrastive:
+            self.loss[2:3].zero_()
+            for idx, cnt in ((self.uidx, self.ucnt), (self.iidx, self.icnt)):
+                if self.kind == "SimGCL":
+                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.V2), ptr(idx), ptr(cnt), B, d, self.temperature, self.ssl_lambda,
+                                                    ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s), "idg_infonce_fwd_bwd_dev")
+                else:
+                    check(l.idg_infonce_fwd_bwd_dev(ptr(cl_view), ptr(self.F), ptr(idx), ptr(cnt), B, d, self.temperature, self.ssl_lambda,
+                                                    ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s), "idg_infonce_fwd_bwd_dev")
+            Gcl = self.Gcl
         self._mark('bpr')
-        # backward Horner chain on the local rows; the first product only gathers batch columns.  The last
-        # product applies Adam in its epilogue and stores the updated parameter rows to every peer: the
-        # gradient never goes to memory and the parameter exchange overlaps the last layer's gathers.
+        # backward Horner chain on the local rows: H_K = G (+cnt Gcl if cl = K); H_l = G + A H_{l+1} (+cnt Gcl if cl = l);
+        # the first product only gathers batch columns; the last product applies Adam in its epilogue and stores the updated
+        # parameter rows to every peer: the gradient never goes to memory.
         import ctypes as _C
         adam = _C.byref(self.adam_args)
-        if K == 1:
-            raise NotImplementedError("distributed Adam-fused path needs K >= 2")
-        check(l.idg_spmm_layer_sparse_in(loc._h, ptr(self.G), ptr(self.H[0]), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
-        self._mark('bwd_sparse')
-        slab.barrier()
-        self._mark('barrier')
-        h = self.H[0]
-        for k in range(1, K - 1):
-            if self.use_closure and k == 1:  # H_{K-1} is zero outside the closure: gather only those columns
-                check(l.idg_spmm_layer_sparse_in(loc._h, ptr(h), ptr(self.H[k]), ptr(self.G), None, None, 1.0, d, ptr(self.closure), 0, s), "idg_spmm_layer_sparse_in")
+        h = self.G
+        if Gcl is not None and self.cl_layer == K:
+            check(l.idg_axpby(ptr(self.Hk), 1.0, ptr(self.G), self.cnt, ptr(Gcl), self.N * d, s), "idg_axpby")
+            h = self.Hk
+        for step_i in range(1, K):
+            layer = K - step_i                                  # index of the H being produced
+            out = self.H[step_i - 1]
+            add2 = Gcl if (Gcl is not None and self.cl_layer == layer) else None
+            if step_i == 1:
+                if add2 is None:
+                    check(l.idg_spmm_layer_sparse_in(loc._h, ptr(h), ptr(out), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
+                else:   # every row is stored (no zero-row skipping with a second addend)
+                    check(l.idg_spmm_layer_add2(loc._h, ptr(h), ptr(out), ptr(self.G), ptr(add2), self.cnt, d, ptr(rows.bitmap), 0, s), "idg_spmm_layer_add2")
+                self._mark('bwd_sparse')
+            elif self.use_closure and step_i == 2:  # H_{K-1} is zero outside the closure: gather only those columns
+                check(l.idg_spmm_layer_sparse_in(loc._h, ptr(h), ptr(out), ptr(self.G), None, None, 1.0, d, ptr(self.closure), 0, s), "idg_spmm_layer_sparse_in")
+                self._mark('bwd_layer')
             else:
-                loc.spmm_layer(h, Y=self.H[k], addend=self.G)
-            self._mark('bwd_layer')
+                if add2 is None:
+                    loc.spmm_layer(h, Y=out, addend=self.G)
+                else:
+                    check(l.idg_spmm_layer_add2(loc._h, ptr(h), ptr(out), ptr(self.G), ptr(add2), self.cnt, d, None, 0, s), "idg_spmm_layer_add2")
+                self._mark('bwd_layer')
             slab.barrier()
             self._mark('barrier')
-            h = self.H[k]
-        check(l.idg_spmm_layer_adam(loc._h, ptr(h), ptr(self.G), float(K + 1), d, adam, s), "idg_spmm_layer_adam")
+            h = out
+        check(l.idg_spmm_layer_adam(loc._h, ptr(h), ptr(self.G) if self.inc0 else None, self.cnt, d, adam, s), "idg_spmm_layer_adam")
         self._mark('bwd_last_adam_push')
         check(l.idg_bpr_finish(ptr(self.E0), None, ptr(self.G), B, d, self.reg_lambda, None, ptr(self.regc), ptr(self.ws), s), "idg_bpr_finish")
+        if Gcl is not None:
+            for idx in (self.uidx, self.iidx):   # entries past the count are stale but valid rows of an all-zero table: harmless
+                check(l.idg_zero_rows(ptr(Gcl), ptr(idx), B, d, s), "idg_zero_rows")
         rows.clear()   # also zeroes the closure words (before the final barrier: peers publish theirs after it)
         self._mark('finish')
         slab.barrier()
@@ -300,18 +387,18 @@ class DistFusedTrainer:
             self._graphs[B].replay()
             self.replayed_launches += self._graph_launches[B]
         self.step_count += 1
-        return self.loss[:2]
+        return self.loss[:self.n_loss]
 
     def pop_epoch_losses(self):
         self.slab.status()   # a peer that missed a flag barrier invalidates the epoch: surface it here, not as a hang
-        out = self.loss_acc[:2].tolist()
+        out = self.loss_acc[:self.n_loss].tolist()
         self.loss_acc.zero_()
         return out
 
     @torch.no_grad()
     def final_embeddings(self):
         """Clean propagation of the current table on the whole graph (every rank, for its evaluation shard)."""
-        return self.full.propagate_fwd(self.E0, self.K, True)
+        return self.full.propagate_fwd(self.E0, self.K, self.inc0)
 
     def profile_steps(self, batches):
         """Eager steps with CUDA events between phases -> {phase: mean ms} (diagnostics)."""

@@ -124,13 +124,15 @@ class PropagationModel(nn.Module):
             cfg = self.config
             import torch.distributed as dist
             world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-            if world > 1 and int(cfg.get('num_gpus', world)) > 1 and self.kind == "LightGCN":
+            if world > 1 and int(cfg.get('num_gpus', world)) > 1 and self.kind in ("LightGCN", "SimGCL", "XSimGCL"):
                 # row-partitioned over the process group: the parameter table moves into the peer slab
                 from .dist import DistFusedTrainer
                 ft = DistFusedTrainer(self.kind, self.Graph.csr, self._table, self.dataset.num_users, self.num_layers, self.reg_lambda,
                                       lr, dist.get_rank(), world, max_batch=max_batch, full_graph=self.Graph,
                                       use_cuda_graph=str(cfg.get('cuda_graph', '1')) not in ('0', 'False', 'false'),
-                                      closure_restrict={'0': False, '1': True}.get(str(cfg.get('closure_restrict', 'auto')), 'auto'))
+                                      closure_restrict={'0': False, '1': True}.get(str(cfg.get('closure_restrict', 'auto')), 'auto'),
+                                      ssl_lambda=float(cfg.get('ssl_lambda', 0.0)), temperature=float(cfg.get('temperature', 0.2)),
+                                      eps=float(cfg.get('epsilon', 0.0)), cl_layer=int(cfg.get('cl_layer', 1)))
                 U = self.dataset.num_users
                 self._table = ft.E0
                 self.user_embedding.weight.data, self.item_embedding.weight.data = ft.E0[:U], ft.E0[U:]

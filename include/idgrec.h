@@ -284,6 +284,12 @@ int idg_propagate_bwd_adam(const idg_graph* g, const float* d_G, const float* d_
                            const idg_adam_args* adam, void* stream);
 int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
                         const idg_adam_args* adam, void* stream);
+/* One step of the backward Horner chain on the handle's rows with a second addend: Y = A X + addend + scale2 * addend2
+ * (XSimGCL.py:57-58,64-66: the gradient of the captured contrast layer joins the chain at that layer); d_bitmap != NULL
+ * makes it the sparse-input product (X zero outside the flagged rows).  Used by the row-partitioned contrastive steps,
+ * where the whole-graph idg_propagate_bwd_ex cannot be. */
+int idg_spmm_layer_add2(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
+                        float scale2, int32_t d, const uint32_t* d_bitmap, int skip_zero_rows, void* stream);
 
 /* Same update with the step counter on the device (*d_step = steps already taken; incremented by
  * the call): lets a captured CUDA graph of the whole train step be replayed unchanged. */

@@ -20,3 +20,15 @@ def test_two_gpu_training_bit_identical(graph, closure):
                         "--master-port", "29731", os.path.join(REPO, "tools", "dist_check.py"), "small", "4"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("kind", ["SimGCL", "XSimGCL", "XSimGCL3"])
+def test_two_gpu_contrastive_training_bit_identical(kind):
+    """Row-partitioned SimGCL / XSimGCL (cl_layer = 1 and = K) with injected noise: losses and tables bit-identical to
+    the single-GPU fused trainer, sharded evaluation identical (tools/dist_check.py)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29741", os.path.join(REPO, "tools", "dist_check.py"), "small", "3", kind],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert "DIST_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -287,3 +287,40 @@ def test_reference_main_py_text_runs_two_epochs(dev, golden_dirs, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Model training process completed." in r.stdout
     assert r.stdout.count("Training time:") == 2
+
+
+# ---------------------------------------------------------------- row-partitioned step, degenerate world of 1
+@pytest.mark.parametrize("kind,cl", [("LightGCN", 1), ("SimGCL", 1), ("XSimGCL", 1), ("XSimGCL", 2), ("XSimGCL", 3)])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_row_partitioned_step_world1_equals_fused_trainer(dev, kind, cl, use_graph):
+    """The row-partitioned trainer (idgrec/dist.py) with a single partition must reproduce the single-GPU fused trainer bit
+    for bit -- losses and tables after several steps, with the same injected noise.  Runs on one GPU, so the driver's
+    1-GPU box exercises the step logic the 2-GPU tests (tests/test_gpu_dist.py) need a second device for."""
+    from idgrec import datagen
+    from idgrec.dist import DistFusedTrainer
+    from idgrec.engine import FusedTrainer
+    from idgrec.graph import Graph, build_norm_adjacency
+    g = datagen.gen_graph("small")
+    U, I = g.num_users, g.num_items
+    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
+    G = Graph(csr)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    table = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
+    kw = dict(ssl_lambda=0.3, temperature=0.2, eps=0.1, cl_layer=cl) if kind != "LightGCN" else {}
+    ref = FusedTrainer(kind, G, table.clone(), U, 3, 1e-4, 1e-3, max_batch=512, use_cuda_graph=False, **kw)
+    ft = DistFusedTrainer(kind, csr, table.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=512, use_cuda_graph=use_graph, full_graph=G, **kw)
+    n_views = {"LightGCN": 0, "SimGCL": 2, "XSimGCL": 1}[kind]
+    rng = np.random.default_rng(8)
+    nz = [torch.empty(3, U + I, 64, device=dev) for _ in range(n_views)]   # stable buffers: a captured step replays the same pointers
+    ref.injected_noise = ft.injected_noise = nz if n_views else None
+    for step in range(3):
+        e = rng.integers(0, len(g.train_user), 512)
+        b = tuple(torch.from_numpy(a).to(dev) for a in (g.train_user[e], g.train_item[e], rng.integers(0, I, 512)))
+        for t in nz:
+            t.copy_(torch.rand(3, U + I, 64, generator=gen, device=dev))
+        lr, ld = ref.step(*b).clone(), ft.step(*b).clone()
+        assert torch.equal(lr, ld), (step, lr, ld)
+    assert torch.equal(ref.E0, ft.E0)
+    fr = G.propagate_fwd(ref.E0, 3, kind == "LightGCN")
+    assert torch.equal(fr, ft.final_embeddings())

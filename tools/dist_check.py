@@ -23,16 +23,23 @@ def main():
     from utility.utility_data.data_loader import Data
     import utility.utility_function.tools as tools
     import utility.utility_train.batch_test as batch_test
-    from models.LightGCN import LightGCN
+    import importlib
     shape = sys.argv[1] if len(sys.argv) > 1 else "small"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    kind = sys.argv[3] if len(sys.argv) > 3 else "LightGCN"          # LightGCN | SimGCL | XSimGCL | XSimGCL3 (cl_layer = 3)
+    extra = {"LightGCN": {}, "SimGCL": {"ssl_lambda": "0.5", "temperature": "0.2", "epsilon": "0.05"},
+             "XSimGCL": {"ssl_lambda": "0.2", "temperature": "0.15", "epsilon": "0.2", "cl_layer": "1"},
+             "XSimGCL3": {"ssl_lambda": "0.2", "temperature": "0.15", "epsilon": "0.2", "cl_layer": "3"}}[kind]
+    kind = kind.rstrip("3")
+    Model = getattr(importlib.import_module("models." + kind), kind)
     cfg = {"embedding_size": "64", "batch_size": "1024", "test_batch_size": "1024", "learn_rate": "0.001", "reg_lambda": "0.0001",
            "GCN_layer": "3", "top_K": "[10, 20]", "sparsity_test": "0", "dataset": "synthetic", "cuda_graph": os.environ.get("IDG_GRAPH", "1"),
            "closure_restrict": os.environ.get("IDG_CLOSURE", "auto")}
+    cfg.update(extra)
     g = datagen.gen_graph(shape)
     data = Data.from_arrays(g.num_users, g.num_items, g.train_user, g.train_item, g.test_user, g.test_item, cfg)
     tools.set_seed(2024)
-    model = LightGCN(cfg, data, dev)
+    model = Model(cfg, data, dev)
     model.to(dev)
     w0 = model._table.clone()
     ft = model.fused_trainer(1e-3, 1024)
@@ -42,8 +49,18 @@ def main():
     for _ in range(steps):
         e = rng.integers(0, len(g.train_user), 1024)
         batches.append(tuple(torch.from_numpy(a).to(dev) for a in (g.train_user[e], g.train_item[e], rng.integers(0, g.num_items, 1024))))
+    # the perturbed views: the same injected noise on every rank and in the single-GPU reference (one [K,N,d] block per
+    # view and step; the trainers' own draws come from the device generator and match across ranks only by seed)
+    n_views = {"LightGCN": 0, "SimGCL": 2, "XSimGCL": 1}[kind]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    noises = [[torch.rand(3, data.num_nodes, 64, generator=gen, device=dev) for _ in range(n_views)] for _ in range(steps)]
+    nz_buf = [torch.empty(3, data.num_nodes, 64, device=dev) for _ in range(n_views)]   # stable pointers for the captured step
+    ft.injected_noise = nz_buf if n_views else None
     losses = []
-    for b in batches:
+    for b, nz in zip(batches, noises):
+        for dst, src in zip(nz_buf, nz):
+            dst.copy_(src)
         losses.append(ft.step(*b).clone())
     torch.cuda.synchronize()
     res = batch_test.Test(data, model, dev, cfg)
@@ -51,8 +68,11 @@ def main():
     ok = True
     if rank == 0:
         # single-GPU reference on the same batches
-        ref = FusedTrainer("LightGCN", model.Graph, w0.clone(), data.num_users, 3, 1e-4, 1e-3, max_batch=1024, use_cuda_graph=False)
-        for b, l in zip(batches, losses):
+        ref = FusedTrainer(kind, model.Graph, w0.clone(), data.num_users, 3, 1e-4, 1e-3, max_batch=1024, use_cuda_graph=False,
+                           ssl_lambda=float(cfg.get("ssl_lambda", 0.0)), temperature=float(cfg.get("temperature", 0.2)),
+                           eps=float(cfg.get("epsilon", 0.0)), cl_layer=int(cfg.get("cl_layer", 1)))
+        for b, l, nz in zip(batches, losses, noises):
+            ref.injected_noise = nz if n_views else None
             lr = ref.step(*b)
             ok &= bool(torch.equal(lr, l))
         same = torch.equal(ref.E0, ft.E0)
@@ -80,7 +100,7 @@ def main():
     if rank == 0:
         class SingleGpuView:   # the 1-GPU trainer's table behind the evaluator's model contract
             def final_embeddings(self_inner):
-                F = model.Graph.propagate_fwd(ref.E0, 3, True)
+                F = model.Graph.propagate_fwd(ref.E0, 3, kind == "LightGCN")
                 return F[:data.num_users], F[data.num_users:]
         ids1, users1 = batch_test.rank_all(data, SingleGpuView(), dev, max(topK))
         sharded = torch.cat([gathered[r][: shard_range(len(all_users), r, world)[1] - shard_range(len(all_users), r, world)[0]] for r in range(world)])
