@@ -25,7 +25,7 @@ namespace idg {
 // csrc/eval_tc.cu: the same candidate pass on tcgen05 tensor cores (d = 64)
 int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
-                              float* list_s, int* list_i, cudaStream_t stream);
+                              float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream);
 constexpr int kTcListCap = 80;  // == kTcCap in eval_tc.cu
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
@@ -42,6 +42,7 @@ struct EvalWs {
     int* cand_ids;     // [nu, kCandOut]
     float* tc_ls;      // [ceil(nu/128)*128, kTcListCap] tensor-core pass: per-row candidate lists
     int* tc_li;
+    float* tc_aug;     // [I, 8] margin operand of the tensor-core pass: column 0 = |i| rounded up to tf32
     void* part;        // per-slice top-K lists of the exact pass (eval_exact_part_bytes)
 };
 
@@ -58,11 +59,14 @@ __host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     w.tc_ls = (float*)p; p += ev_align(sizeof(float) * nup * kTcListCap);
     w.tc_li = (int*)p; p += ev_align(sizeof(int) * nup * kTcListCap);
+    w.tc_aug = (float*)p; p += ev_align(sizeof(float) * 8 * (size_t)I);
     w.part = (void*)p;
     return w;
 }
 
-__global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, float* __restrict__ max_norm) {
+// max_i |i| (CUDA-core pass: one margin per user) and, for the tensor-core pass, the per-item margin operand
+// aug[i] = {|i| rounded UP to a tf32-exact value (plus a relative 2^-20 for the rounding of the norm itself), 0 x 7}
+__global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, float* __restrict__ max_norm, float* __restrict__ aug) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= I) return;
@@ -70,7 +74,12 @@ __global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, flo
     for (int k = lane; k < d; k += 32) { const float v = Fi[(size_t)i * d + k]; ss = fmaf(v, v, ss); }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
-    if (lane == 0) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(sqrtf(ss)));
+    const float nrm = sqrtf(ss);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm));
+    if (aug && lane < 8) {
+        const float up = __uint_as_float((__float_as_uint(nrm * 1.000001f) + 0x1fffu) & 0xffffe000u);
+        aug[(size_t)i * 8 + lane] = (lane == 0) ? up : 0.f;
+    }
 }
 
 __device__ __forceinline__ bool masked(const int32_t* __restrict__ ind, int lo, int hi, int item) {
@@ -389,7 +398,7 @@ extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, in
     const size_t metrics = ev_align(sizeof(double) * (size_t)nu * 3 * 8);
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
-                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) +
+                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) + ev_align(sizeof(float) * 8 * (size_t)I) +
                        ev_align(eval_exact_part_bytes(nu, K > 0 ? K : 1));
     return (int64_t)(sel > metrics ? sel : metrics);
 }
@@ -411,15 +420,15 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
         IDG_LAUNCH_CHECK("eval_flag_all_kernel");
         return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
     }
-    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm);
+    static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, (d == 64 && use_tc) ? w.tc_aug : nullptr);
     IDG_LAUNCH_CHECK("item_norm_kernel");
     const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
     const unsigned grid = (unsigned)((nu + kTU - 1) / kTU);
     // IDG_EVAL_IMPL=fma selects the CUDA-core candidate pass (kept as a cross-check of the tensor-core one)
-    static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
     if (d == 64 && use_tc) {
         if (int rc = launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
-                                               w.flag_list, w.cand_cnt, w.cand_ids, w.tc_ls, w.tc_li, stream))
+                                               w.flag_list, w.cand_cnt, w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, nullptr, stream))
             return rc;
     } else if (d == 64) {
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -438,6 +447,22 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     eval_rescore_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_Fu, d_Fi, d, d_users, nu, K, w, d_out_ids, d_out_scores);
     IDG_LAUNCH_CHECK("eval_rescore_kernel");
     return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
+}
+
+// Self-check of the tensor-core candidate pass: the raw accumulators (UPPER bounds w = s~ + c|u||i|) of the first 128 users
+// against item tile 0 (items 0..127), as the epilogue sees them.  tests/ compare them with the fp64 scores: w >= s must
+// hold everywhere and w - s~ must equal the margin product -- the only direct evidence that the ninth k-step is wired.
+extern "C" int idg_eval_tc_bounds(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d, const int32_t* d_mask_indptr,
+                                  const int32_t* d_mask_indices, const int64_t* d_users, int32_t nu, float* d_out_tile, void* d_ws, void* stream_) {
+    if (!d_Fu || !d_Fi || !d_mask_indptr || !d_users || !d_out_tile || !d_ws) return fail(-1, "idg_eval_tc_bounds: null argument%s");
+    if (d != 64 || nu <= 0 || nu > 128 || I <= 0 || U <= 0) return fail(-1, "idg_eval_tc_bounds: needs d = 64 and 1 <= nu <= 128%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EvalWs w = eval_carve(d_ws, nu, I);
+    IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, w.tc_aug);
+    IDG_LAUNCH_CHECK("item_norm_kernel");
+    return launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, 1, w.max_norm, w.flag_cnt, w.flag_list, w.cand_cnt,
+                                     w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, d_out_tile, stream);
 }
 
 extern "C" int idg_eval_metrics(const int64_t* d_topk_ids, const int64_t* d_users, int32_t nu, int32_t K, const int32_t* d_test_indptr,

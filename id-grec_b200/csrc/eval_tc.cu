@@ -6,8 +6,13 @@
 //
 //   scores:  S[128 users, 128 items] = Fu_tile . Fi_tile^T, d = 64, one tcgen05.mma.kind::tf32 chain
 //            (8 instructions of K = 8) per item tile, accumulators in TMEM (4 buffers x 128 columns).
-//            fp32 operands are read as tf32 (low 13 mantissa bits ignored):
-//            |s~ - s| <= (2^-9 + small) * |u||i|  -> candidate margin 2*delta_u.
+//            fp32 operands are read as tf32 (low 13 mantissa bits ignored): |s~ - s| <= m_ui = c * |u||i|, c = 1.25 (2^-9 + 1e-4).
+//            The margin is PER ITEM and costs nothing in the epilogue: a ninth k-step multiplies an extra operand column
+//            (c|u| per user row, |i| per item row, both rounded up to tf32) so the accumulator holds the UPPER bound
+//            w_ui = s~_ui + m_ui directly.  An item is kept iff w_ui >= L_u, L_u = the K-th largest LOWER bound
+//            w - 2m seen so far (computed when a row's list is pruned): that set provably contains the exact top-K.
+//            (Round 1 used one margin per user from the largest item norm: after a few epochs of training the largest
+//            norm is ~8x the median and the lists flooded -- 12 ms instead of 5.5 ms at the amazon-book shape.)
 //   roles:   warp 0      MMA issuer (one elected thread) + TMEM alloc/dealloc
 //            warps 2-3   operand loaders: the user tile (gathered rows) by cp.async into the 128B-swizzled K-major
 //                        UMMA layout; item tiles by TMA (cp.async.bulk.tensor.2d, 128B-swizzle tensor map, one
@@ -30,6 +35,8 @@ constexpr uint32_t kTcTmemCols = kTcBufs * 128;
 constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
+constexpr uint32_t kAugTile = 128 * 32;   // bytes of one [128 rows x 32 B] margin operand (32-byte swizzle atoms)
+constexpr float kTcMarginCoef = 1.25f * (0.001953125f + 0.0001f);
 
 struct EvalWsTc {
     float* max_norm;
@@ -39,7 +46,19 @@ struct EvalWsTc {
     int* cand_ids;
     float* list_s;  // [ceil(nu/128)*128, kTcCap] per-row candidate scores in L2 (rare appends): frees shared memory for 2 CTAs/SM
     int* list_i;
+    const float* aug;  // [I, 8]: column 0 = |i| rounded up to tf32, columns 1..7 zero (the item half of the margin k-step)
+    float* dbg_tile;   // self-check (idg_eval_tc_bounds): CTA 0 dumps the raw accumulators of item tile 0, [128,128]; else NULL
 };
+
+// x >= 0 rounded UP to a value the tensor core reads exactly (tf32: 10 explicit mantissa bits)
+__device__ __forceinline__ float tf32_ceil(float x) { return __uint_as_float((__float_as_uint(x) + 0x1fffu) & 0xffffe000u); }
+
+// c|u| of one user row, rounded up to tf32; the loader (operand) and the epilogue (lower bounds) must agree bit for bit
+__device__ __forceinline__ float tc_user_coef(const float* __restrict__ urow) {
+    float ss = 0.f;
+    for (int k = 0; k < kTcD; ++k) { const float v = __ldg(urow + k); ss = fmaf(v, v, ss); }
+    return tf32_ceil(kTcMarginCoef * sqrtf(ss) + 1e-30f);
+}
 
 // smem byte offset of the 16-byte chunk kc (0..15) of row r inside an operand tile [128 rows x 64 fp32]
 __device__ __forceinline__ uint32_t sw128_offset(int r, int kc) {
@@ -57,31 +76,34 @@ __device__ __noinline__ int tc_group_append(float v0, float v1, float v2, float 
     return cnt;
 }
 
-// warp-cooperative prune of one row's candidate list: tau = (K-th largest) - 2*delta, keep >= tau
-__device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2, int K, int lane, int& new_cnt, float& new_tau) {
-    float s[3]; int id[3]; int rank[3];
+// warp-cooperative prune of one row's candidate list.  Entries hold UPPER bounds w; lower_j = w_j - c2 * |i_j| (c2 = 2 c|u|).
+// L = K-th largest lower bound; keep w >= L.
+__device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float c2, const float* __restrict__ aug, int K, int lane, int& new_cnt,
+                                         float& new_tau) {
+    float s[3], lo[3]; int id[3]; int rank[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         const int idx = lane + 32 * q;
         s[q] = (idx < m) ? __ldcg(ls + idx) : -INFINITY; id[q] = (idx < m) ? __ldcg(li + idx) : 0; rank[q] = 0;
+        lo[q] = (idx < m) ? fmaf(-c2, __ldg(aug + (size_t)id[q] * 8), s[q]) : -INFINITY;
     }
-    // rank counting over the list held in registers (3 entries per lane), broadcast by shuffle
+    // rank counting over the lower bounds held in registers (3 entries per lane), broadcast by shuffle
 #pragma unroll
     for (int qq = 0; qq < 3; ++qq) {
         for (int l = 0; l < 32; ++l) {
             const int j = l + 32 * qq;
             if (j >= m) break;
-            const float sj = __shfl_sync(0xffffffffu, s[qq], l);
+            const float sj = __shfl_sync(0xffffffffu, lo[qq], l);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) rank[q] += (sj > s[q]) || (sj == s[q] && j < lane + 32 * q);
+            for (int q = 0; q < 3; ++q) rank[q] += (sj > lo[q]) || (sj == lo[q] && j < lane + 32 * q);
         }
     }
     float vk = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = s[q];
+    for (int q = 0; q < 3; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = lo[q];
 #pragma unroll
     for (int mm = 16; mm >= 1; mm >>= 1) vk = fmaxf(vk, __shfl_xor_sync(0xffffffffu, vk, mm));
-    const float tau = vk - delta2;
+    const float tau = vk;
     __syncwarp();
     int kept = 0;
 #pragma unroll
@@ -98,11 +120,14 @@ __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float delta2
 __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
                                                                     const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
                                                                     const int64_t* __restrict__ users, int nu, int K, EvalWsTc w,
-                                                                    const __grid_constant__ CUtensorMap tmap_items) {
+                                                                    const __grid_constant__ CUtensorMap tmap_items,
+                                                                    const __grid_constant__ CUtensorMap tmap_aug) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sA = smem;                                        // 32 KB
     unsigned char* sB = smem + 2 * kSubTile;                         // kTcStages x 32 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kTcStages * 2 * kSubTile);
+    unsigned char* sAaug = sB + kTcStages * 2 * kSubTile;            // 4 KB: c|u| per user row (32-byte swizzle layout)
+    unsigned char* sBaug = sAaug + kAugTile;                         // kTcStages x 4 KB: |i| per item row, by TMA
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBaug + kTcStages * kAugTile);
     uint64_t* full = bars;                   // [kTcStages] loaders -> MMA
     uint64_t* empty = bars + kTcStages;      // [kTcStages] MMA -> loaders
     uint64_t* tfull = empty + kTcStages;     // [kTcBufs]   MMA -> epilogue
@@ -147,6 +172,8 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
                     const uint32_t koff = (uint32_t)(k >> 2) * kSubTile + (uint32_t)(k & 3) * 32u;
                     umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc(a0 + koff), umma_desc(b0 + koff), idesc, k > 0);
                 }
+                // margin k-step: + c|u| * |i|  (operands in 32-byte-swizzle K-major atoms)
+                umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc_sw32(smem_u32(sAaug)), umma_desc_sw32(smem_u32(sBaug + (size_t)s * kAugTile)), idesc, 1);
                 umma_commit(empty + s);
                 umma_commit(tfull + b);
             }
@@ -161,6 +188,15 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
             const int64_t u = (p < nu) ? users[p] : users[0];
             cp_async16(smem_u32(sA) + sw128_offset(r, kc), Fu + (size_t)u * kTcD + kc * 4, (p < nu) ? 16 : 0);
         }
+        // margin operand of the user tile: row r = [c|u_r|, 0, 0, 0 | c|u_r|, 0, 0, 0].  Both 16-byte chunks carry the value so the
+        // product with the item row [|i|, 0, ... 0] is c|u||i| whichever way the 32-byte swizzle orders the two chunks of a row.
+        for (int r = lt; r < kTcM; r += kTcLoaders) {
+            const int p = u0 + r;
+            const float cu = (p < nu) ? tc_user_coef(Fu + (size_t)users[p] * kTcD) : 0.f;
+            float4* dst = reinterpret_cast<float4*>(sAaug + (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 32);
+            dst[0] = make_float4(cu, 0.f, 0.f, 0.f);
+            dst[1] = make_float4(cu, 0.f, 0.f, 0.f);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -169,13 +205,15 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         // directly in the UMMA K-major layout; rows past I are zero-filled by the hardware.  One elected thread.
         if (lt == 0) {
             tma_prefetch_desc(&tmap_items);
+            tma_prefetch_desc(&tmap_aug);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % kTcStages;
                 mbar_wait(empty + s, ((t / kTcStages) & 1) ^ 1);
                 const uint32_t dst = smem_u32(sB + (size_t)s * 2 * kSubTile);
-                mbar_arrive_expect_tx(full + s, 2 * kSubTile);
+                mbar_arrive_expect_tx(full + s, 2 * kSubTile + kAugTile);
                 tma_load_2d(dst, &tmap_items, 0, t * kTcN, full + s);
                 tma_load_2d(dst + kSubTile, &tmap_items, 32, t * kTcN, full + s);
+                tma_load_2d(smem_u32(sBaug + (size_t)s * kAugTile), &tmap_aug, 0, t * kTcN, full + s);
             }
         }
     } else if (warp >= 4) {
@@ -185,10 +223,9 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         const int p = u0 + row;
         const bool valid = p < nu;
         const int u = valid ? (int)users[p] : 0;
-        float ss = 0.f;
-        if (valid) for (int k = 0; k < kTcD; ++k) { const float v = __ldg(Fu + (size_t)u * kTcD + k); ss = fmaf(v, v, ss); }
-        // tf32 operand truncation: |err| <= (2*2^-10 + 2^-20)|u||i| plus fp32 accumulation; 1.25x slack
-        const float delta2 = 2.f * 1.25f * (0.001953125f + 0.0001f) * sqrtf(ss) * (*w.max_norm) + 1e-30f;
+        // tf32 operand truncation: |err| <= (2*2^-10 + 2^-20)|u||i| plus fp32 accumulation; 1.25x slack (kTcMarginCoef).
+        // The accumulator already holds s~ + c|u||i|; lower bound of an entry = w - 2 c|u||i|.
+        const float delta2 = valid ? 2.f * tc_user_coef(Fu + (size_t)u * kTcD) : 0.f;
         float tau = valid ? -3.0e38f : INFINITY;  // finite: masked scores (-inf) never pass
         int cnt = 0, overflow = 0;
         int cur = valid ? mptr[u] : 0;
@@ -215,6 +252,10 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                if (w.dbg_tile && t == 0 && blockIdx.x == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w.dbg_tile[(size_t)row * kTcN + c * 32 + j] = v[j];
+                }
                 const int c0 = t * kTcN + c * 32;
                 // train positives of this row that fall into [c0, c0+32): remove (batch_test.py:62-65)
                 while (next_mask < c0 + 32) {
@@ -243,7 +284,7 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
                     const float dL = __shfl_sync(0xffffffffu, delta2, L);
                     int nc; float nt;
                     __syncwarp();
-                    tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, K, lane, nc, nt);
+                    tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, w.aug, K, lane, nc, nt);
                     if (lane == L) {
                         cnt = nc;
                         if (nc > kTcTrig) { overflow = 1; tau = INFINITY; } else tau = nt;
@@ -258,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
             if (mL >= K) {
                 int nc; float nt;
                 __syncwarp();
-                tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, K, lane, nc, nt);
+                tc_prune(ls + (q * 32 + L) * kTcCap, li + (q * 32 + L) * kTcCap, mL, dL, w.aug, K, lane, nc, nt);
                 if (lane == L) cnt = nc;
             }
         }
@@ -284,8 +325,8 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
 
 int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
-                              float* list_s, int* list_i, cudaStream_t stream) {
-    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids, list_s, list_i};
+                              float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream) {
+    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids, list_s, list_i, aug, dbg_tile};
     // tensor map of the item table [I rows x 64 fp32]: driver entry point fetched through the runtime (no libcuda link)
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
@@ -303,9 +344,17 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Fi), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(-1, "cuTensorMapEncodeTiled failed (%s%lld)", "", (long long)cr);
-    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
+    // margin operand [I rows x 8 fp32] (idg::item_norm_kernel): box 8 floats x 128 rows, 32-byte swizzle = the UMMA SWIZZLE_32B K-major atom
+    CUtensorMap tmap_aug;
+    const cuuint64_t gdim2[2] = {8, (cuuint64_t)I};
+    const cuuint64_t gstride2[1] = {8 * sizeof(float)};
+    const cuuint32_t box2[2] = {8, (cuuint32_t)kTcN};
+    const CUresult cr2 = encode(&tmap_aug, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(aug), gdim2, gstride2, box2, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr2 != CUDA_SUCCESS) return fail(-1, "cuTensorMapEncodeTiled (margin operand) failed (%s%lld)", "", (long long)cr2);
+    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + (1 + kTcStages) * (size_t)kAugTile + sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
     IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap);
+    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap, tmap_aug);
     IDG_LAUNCH_CHECK("eval_candidates_tc_kernel");
     return 0;
 }

@@ -35,6 +35,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major, 32-byte swizzle (one 8 x 32 B atom per 8 rows): row pitch 32 B, 8-row groups 256 B apart (SBO), LBO = 1 (unused)
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

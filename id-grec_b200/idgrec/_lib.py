@@ -100,6 +100,7 @@ SIGNATURES = {
     "idg_eval_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "idg_eval_topk": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_rating_matrix": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),
+    "idg_eval_tc_bounds": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _p, _p, _p]),
     "idg_eval_metrics": (C.c_int, [_p, _p, _i32, _i32, _p, _p, C.POINTER(_i32), _i32, _p, _p, _p]),
     "idg_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i32, _p]),
     "idg_adam_prepare": (C.c_int, [_p, _p, _f32, _f32, _f32, _p]),

@@ -256,6 +256,13 @@ int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, in
                   const int32_t* d_mask_indptr, const int32_t* d_mask_indices, const int64_t* d_users,
                   int32_t nu, int32_t K, int64_t* d_out_ids, float* d_out_scores, void* d_ws, void* stream);
 
+/* Self-check of the tensor-core candidate pass (d = 64, nu <= 128): writes the raw accumulators of the first item tile,
+ * d_out_tile[128,128] (row = position in d_users, column = item id 0..127), i.e. the per-item UPPER bounds
+ * s~ + c |u||i| the epilogue filters on.  Test infrastructure for the exactness proof; Test() never calls it. */
+int idg_eval_tc_bounds(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d, const int32_t* d_mask_indptr,
+                       const int32_t* d_mask_indices, const int64_t* d_users, int32_t nu, float* d_out_tile, void* d_ws,
+                       void* stream);
+
 /* get_rating_for_test as the reference writes it (models/LightGCN.py:74-80): d_out [nu, I] = sigmoid(Fu[users] . Fi^T).
  * API completeness only: the evaluator ranks through idg_eval_topk and never materialises this matrix. */
 int idg_rating_matrix(const float* d_Fu, const float* d_Fi, const int64_t* d_users, int32_t nu, int32_t I, int32_t d,

@@ -324,3 +324,39 @@ def test_row_partitioned_step_world1_equals_fused_trainer(dev, kind, cl, use_gra
     assert torch.equal(ref.E0, ft.E0)
     fr = G.propagate_fwd(ref.E0, 3, kind == "LightGCN")
     assert torch.equal(fr, ft.final_embeddings())
+
+
+# ---------------------------------------------------------------- tensor-core candidate pass: per-item upper bounds
+def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
+    """The tcgen05 candidate pass keeps item i for user u iff w_ui >= L_u, where w_ui = s~_ui + c|u||i| comes out of the
+    accumulator (ninth k-step: margin operand).  Direct check of that operand on heavy-tailed item norms: the dumped
+    accumulators must (1) dominate the exact fp64 scores everywhere and (2) exceed the tf32-truncated product by exactly the
+    per-item margin.  Without this the exact-rank tests could not tell a silently missing margin from a working one."""
+    import ctypes as C
+    from idgrec import _lib
+    l = _lib.lib()
+    U, I, d = 128, 640, 64
+    gen = torch.Generator().manual_seed(17)
+    Fu = (torch.randn(U, d, generator=gen) * 0.5).numpy()
+    Fi = (torch.randn(I, d, generator=gen) * 0.3).numpy()
+    Fi[::7] *= 8.0            # heavy-tailed norms, like a trained table (largest norm ~8x the median)
+    Fi[3] = 0.0               # a zero row: zero margin, zero score
+    users = np.arange(U, dtype=np.int64)[::-1].copy()
+    mp = torch.zeros(U + 1, dtype=torch.int32, device=dev)
+    mi = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.full((128, 128), float("nan"), dtype=torch.float32, device=dev)
+    ws = torch.empty(int(l.idg_eval_workspace_bytes(U, I, d, 20)), dtype=torch.uint8, device=dev)
+    fu_d, fi_d, us_d = torch.from_numpy(Fu).to(dev), torch.from_numpy(Fi).to(dev), torch.from_numpy(users).to(dev)
+    _lib.check(l.idg_eval_tc_bounds(fu_d.data_ptr(), fi_d.data_ptr(), U, I, d, mp.data_ptr(), mi.data_ptr(), us_d.data_ptr(), U, out.data_ptr(),
+                                    ws.data_ptr(), torch.cuda.current_stream().cuda_stream), "idg_eval_tc_bounds")
+    w = out.cpu().numpy().astype(np.float64)
+    assert np.isfinite(w).all()
+    exact = O.scores_fp64_sequential(Fu[users], Fi[:128])
+    assert (w >= exact).all(), "an accumulator is below the exact score: the upper bound does not hold"
+    tf = lambda a: (a.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
+    approx = tf(Fu[users].copy()) @ tf(Fi[:128].copy()).T
+    nu_, ni_ = np.linalg.norm(Fu[users].astype(np.float64), axis=1), np.linalg.norm(Fi[:128].astype(np.float64), axis=1)
+    margin = 1.25 * (2.0 ** -9 + 1e-4) * nu_[:, None] * ni_[None, :]
+    got = w - approx
+    assert np.all(np.abs(got - margin) <= 0.01 * margin + 8e-6 * nu_[:, None] * ni_[None, :] + 1e-30), float(np.abs(got - margin).max())
+    assert np.all(got[:, 3] == 0.0)
