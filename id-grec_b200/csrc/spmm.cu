@@ -69,6 +69,7 @@ struct SpmmArgs {
     int skip_zero_rows;       // SPARSE kernels: rows that come out exactly zero are not stored (outputs pre-zeroed by the caller)
     const unsigned* rowmask;  // ROWMASK kernels: rows whose bit is clear are skipped (outputs untouched)
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
+    const unsigned* addend_mask;  // optional: rows whose bit is clear have an all-zero addend / addend2 (not loaded)
 };
 
 }  // namespace idg
@@ -103,8 +104,11 @@ template <int LPR, bool ADAM>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
     constexpr int d = 4 * LPR;
     const size_t off = (size_t)grow * d + sub * 4;
-    if (a.addend) y = f4add(y, ldcs4(a.addend + off));
-    if (a.addend2) y = f4fma(a.scale2, ldcs4(a.addend2 + off), y);
+    // backward chain: the Horner addend (the loss gradient G) is non-zero on the batch rows only -- with the batch-row
+    // bitmap at hand the other rows skip the 4 d bytes of zeros (N d 4 bytes per layer at full size)
+    const bool has_addend = !a.addend_mask || ((__ldg(a.addend_mask + (grow >> 5)) >> (grow & 31)) & 1u);
+    if (a.addend && has_addend) y = f4add(y, ldcs4(a.addend + off));
+    if (a.addend2 && has_addend) y = f4fma(a.scale2, ldcs4(a.addend2 + off), y);
     if (a.noise) {
         // x += sign(x) * F.normalize(noise, dim=-1) * eps   (SimGCL.py:49-51)
         float4 nz = ldcs4(a.noise + off);
@@ -188,6 +192,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     }
     const float* __restrict__ X = a.X + sub * 4;
     const int2* __restrict__ cvp = a.colval;
+    if (ADAM && (sub & 7) == 0) {
+        // the epilogue reads this row of p / m / v from HBM: start those lines towards L2 now, under the gather loop
+        const size_t poff = (size_t)(a.row_offset + ((it.w < 0) ? it.x : a.heavy[it.x].row)) * d + sub * 4;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_p + poff));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_m + poff));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_v + poff));
+    }
 
     float4 acc = f4zero();
     int k = it.y;
@@ -357,6 +368,7 @@ struct SpmmExtra {
     int max_wl = 0;
     const unsigned* bitmap = nullptr;  // sparse-input launch
     const unsigned* rowmask = nullptr; // row-masked launch
+    const unsigned* addend_mask = nullptr;  // rows with a non-zero addend (others skip the addend load)
     int skip_zero_rows = 0;
     const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
@@ -377,6 +389,7 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.acc_in = d_acc_in; a.acc_out = d_acc_out; a.acc_div = acc_div;
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap; a.skip_zero_rows = ex.skip_zero_rows;
     a.rowmask = ex.rowmask;
+    a.addend_mask = ex.addend_mask;
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
     a.adam_p = nullptr; a.adam_m = a.adam_v = nullptr; a.adam_regc = a.adam_scalars = nullptr; a.adam_mc_p = nullptr;
     a.adam_b1 = a.adam_b2 = a.adam_eps = 0.f;
@@ -755,6 +768,7 @@ static int propagate_bwd_impl(const idg_graph* g, const float* d_G, const float*
     for (int s = 1; s <= K; ++s) {
         const int layer = K - s;  // index of the H being produced; 0 => gX0
         SpmmExtra ex;
+        ex.addend_mask = d_bitmap;   // G (and Gcl) are zero outside the flagged rows
         if (s == 1) ex.bitmap = d_bitmap;
         // H_{K-1} = G + A G is non-zero only on the batch rows and their neighbours: the next product gathers just those
         if (s == 2 && layer > 0 && d_bitmap && g->closure) ex.bitmap = g->closure;

@@ -90,6 +90,7 @@ SIGNATURES = {
     "idg_bpr_finish": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _p, _p, _p, _p]),
     "idg_axpby": (C.c_int, [_p, _f32, _p, _f32, _p, _i64, _p]),
     "idg_zero_rows": (C.c_int, [_p, _p, _i32, _i32, _p]),
+    "idg_zero_rows_bitmap": (C.c_int, [_p, _p, _i32, _i32, _p]),
     "idg_infonce_workspace_bytes": (_i64, [_i32, _i32]),
     "idg_infonce_fwd_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _f32, _f32, _p, _p, _p, _p, _p]),
     "idg_unique_rows": (C.c_int, [_p, _i32, _i64, _p, _p, _p]),

@@ -287,9 +287,12 @@ class DistFusedTrainer:
             rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
         else:
             rows.build(u, p, n, B, self.U)
-        # the first backward product only publishes non-zero rows: clear this rank's copy of its output now; every
-        # peer passes two barriers (after this point in stream order) before it writes into it
-        self.H[0].zero_()
+        # the first backward product only publishes non-zero rows: this rank's copy of its output must be clear before the
+        # peers write into it (they pass two barriers after this point in stream order first).  With the closure bitmap
+        # the rows a step can write are known (batch rows + neighbours): they are re-zeroed at the END of the step
+        # instead of the whole [N,d] buffer here (512 MB at the 1M x 1M size).
+        if not self.use_closure:
+            self.H[0].zero_()
         if self.use_closure:
             check(l.idg_closure_bitmap(loc._h, ptr(rows.bitmap), ptr(self.closure), s), "idg_closure_bitmap")
             w0, w1 = self.b0 // 32, (self.b1 + 31) // 32
@@ -362,6 +365,8 @@ class DistFusedTrainer:
         if Gcl is not None:
             for idx in (self.uidx, self.iidx):   # entries past the count are stale but valid rows of an all-zero table: harmless
                 check(l.idg_zero_rows(ptr(Gcl), ptr(idx), B, d, s), "idg_zero_rows")
+        if self.use_closure:
+            check(l.idg_zero_rows_bitmap(ptr(self.H[0]), ptr(self.closure), self.N, d, s), "idg_zero_rows_bitmap")
         rows.clear()   # also zeroes the closure words (before the final barrier: peers publish theirs after it)
         self._mark('finish')
         slab.barrier()

@@ -108,6 +108,9 @@ class FusedTrainer:
         for with_adam in (False, True):
             self._tail[with_adam] = _lib.StepTail(ptr(self.loss_acc) if self._tail_acc else None, ptr(self.d_step) if with_adam else None,
                                                   ptr(self.adam_scalars) if with_adam else None, lr, betas[0], betas[1])
+        # the batch row set does not depend on the first K-1 propagation layers: it is built on a side stream (a parallel
+        # branch of the captured graph) while they run
+        self._side = torch.cuda.Stream(device=dev) if (self.rows is not None and kind != "MFBPR") else None
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -178,6 +181,32 @@ class FusedTrainer:
             for k in range(self.K):
                 self.noise[k].uniform_()
 
+    def _build_rows(self, B, u, p, n, contrastive):
+        rows = self.rows
+        if contrastive:
+            rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
+        else:
+            rows.build(u, p, n, B, self.U)
+
+    def _forward_mean_on_batch_rows(self):
+        """LightGCN.py:36-52 for a step whose loss reads the final mean at the batch rows only: layers 1..K-1 are plain
+        products (no running-sum traffic: the full-size layer sum is never formed), the last layer and the mean
+        ((E0 + X1) + X2 + X3) / (K+1) -- the reference's summation order -- are evaluated on the batch rows."""
+        g, K, d, rows = self.graph, self.K, self.d, self.rows
+        w = g.work(d)
+        bufs = [w[:self.N * d].view(self.N, d), w[self.N * d:].view(self.N, d)]
+        x, layers = self.E0, [self.E0]
+        for k in range(K - 1):
+            y = bufs[k & 1]
+            g.spmm_layer(x, Y=y)
+            layers.append(y)
+            x = y
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)     # join: the row set is ready
+        layers += [None] * (3 - len(layers))
+        check(self.l.idg_spmm_layer_rows(g._h, ptr(x), None, None, 0.0, ptr(layers[0]), ptr(layers[1]), ptr(layers[2]), ptr(self.F), float(K + 1), d,
+                                         ptr(rows.rowlist), ptr(rows.count), rows.max_rows, ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
+
     def _body(self, B, u, p, n, users_t=None, pos_t=None, fused=False):
         """Kernels of one step for batch pointers u/p/n (device int64).  ``fused``: Adam inside the last backward layer."""
         g, K = self.graph, self.K
@@ -185,21 +214,32 @@ class FusedTrainer:
         out = None if fused else self.gE0
         rows = self.rows
         contrastive = self.kind in ("SimGCL", "XSimGCL") or self.kind == "SCCF"   # SCCF needs the two unique counts
-        if rows is not None and contrastive:
-            rows.build_unique(u, p, n, B, self.U, self.uidx, self.ucnt, self.iidx, self.icnt)
+        # forward of the LightGCN-encoder steps without the full-size layer sum, row set built on a parallel branch
+        split_fwd = (rows is not None and not self.use_closure and 2 <= K <= 3 and (self.kind == "LightGCN" or self.kind in PAIR_MODELS))
+        if rows is not None and split_fwd and self._side is not None:
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)                            # fork: after the batch copy / the previous step's clean-up
+            with torch.cuda.stream(self._side):
+                self._build_rows(B, u, p, n, contrastive)
         elif rows is not None:
-            rows.build(u, p, n, B, self.U)
+            self._build_rows(B, u, p, n, contrastive)
         if self.use_closure:
             rows.build_closure(g)
         if self.kind == "LightGCN":
-            g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
+            if split_fwd:
+                self._forward_mean_on_batch_rows()
+            else:
+                g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
             self._bpr(B, u, p, n, fused)
             g.propagate_bwd(self.G, K, True, out=out, rows=rows, adam=adam)
         elif self.kind in PAIR_MODELS:
             if rows is None and self.kind == "SCCF":
                 check(self.l.idg_unique_rows(u, B, 0, ptr(self.uidx), ptr(self.ucnt), cur_stream()), "idg_unique_rows")
                 check(self.l.idg_unique_rows(p, B, self.U, ptr(self.iidx), ptr(self.icnt), cur_stream()), "idg_unique_rows")
-            g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
+            if split_fwd:
+                self._forward_mean_on_batch_rows()
+            else:
+                g.propagate_fwd(self.E0, K, True, out_mean=self.F, rows=rows)
             self._bpr(B, u, p, n, fused)
             self._pair(B, u, p)
             g.propagate_bwd(self.G, K, True, out=out, rows=rows, adam=adam)

@@ -204,6 +204,9 @@ int idg_bpr_finish_clear(const float* d_E0, float* d_gE0, float* d_G, int32_t B,
                          const float* d_upstream, float* d_regc, uint32_t* d_bitmap, void* d_ws, void* stream);
 int idg_axpby(float* d_out, float a, const float* d_x, float b, const float* d_y, int64_t n, void* stream);
 int idg_zero_rows(float* d_buf, const int64_t* d_idx, int32_t n, int32_t d, void* stream);
+/* rows of d_buf [n_rows, d] whose bit is set in d_bitmap are zeroed (the row-partitioned step re-zeroes only the rows its
+ * sparse first backward product can have written: the batch neighbourhood, not the whole [N,d] buffer) */
+int idg_zero_rows_bitmap(float* d_buf, const uint32_t* d_bitmap, int32_t n_rows, int32_t d, void* stream);
 
 /* ---- a10: utility_function/losses.py:24-35 (in-batch InfoNCE) --------------
  * V1,V2 [N,d] views; d_idx n sorted-unique row ids (torch.unique, SimGCL.py:80-81)

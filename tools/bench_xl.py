@@ -121,12 +121,16 @@ def run(rank, world, dev, users=1000000, items=1000000, edges=100000000, steps=2
     sync()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    flagged = 0
+    marks = [a]
     for c0 in range(s0, s1, chunk):
         ops.eval_topk(F[:U], F[U:], torch.arange(c0, min(s1, c0 + chunk), device=dev), ip, mask_idx, 20, ws=ws)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append(e)
     b.record()
     sync()
     eval_ms = a.elapsed_time(b)
+    chunk_ms = [round(x.elapsed_time(y), 3) for x, y in zip(marks[:-1], marks[1:])]
     vals = [step_ms, layer_ms, eval_ms, n1_ms if n1_ms is not None else 0.0]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     nus = torch.tensor([nu], dtype=torch.int64, device=dev)
@@ -151,7 +155,7 @@ def run(rank, world, dev, users=1000000, items=1000000, edges=100000000, steps=2
                "hbm_peak_GBs": hbm, "hbm_peak_source": hbm_src,
                "bytes_received_per_exchanged_layer_per_gpu": recv, "exchanged_layers_per_step": 4 if world > 1 else 0,
                "nvlink_floor_ms_per_layer": recv / 770e6 if world > 1 else 0.0,
-               "eval_users_total": int(nus.item()), "eval_ms": eval_ms, "eval_users_per_s_total": int(nus.item()) / eval_ms * 1e3,
+               "eval_users_total": int(nus.item()), "eval_ms": eval_ms, "eval_chunk_users": chunk, "eval_chunk_ms_rank0": chunk_ms, "eval_users_per_s_total": int(nus.item()) / eval_ms * 1e3,
                "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": bool(use_graph), "breakdown_ms": phases,
                "closure_restrict": ft.use_closure, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}
     del ft, F, full, csr, ws
