@@ -18,7 +18,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed_pipe_tensor_op_utcmma.sum", "sm__pipe_tensor_subpipe_utcmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor", "lts__t_bytes.sum"]
 
 
 def launches(tag):
@@ -72,8 +74,13 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    for rep, name in (("prof_spmm_ab_v2.ncu-rep", "spmm_amazon-book_%s_ncu_full.json" % tag), ("prof_eval_ab.ncu-rep", "eval_amazon-book_%s_ncu_full.json" % tag),
-                      ("prof_spmm_ab.ncu-rep", "spmm_amazon-book_%s_first_kernel_ncu_full.json" % tag),
-                      ("prof_pair.ncu-rep", "pairloss_lightccf_B4096_%s_ncu_full.json" % tag),
-                      ("prof_pair_tc.ncu-rep", "pairloss_tc_lightccf_B4096_%s_ncu_full.json" % tag)):
+    if tag == "r1":
+        reps = (("prof_spmm_ab_v2.ncu-rep", "spmm_amazon-book_%s_ncu_full.json" % tag), ("prof_eval_ab.ncu-rep", "eval_amazon-book_%s_ncu_full.json" % tag),
+                ("prof_spmm_ab.ncu-rep", "spmm_amazon-book_%s_first_kernel_ncu_full.json" % tag),
+                ("prof_pair.ncu-rep", "pairloss_lightccf_B4096_%s_ncu_full.json" % tag),
+                ("prof_pair_tc.ncu-rep", "pairloss_tc_lightccf_B4096_%s_ncu_full.json" % tag))
+    else:
+        reps = (("prof_spmm_%s.ncu-rep" % tag, "spmm_amazon-book_%s_ncu_full.json" % tag), ("prof_eval_%s.ncu-rep" % tag, "eval_amazon-book_%s_ncu_full.json" % tag),
+                ("prof_nce_%s.ncu-rep" % tag, "infonce_n1923_%s_ncu_full.json" % tag))
+    for rep, name in reps:
         report(rep, name)
