@@ -16,6 +16,7 @@
 // passes lose), tcgen05 with 2 loader warps 220 us, with 7 operand-builder warps and batched loads ~122 us (now bound by the
 // one-tile-per-CTA pipeline and the row-per-thread epilogue stores, not by the MMA).
 #include <math.h>
+#include <curand_kernel.h>
 
 #include "idg_common.cuh"
 
@@ -170,9 +171,59 @@ __global__ void __launch_bounds__(256) ngcf_reduce_kernel(const float* __restric
     }
 }
 
+// nn.Dropout's Bernoulli(1 - p) draws for all layers of one step in ONE launch (NGCF.py:99-100 constructs nn.Dropout inline, so
+// it is always active): keep[l][i] = 1 with probability 1 - p_l.  Counter-based Philox: element quad q of step t reads
+// stream (seed, subsequence q, offset t), so a captured step replays with fresh draws (t comes from the device step
+// counter) and the result does not depend on the launch geometry.  torch's own bernoulli_ costs three launches per mask
+// (uniform, compare, cast): 150 us of the 1.76 ms fused step at the amazon-book shape.
+__global__ void __launch_bounds__(256) ngcf_keep_masks_kernel(float* __restrict__ keep, int64_t per_layer4, int n_layers, float k0, float k1,
+                                                              float k2, float k3, unsigned long long seed, const int* __restrict__ d_step) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= per_layer4 * n_layers) return;
+    const int layer = (int)(q / per_layer4);
+    const float pk = layer == 0 ? k0 : (layer == 1 ? k1 : (layer == 2 ? k2 : k3));
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)q, (unsigned long long)(d_step ? *d_step : 0), &st);
+    const float4 r = curand_uniform4(&st);   // (0, 1]
+    reinterpret_cast<float4*>(keep)[q] = make_float4(r.x <= pk ? 1.f : 0.f, r.y <= pk ? 1.f : 0.f, r.z <= pk ? 1.f : 0.f, r.w <= pk ? 1.f : 0.f);
+}
+
+// dst[row] = src[row] for the rows idx[i] + row_offset (row strides in floats): the 64-column ego block of the [N,256] concat is
+// only read at the batch rows by the BPR kernels, so the step copies those instead of the whole table
+__global__ void __launch_bounds__(256) copy_rows_strided_kernel(const float* __restrict__ src, int src_stride, const int64_t* __restrict__ idx, int n,
+                                                                int row_offset, int d4, float* __restrict__ dst, int dst_stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / d4, c = t % d4;
+    if (i >= n) return;
+    const size_t row = (size_t)idx[i] + row_offset;
+    reinterpret_cast<float4*>(dst + row * dst_stride)[c] = __ldg(reinterpret_cast<const float4*>(src + row * src_stride) + c);
+}
+
 }  // namespace idg
 
 using namespace idg;
+
+extern "C" int idg_ngcf_keep_masks(float* d_keep, int64_t per_layer, int32_t n_layers, const float* h_keep_prob, uint64_t seed,
+                                   const int32_t* d_step, void* stream) {
+    if (!d_keep || !h_keep_prob || per_layer <= 0 || (per_layer & 3) || n_layers < 1 || n_layers > 4) return fail(-1, "idg_ngcf_keep_masks: bad argument%s");
+    float k[4] = {1.f, 1.f, 1.f, 1.f};
+    for (int l = 0; l < n_layers; ++l) k[l] = h_keep_prob[l];
+    const int64_t quads = per_layer / 4 * n_layers;
+    ngcf_keep_masks_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_keep, per_layer / 4, n_layers, k[0], k[1], k[2], k[3],
+                                                                                        (unsigned long long)seed, d_step);
+    IDG_LAUNCH_CHECK("ngcf_keep_masks_kernel");
+    return 0;
+}
+
+extern "C" int idg_copy_rows_strided(const float* d_src, int32_t src_stride, const int64_t* d_idx, int32_t n, int32_t row_offset, int32_t d,
+                                     float* d_dst, int32_t dst_stride, void* stream) {
+    if (!d_src || !d_idx || !d_dst || n < 0 || d <= 0 || (d & 3) || (src_stride & 3) || (dst_stride & 3)) return fail(-1, "idg_copy_rows_strided: bad argument%s");
+    if (n == 0) return 0;
+    const int th = n * (d / 4);
+    copy_rows_strided_kernel<<<(th + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_src, src_stride, d_idx, n, row_offset, d / 4, d_dst, dst_stride);
+    IDG_LAUNCH_CHECK("copy_rows_strided_kernel");
+    return 0;
+}
 
 extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
                                   const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,

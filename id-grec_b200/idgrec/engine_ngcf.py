@@ -53,7 +53,10 @@ class NgcfFusedTrainer:
         N, d, K = self.N, self.d, self.K
         self.final = z(N, (K + 1) * d)
         self.side, self.S, self.D = ([z(N, d) for _ in range(K)] for _ in range(3))
-        self.keep = [z(N, d) for _ in range(K)]
+        self.keep_all = z(K, N, d)                       # the K dropout masks of a step, drawn in one launch
+        self.keep = [self.keep_all[k] for k in range(K)]
+        self._keep_prob = (C.c_float * K)(*[1.0 - float(p) for p in self.drop[:K]])
+        self._seed = int(torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()) & ((1 << 63) - 1)
         self.G = z(N, (K + 1) * d)                       # dL/dfinal: non-zero on the batch rows only, re-zeroed by bpr_finish
         self.G64 = z(N, d)                               # scratch for the reg-only BPR call (stays zero)
         self.dside, self.dEd = z(N, d), z(N, d)
@@ -78,14 +81,17 @@ class NgcfFusedTrainer:
         l, s, g, K, d, N = self.l, cur_stream(), self.graph, self.K, self.d, self.N
         wd, W = self.w, (K + 1) * d
         fbase, gbase = ptr(self.final), ptr(self.G)
-        self.final[:, :d].copy_(self.E0)
+        # block 0 of the concat = the ego table, read by the BPR kernels at the batch rows only
+        for idx, off in ((u, 0), (p, self.U), (n, self.U)):
+            check(l.idg_copy_rows_strided(ptr(self.E0), d, idx, B, off, d, fbase, W, s), "idg_copy_rows_strided")
+        if self.injected_keep is None:
+            # nn.Dropout(p)'s draws (NGCF.py:99-100: always active): Bernoulli(1 - p) per element, all layers in one launch
+            check(l.idg_ngcf_keep_masks(ptr(self.keep_all), N * d, K, self._keep_prob, self._seed, ptr(self.step_a), s), "idg_ngcf_keep_masks")
         E = self.E0
         for layer in range(K):
             pr = self.drop[layer]
             if self.injected_keep is not None:
                 self.keep[layer].copy_(self.injected_keep[layer])
-            else:  # nn.Dropout(p)'s draw (NGCF.py:99-100: always active): Bernoulli(1 - p) per element from the device generator
-                self.keep[layer].bernoulli_(1.0 - pr)
             g.spmm_layer(E, Y=self.side[layer])
             check(l.idg_ngcf_dense_fwd(ptr(E), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['b_gcn_%d' % layer]),
                                        ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]), ptr(self.keep[layer]), pr, N, ptr(self.S[layer]),

@@ -238,6 +238,15 @@ int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg,
                        const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D,
                        float* d_out, int32_t out_stride, void* stream);
 int64_t idg_ngcf_workspace_bytes(void);
+/* The dropout draws of one NGCF step (NGCF.py:99-100, nn.Dropout constructed inline = always active) for all layers in one
+ * launch: d_keep [n_layers, per_layer] floats, keep = 1 with probability h_keep_prob[l] = 1 - p_l.  Philox stream
+ * (seed, subsequence = element quad, offset = *d_step): a captured step replays with fresh, launch-geometry independent draws. */
+int idg_ngcf_keep_masks(float* d_keep, int64_t per_layer, int32_t n_layers, const float* h_keep_prob, uint64_t seed,
+                        const int32_t* d_step, void* stream);
+/* dst[idx[i] + row_offset, 0:d] = src[idx[i] + row_offset, 0:d] with row strides in floats (the ego block of NGCF's [N,256]
+ * concat is read at the batch rows only). */
+int idg_copy_rows_strided(const float* d_src, int32_t src_stride, const int64_t* d_idx, int32_t n, int32_t row_offset, int32_t d,
+                          float* d_dst, int32_t dst_stride, void* stream);
 int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep,
                        float drop_p, const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride,
                        const float* d_dD_ext, int32_t N, float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb,

@@ -360,3 +360,27 @@ def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
     got = w - approx
     assert np.all(np.abs(got - margin) <= 0.01 * margin + 8e-6 * nu_[:, None] * ni_[None, :] + 1e-30), float(np.abs(got - margin).max())
     assert np.all(got[:, 3] == 0.0)
+
+
+# ---------------------------------------------------------------- NGCF: one-launch dropout draws
+def test_ngcf_keep_masks_are_bernoulli_and_step_dependent(dev):
+    """idg_ngcf_keep_masks replaces three torch launches per mask (NGCF.py:99-100's nn.Dropout draw): per-layer keep rates match
+    1 - p, the draw depends on (seed, step) only -- same inputs, same mask; next step, fresh mask -- and the entries are 0/1."""
+    import ctypes as C
+    from idgrec import _lib
+    l = _lib.lib()
+    per, K = 1 << 20, 3
+    keep = torch.empty(K, per, device=dev)
+    probs = (C.c_float * K)(0.9, 0.5, 1.0)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(l.idg_ngcf_keep_masks(keep.data_ptr(), per, K, probs, 1234, step.data_ptr(), s), "keep_masks")
+    a = keep.clone()
+    assert set(torch.unique(a).tolist()) <= {0.0, 1.0}
+    rates = a.mean(dim=1).cpu().numpy()
+    np.testing.assert_allclose(rates, [0.9, 0.5, 1.0], atol=3e-3)
+    _lib.check(l.idg_ngcf_keep_masks(keep.data_ptr(), per, K, probs, 1234, step.data_ptr(), s), "keep_masks")
+    assert torch.equal(a, keep)
+    step += 1
+    _lib.check(l.idg_ngcf_keep_masks(keep.data_ptr(), per, K, probs, 1234, step.data_ptr(), s), "keep_masks")
+    assert not torch.equal(a[0], keep[0]) and abs(float((a[0] * keep[0]).mean()) - 0.81) < 5e-3      # independent draws
