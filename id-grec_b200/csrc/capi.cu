@@ -109,18 +109,24 @@ extern "C" int idg_accumulate_f64(double* d_acc, const float* d_x, int32_t n, vo
     return 0;
 }
 
-// rows whose bit is set in the bitmap are zeroed (one lane group of d/4 lanes per row)
-__global__ void zero_rows_bitmap_kernel(float* __restrict__ buf, const unsigned* __restrict__ bitmap, int n_rows, int d4) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(t / d4), c = (int)(t % d4);
-    if (r >= n_rows) return;
-    if ((__ldg(bitmap + (r >> 5)) >> (r & 31)) & 1u) reinterpret_cast<float4*>(buf)[(size_t)r * d4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+// rows whose bit is set in the bitmap are zeroed: one warp per bitmap word (32 rows), d/4 lanes store one row per set bit,
+// so the cost follows the number of flagged rows, not N
+__global__ void __launch_bounds__(256) zero_rows_bitmap_kernel(float* __restrict__ buf, const unsigned* __restrict__ bitmap, int n_rows, int d4) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w * 32 >= n_rows) return;
+    unsigned m = __ldg(bitmap + w);
+    while (m) {
+        const int r = w * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        if (r < n_rows) for (int c = lane; c < d4; c += 32) reinterpret_cast<float4*>(buf)[(size_t)r * d4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 extern "C" int idg_zero_rows_bitmap(float* d_buf, const uint32_t* d_bitmap, int32_t n_rows, int32_t d, void* stream) {
     if (!d_buf || !d_bitmap || n_rows < 0 || d <= 0 || (d & 3)) return fail(-1, "idg_zero_rows_bitmap: bad argument%s");
     if (n_rows == 0) return 0;
-    const int64_t th = (int64_t)n_rows * (d / 4);
-    zero_rows_bitmap_kernel<<<(unsigned)((th + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_buf, d_bitmap, n_rows, d / 4);
+    const int words = (n_rows + 31) / 32;
+    zero_rows_bitmap_kernel<<<(unsigned)((words + 7) / 8), 256, 0, (cudaStream_t)stream>>>(d_buf, d_bitmap, n_rows, d / 4);
     IDG_LAUNCH_CHECK("zero_rows_bitmap_kernel");
     return 0;
 }

@@ -437,6 +437,12 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
         if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
         else spmm_kernel<32, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap && ex.rowmask) {
+        // sparse-input product restricted to the rows that can come out non-zero (batch rows + their neighbours): the other
+        // rows would stream their whole (col, val) list only to find no flagged column
+        if (d == 64) spmm_kernel<16, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
     } else if (ex.bitmap) {
         if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
@@ -691,6 +697,18 @@ extern "C" int idg_spmm_layer_add2(const idg_graph* g, const float* d_X, float* 
     return spmm_launch(g, d_X, d_Y, d_addend, d_addend2, scale2, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);
 }
 
+// idg_spmm_layer_sparse_in evaluated only on the rows flagged in d_rowmask (others untouched): the row-partitioned first backward
+// product, whose output is pre-zeroed and can only be non-zero on the batch neighbourhood
+extern "C" int idg_spmm_layer_sparse_in_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, int32_t d,
+                                               const uint32_t* d_bitmap, const uint32_t* d_rowmask, int skip_zero_rows, void* stream) {
+    if (!d_bitmap || !d_rowmask) return fail(-1, "idg_spmm_layer_sparse_in_masked: null bitmap%s");
+    SpmmExtra ex;
+    ex.bitmap = d_bitmap;
+    ex.rowmask = d_rowmask;
+    ex.skip_zero_rows = skip_zero_rows;
+    return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);
+}
+
 extern "C" int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
                                    const idg_adam_args* adam, void* stream) {
     if (!adam) return fail(-1, "idg_spmm_layer_adam: null adam%s");
@@ -771,6 +789,9 @@ static int propagate_bwd_impl(const idg_graph* g, const float* d_G, const float*
         SpmmExtra ex;
         ex.addend_mask = d_bitmap;   // G (and Gcl) are zero outside the flagged rows
         if (s == 1) ex.bitmap = d_bitmap;
+        // with the closure registered and K >= 3 the next product reads H_{K-1} at closure columns only: rows outside it
+        // need not be produced at all (they would be exact zeros)
+        if (s == 1 && K >= 3 && d_bitmap && g->closure) ex.rowmask = g->closure;
         // H_{K-1} = G + A G is non-zero only on the batch rows and their neighbours: the next product gathers just those
         if (s == 2 && layer > 0 && d_bitmap && g->closure) ex.bitmap = g->closure;
         if (layer > 0) {

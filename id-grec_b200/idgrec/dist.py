@@ -342,7 +342,10 @@ class DistFusedTrainer:
             out = self.H[step_i - 1]
             add2 = Gcl if (Gcl is not None and self.cl_layer == layer) else None
             if step_i == 1:
-                if add2 is None:
+                if add2 is None and self.use_closure:   # only the batch neighbourhood can come out non-zero
+                    check(l.idg_spmm_layer_sparse_in_masked(loc._h, ptr(h), ptr(out), ptr(self.G), d, ptr(rows.bitmap), ptr(self.closure), 1, s),
+                          "idg_spmm_layer_sparse_in_masked")
+                elif add2 is None:
                     check(l.idg_spmm_layer_sparse_in(loc._h, ptr(h), ptr(out), ptr(self.G), None, None, 1.0, d, ptr(rows.bitmap), 1, s), "idg_spmm_layer_sparse_in")
                 else:   # every row is stored (no zero-row skipping with a second addend)
                     check(l.idg_spmm_layer_add2(loc._h, ptr(h), ptr(out), ptr(self.G), ptr(add2), self.cnt, d, ptr(rows.bitmap), 0, s), "idg_spmm_layer_add2")

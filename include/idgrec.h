@@ -303,6 +303,10 @@ int idg_propagate_bwd_adam(const idg_graph* g, const float* d_G, const float* d_
                            const idg_adam_args* adam, void* stream);
 int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
                         const idg_adam_args* adam, void* stream);
+/* idg_spmm_layer_sparse_in on the rows flagged in d_rowmask only (the others are left untouched): for an output that is
+ * pre-zeroed and can only be non-zero on the batch rows and their neighbours (the closure bitmap). */
+int idg_spmm_layer_sparse_in_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, int32_t d,
+                                    const uint32_t* d_bitmap, const uint32_t* d_rowmask, int skip_zero_rows, void* stream);
 /* One step of the backward Horner chain on the handle's rows with a second addend: Y = A X + addend + scale2 * addend2
  * (XSimGCL.py:57-58,64-66: the gradient of the captured contrast layer joins the chain at that layer); d_bitmap != NULL
  * makes it the sparse-input product (X zero outside the flagged rows).  Used by the row-partitioned contrastive steps,

@@ -384,3 +384,31 @@ def test_ngcf_keep_masks_are_bernoulli_and_step_dependent(dev):
     step += 1
     _lib.check(l.idg_ngcf_keep_masks(keep.data_ptr(), per, K, probs, 1234, step.data_ptr(), s), "keep_masks")
     assert not torch.equal(a[0], keep[0]) and abs(float((a[0] * keep[0]).mean()) - 0.81) < 5e-3      # independent draws
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_row_partitioned_step_world1_with_neighbourhood_restriction(dev, use_graph):
+    """Same bit-identity with the batch-neighbourhood (closure) restriction forced on: masked layer K-1, row-masked sparse first
+    backward product, closure-column second product, closure-based re-zeroing -- against the DENSE single-GPU fused trainer."""
+    from idgrec import datagen
+    from idgrec.dist import DistFusedTrainer
+    from idgrec.engine import FusedTrainer
+    from idgrec.graph import Graph, build_norm_adjacency
+    g = datagen.gen_graph("small")
+    U, I = g.num_users, g.num_items
+    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
+    G = Graph(csr)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(6)
+    table = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
+    ref = FusedTrainer("LightGCN", G, table.clone(), U, 3, 1e-4, 1e-3, max_batch=64, use_cuda_graph=False, restrict_rows=False)
+    ref2 = FusedTrainer("LightGCN", Graph(csr), table.clone(), U, 3, 1e-4, 1e-3, max_batch=64, use_cuda_graph=use_graph, closure_restrict=True)
+    ft = DistFusedTrainer("LightGCN", csr, table.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=64, use_cuda_graph=use_graph, closure_restrict=True)
+    assert ft.use_closure and ref2.use_closure
+    rng = np.random.default_rng(9)
+    for step in range(4):
+        e = rng.integers(0, len(g.train_user), 64)          # a small batch: its neighbourhood is a small part of the graph
+        b = tuple(torch.from_numpy(a).to(dev) for a in (g.train_user[e], g.train_item[e], rng.integers(0, I, 64)))
+        l0, l1, l2 = ref.step(*b).clone(), ref2.step(*b).clone(), ft.step(*b).clone()
+        assert torch.equal(l0, l1) and torch.equal(l0, l2), (step, l0, l1, l2)
+    assert torch.equal(ref.E0, ref2.E0) and torch.equal(ref.E0, ft.E0)
