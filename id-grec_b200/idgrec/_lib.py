@@ -76,6 +76,7 @@ SIGNATURES = {
     "idg_batch_rows_clear": (C.c_int, [_p, _p, _i32, _p, _p]),
     "idg_closure_bitmap": (C.c_int, [_p, _p, _p, _p]),
     "idg_graph_set_closure": (C.c_int, [_p, _p]),
+    "idg_closure_from_rows": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p]),
     "idg_spmm_layer_masked": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _f32, _i32, _p, _p]),
     "idg_graph_worklist_ints": (_i64, [_p, _i32]),
     "idg_spmm_layer_rows": (C.c_int, [_p, _p, _p, _p, _f32, _p, _p, _p, _p, _f32, _i32, _p, _p, _i32, _p, _p]),

@@ -192,8 +192,8 @@ class DistFusedTrainer:
         self.rows = BatchRows(N, max_batch, dev)
         self.rows.worklist(self.full)
         contrastive = kind != "LightGCN"
-        # batch-neighbourhood restriction of forward layer K-1 and of the second backward product (see engine.py);
-        # every rank computes the closure bits of its own rows and publishes its words to the peers
+        # batch-neighbourhood restriction of forward layer K-1 and of the first two backward products (see engine.py);
+        # every rank derives the closure bitmap locally from the batch rows' neighbour lists (it holds the whole graph handle)
         if closure_restrict == "auto":
             from .graph import expected_closure_fraction
             closure_restrict = K >= 3 and not contrastive and expected_closure_fraction(csr, num_users, max_batch) < 0.4
@@ -294,11 +294,9 @@ class DistFusedTrainer:
         if not self.use_closure:
             self.H[0].zero_()
         if self.use_closure:
-            check(l.idg_closure_bitmap(loc._h, ptr(rows.bitmap), ptr(self.closure), s), "idg_closure_bitmap")
-            w0, w1 = self.b0 // 32, (self.b1 + 31) // 32
-            if w1 > w0:
-                slab.push(self.closure[w0:(w1 + 3) // 4 * 4])  # whole 16-byte groups: inner bounds are multiples of 128 rows
-            slab.barrier()
+            # every rank holds the whole graph handle (restricted last layer, evaluation): the closure of the batch is computed
+            # locally from the batch rows' own neighbour lists -- identical on all ranks, no exchange, no barrier
+            rows.build_closure(self.full)
         self._mark('batch_rows')
         cl_view = None
         if self.kind == "LightGCN":

@@ -194,7 +194,11 @@ class BatchRows:
         check(_lib.lib().idg_graph_set_closure(graph._h, ptr(self.closure)), "idg_graph_set_closure")
 
     def build_closure(self, graph):
-        check(_lib.lib().idg_closure_bitmap(graph._h, ptr(self.bitmap), ptr(self.closure), cur_stream()), "idg_closure_bitmap")
+        if graph.is_whole:   # from the batch side: ~3 B neighbour lists instead of a pass over every nonzero
+            check(_lib.lib().idg_closure_from_rows(graph._h, ptr(self.rowlist), ptr(self.count), self.max_rows, ptr(self.bitmap), ptr(self.closure),
+                                                   cur_stream()), "idg_closure_from_rows")
+        else:
+            check(_lib.lib().idg_closure_bitmap(graph._h, ptr(self.bitmap), ptr(self.closure), cur_stream()), "idg_closure_bitmap")
 
     def build_unique(self, users_ptr, pos_ptr, neg_ptr, B, num_users, uidx, ucnt, iidx, icnt):
         check(_lib.lib().idg_batch_rows_unique(users_ptr, pos_ptr, neg_ptr, B, num_users, ptr(self.rowlist), ptr(self.count), ptr(self.bitmap),

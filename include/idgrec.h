@@ -138,6 +138,10 @@ int idg_batch_rows_clear(const int32_t* d_rowlist, const int32_t* d_count, int32
  * graph (1M x 1M scale-up: ~20 %); identical results.  idg_spmm_layer_masked is the masked layer alone. */
 int idg_closure_bitmap(const idg_graph* g, const uint32_t* d_batch_bitmap, uint32_t* d_closure, void* stream);
 int idg_graph_set_closure(idg_graph* g, const uint32_t* d_closure);
+/* The same bitmap from the batch side (the structure of A_hat is symmetric: rows with a neighbour in the batch = union of the
+ * column lists of the batch rows): cost ~ batch rows x degree instead of one pass over all nonzeros.  Whole-graph handle only. */
+int idg_closure_from_rows(const idg_graph* g, const int32_t* d_rowlist, const int32_t* d_count, int32_t max_rows,
+                          const uint32_t* d_batch_bitmap, uint32_t* d_closure, void* stream);
 int idg_spmm_layer_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise, float eps,
                           const float* d_acc_in, float* d_acc_out, float acc_div, int32_t d,
                           const uint32_t* d_rowmask, void* stream);
