@@ -76,7 +76,8 @@ template <int EPI>
 __global__ void __launch_bounds__(256, 1) nce_tc_scores_kernel(const float* __restrict__ XH, const float* __restrict__ XL,
                                                                const float* __restrict__ YH, const float* __restrict__ YL,
                                                                const int* __restrict__ d_n, int n_in, int n_pad, float inv_tau,
-                                                               float* __restrict__ EH, float* __restrict__ EL, float* __restrict__ part_sum) {
+                                                               float* __restrict__ EH, float* __restrict__ EL, float* __restrict__ part_sum,
+                                                               float* __restrict__ ETH = nullptr, float* __restrict__ ETL = nullptr) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int n = d_n ? *d_n : n_in;
     const int r0 = blockIdx.x * 128;
@@ -203,6 +204,15 @@ __global__ void __launch_bounds__(256, 1) nce_tc_scores_kernel(const float* __re
                         }
                         eh[j4] = make_float4(h[0], h[1], h[2], h[3]);
                         el[j4] = make_float4(l[0], l[1], l[2], l[3]);
+                        if (ETH) {
+                            // E^T for the second gradient contraction, from the same accumulators (exp(B A^T) = E^T exactly as computed
+                            // here): lanes hold consecutive rows r, so each scalar store of a warp covers 128 contiguous bytes of row c
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const size_t o = (size_t)(c0 + j4 * 4 + jj) * n_pad + r;
+                                ETH[o] = h[jj]; ETL[o] = l[jj];
+                            }
+                        }
                     } else {
                         float v[4];
 #pragma unroll
@@ -356,7 +366,7 @@ size_t nce_tc_extra_bytes(int n_max) {
 // A, Bm: normalised rows [n,64]; beta [n] or NULL until known.  Stage 0: splits + E + row-sum partials.
 // Stage 1 (after the row kernel produced beta): E', transposes, the two gemms into part_pb / part_qa.
 int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, const int* d_n, int n_max, float inv_tau, float* part_sum,
-                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream) {
+                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream, int want_grad) {
     const int np = (n_max + 127) / 128 * 128;
     float* p = (float*)(((uintptr_t)extra + 1023) & ~(uintptr_t)1023);
     float *AH = p, *AL = AH + (size_t)np * 64, *BH = AL + (size_t)np * 64, *BL = BH + (size_t)np * 64;
@@ -368,12 +378,12 @@ int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, 
         nce_tc_split_kernel<<<(np + 7) / 8, 256, 0, stream>>>(A, Bm, d_n, n_max, np, AH, AL, BH, BL);
         IDG_LAUNCH_CHECK("nce_tc_split_kernel");
         IDG_CUDA(cudaFuncSetAttribute(nce_tc_scores_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-        nce_tc_scores_kernel<0><<<grid, 256, smem_s, stream>>>(AH, AL, BH, BL, d_n, n_max, np, inv_tau, E1H, E1L, part_sum);
+        // one pass writes E and (when gradients follow) E^T: round 1 recomputed exp(B A^T) with a second launch of this kernel
+        nce_tc_scores_kernel<0><<<grid, 256, smem_s, stream>>>(AH, AL, BH, BL, d_n, n_max, np, inv_tau, E1H, E1L, part_sum, want_grad ? E2H : nullptr,
+                                                              want_grad ? E2L : nullptr);
         IDG_LAUNCH_CHECK("nce_tc_scores_kernel");
         return 0;
     }
-    nce_tc_scores_kernel<0><<<grid, 256, smem_s, stream>>>(BH, BL, AH, AL, d_n, n_max, np, inv_tau, E2H, E2L, nullptr);
-    IDG_LAUNCH_CHECK("nce_tc_scores_kernel");
     nce_tc_transpose_kernel<<<np / 32, 256, 0, stream>>>(Bm, nullptr, d_n, n_max, np, BtH, BtL);
     IDG_LAUNCH_CHECK("nce_tc_transpose_kernel");
     nce_tc_transpose_kernel<<<np / 32, 256, 0, stream>>>(A, beta, d_n, n_max, np, AtH, AtL);

@@ -562,13 +562,14 @@ __global__ void __launch_bounds__(256) closure_kernel(const int4* __restrict__ i
 __global__ void __launch_bounds__(256) closure_from_rows_kernel(const int* __restrict__ rowlist, const int* __restrict__ count, const int2* __restrict__ row_items,
                                                                 const int4* __restrict__ items, const int2* __restrict__ colval, int row_offset, int n_rows,
                                                                 unsigned* __restrict__ closure) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    // one CTA per listed row, its work items (256-nonzero chunks of a popular item's row) spread over the 8 warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x;
     if (i >= *count) return;
     const int r = rowlist[i] - row_offset;
     if (r < 0 || r >= n_rows) return;
     const int2 ri = row_items[r];
-    for (int q = 0; q < ri.y; ++q) {
+    for (int q = warp; q < ri.y; q += 8) {
         const int4 it = __ldg(items + ri.x + q);
         for (int k = it.y + lane; k < it.z; k += 32) {
             const int c = __ldg(colval + k).x;
@@ -660,7 +661,7 @@ extern "C" int idg_closure_from_rows(const idg_graph* g, const int32_t* d_rowlis
     if (g->row_offset != 0 || g->n_rows != g->n_cols) return fail(-1, "idg_closure_from_rows: needs the whole (square, symmetric) graph%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (g->n_items > 0) {
-        closure_from_rows_kernel<<<(max_rows + 7) / 8, 256, 0, stream>>>(d_rowlist, d_count, g->row_items, g->items, g->colval, g->row_offset, g->n_rows, d_closure);
+        closure_from_rows_kernel<<<max_rows, 256, 0, stream>>>(d_rowlist, d_count, g->row_items, g->items, g->colval, g->row_offset, g->n_rows, d_closure);
         IDG_LAUNCH_CHECK("closure_from_rows_kernel");
     }
     const int w1 = (g->n_rows + 31) >> 5;
