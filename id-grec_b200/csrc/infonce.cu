@@ -20,10 +20,10 @@ namespace idg {
 // csrc/infonce_tc.cu: the four n x n x 64 contractions on tcgen05 tensor cores (3xTF32)
 size_t nce_tc_extra_bytes(int n_max);
 int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, const int* d_n, int n_max, float inv_tau, float* part_sum,
-                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream, int want_grad);
+                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream, int want_grad, int splits);
 
 constexpr int kNT = 64;      // tile edge
-constexpr int kNceSplits = 4;
+constexpr int kNceSplits = 8;
 
 struct NceWs {
     float* A;      // [n,d] normalised view 1 rows
@@ -267,11 +267,11 @@ static int infonce_impl(const float* d_V1, const float* d_V2, const int64_t* d_i
     IDG_LAUNCH_CHECK("nce_prep_kernel");
     if (nce_use_tc(n)) {
         // tensor-core path: E = exp(A B^T/tau) and its row sums, then (if gradients are wanted) E^T, PB = E B, QA = E^T (beta A)
-        if (int rc = nce_tc_stage(0, w.A, w.Bm, nullptr, d_n, n, inv_tau, w.part_sum, nullptr, nullptr, w.extra, stream, (d_gV1 || d_gV2) ? 1 : 0)) return rc;
+        if (int rc = nce_tc_stage(0, w.A, w.Bm, nullptr, d_n, n, inv_tau, w.part_sum, nullptr, nullptr, w.extra, stream, (d_gV1 || d_gV2) ? 1 : 0, kNceSplits)) return rc;
         nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, np, loss_scale, d_loss);
         IDG_LAUNCH_CHECK("nce_rows_kernel");
         if (d_gV1 || d_gV2) {
-            if (int rc = nce_tc_stage(1, w.A, w.Bm, w.beta, d_n, n, inv_tau, nullptr, w.part_pb, w.part_qa, w.extra, stream, 1)) return rc;
+            if (int rc = nce_tc_stage(1, w.A, w.Bm, w.beta, d_n, n, inv_tau, nullptr, w.part_pb, w.part_qa, w.extra, stream, 1, kNceSplits)) return rc;
             nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, np, inv_tau, loss_scale, d_gV1, d_gV2);
             IDG_LAUNCH_CHECK("nce_grad_kernel");
         }

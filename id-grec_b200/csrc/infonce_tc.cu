@@ -18,7 +18,7 @@
 namespace idg {
 
 constexpr int kNtLoaders = 64;
-constexpr int kNtSplits = 4;           // == kNceSplits of csrc/infonce.cu (partials are summed in split order)
+constexpr int kNtSplits = 4;           // column splits of the csrc/pairloss.cu entry points (partials are summed in split order)
 constexpr uint32_t kAtom128 = 128 * 128;  // bytes: [128 rows x 128 B]
 constexpr uint32_t kAtom64 = 64 * 128;    // bytes: [ 64 rows x 128 B]
 
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256, 1) nce_tc_scores_kernel(const float* __re
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_total = (n + 127) / 128;
-    const int t_begin = (int)((long long)tiles_total * blockIdx.y / kNtSplits), t_end = (int)((long long)tiles_total * (blockIdx.y + 1) / kNtSplits);
+    const int t_begin = (int)((long long)tiles_total * blockIdx.y / gridDim.y), t_end = (int)((long long)tiles_total * (blockIdx.y + 1) / gridDim.y);
     const int ntiles = t_end - t_begin;
 
     if (tid == 0) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, 1) nce_tc_gemm_kernel(const float* __rest
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunks_total = (n + 31) / 32;
-    const int k_begin = (int)((long long)chunks_total * blockIdx.y / kNtSplits), k_end = (int)((long long)chunks_total * (blockIdx.y + 1) / kNtSplits);
+    const int k_begin = (int)((long long)chunks_total * blockIdx.y / gridDim.y), k_end = (int)((long long)chunks_total * (blockIdx.y + 1) / gridDim.y);
     const int nchunks = k_end - k_begin;
 
     if (tid == 0) {
@@ -366,14 +366,16 @@ size_t nce_tc_extra_bytes(int n_max) {
 // A, Bm: normalised rows [n,64]; beta [n] or NULL until known.  Stage 0: splits + E + row-sum partials.
 // Stage 1 (after the row kernel produced beta): E', transposes, the two gemms into part_pb / part_qa.
 int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, const int* d_n, int n_max, float inv_tau, float* part_sum,
-                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream, int want_grad) {
+                 float* part_pb, float* part_qa, void* extra, cudaStream_t stream, int want_grad, int splits) {
     const int np = (n_max + 127) / 128 * 128;
     float* p = (float*)(((uintptr_t)extra + 1023) & ~(uintptr_t)1023);
     float *AH = p, *AL = AH + (size_t)np * 64, *BH = AL + (size_t)np * 64, *BL = BH + (size_t)np * 64;
     float *BtH = BL + (size_t)np * 64, *BtL = BtH + (size_t)np * 64, *AtH = BtL + (size_t)np * 64, *AtL = AtH + (size_t)np * 64;
     float *E1H = AtL + (size_t)np * 64, *E1L = E1H + (size_t)np * np, *E2H = E1L + (size_t)np * np, *E2L = E2H + (size_t)np * np;
     const size_t smem_s = 4 * kAtom128 + 2 * 4 * kAtom128 + 128, smem_g = 4 * (2 * kAtom128 + 2 * kAtom64) + 128;
-    const dim3 grid(np / 128, kNtSplits);
+    // `splits` column splits (== kNceSplits of csrc/infonce.cu): 16 row tiles x 8 = 128 CTAs at n ~ 2,000 (4 splits left 84 of
+    // the 148 SMs idle and measured 41 us per scores launch)
+    const dim3 grid(np / 128, splits);
     if (stage == 0) {
         nce_tc_split_kernel<<<(np + 7) / 8, 256, 0, stream>>>(A, Bm, d_n, n_max, np, AH, AL, BH, BL);
         IDG_LAUNCH_CHECK("nce_tc_split_kernel");
