@@ -70,6 +70,10 @@ struct SpmmArgs {
     const unsigned* rowmask;  // ROWMASK kernels: rows whose bit is clear are skipped (outputs untouched)
     const unsigned* bitmap;   // SPARSE kernels: only columns whose bit is set contribute (rows of X outside are zero)
     const unsigned* addend_mask;  // optional: rows whose bit is clear have an all-zero addend / addend2 (not loaded)
+    // SimGCL: the first layer of the clean propagation and of both perturbed views gathers the same A_hat . E0; one launch writes
+    // the clean row to Y and row + sign(row) * normalize(noise_v) * eps to view_Y[v] (SimGCL.py:47-51 for each view)
+    const float* view_noise[2];
+    float* view_Y[2];
 };
 
 }  // namespace idg
@@ -120,6 +124,22 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
         y.y += (sgn(y.y) * (nz.y / nrm)) * a.eps;
         y.z += (sgn(y.z) * (nz.z / nrm)) * a.eps;
         y.w += (sgn(y.w) * (nz.w / nrm)) * a.eps;
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        if (a.view_noise[v]) {
+            const float4 nz = ldcs4(a.view_noise[v] + off);
+            float ss = nz.x * nz.x + nz.y * nz.y + nz.z * nz.z + nz.w * nz.w;
+#pragma unroll
+            for (int m = LPR / 2; m >= 1; m >>= 1) ss += __shfl_xor_sync(gmask, ss, m);
+            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+            float4 yv = y;
+            yv.x += (sgn(y.x) * (nz.x / nrm)) * a.eps;
+            yv.y += (sgn(y.y) * (nz.y / nrm)) * a.eps;
+            yv.z += (sgn(y.z) * (nz.z / nrm)) * a.eps;
+            yv.w += (sgn(y.w) * (nz.w / nrm)) * a.eps;
+            st4(a.view_Y[v] + off, yv);
+        }
     }
     if (a.mcY) {
         multimem_st4(a.mcY + off, y);  // one NVLink store, replicated by the switch (NVLS)
@@ -369,6 +389,8 @@ struct SpmmExtra {
     const unsigned* bitmap = nullptr;  // sparse-input launch
     const unsigned* rowmask = nullptr; // row-masked launch
     const unsigned* addend_mask = nullptr;  // rows with a non-zero addend (others skip the addend load)
+    const float* view_noise[2] = {nullptr, nullptr};  // extra perturbed copies of the output row (SimGCL's shared first layer)
+    float* view_Y[2] = {nullptr, nullptr};
     int skip_zero_rows = 0;
     const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
@@ -390,6 +412,7 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     a.worklist = ex.worklist; a.d_wl_count = ex.d_wl_count; a.bitmap = ex.bitmap; a.skip_zero_rows = ex.skip_zero_rows;
     a.rowmask = ex.rowmask;
     a.addend_mask = ex.addend_mask;
+    for (int v = 0; v < 2; ++v) { a.view_noise[v] = ex.view_noise[v]; a.view_Y[v] = ex.view_Y[v]; }
     a.acc_in2 = ex.acc_in2; a.acc_in3 = ex.acc_in3;
     a.adam_p = nullptr; a.adam_m = a.adam_v = nullptr; a.adam_regc = a.adam_scalars = nullptr; a.adam_mc_p = nullptr;
     a.adam_b1 = a.adam_b2 = a.adam_eps = 0.f;
@@ -745,6 +768,19 @@ extern "C" int idg_spmm_layer_sparse_in_masked(const idg_graph* g, const float* 
     ex.rowmask = d_rowmask;
     ex.skip_zero_rows = skip_zero_rows;
     return spmm_launch(g, d_X, d_Y, d_addend, nullptr, 0.f, nullptr, 0.f, nullptr, nullptr, 1.f, d, stream, ex);
+}
+
+// One layer whose (clean) output row also yields up to two sign-noise perturbed copies: SimGCL's three propagations of a step share
+// their first product A_hat . E0 (SimGCL.py:62-66 calls aggregate() three times on the same ego table).
+extern "C" int idg_spmm_layer_views(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise_a, float* d_Y_a,
+                                    const float* d_noise_b, float* d_Y_b, float eps, int32_t d, void* stream) {
+    if (!d_Y) return fail(-1, "idg_spmm_layer_views: the clean output is required%s");
+    if ((d_noise_a && !d_Y_a) || (d_noise_b && !d_Y_b)) return fail(-1, "idg_spmm_layer_views: a view needs its output%s");
+    if (d_X == d_Y_a || d_X == d_Y_b) return fail(-1, "idg_spmm_layer_views: X must not alias an output%s");
+    SpmmExtra ex;
+    ex.view_noise[0] = d_noise_a; ex.view_Y[0] = d_Y_a;
+    ex.view_noise[1] = d_noise_b; ex.view_Y[1] = d_Y_b;
+    return spmm_launch(g, d_X, d_Y, nullptr, nullptr, 0.f, nullptr, eps, nullptr, nullptr, 1.f, d, stream, ex);
 }
 
 extern "C" int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,

@@ -111,6 +111,7 @@ SIGNATURES = {
     "idg_propagate_bwd_adam": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p, _p]),
     "idg_spmm_layer_adam": (C.c_int, [_p, _p, _p, _f32, _i32, _p, _p]),
     "idg_spmm_layer_sparse_in_masked": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, C.c_int, _p]),
+    "idg_spmm_layer_views": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _f32, _i32, _p]),
     "idg_spmm_layer_add2": (C.c_int, [_p, _p, _p, _p, _p, _f32, _i32, _p, C.c_int, _p]),
     "idg_adam_step_dev": (C.c_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p]),
     "idg_device_alloc": (C.c_int, [_i64, C.POINTER(_p)]),

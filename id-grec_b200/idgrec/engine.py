@@ -68,6 +68,7 @@ class FusedTrainer:
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         if kind in ("SimGCL", "XSimGCL"):
             self.noise = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev)
+            self.noise_b = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev) if kind == "SimGCL" else None
             self.nce_ws = torch.empty(int(self.l.idg_infonce_workspace_bytes(max_batch, self.d)), dtype=torch.uint8, device=dev)
             self.V1 = torch.empty_like(table)
             self.V2 = torch.empty_like(table) if kind == "SimGCL" else None
@@ -174,12 +175,13 @@ class FusedTrainer:
         scatter(self.gA, u, 0)
         scatter(self.gP, p, item_off)
 
-    def _draw_noise(self, view):
+    def _draw_noise(self, view, buf=None):
+        buf = self.noise if buf is None else buf
         if self.injected_noise is not None:
-            self.noise.copy_(self.injected_noise[view])
+            buf.copy_(self.injected_noise[view])
         else:  # same call pattern as SimGCL.py:50: one rand_like([N,d]) per layer, views in order
             for k in range(self.K):
-                self.noise[k].uniform_()
+                buf[k].uniform_()
 
     def _build_rows(self, B, u, p, n, contrastive):
         rows = self.rows
@@ -207,6 +209,29 @@ class FusedTrainer:
         check(self.l.idg_spmm_layer_rows(g._h, ptr(x), None, None, 0.0, ptr(layers[0]), ptr(layers[1]), ptr(layers[2]), ptr(self.F), float(K + 1), d,
                                          ptr(rows.rowlist), ptr(rows.count), rows.max_rows, ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
 
+    def _simgcl_forward_shared(self):
+        """SimGCL.py:62-66 runs aggregate() three times on the same ego table (clean, view 1, view 2).  Their first product
+        A_hat . E0 is the same gather: one launch writes the clean row and both perturbed copies (idg_spmm_layer_views); the
+        later layers run per propagation; the last layer and the mean over layers 1..K (SimGCL.py:45,55-56: no layer 0) are
+        evaluated on the batch rows.  Bit-identical to three separate propagations."""
+        g, K, d, N, rows, l = self.graph, self.K, self.d, self.N, self.rows, self.l
+        if getattr(self, "_sg", None) is None:
+            self._sg = [[torch.empty(N, d, dtype=torch.float32, device=self.dev) for _ in range(K - 1)] for _ in range(3)]
+        X = self._sg
+        nz = (None, self.noise, self.noise_b)
+        check(l.idg_spmm_layer_views(g._h, ptr(self.E0), ptr(X[0][0]), ptr(self.noise[0]), ptr(X[1][0]), ptr(self.noise_b[0]), ptr(X[2][0]),
+                                     float(self.eps), d, cur_stream()), "idg_spmm_layer_views")
+        for k in range(1, K - 1):
+            for v in range(3):
+                g.spmm_layer(X[v][k - 1], Y=X[v][k], noise=None if v == 0 else nz[v][k], eps=0.0 if v == 0 else self.eps)
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)     # join: the row set is ready
+        for v, out in enumerate((self.F, self.V1, self.V2)):
+            acc = list(X[v]) + [None] * (3 - (K - 1))
+            check(l.idg_spmm_layer_rows(g._h, ptr(X[v][K - 2]), None, None if v == 0 else ptr(nz[v][K - 1]), 0.0 if v == 0 else float(self.eps),
+                                        ptr(acc[0]), ptr(acc[1]), ptr(acc[2]), ptr(out), float(K), d, ptr(rows.rowlist), ptr(rows.count), rows.max_rows,
+                                        ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
+
     def _body(self, B, u, p, n, users_t=None, pos_t=None, fused=False):
         """Kernels of one step for batch pointers u/p/n (device int64).  ``fused``: Adam inside the last backward layer."""
         g, K = self.graph, self.K
@@ -216,6 +241,8 @@ class FusedTrainer:
         contrastive = self.kind in ("SimGCL", "XSimGCL") or self.kind == "SCCF"   # SCCF needs the two unique counts
         # forward of the LightGCN-encoder steps without the full-size layer sum, row set built on a parallel branch
         split_fwd = (rows is not None and not self.use_closure and 2 <= K <= 3 and (self.kind == "LightGCN" or self.kind in PAIR_MODELS))
+        shared_fwd = rows is not None and not self.use_closure and 2 <= K <= 4 and self.kind == "SimGCL"
+        split_fwd = split_fwd or shared_fwd
         if rows is not None and split_fwd and self._side is not None:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)                            # fork: after the batch copy / the previous step's clean-up
@@ -252,7 +279,11 @@ class FusedTrainer:
                 check(l.idg_unique_rows(u, B, 0, ptr(self.uidx), ptr(self.ucnt), s), "idg_unique_rows")
                 check(l.idg_unique_rows(p, B, self.U, ptr(self.iidx), ptr(self.icnt), s), "idg_unique_rows")
             uniq = ((self.uidx, self.ucnt), (self.iidx, self.icnt))
-            if self.kind == "SimGCL":
+            if self.kind == "SimGCL" and shared_fwd:
+                self._draw_noise(0)
+                self._draw_noise(1, self.noise_b)
+                self._simgcl_forward_shared()
+            elif self.kind == "SimGCL":
                 g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)
                 self._draw_noise(0)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1, rows=rows)

@@ -307,6 +307,11 @@ int idg_propagate_bwd_adam(const idg_graph* g, const float* d_G, const float* d_
                            const idg_adam_args* adam, void* stream);
 int idg_spmm_layer_adam(const idg_graph* g, const float* d_X, const float* d_addend, float acc_div, int32_t d,
                         const idg_adam_args* adam, void* stream);
+/* SimGCL (models/SimGCL.py:62-66): the clean propagation and the two perturbed views of one step start from the same ego
+ * table, so their first product A_hat . E0 is the same gather.  One launch: Y = A X (clean) and, per view v with noise_v != NULL,
+ * Y_v = Y + sign(Y) * normalize(noise_v, dim=-1) * eps -- bit-identical to three separate idg_spmm_layer calls. */
+int idg_spmm_layer_views(const idg_graph* g, const float* d_X, float* d_Y, const float* d_noise_a, float* d_Y_a,
+                         const float* d_noise_b, float* d_Y_b, float eps, int32_t d, void* stream);
 /* idg_spmm_layer_sparse_in on the rows flagged in d_rowmask only (the others are left untouched): for an output that is
  * pre-zeroed and can only be non-zero on the batch rows and their neighbours (the closure bitmap). */
 int idg_spmm_layer_sparse_in_masked(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, int32_t d,
