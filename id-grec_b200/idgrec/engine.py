@@ -279,16 +279,17 @@ class FusedTrainer:
                 check(l.idg_unique_rows(u, B, 0, ptr(self.uidx), ptr(self.ucnt), s), "idg_unique_rows")
                 check(l.idg_unique_rows(p, B, self.U, ptr(self.iidx), ptr(self.icnt), s), "idg_unique_rows")
             uniq = ((self.uidx, self.ucnt), (self.iidx, self.icnt))
-            if self.kind == "SimGCL" and shared_fwd:
-                self._draw_noise(0)
-                self._draw_noise(1, self.noise_b)
-                self._simgcl_forward_shared()
-            elif self.kind == "SimGCL":
-                g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)
-                self._draw_noise(0)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1, rows=rows)
-                self._draw_noise(1)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2, rows=rows)
+            if self.kind == "SimGCL":
+                if shared_fwd:
+                    self._draw_noise(0)
+                    self._draw_noise(1, self.noise_b)
+                    self._simgcl_forward_shared()
+                else:
+                    g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)
+                    self._draw_noise(0)
+                    g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V1, rows=rows)
+                    self._draw_noise(1)
+                    g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, out_mean=self.V2, rows=rows)
                 self._bpr(B, u, p, n, fused)
                 self.loss[2:3].zero_()
                 # the three propagations share one linear backward operator: accumulate all row
