@@ -268,8 +268,10 @@ def main():
     d2h = 4 * 4 + 3 * 2 * 8
     barrier()
     e0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
-    nxt = trainer.sample_epoch(data, dev)                    # host sampler + shuffle + pinned H2D (inside the timed region)
+    n_e2e = max(1, min(args.steps, 8))
+    t_s = time.perf_counter()
+    nxt = trainer.sample_epoch(data, dev)                    # host sampler + shuffle + pinned H2D (inside the timed region, not overlapped)
+    t_first_sampling = time.perf_counter() - t_s
     for i in range(n_e2e):
         u2, p2, n2 = nxt
         train_epoch(u2, p2, n2)                              # enqueues the epoch's steps
@@ -335,7 +337,9 @@ def main():
     line = {"metric": METRIC, "value": tot, "unit": "s/epoch", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, g), "clocks": clk,
-            "e2e": {"value": e2e, "unit": "s/epoch", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e, "unit": "s/epoch", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "epochs_timed": n_e2e,
+                    "first_epoch_host_sampling_s": t_first_sampling,
+                    "note": "host negative sampling + shuffle of epoch i+1 overlap the kernels of epoch i (as in universal_trainer); the first epoch's sampling is exposed and inside the timed region"},
             "gpu_launches": launches, "roofline": roof,
             "breakdown": {"train_s": t_train, "eval_s": t_eval, "train_batches": nb, "ms_per_train_batch": t_train * 1e3 / max(nb, 1),
                           "eval_users_per_s": len(data.test_dict) / t_eval, "wall_s_per_step": wall,

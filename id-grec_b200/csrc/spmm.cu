@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     const int lane = threadIdx.x & 31;
     const int group = lane / LPR, sub = lane % LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (group * LPR));
-    const int slot = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * G + group;
+    const int slot = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + group;
     int item = slot;
     if (a.worklist) {
         if (slot >= __ldg(a.d_wl_count)) return;
@@ -226,22 +226,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     if (SPARSE) {
         // X is zero outside the rows flagged in the bitmap (first backward layer: dL/dF touches only
         // the batch rows): stream the (col,val) list, gather only flagged columns, same ascending order.
-        for (int base = k; base < end; base += LPR) {
-            const int kk = base + sub;
-            int2 c = make_int2(0, 0);
-            bool hit = false;
-            if (kk < end) {
-                c = __ldg(cvp + kk);
-                hit = (__ldg(a.bitmap + (c.x >> 5)) >> (c.x & 31)) & 1u;
+        // kSU x LPR nonzeros per step: the (col, val) loads and the bitmap tests of a step are independent, so their latencies
+        // overlap (hits are rare -- the batch is a few thousand of N rows -- and most steps end after the tests)
+        constexpr int kSU = 4;
+        for (int base = k; base < end; base += kSU * LPR) {
+            int2 c[kSU];
+            bool hit[kSU];
+#pragma unroll
+            for (int u = 0; u < kSU; ++u) {
+                const int kk = base + u * LPR + sub;
+                c[u] = (kk < end) ? __ldg(cvp + kk) : make_int2(0, 0);
             }
-            unsigned m = __ballot_sync(gmask, hit);
-            if (LPR < 32) m = (m >> (group * LPR)) & ((1u << (LPR & 31)) - 1u);
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const int col = __shfl_sync(gmask, c.x, group * LPR + j);
-                const float w = __int_as_float(__shfl_sync(gmask, c.y, group * LPR + j));
-                acc = f4fma(w, ldg4(X + (size_t)col * d), acc);
+#pragma unroll
+            for (int u = 0; u < kSU; ++u) {
+                const int kk = base + u * LPR + sub;
+                hit[u] = (kk < end) && ((__ldg(a.bitmap + (c[u].x >> 5)) >> (c[u].x & 31)) & 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < kSU; ++u) {
+                unsigned m = __ballot_sync(gmask, hit[u]);
+                if (LPR < 32) m = (m >> (group * LPR)) & ((1u << (LPR & 31)) - 1u);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int col = __shfl_sync(gmask, c[u].x, group * LPR + j);
+                    const float w = __int_as_float(__shfl_sync(gmask, c[u].y, group * LPR + j));
+                    acc = f4fma(w, ldg4(X + (size_t)col * d), acc);
+                }
             }
         }
         k = end;
@@ -446,12 +457,15 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
             }
         }
     }
-    const int per_cta = kWarpsPerCta * (32 / (d / 4));  // items per CTA: one lane group each
+    // warps per CTA: 8 by default; IDG_SPMM_WARPS = 2 | 4 | 8 for tuning (smaller CTAs = finer tail, more CTA launches)
+    static const int warps_env = getenv("IDG_SPMM_WARPS") ? atoi(getenv("IDG_SPMM_WARPS")) : 0;
+    const int warps_per_cta = (warps_env == 2 || warps_env == 4) ? warps_env : kWarpsPerCta;
+    const int per_cta = warps_per_cta * (32 / (d / 4));  // items per CTA: one lane group each
     const int n_slots = ex.worklist ? ex.max_wl : g->n_items;
     if (n_slots <= 0) return 0;
     const unsigned grid = (unsigned)((n_slots + per_cta - 1) / per_cta);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int T = kWarpsPerCta * 32;
+    const int T = warps_per_cta * 32;
     // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
     // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
     if (ex.adam) {
