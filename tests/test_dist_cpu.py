@@ -59,3 +59,42 @@ def test_gloo_world2_exchange_and_reduce():
     [p.join(timeout=60) for p in ps]
     for rank, ok, t in out:
         assert ok and t == [5050.0, 101.0]
+
+
+def _sample_check_worker(rank, world, port, q, same):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import utility.utility_train.trainer as trainer
+        E = 1000
+        rng = np.random.default_rng(7 if same else 7 + rank)      # equal seeds <=> equal negatives + permutation
+        t = torch.from_numpy(np.stack([rng.integers(0, 500, E), rng.permutation(E)]).astype(np.int64))
+        try:
+            trainer._check_same_samples(t, E)
+            q.put((rank, "ok"))
+        except RuntimeError as e:
+            q.put((rank, "raised: " + str(e)[:40]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run2(target, *extra):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=target, args=(r, 2, port, q) + extra) for r in range(2)]
+    [p.start() for p in ps]
+    out = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(timeout=60) for p in ps]
+    return out
+
+
+def test_gloo_world2_rank_sample_checksum():
+    """Row-partitioned training evaluates the loss redundantly on every rank (no gradient reduction), so all ranks must draw the
+    same negatives and the same shuffle: trainer._check_same_samples passes on equal draws and raises on every rank otherwise."""
+    assert [r for _, r in _run2(_sample_check_worker, True)] == ["ok", "ok"]
+    out = _run2(_sample_check_worker, False)
+    assert all(r.startswith("raised: ranks drew different epoch samples") for _, r in out), out
