@@ -139,3 +139,67 @@ def test_topk_properties_full_size(ab, scale):
         S[j, net.indices[net.indptr[uu]:net.indptr[uu + 1]]] = -float("inf")
     ref = torch.sort(-S, dim=1, stable=True).indices[:, :K]
     assert torch.equal(ids[samp], ref)
+
+
+# ---------------------------------------------------------------- the scale-up shape (BASELINE.json configs[4])
+def test_xl_shape_properties():
+    """1M users x 1M items x 100M edges (nnz 200M), generated on the device like bench.py's xl record.  The CPU oracle cannot
+    run at this size, so parity rests on size-independent properties: CSR structure, sampled rows of one propagation layer
+    against an fp64 evaluation straight from the CSR, both closure constructions agreeing bit for bit, and the row-partitioned
+    trainer (one partition, neighbourhood restriction on) reproducing the dense single-GPU fused trainer bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~40 GB of device memory")
+    from idgrec import _lib, datagen
+    from idgrec._lib import check, cur_stream, ptr
+    from idgrec.dist import DistFusedTrainer
+    from idgrec.engine import FusedTrainer
+    from idgrec.graph import BatchRows, Graph, build_norm_adjacency
+    dev = torch.device("cuda:0")
+    U = I = 1000000
+    E = 100000000
+    N = U + I
+    eu, ei = datagen.gen_edges_device(U, I, E, 2024, dev)
+    csr = build_norm_adjacency(eu, ei, U, I, device=dev)
+    ip, ix = csr.indptr.long(), csr.indices
+    assert csr.nnz == 2 * E and int(ip[0]) == 0 and int(ip[-1]) == 2 * E
+    assert bool((ip[1:] >= ip[:-1]).all())
+    assert int(ix[: int(ip[U])].min()) >= U and int(ix[int(ip[U]):].max()) < U          # bipartite blocks
+    G = Graph(csr)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    X = (torch.rand(N, 64, generator=gen, device=dev) - 0.5) * 0.1
+    Y = torch.empty_like(X)
+    G.spmm_layer(X, Y=Y)
+    rows = torch.randint(0, N, (256,), generator=gen, device=dev)
+    for r in rows.tolist()[:256]:
+        s, e = int(ip[r]), int(ip[r + 1])
+        want = (csr.data[s:e].double()[:, None] * X[ix[s:e].long()].double()).sum(0)
+        got = Y[r].double()
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-12, r
+    # closure of a batch: pass over all nonzeros (idg_closure_bitmap) == union of the batch rows' neighbour lists (idg_closure_from_rows)
+    B = 1024
+    sel = torch.randint(0, E, (B,), generator=gen, device=dev)
+    bu, bp, bn = eu[sel].contiguous(), ei[sel].contiguous(), torch.randint(0, I, (B,), generator=gen, device=dev)
+    br = BatchRows(N, B, dev)
+    br.build(ptr(bu), ptr(bp), ptr(bn), B, U)
+    c1, c2 = torch.zeros_like(br.bitmap), torch.zeros_like(br.bitmap)
+    l = _lib.lib()
+    check(l.idg_closure_bitmap(G._h, ptr(br.bitmap), ptr(c1), cur_stream()), "idg_closure_bitmap")
+    check(l.idg_closure_from_rows(G._h, ptr(br.rowlist), ptr(br.count), br.max_rows, ptr(br.bitmap), ptr(c2), cur_stream()), "idg_closure_from_rows")
+    assert torch.equal(c1, c2)
+    frac = float(sum(bin(w & 0xffffffff).count("1") for w in c1.cpu().tolist())) / N
+    assert 0.05 < frac < 0.9, frac
+    del Y, c1, c2, br
+    # row-partitioned trainer with one partition and the neighbourhood restriction vs the dense single-GPU trainer
+    table = (torch.rand(N, 64, generator=gen, device=dev) * 2 - 1) * (6.0 / (U + 64)) ** 0.5
+    ref = FusedTrainer("LightGCN", G, table.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=False, restrict_rows=False)
+    ft = DistFusedTrainer("LightGCN", csr, table.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=B, use_cuda_graph=True, full_graph=G, closure_restrict=True)
+    del table
+    for step in range(3):
+        sel = torch.randint(0, E, (B,), generator=gen, device=dev)
+        b = (eu[sel].contiguous(), ei[sel].contiguous(), torch.randint(0, I, (B,), generator=gen, device=dev))
+        l0, l1 = ref.step(*b).clone(), ft.step(*b).clone()
+        assert torch.equal(l0, l1), (step, l0, l1)
+    assert torch.equal(ref.E0, ft.E0)
