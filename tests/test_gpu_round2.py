@@ -429,19 +429,35 @@ def test_contrastive_step_losses_and_gradient_vs_fp64(dev, kind, cl):
     U, I, K, B = g.num_users, g.num_items, 3, 512
     N = U + I
     csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
-    gen = torch.Generator().manual_seed(12)
-    table = (torch.rand(N, 64, generator=gen) - 0.5) * 0.2
     n_views = 2 if kind == "SimGCL" else 1
-    noise = [torch.rand(K, N, 64, generator=gen) for _ in range(n_views)]
-    rng = np.random.default_rng(4)
-    e = rng.integers(0, len(g.train_user), B)
-    bu, bp, bn = g.train_user[e], g.train_item[e], rng.integers(0, I, B)
-    eps, tau, lam, reg = 0.1, 0.2, 0.3, 1e-4
-    # ---- float64 evaluation of the reference formulas
+    eps = 0.1
     net = sp.csr_matrix((np.ones(len(g.train_user)), (g.train_user, g.train_item)), shape=(U, I))
     net.sort_indices()
     ip, ix, dt, _ = O.norm_adjacency(net)
     A = O.csr_to_torch_coo(ip, ix, dt, N).double()
+    # x += sign(x) * ... is discontinuous at x = 0: an entry whose fp32 and fp64 values straddle zero flips a whole noise component
+    # (observed: one flip in 1.9 M entries moved the gradient by 4e-3).  Draw inputs until no pre-noise entry of a perturbed
+    # layer is within 1e-8 of zero (fp32 rounding of these sums is ~1e-9), so the comparison measures arithmetic, not the jump.
+    for seed in range(12, 40):
+        gen = torch.Generator().manual_seed(seed)
+        table = (torch.rand(N, 64, generator=gen) - 0.5) * 0.2
+        noise = [torch.rand(K, N, 64, generator=gen) for _ in range(n_views)]
+        closest = float("inf")
+        for v in noise:
+            x = table.double()
+            for k in range(K):
+                x = torch.sparse.mm(A, x)
+                closest = min(closest, float(x.abs()[x != 0].min()))      # rows without neighbours are exactly 0 on both sides
+                x = x + torch.sign(x) * torch.nn.functional.normalize(v[k].double(), dim=-1) * eps
+        if closest > 1e-8:
+            break
+    else:
+        pytest.skip("no draw without a near-zero pre-noise entry")
+    rng = np.random.default_rng(4)
+    e = rng.integers(0, len(g.train_user), B)
+    bu, bp, bn = g.train_user[e], g.train_item[e], rng.integers(0, I, B)
+    tau, lam, reg = 0.2, 0.3, 1e-4
+    # ---- float64 evaluation of the reference formulas
     X0 = table.double().requires_grad_(True)
     u, p, n = (torch.as_tensor(a, dtype=torch.long) for a in (bu, bp, bn))
     nz = [[t.double() for t in v] for v in noise]
