@@ -272,13 +272,20 @@ def main():
     t_s = time.perf_counter()
     nxt = trainer.sample_epoch(data, dev)                    # host sampler + shuffle + pinned H2D (inside the timed region, not overlapped)
     t_first_sampling = time.perf_counter() - t_s
+    phases = np.zeros(4)
     for i in range(n_e2e):
         u2, p2, n2 = nxt
+        h0 = time.perf_counter()
         train_epoch(u2, p2, n2)                              # enqueues the epoch's steps
+        h1 = time.perf_counter()
         if i + 1 < n_e2e:
             nxt = trainer.sample_epoch(data, dev)            # next epoch's sampling overlaps the GPU, as in universal_trainer
+        h2 = time.perf_counter()
         ft.pop_epoch_losses()                                # D2H of the epoch losses
+        h3 = time.perf_counter()
         eval_once()                                          # D2H of the metric sums
+        h4 = time.perf_counter()
+        phases += [h1 - h0, h2 - h1, h3 - h2, h4 - h3]
     barrier()
     e2e = (time.perf_counter() - e0) / n_e2e
     if dist is not None:
@@ -339,6 +346,8 @@ def main():
             "config": workload_config(args, g), "clocks": clk,
             "e2e": {"value": e2e, "unit": "s/epoch", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "epochs_timed": n_e2e,
                     "first_epoch_host_sampling_s": t_first_sampling,
+                    "host_wall_per_epoch_s": {"enqueue_steps": phases[0] / n_e2e, "sample_next_epoch_incl_wait_for_gpu": phases[1] / n_e2e,
+                                              "read_losses": phases[2] / n_e2e, "Test": phases[3] / n_e2e},
                     "note": "host negative sampling + shuffle of epoch i+1 overlap the kernels of epoch i (as in universal_trainer); the first epoch's sampling is exposed and inside the timed region"},
             "gpu_launches": launches, "roofline": roof,
             "breakdown": {"train_s": t_train, "eval_s": t_eval, "train_batches": nb, "ms_per_train_batch": t_train * 1e3 / max(nb, 1),

@@ -419,8 +419,8 @@ def test_row_partitioned_step_world1_with_neighbourhood_restriction(dev, use_gra
 def test_contrastive_step_losses_and_gradient_vs_fp64(dev, kind, cl):
     """The golden comparisons of the contrastive models state 1e-4 on gradients because the goldens are the reference's own fp32
     CPU autograd, which is itself ~1e-4 from the exact value.  Against the SAME formulas (oracle/ref_oracle.py: propagate,
-    bpr_loss, reg_loss, infonce_loss) evaluated in float64 the fused CUDA step is held to 1e-5 on the three losses and 3e-5 of
-    the largest entry on the ego-table gradient."""
+    bpr_loss, reg_loss, infonce_loss) evaluated in float64 the fused CUDA step is held to 1e-5 on the three losses and 1e-5 of
+    the largest entry on the ego-table gradient (measured: 0.7e-6 .. 2.6e-6)."""
     import scipy.sparse as sp
     from idgrec import datagen
     from idgrec.engine import FusedTrainer
@@ -480,4 +480,4 @@ def test_contrastive_step_losses_and_gradient_vs_fp64(dev, kind, cl):
     np.testing.assert_allclose(got, want_loss, rtol=1e-5)
     err = np.abs(ft.gE0.cpu().numpy().astype(np.float64) - want_grad).max() / np.abs(want_grad).max()
     print("%s cl=%d: gradient max error / max entry = %.2e" % (kind, cl, err))
-    assert err <= 3e-5, err
+    assert err <= 1e-5, err
