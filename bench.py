@@ -276,10 +276,11 @@ def main():
     for i in range(n_e2e):
         u2, p2, n2 = nxt
         h0 = time.perf_counter()
+        worker = trainer.EpochPrefetch(data) if i + 1 < n_e2e else None   # next epoch's host sampling on a worker thread, as in universal_trainer
         train_epoch(u2, p2, n2)                              # enqueues the epoch's steps
         h1 = time.perf_counter()
-        if i + 1 < n_e2e:
-            nxt = trainer.sample_epoch(data, dev)            # next epoch's sampling overlaps the GPU, as in universal_trainer
+        if worker is not None:
+            nxt = worker.finish(dev)                         # pinned H2D + device-side shuffle gather
         h2 = time.perf_counter()
         ft.pop_epoch_losses()                                # D2H of the epoch losses
         h3 = time.perf_counter()

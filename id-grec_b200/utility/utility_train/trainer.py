@@ -25,7 +25,12 @@ def sample_epoch(dataset, device):
         np.random.shuffle(perm)                   # tools.shuffle (tools.py:41-42), same stream position
         t = torch.from_numpy(np.ascontiguousarray(sample_data[perm].T))
         return t[0], t[1], t[2]
-    from idgrec import _lib
+    return _samples_to_device(dataset, device, _sample_epoch_host(dataset))
+
+
+def _sample_epoch_host(dataset):
+    """Host half of sample_epoch: the epoch's negatives (exact replay of data_loader.py:108-127) and the shuffle permutation
+    (tools.py:41-42), drawn from the numpy global stream in the reference's order, into the pinned [2, E] staging block."""
     E = len(dataset.train_user)
     stage = _PINNED.get(E)
     if stage is None:
@@ -35,6 +40,13 @@ def sample_epoch(dataset, device):
     perm = host[1, :E]
     perm[:] = np.arange(E)
     np.random.shuffle(perm)                       # same generator position as the reference: right after the sampler
+    return stage
+
+
+def _samples_to_device(dataset, device, stage):
+    """Device half: one pinned H2D copy, then tools.shuffle's fancy indexing on the device (idg_permute3)."""
+    from idgrec import _lib
+    E = len(dataset.train_user)
     cache = dataset.device_cache(device)
     t = stage.to(device, non_blocking=True)
     _check_same_samples(t, E)
@@ -43,6 +55,31 @@ def sample_epoch(dataset, device):
                                        _lib.ptr(out), _lib.cur_stream()), "idg_permute3")
     torch.cuda.current_stream().synchronize()      # the staging buffer is reused by the next epoch's prefetch
     return out[0], out[1], out[2]
+
+
+class EpochPrefetch:
+    """The next epoch's host sampling on a worker thread, started BEFORE the current epoch's steps are enqueued: the launch queue
+    holds only a few hundred steps, so the enqueue loop of an epoch runs for as long as the GPU does and sampling after it
+    (round 1) overlapped only its tail.  numpy's generators and the C sampler walk release the GIL; nothing else reads the numpy
+    global stream while the worker runs, so the stream -- and every batch -- stays the reference's."""
+
+    def __init__(self, dataset):
+        import threading
+        self.dataset, self.stage, self.error = dataset, None, None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            self.stage = _sample_epoch_host(self.dataset)
+        except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
+            self.error = e
+
+    def finish(self, device):
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        return _samples_to_device(self.dataset, device, self.stage)
 
 
 _PINNED = {}
@@ -97,14 +134,17 @@ def universal_trainer(model, args, config, dataset, device, logger):
         num_batch = len(users) // batch_size + 1          # trainer.py:36 (over-counts when divisible)
 
         if fused is not None:
+            # draw the next epoch's samples on a worker thread while this epoch's steps are enqueued and run.  Nothing else
+            # reads the numpy global generator in between, so the stream (and every batch) stays the reference's.
+            worker = EpochPrefetch(dataset) if (epoch + 1 < n_epochs and torch.device(device).type == "cuda") else None
             for bu, bp, bn in tools.mini_batch(users, pos_items, neg_items, batch_size=batch_size):
                 fused.step(bu, bp, bn)
-            # the steps are only enqueued: draw the next epoch's samples on the host while the GPU trains.  Nothing else
-            # reads the numpy global generator in between, so the stream (and every batch) stays the reference's.
             enqueue_time = time()
-            if epoch + 1 < n_epochs:
+            if worker is not None:
+                prefetched = worker.finish(device)
+            elif epoch + 1 < n_epochs:
                 prefetched = sample_epoch(dataset, device)
-            sampling_time = time() - enqueue_time         # host time of the NEXT epoch's sampler, hidden behind this epoch's kernels
+            sampling_time = time() - enqueue_time         # what the NEXT epoch's samples still cost after this epoch's steps were enqueued
             total_loss_list = fused.pop_epoch_losses()    # one device read per epoch (waits for the epoch's last step)
         else:
             acc = None
