@@ -32,7 +32,11 @@ namespace idg {
 constexpr int kTcM = 128, kTcN = 128, kTcD = 64;
 constexpr int kTcStages = 2, kTcBufs = 2;   // per CTA; two CTAs share an SM (2 x 97 KB smem, 2 x 256 TMEM columns)
 constexpr uint32_t kTcTmemCols = kTcBufs * 128;
-constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
+// per-row candidate list (in L2): pruned when it exceeds kTcTrig entries.  After training the item norms are heavy-tailed and ~30-40
+// entries survive each prune (margin band at the top of the ranking); with the round-1 trigger of 48 a row then pruned every ~10
+// appends and the kernel ran 8 ms instead of 3.4 ms.  128 of 160 leaves ~90 appends between prunes.
+constexpr int kTcCap = 160, kTcTrig = 128, kTcCandOut = 64;
+constexpr int kTcPruneQ = kTcCap / 32;   // list entries per lane in the warp-cooperative prune
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
 constexpr uint32_t kAugTile = 128 * 32;   // bytes of one [128 rows x 32 B] margin operand (32-byte swizzle atoms)
@@ -80,34 +84,34 @@ __device__ __noinline__ int tc_group_append(float v0, float v1, float v2, float 
 // L = K-th largest lower bound; keep w >= L.
 __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float c2, const float* __restrict__ aug, int K, int lane, int& new_cnt,
                                          float& new_tau) {
-    float s[3], lo[3]; int id[3]; int rank[3];
+    float s[kTcPruneQ], lo[kTcPruneQ]; int id[kTcPruneQ]; int rank[kTcPruneQ];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < kTcPruneQ; ++q) {
         const int idx = lane + 32 * q;
         s[q] = (idx < m) ? __ldcg(ls + idx) : -INFINITY; id[q] = (idx < m) ? __ldcg(li + idx) : 0; rank[q] = 0;
         lo[q] = (idx < m) ? fmaf(-c2, __ldg(aug + (size_t)id[q] * 8), s[q]) : -INFINITY;
     }
-    // rank counting over the lower bounds held in registers (3 entries per lane), broadcast by shuffle
+    // rank counting over the lower bounds held in registers (kTcPruneQ entries per lane), broadcast by shuffle
 #pragma unroll
-    for (int qq = 0; qq < 3; ++qq) {
+    for (int qq = 0; qq < kTcPruneQ; ++qq) {
         for (int l = 0; l < 32; ++l) {
             const int j = l + 32 * qq;
             if (j >= m) break;
             const float sj = __shfl_sync(0xffffffffu, lo[qq], l);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) rank[q] += (sj > lo[q]) || (sj == lo[q] && j < lane + 32 * q);
+            for (int q = 0; q < kTcPruneQ; ++q) rank[q] += (sj > lo[q]) || (sj == lo[q] && j < lane + 32 * q);
         }
     }
     float vk = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = lo[q];
+    for (int q = 0; q < kTcPruneQ; ++q) if (lane + 32 * q < m && rank[q] == K - 1) vk = lo[q];
 #pragma unroll
     for (int mm = 16; mm >= 1; mm >>= 1) vk = fmaxf(vk, __shfl_xor_sync(0xffffffffu, vk, mm));
     const float tau = vk;
     __syncwarp();
     int kept = 0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < kTcPruneQ; ++q) {
         const bool keep = (lane + 32 * q < m) && (s[q] >= tau);
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (keep) { const int p = kept + __popc(b & ((1u << lane) - 1)); ls[p] = s[q]; li[p] = id[q]; }
