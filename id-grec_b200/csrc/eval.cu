@@ -26,7 +26,7 @@ namespace idg {
 int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
                               float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream);
-constexpr int kTcListCap = 160;  // == kTcCap in eval_tc.cu
+constexpr int kTcListCap = 80;  // == kTcCap in eval_tc.cu
 
 constexpr int kTU = 64, kTI = 64, kCap = 128, kPruneAt = 64, kCandOut = 64;
 // csrc/eval_exact.cu: pass C, exact sliced ranking of the flagged users (and of every user for shapes outside the tiles)

@@ -32,10 +32,10 @@ namespace idg {
 constexpr int kTcM = 128, kTcN = 128, kTcD = 64;
 constexpr int kTcStages = 2, kTcBufs = 2;   // per CTA; two CTAs share an SM (2 x 97 KB smem, 2 x 256 TMEM columns)
 constexpr uint32_t kTcTmemCols = kTcBufs * 128;
-// per-row candidate list (in L2): pruned when it exceeds kTcTrig entries.  After training the item norms are heavy-tailed and ~30-40
-// entries survive each prune (margin band at the top of the ranking); with the round-1 trigger of 48 a row then pruned every ~10
-// appends and the kernel ran 8 ms instead of 3.4 ms.  128 of 160 leaves ~90 appends between prunes.
-constexpr int kTcCap = 160, kTcTrig = 128, kTcCandOut = 64;
+// per-row candidate list (in L2): pruned when it exceeds kTcTrig entries.  The filter threshold only moves at a prune, so the trigger
+// trades prune count against appends through a stale threshold: 128 / 160 was measured and is 2x SLOWER than 48 / 80 (18 vs 9.6 ms
+// after three epochs of training, when ~35 entries survive each prune because of the margin band at the top of the ranking).
+constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
 constexpr int kTcPruneQ = kTcCap / 32;   // list entries per lane in the warp-cooperative prune
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
