@@ -43,6 +43,7 @@ struct EvalWs {
     float* tc_ls;      // [ceil(nu/128)*128, kTcListCap] tensor-core pass: per-row candidate lists
     int* tc_li;
     float* tc_aug;     // [I, 8] margin operand of the tensor-core pass: column 0 = |i| rounded up to tf32
+    float* tc_fir;     // [I, 64] item table rounded to nearest tf32 (what the tensor core reads through TMA)
     void* part;        // per-slice top-K lists of the exact pass (eval_exact_part_bytes)
 };
 
@@ -60,18 +61,28 @@ __host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
     w.tc_ls = (float*)p; p += ev_align(sizeof(float) * nup * kTcListCap);
     w.tc_li = (int*)p; p += ev_align(sizeof(int) * nup * kTcListCap);
     w.tc_aug = (float*)p; p += ev_align(sizeof(float) * 8 * (size_t)I);
+    w.tc_fir = (float*)p; p += ev_align(sizeof(float) * 64 * (size_t)I);
     w.part = (void*)p;
     return w;
 }
 
 // max_i |i| (CUDA-core pass: one margin per user) and, for the tensor-core pass, the per-item margin operand
 // aug[i] = {|i| rounded UP to a tf32-exact value (plus a relative 2^-20 for the rounding of the norm itself), 0 x 7}
-__global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, float* __restrict__ max_norm, float* __restrict__ aug) {
+__global__ void item_norm_kernel(const float* __restrict__ Fi, int I, int d, float* __restrict__ max_norm, float* __restrict__ aug,
+                                 float* __restrict__ Fi_tf32) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= I) return;
     float ss = 0.f;
-    for (int k = lane; k < d; k += 32) { const float v = Fi[(size_t)i * d + k]; ss = fmaf(v, v, ss); }
+    for (int k = lane; k < d; k += 32) {
+        const float v = Fi[(size_t)i * d + k];
+        ss = fmaf(v, v, ss);
+        if (Fi_tf32) {   // the copy the tensor core reads: rounded to nearest tf32, so the unit's own truncation is exact
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            Fi_tf32[(size_t)i * d + k] = __uint_as_float(r);
+        }
+    }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
     const float nrm = sqrtf(ss);
@@ -398,7 +409,7 @@ extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, in
     const size_t metrics = ev_align(sizeof(double) * (size_t)nu * 3 * 8);
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
-                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) + ev_align(sizeof(float) * 8 * (size_t)I) +
+                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) + ev_align(sizeof(float) * 8 * (size_t)I) + ev_align(sizeof(float) * 64 * (size_t)I) +
                        ev_align(eval_exact_part_bytes(nu, K > 0 ? K : 1));
     return (int64_t)(sel > metrics ? sel : metrics);
 }
@@ -421,13 +432,13 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
         return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
     }
     static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
-    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, (d == 64 && use_tc) ? w.tc_aug : nullptr);
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, (d == 64 && use_tc) ? w.tc_aug : nullptr, (d == 64 && use_tc) ? w.tc_fir : nullptr);
     IDG_LAUNCH_CHECK("item_norm_kernel");
     const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
     const unsigned grid = (unsigned)((nu + kTU - 1) / kTU);
     // IDG_EVAL_IMPL=fma selects the CUDA-core candidate pass (kept as a cross-check of the tensor-core one)
     if (d == 64 && use_tc) {
-        if (int rc = launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
+        if (int rc = launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
                                                w.flag_list, w.cand_cnt, w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, nullptr, stream))
             return rc;
     } else if (d == 64) {
@@ -459,9 +470,9 @@ extern "C" int idg_eval_tc_bounds(const float* d_Fu, const float* d_Fi, int32_t 
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalWs w = eval_carve(d_ws, nu, I);
     IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
-    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, w.tc_aug);
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, w.tc_aug, w.tc_fir);
     IDG_LAUNCH_CHECK("item_norm_kernel");
-    return launch_eval_candidates_tc(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, 1, w.max_norm, w.flag_cnt, w.flag_list, w.cand_cnt,
+    return launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d_mask_indptr, d_mask_indices, d_users, nu, 1, w.max_norm, w.flag_cnt, w.flag_list, w.cand_cnt,
                                      w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, d_out_tile, stream);
 }
 

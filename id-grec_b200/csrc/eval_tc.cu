@@ -6,7 +6,7 @@
 //
 //   scores:  S[128 users, 128 items] = Fu_tile . Fi_tile^T, d = 64, one tcgen05.mma.kind::tf32 chain
 //            (8 instructions of K = 8) per item tile, accumulators in TMEM (4 buffers x 128 columns).
-//            fp32 operands are read as tf32 (low 13 mantissa bits ignored): |s~ - s| <= m_ui = c * |u||i|, c = 1.25 (2^-9 + 1e-4).
+//            operands are rounded to nearest tf32 before the unit sees them: |s~ - s| <= m_ui = c * |u||i|, c ~ 1.01e-3 (kTcMarginCoef).
 //            The margin is PER ITEM and costs nothing in the epilogue: a ninth k-step multiplies an extra operand column
 //            (c|u| per user row, |i| per item row, both rounded up to tf32) so the accumulator holds the UPPER bound
 //            w_ui = s~_ui + m_ui directly.  An item is kept iff w_ui >= L_u, L_u = the K-th largest LOWER bound
@@ -40,7 +40,17 @@ constexpr int kTcPruneQ = kTcCap / 32;   // list entries per lane in the warp-co
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
 constexpr uint32_t kAugTile = 128 * 32;   // bytes of one [128 rows x 32 B] margin operand (32-byte swizzle atoms)
-constexpr float kTcMarginCoef = 1.25f * (0.001953125f + 0.0001f);
+// Both operands reach the tensor core already ROUNDED TO NEAREST tf32 (cvt.rna: the item table as a rounded copy written by
+// item_norm_kernel, the user tile rounded by its loader), so the unit reads them exactly: per element |delta| <= 2^-11, per product
+// <= 2^-10 + 2^-22, per score <= (2^-10 + 2^-22) sum_k |u_k i_k| <= (2^-10 + 2^-22) |u||i|, plus the fp32 accumulation of 65 terms
+// (<= 65 * 2^-24 |u||i| = 3.9e-6).  3 % slack on top.  (Round 1 let the hardware truncate: 2^-9, and the candidate lists of a trained
+// table carried ~35 entries through every prune.)
+constexpr float kTcMarginCoef = 1.03f * (0.0009765625f + 2.4e-7f + 3.9e-6f);
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 
 struct EvalWsTc {
     float* max_norm;
@@ -190,7 +200,9 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
             const int r = c >> 4, kc = c & 15;
             const int p = u0 + r;
             const int64_t u = (p < nu) ? users[p] : users[0];
-            cp_async16(smem_u32(sA) + sw128_offset(r, kc), Fu + (size_t)u * kTcD + kc * 4, (p < nu) ? 16 : 0);
+            float4 v = (p < nu) ? __ldg(reinterpret_cast<const float4*>(Fu + (size_t)u * kTcD + kc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+            *reinterpret_cast<float4*>(sA + sw128_offset(r, kc)) = v;
         }
         // margin operand of the user tile: row r = [c|u_r|, 0, 0, 0 | c|u_r|, 0, 0, 0].  Both 16-byte chunks carry the value so the
         // product with the item row [|i|, 0, ... 0] is c|u||i| whichever way the 32-byte swizzle orders the two chunks of a row.

@@ -330,8 +330,8 @@ def test_row_partitioned_step_world1_equals_fused_trainer(dev, kind, cl, use_gra
 def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
     """The tcgen05 candidate pass keeps item i for user u iff w_ui >= L_u, where w_ui = s~_ui + c|u||i| comes out of the
     accumulator (ninth k-step: margin operand).  Direct check of that operand on heavy-tailed item norms: the dumped
-    accumulators must (1) dominate the exact fp64 scores everywhere and (2) exceed the tf32-truncated product by exactly the
-    per-item margin.  Without this the exact-rank tests could not tell a silently missing margin from a working one."""
+    accumulators must (1) dominate the exact fp64 scores everywhere and (2) exceed the product of the tf32-rounded operands by
+    exactly the per-item margin (and that product must itself be within the bound of the exact score).  Without this the exact-rank tests could not tell a silently missing margin from a working one."""
     import ctypes as C
     from idgrec import _lib
     l = _lib.lib()
@@ -353,10 +353,12 @@ def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
     assert np.isfinite(w).all()
     exact = O.scores_fp64_sequential(Fu[users], Fi[:128])
     assert (w >= exact).all(), "an accumulator is below the exact score: the upper bound does not hold"
-    tf = lambda a: (a.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
+    # cvt.rna.tf32: round to nearest (ties away) on the 13 dropped mantissa bits -- what both operands go through before the MMA
+    tf = lambda a: ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
     approx = tf(Fu[users].copy()) @ tf(Fi[:128].copy()).T
     nu_, ni_ = np.linalg.norm(Fu[users].astype(np.float64), axis=1), np.linalg.norm(Fi[:128].astype(np.float64), axis=1)
-    margin = 1.25 * (2.0 ** -9 + 1e-4) * nu_[:, None] * ni_[None, :]
+    margin = 1.03 * (2.0 ** -10 + 2.4e-7 + 3.9e-6) * nu_[:, None] * ni_[None, :]
+    assert (np.abs(approx - exact) <= margin / 1.03 + 1e-30).all(), "the rounded-operand product is further from the exact score than the bound"
     got = w - approx
     assert np.all(np.abs(got - margin) <= 0.01 * margin + 8e-6 * nu_[:, None] * ni_[None, :] + 1e-30), float(np.abs(got - margin).max())
     assert np.all(got[:, 3] == 0.0)
