@@ -36,7 +36,8 @@ constexpr uint32_t kTcTmemCols = kTcBufs * 128;
 // trades prune count against appends through a stale threshold: 128 / 160 was measured and is 2x SLOWER than 48 / 80 (18 vs 9.6 ms
 // after three epochs of training, when ~35 entries survive each prune because of the margin band at the top of the ranking).
 constexpr int kTcCap = 80, kTcTrig = 48, kTcCandOut = 64;
-constexpr int kTcPruneQ = kTcCap / 32;   // list entries per lane in the warp-cooperative prune
+constexpr int kTcPruneQ = (kTcCap + 31) / 32;   // list entries per lane in the warp-cooperative prune (80 -> 3)
+static_assert(kTcPruneQ * 32 >= kTcCap && kTcCap >= kTcTrig + 32, "the prune must see the whole list; a chunk appends up to 32 entries");
 constexpr int kTcLoaders = 64;
 constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swizzle-atom column
 constexpr uint32_t kAugTile = 128 * 32;   // bytes of one [128 rows x 32 B] margin operand (32-byte swizzle atoms)
