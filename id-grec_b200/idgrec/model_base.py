@@ -44,6 +44,8 @@ def validate_config(kind, config, dataset):
         problems.append("top_K has %d cut-offs: the metric kernel takes at most 8 per evaluation" % len(topk))
     elif max(topk) > dataset.num_items:
         problems.append("top_K = %s exceeds the number of items (%d)" % (topk, dataset.num_items))
+    elif max(topk) > 256:
+        problems.append("top_K = %s: the ranking kernels keep at most 256 entries per user" % (topk,))
     if problems:
         raise ValueError("configuration outside the accelerated path of %s:\n  - %s" % (kind, "\n  - ".join(problems)))
 
