@@ -22,8 +22,8 @@
 
 namespace idg {
 
-// csrc/eval_tc.cu: the same candidate pass on tcgen05 tensor cores (d = 64)
-int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
+// csrc/eval_tc.cu: the same candidate pass on tcgen05 tensor cores (d = 64, and d = 256 for NGCF's concatenated layers)
+int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, int d, const int32_t* mptr, const int32_t* mind, const int64_t* users,
                               int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
                               float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream);
 constexpr int kTcListCap = 80;  // == kTcCap in eval_tc.cu
@@ -43,13 +43,13 @@ struct EvalWs {
     float* tc_ls;      // [ceil(nu/128)*128, kTcListCap] tensor-core pass: per-row candidate lists
     int* tc_li;
     float* tc_aug;     // [I, 8] margin operand of the tensor-core pass: column 0 = |i| rounded up to tf32
-    float* tc_fir;     // [I, 64] item table rounded to nearest tf32 (what the tensor core reads through TMA)
+    float* tc_fir;     // [I, d] item table rounded to nearest tf32 (what the tensor core reads through TMA)
     void* part;        // per-slice top-K lists of the exact pass (eval_exact_part_bytes)
 };
 
 __host__ __device__ inline size_t ev_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
-__host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
+__host__ inline EvalWs eval_carve(void* ws, int nu, int I, int d) {
     char* p = (char*)ws;
     EvalWs w;
     w.max_norm = (float*)p; p += 256;
@@ -61,7 +61,7 @@ __host__ inline EvalWs eval_carve(void* ws, int nu, int I) {
     w.tc_ls = (float*)p; p += ev_align(sizeof(float) * nup * kTcListCap);
     w.tc_li = (int*)p; p += ev_align(sizeof(int) * nup * kTcListCap);
     w.tc_aug = (float*)p; p += ev_align(sizeof(float) * 8 * (size_t)I);
-    w.tc_fir = (float*)p; p += ev_align(sizeof(float) * 64 * (size_t)I);
+    w.tc_fir = (float*)p; p += ev_align(sizeof(float) * (size_t)(d == 256 ? 256 : 64) * (size_t)I);
     w.part = (void*)p;
     return w;
 }
@@ -409,7 +409,7 @@ extern "C" int64_t idg_eval_workspace_bytes(int32_t nu, int32_t I, int32_t d, in
     const size_t metrics = ev_align(sizeof(double) * (size_t)nu * 3 * 8);
     const size_t nup = ((size_t)nu + 127) / 128 * 128;
     const size_t sel = 512 + 2 * ev_align(sizeof(int) * (size_t)nu) + ev_align(sizeof(int) * (size_t)nu * kCandOut) +
-                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) + ev_align(sizeof(float) * 8 * (size_t)I) + ev_align(sizeof(float) * 64 * (size_t)I) +
+                       ev_align(sizeof(float) * nup * kTcListCap) + ev_align(sizeof(int) * nup * kTcListCap) + ev_align(sizeof(float) * 8 * (size_t)I) + ev_align(sizeof(float) * (size_t)(d == 256 ? 256 : 64) * (size_t)I) +
                        ev_align(eval_exact_part_bytes(nu, K > 0 ? K : 1));
     return (int64_t)(sel > metrics ? sel : metrics);
 }
@@ -422,7 +422,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
     if (K < 1 || K > I) return fail(-1, "idg_eval_topk: K must be in [1, I] (%s%lld)", "", K);
     if (d < 1) return fail(-1, "idg_eval_topk: d must be positive (%s%lld)", "", d);
     cudaStream_t stream = (cudaStream_t)stream_;
-    EvalWs w = eval_carve(d_ws, nu, I);
+    EvalWs w = eval_carve(d_ws, nu, I, d);
     IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
     if (K > 48 || (d != 32 && d != 64 && d != 128 && d != 256)) {
         // reference-legal but outside the tiled kernels (any embedding_size / top_K parses in the reference): exact
@@ -431,14 +431,15 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
         IDG_LAUNCH_CHECK("eval_flag_all_kernel");
         return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
     }
-    static const bool use_tc = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
-    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, (d == 64 && use_tc) ? w.tc_aug : nullptr, (d == 64 && use_tc) ? w.tc_fir : nullptr);
+    static const bool tc_on = !(getenv("IDG_EVAL_IMPL") && strcmp(getenv("IDG_EVAL_IMPL"), "fma") == 0);
+    const bool use_tc = tc_on && (d == 64 || d == 256);   // tcgen05 pass: LightGCN-family width and NGCF's concatenated 256
+    item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, use_tc ? w.tc_aug : nullptr, use_tc ? w.tc_fir : nullptr);
     IDG_LAUNCH_CHECK("item_norm_kernel");
     const size_t smem = sizeof(float) * ((size_t)d * (kTU + kTI) + (size_t)kTU * kCap) + sizeof(int) * (size_t)kTU * kCap + sizeof(float) * 2 * kTU + sizeof(int) * 2 * kTU;
     const unsigned grid = (unsigned)((nu + kTU - 1) / kTU);
     // IDG_EVAL_IMPL=fma selects the CUDA-core candidate pass (kept as a cross-check of the tensor-core one)
-    if (d == 64 && use_tc) {
-        if (int rc = launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
+    if (use_tc) {
+        if (int rc = launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d, d_mask_indptr, d_mask_indices, d_users, nu, K, w.max_norm, w.flag_cnt,
                                                w.flag_list, w.cand_cnt, w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, nullptr, stream))
             return rc;
     } else if (d == 64) {
@@ -454,7 +455,7 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
         IDG_CUDA(cudaFuncSetAttribute(eval_candidates_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         eval_candidates_kernel<256><<<grid, 256, smem, stream>>>(d_Fu, d_Fi, I, d_mask_indptr, d_mask_indices, d_users, nu, K, w);
     }
-    if (!(d == 64 && use_tc)) IDG_LAUNCH_CHECK("eval_candidates_kernel");
+    if (!use_tc) IDG_LAUNCH_CHECK("eval_candidates_kernel");
     eval_rescore_kernel<<<(nu + 7) / 8, 256, 0, stream>>>(d_Fu, d_Fi, d, d_users, nu, K, w, d_out_ids, d_out_scores);
     IDG_LAUNCH_CHECK("eval_rescore_kernel");
     return launch_eval_exact(d_Fu, d_Fi, I, d, d_mask_indptr, d_mask_indices, d_users, K, w.flag_cnt, w.flag_list, w.part, d_out_ids, d_out_scores, stream);
@@ -466,13 +467,13 @@ extern "C" int idg_eval_topk(const float* d_Fu, const float* d_Fi, int32_t U, in
 extern "C" int idg_eval_tc_bounds(const float* d_Fu, const float* d_Fi, int32_t U, int32_t I, int32_t d, const int32_t* d_mask_indptr,
                                   const int32_t* d_mask_indices, const int64_t* d_users, int32_t nu, float* d_out_tile, void* d_ws, void* stream_) {
     if (!d_Fu || !d_Fi || !d_mask_indptr || !d_users || !d_out_tile || !d_ws) return fail(-1, "idg_eval_tc_bounds: null argument%s");
-    if (d != 64 || nu <= 0 || nu > 128 || I <= 0 || U <= 0) return fail(-1, "idg_eval_tc_bounds: needs d = 64 and 1 <= nu <= 128%s");
+    if ((d != 64 && d != 256) || nu <= 0 || nu > 128 || I <= 0 || U <= 0) return fail(-1, "idg_eval_tc_bounds: needs d = 64 or 256 and 1 <= nu <= 128%s");
     cudaStream_t stream = (cudaStream_t)stream_;
-    EvalWs w = eval_carve(d_ws, nu, I);
+    EvalWs w = eval_carve(d_ws, nu, I, d);
     IDG_CUDA(cudaMemsetAsync(d_ws, 0, 512, stream));
     item_norm_kernel<<<(I + 7) / 8, 256, 0, stream>>>(d_Fi, I, d, w.max_norm, w.tc_aug, w.tc_fir);
     IDG_LAUNCH_CHECK("item_norm_kernel");
-    return launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d_mask_indptr, d_mask_indices, d_users, nu, 1, w.max_norm, w.flag_cnt, w.flag_list, w.cand_cnt,
+    return launch_eval_candidates_tc(d_Fu, w.tc_fir, I, d, d_mask_indptr, d_mask_indices, d_users, nu, 1, w.max_norm, w.flag_cnt, w.flag_list, w.cand_cnt,
                                      w.cand_ids, w.tc_ls, w.tc_li, w.tc_aug, d_out_tile, stream);
 }
 

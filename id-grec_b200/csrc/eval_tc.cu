@@ -6,7 +6,7 @@
 //
 //   scores:  S[128 users, 128 items] = Fu_tile . Fi_tile^T, d = 64, one tcgen05.mma.kind::tf32 chain
 //            (8 instructions of K = 8) per item tile, accumulators in TMEM (4 buffers x 128 columns).
-//            operands are rounded to nearest tf32 before the unit sees them: |s~ - s| <= m_ui = c * |u||i|, c ~ 1.01e-3 (kTcMarginCoef).
+//            operands are rounded to nearest tf32 before the unit sees them: |s~ - s| <= m_ui = c * |u||i|, c ~ 1.01e-3 (tc_margin_coef).
 //            The margin is PER ITEM and costs nothing in the epilogue: a ninth k-step multiplies an extra operand column
 //            (c|u| per user row, |i| per item row, both rounded up to tf32) so the accumulator holds the UPPER bound
 //            w_ui = s~_ui + m_ui directly.  An item is kept iff w_ui >= L_u, L_u = the K-th largest LOWER bound
@@ -29,7 +29,7 @@
 
 namespace idg {
 
-constexpr int kTcM = 128, kTcN = 128, kTcD = 64;
+constexpr int kTcM = 128, kTcN = 128;
 constexpr int kTcStages = 2, kTcBufs = 2;   // per CTA; two CTAs share an SM (2 x 97 KB smem, 2 x 256 TMEM columns)
 constexpr uint32_t kTcTmemCols = kTcBufs * 128;
 // per-row candidate list (in L2): pruned when it exceeds kTcTrig entries.  The filter threshold only moves at a prune, so the trigger
@@ -43,10 +43,10 @@ constexpr uint32_t kSubTile = 128 * 128;  // bytes of one [128 rows x 128 B] swi
 constexpr uint32_t kAugTile = 128 * 32;   // bytes of one [128 rows x 32 B] margin operand (32-byte swizzle atoms)
 // Both operands reach the tensor core already ROUNDED TO NEAREST tf32 (cvt.rna: the item table as a rounded copy written by
 // item_norm_kernel, the user tile rounded by its loader), so the unit reads them exactly: per element |delta| <= 2^-11, per product
-// <= 2^-10 + 2^-22, per score <= (2^-10 + 2^-22) sum_k |u_k i_k| <= (2^-10 + 2^-22) |u||i|, plus the fp32 accumulation of 65 terms
-// (<= 65 * 2^-24 |u||i| = 3.9e-6).  3 % slack on top.  (Round 1 let the hardware truncate: 2^-9, and the candidate lists of a trained
-// table carried ~35 entries through every prune.)
-constexpr float kTcMarginCoef = 1.03f * (0.0009765625f + 2.4e-7f + 3.9e-6f);
+// <= 2^-10 + 2^-22, per score <= (2^-10 + 2^-22) sum_k |u_k i_k| <= (2^-10 + 2^-22) |u||i|, plus the fp32 accumulation of D + 1 terms
+// (<= (D + 1) * 2^-24 |u||i|: 3.9e-6 at D = 64, 1.54e-5 at D = 256).  3 % slack on top.  (Round 1 let the hardware truncate: 2^-9, and
+// the candidate lists of a trained table carried ~35 entries through every prune.)
+template <int D> __host__ __device__ constexpr float tc_margin_coef() { return 1.03f * (0.0009765625f + 2.4e-7f + (D == 64 ? 3.9e-6f : 1.54e-5f)); }
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -69,10 +69,11 @@ struct EvalWsTc {
 __device__ __forceinline__ float tf32_ceil(float x) { return __uint_as_float((__float_as_uint(x) + 0x1fffu) & 0xffffe000u); }
 
 // c|u| of one user row, rounded up to tf32; the loader (operand) and the epilogue (lower bounds) must agree bit for bit
+template <int D>
 __device__ __forceinline__ float tc_user_coef(const float* __restrict__ urow) {
     float ss = 0.f;
-    for (int k = 0; k < kTcD; ++k) { const float v = __ldg(urow + k); ss = fmaf(v, v, ss); }
-    return tf32_ceil(kTcMarginCoef * sqrtf(ss) + 1e-30f);
+    for (int k = 0; k < D; ++k) { const float v = __ldg(urow + k); ss = fmaf(v, v, ss); }
+    return tf32_ceil(tc_margin_coef<D>() * sqrtf(ss) + 1e-30f);
 }
 
 // smem byte offset of the 16-byte chunk kc (0..15) of row r inside an operand tile [128 rows x 64 fp32]
@@ -132,14 +133,19 @@ __device__ __forceinline__ void tc_prune(float* ls, int* li, int m, float c2, co
     new_cnt = kept; new_tau = tau;
 }
 
-__global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
+// D = 64: the whole K extent is one 64-wide chunk per item tile, two CTAs per SM.  D = 256 (NGCF's concatenated layers,
+// models/NGCF.py:108,132-138): the user tile (128 KB) stays resident and each item tile streams through the stage ring as four
+// 64-wide k-chunks accumulating in the same TMEM buffer; one CTA per SM.  The margin operand rides with the LAST chunk of a tile.
+template <int D>
+__global__ void __launch_bounds__(256, (D == 64) ? 2 : 1) eval_candidates_tc_kernel(const float* __restrict__ Fu, const float* __restrict__ Fi, int I,
                                                                     const int32_t* __restrict__ mptr, const int32_t* __restrict__ mind,
                                                                     const int64_t* __restrict__ users, int nu, int K, EvalWsTc w,
                                                                     const __grid_constant__ CUtensorMap tmap_items,
                                                                     const __grid_constant__ CUtensorMap tmap_aug) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* sA = smem;                                        // 32 KB
-    unsigned char* sB = smem + 2 * kSubTile;                         // kTcStages x 32 KB
+    constexpr int NCH = D / 64;                                      // k-chunks of 64 floats per item tile
+    unsigned char* sA = smem;                                        // D / 32 sub-tiles of 16 KB (32 KB at D = 64, 128 KB at D = 256)
+    unsigned char* sB = smem + (D / 32) * kSubTile;                  // kTcStages x 32 KB: one k-chunk of one item tile per stage
     unsigned char* sAaug = sB + kTcStages * 2 * kSubTile;            // 4 KB: c|u| per user row (32-byte swizzle layout)
     unsigned char* sBaug = sAaug + kAugTile;                         // kTcStages x 4 KB: |i| per item row, by TMA
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBaug + kTcStages * kAugTile);
@@ -177,19 +183,24 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
             const uint32_t idesc = umma_idesc_tf32(kTcM, kTcN);
             mbar_wait(afull, 0);
             for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kTcStages, b = t % kTcBufs;
-                mbar_wait(full + s, (t / kTcStages) & 1);
+                const int b = t % kTcBufs;
                 mbar_wait(tempty + b, ((t / kTcBufs) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * 2 * kSubTile);
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int it = t * NCH + ch, s = it % kTcStages;
+                    mbar_wait(full + s, (it / kTcStages) & 1);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA) + (uint32_t)(2 * ch) * kSubTile, b0 = smem_u32(sB + (size_t)s * 2 * kSubTile);
 #pragma unroll
-                for (int k = 0; k < kTcD / 8; ++k) {
-                    const uint32_t koff = (uint32_t)(k >> 2) * kSubTile + (uint32_t)(k & 3) * 32u;
-                    umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc(a0 + koff), umma_desc(b0 + koff), idesc, k > 0);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t koff = (uint32_t)(k >> 2) * kSubTile + (uint32_t)(k & 3) * 32u;
+                        umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc(a0 + koff), umma_desc(b0 + koff), idesc, (ch | k) != 0);
+                    }
+                    // margin k-step after the last chunk: + c|u| * |i|  (operands in 32-byte-swizzle K-major atoms)
+                    if (ch == NCH - 1)
+                        umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc_sw32(smem_u32(sAaug)), umma_desc_sw32(smem_u32(sBaug + (size_t)s * kAugTile)), idesc, 1);
+                    umma_commit(empty + s);
                 }
-                // margin k-step: + c|u| * |i|  (operands in 32-byte-swizzle K-major atoms)
-                umma_tf32(tmem_base + (uint32_t)b * kTcN, umma_desc_sw32(smem_u32(sAaug)), umma_desc_sw32(smem_u32(sBaug + (size_t)s * kAugTile)), idesc, 1);
-                umma_commit(empty + s);
                 umma_commit(tfull + b);
             }
         }
@@ -197,11 +208,11 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         // ===================== operand loaders =====================
         const int lt = tid - 64;  // 0..63
         // A: the CTA's 128 user rows (gathered through users[]), once
-        for (int c = lt; c < kTcM * 16; c += kTcLoaders) {
-            const int r = c >> 4, kc = c & 15;
+        for (int c = lt; c < kTcM * (D / 4); c += kTcLoaders) {
+            const int r = c / (D / 4), kc = c % (D / 4);
             const int p = u0 + r;
             const int64_t u = (p < nu) ? users[p] : users[0];
-            float4 v = (p < nu) ? __ldg(reinterpret_cast<const float4*>(Fu + (size_t)u * kTcD + kc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v = (p < nu) ? __ldg(reinterpret_cast<const float4*>(Fu + (size_t)u * D + kc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             v = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
             *reinterpret_cast<float4*>(sA + sw128_offset(r, kc)) = v;
         }
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         // product with the item row [|i|, 0, ... 0] is c|u||i| whichever way the 32-byte swizzle orders the two chunks of a row.
         for (int r = lt; r < kTcM; r += kTcLoaders) {
             const int p = u0 + r;
-            const float cu = (p < nu) ? tc_user_coef(Fu + (size_t)users[p] * kTcD) : 0.f;
+            const float cu = (p < nu) ? tc_user_coef<D>(Fu + (size_t)users[p] * D) : 0.f;
             float4* dst = reinterpret_cast<float4*>(sAaug + (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 32);
             dst[0] = make_float4(cu, 0.f, 0.f, 0.f);
             dst[1] = make_float4(cu, 0.f, 0.f, 0.f);
@@ -223,14 +234,15 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         if (lt == 0) {
             tma_prefetch_desc(&tmap_items);
             tma_prefetch_desc(&tmap_aug);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kTcStages;
-                mbar_wait(empty + s, ((t / kTcStages) & 1) ^ 1);
+            for (int it = 0; it < ntiles * NCH; ++it) {
+                const int t = it / NCH, ch = it % NCH, s = it % kTcStages;
+                mbar_wait(empty + s, ((it / kTcStages) & 1) ^ 1);
                 const uint32_t dst = smem_u32(sB + (size_t)s * 2 * kSubTile);
-                mbar_arrive_expect_tx(full + s, 2 * kSubTile + kAugTile);
-                tma_load_2d(dst, &tmap_items, 0, t * kTcN, full + s);
-                tma_load_2d(dst + kSubTile, &tmap_items, 32, t * kTcN, full + s);
-                tma_load_2d(smem_u32(sBaug + (size_t)s * kAugTile), &tmap_aug, 0, t * kTcN, full + s);
+                const bool last = ch == NCH - 1;   // the margin operand of the tile travels with its last k-chunk (same stage, same barrier)
+                mbar_arrive_expect_tx(full + s, 2 * kSubTile + (last ? kAugTile : 0u));
+                tma_load_2d(dst, &tmap_items, ch * 64, t * kTcN, full + s);
+                tma_load_2d(dst + kSubTile, &tmap_items, ch * 64 + 32, t * kTcN, full + s);
+                if (last) tma_load_2d(smem_u32(sBaug + (size_t)s * kAugTile), &tmap_aug, 0, t * kTcN, full + s);
             }
         }
     } else if (warp >= 4) {
@@ -240,9 +252,9 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
         const int p = u0 + row;
         const bool valid = p < nu;
         const int u = valid ? (int)users[p] : 0;
-        // tf32 operand truncation: |err| <= (2*2^-10 + 2^-20)|u||i| plus fp32 accumulation; 1.25x slack (kTcMarginCoef).
+        // tf32 operand truncation: |err| <= (2*2^-10 + 2^-20)|u||i| plus fp32 accumulation (tc_margin_coef).
         // The accumulator already holds s~ + c|u||i|; lower bound of an entry = w - 2 c|u||i|.
-        const float delta2 = valid ? 2.f * tc_user_coef(Fu + (size_t)u * kTcD) : 0.f;
+        const float delta2 = valid ? 2.f * tc_user_coef<D>(Fu + (size_t)u * D) : 0.f;
         float tau = valid ? -3.0e38f : INFINITY;  // finite: masked scores (-inf) never pass
         int cnt = 0, overflow = 0;
         int cur = valid ? mptr[u] : 0;
@@ -340,11 +352,10 @@ __global__ void __launch_bounds__(256, 2) eval_candidates_tc_kernel(const float*
     }
 }
 
-int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
-                              int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
-                              float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream) {
-    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids, list_s, list_i, aug, dbg_tile};
-    // tensor map of the item table [I rows x 64 fp32]: driver entry point fetched through the runtime (no libcuda link)
+template <int D>
+static int launch_eval_candidates_tc_d(const float* Fu, const float* Fi, int I, const int32_t* mptr, const int32_t* mind, const int64_t* users,
+                                       int nu, int K, const EvalWsTc& w, cudaStream_t stream) {
+    // tensor map of the (rounded) item table [I rows x D fp32]: driver entry point fetched through the runtime (no libcuda link)
     static PFN_cuTensorMapEncodeTiled encode = nullptr;
     if (!encode) {
         cudaDriverEntryPointQueryResult qres;
@@ -354,8 +365,8 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
         encode = (PFN_cuTensorMapEncodeTiled)fn;
     }
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)kTcD, (cuuint64_t)I};
-    const cuuint64_t gstride[1] = {(cuuint64_t)kTcD * sizeof(float)};
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)I};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
     const cuuint32_t box[2] = {32, (cuuint32_t)kTcN};
     const cuuint32_t estride[2] = {1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Fi), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -366,14 +377,24 @@ int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, const int
     const cuuint64_t gdim2[2] = {8, (cuuint64_t)I};
     const cuuint64_t gstride2[1] = {8 * sizeof(float)};
     const cuuint32_t box2[2] = {8, (cuuint32_t)kTcN};
-    const CUresult cr2 = encode(&tmap_aug, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(aug), gdim2, gstride2, box2, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult cr2 = encode(&tmap_aug, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w.aug), gdim2, gstride2, box2, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr2 != CUDA_SUCCESS) return fail(-1, "cuTensorMapEncodeTiled (margin operand) failed (%s%lld)", "", (long long)cr2);
-    const size_t smem = 2 * kSubTile + (size_t)kTcStages * 2 * kSubTile + (1 + kTcStages) * (size_t)kAugTile + sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
-    IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    eval_candidates_tc_kernel<<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap, tmap_aug);
+    const size_t smem = (size_t)(D / 32) * kSubTile + (size_t)kTcStages * 2 * kSubTile + (1 + kTcStages) * (size_t)kAugTile +
+                        sizeof(uint64_t) * (2 * kTcStages + 2 * kTcBufs + 1) + 16;
+    IDG_CUDA(cudaFuncSetAttribute(eval_candidates_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    eval_candidates_tc_kernel<D><<<(unsigned)((nu + kTcM - 1) / kTcM), 256, smem, stream>>>(Fu, Fi, I, mptr, mind, users, nu, K, w, tmap, tmap_aug);
     IDG_LAUNCH_CHECK("eval_candidates_tc_kernel");
     return 0;
+}
+
+int launch_eval_candidates_tc(const float* Fu, const float* Fi, int I, int d, const int32_t* mptr, const int32_t* mind, const int64_t* users,
+                              int nu, int K, float* max_norm, int* flag_cnt, int* flag_list, int* cand_cnt, int* cand_ids,
+                              float* list_s, int* list_i, const float* aug, float* dbg_tile, cudaStream_t stream) {
+    EvalWsTc w{max_norm, flag_cnt, flag_list, cand_cnt, cand_ids, list_s, list_i, aug, dbg_tile};
+    if (d == 64) return launch_eval_candidates_tc_d<64>(Fu, Fi, I, mptr, mind, users, nu, K, w, stream);
+    if (d == 256) return launch_eval_candidates_tc_d<256>(Fu, Fi, I, mptr, mind, users, nu, K, w, stream);
+    return fail(-1, "eval_candidates_tc: d must be 64 or 256 (%s%lld)", "", d);
 }
 
 }  // namespace idg

@@ -327,7 +327,8 @@ def test_row_partitioned_step_world1_equals_fused_trainer(dev, kind, cl, use_gra
 
 
 # ---------------------------------------------------------------- tensor-core candidate pass: per-item upper bounds
-def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
+@pytest.mark.parametrize("d", [64, 256])
+def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev, d):
     """The tcgen05 candidate pass keeps item i for user u iff w_ui >= L_u, where w_ui = s~_ui + c|u||i| comes out of the
     accumulator (ninth k-step: margin operand).  Direct check of that operand on heavy-tailed item norms: the dumped
     accumulators must (1) dominate the exact fp64 scores everywhere and (2) exceed the product of the tf32-rounded operands by
@@ -335,7 +336,7 @@ def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
     import ctypes as C
     from idgrec import _lib
     l = _lib.lib()
-    U, I, d = 128, 640, 64
+    U, I = 128, 640           # d = 256 (NGCF's concatenated layers): four k-chunks per item tile, margin with the last
     gen = torch.Generator().manual_seed(17)
     Fu = (torch.randn(U, d, generator=gen) * 0.5).numpy()
     Fi = (torch.randn(I, d, generator=gen) * 0.3).numpy()
@@ -357,11 +358,32 @@ def test_tc_candidate_upper_bounds_carry_the_per_item_margin(dev):
     tf = lambda a: ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32).astype(np.float64)
     approx = tf(Fu[users].copy()) @ tf(Fi[:128].copy()).T
     nu_, ni_ = np.linalg.norm(Fu[users].astype(np.float64), axis=1), np.linalg.norm(Fi[:128].astype(np.float64), axis=1)
-    margin = 1.03 * (2.0 ** -10 + 2.4e-7 + 3.9e-6) * nu_[:, None] * ni_[None, :]
+    margin = 1.03 * (2.0 ** -10 + 2.4e-7 + (3.9e-6 if d == 64 else 1.54e-5)) * nu_[:, None] * ni_[None, :]
     assert (np.abs(approx - exact) <= margin / 1.03 + 1e-30).all(), "the rounded-operand product is further from the exact score than the bound"
     got = w - approx
     assert np.all(np.abs(got - margin) <= 0.01 * margin + 8e-6 * nu_[:, None] * ni_[None, :] + 1e-30), float(np.abs(got - margin).max())
     assert np.all(got[:, 3] == 0.0)
+
+
+@pytest.mark.parametrize("scale", [0.05, 0.3])
+def test_eval_topk_exact_rank_width_256_on_tensor_cores(dev, scale):
+    """NGCF ranks on the concatenation of its layers (models/NGCF.py:108,132-138: 64 + 64*3 = 256 columns).  That width goes
+    through the tcgen05 candidate pass too (user tile resident, item tiles as four 64-wide k-chunks): ids bit-exact against the
+    fp64 exact-rank oracle, several item tiles, a ragged last tile, duplicated rows (ties by id), heavy-tailed norms."""
+    from idgrec import ops
+    U, I, d, K = 300, 128 * 9 + 37, 256, 20
+    net = _rand_net(U, I, 9000, 256)
+    gen = torch.Generator().manual_seed(256)
+    Fu = (torch.randn(U, d, generator=gen) * scale).numpy()
+    Fi = (torch.randn(I, d, generator=gen) * scale).numpy()
+    Fi[::11] *= 4.0
+    Fi[200:215] = Fi[200]
+    users = np.arange(U, dtype=np.int64)[::-1].copy()
+    ref_ids, ref_sc = O.topk_exact(Fu, Fi, users, net.indptr, net.indices, K)
+    mp, mi = _mask(net, dev)
+    ids, sc = ops.eval_topk(torch.from_numpy(Fu).to(dev), torch.from_numpy(Fi).to(dev), torch.from_numpy(users).to(dev), mp, mi, K, want_scores=True)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids)
+    np.testing.assert_allclose(sc.cpu().numpy(), ref_sc, rtol=1e-6)
 
 
 # ---------------------------------------------------------------- NGCF: one-launch dropout draws
