@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(1024) nce_rows_kernel(NceWs w, const int* __re
     sh[threadIdx.x] = a;
     __syncthreads();
     for (int s = 512; s >= 1; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
-    if (threadIdx.x == 0 && n > 0) loss[0] += loss_scale * (sh[0] / (float)n);
+    // atomic: the user-side and item-side calls of one step run on two streams; two addends onto a zeroed slot commute exactly
+    if (threadIdx.x == 0 && n > 0) atomicAdd(loss, loss_scale * (sh[0] / (float)n));
 }
 
 // final gradients, through the normalisation, accumulated into rows idx of gV1/gV2; one warp per row

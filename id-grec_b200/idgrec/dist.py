@@ -215,6 +215,8 @@ class DistFusedTrainer:
         if contrastive:
             self.noise = torch.empty(K, N, d, dtype=torch.float32, device=dev)
             self.nce_ws = torch.empty(int(self.l.idg_infonce_workspace_bytes(max_batch, d)), dtype=torch.uint8, device=dev)
+            self.nce_ws2 = torch.empty_like(self.nce_ws)            # item-side term on a second stream (engine.py:_contrast_pair)
+            self._nce_side = torch.cuda.Stream(device=dev)
             self.V1 = z()
             self.V2 = z() if kind == "SimGCL" else None
             self.Gcl = z() if kind == "XSimGCL" else None
@@ -317,13 +319,14 @@ class DistFusedTrainer:
         Gcl = None
         if contrastive:
             self.loss[2:3].zero_()
-            for idx, cnt in ((self.uidx, self.ucnt), (self.iidx, self.icnt)):
-                if self.kind == "SimGCL":
-                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.V2), ptr(idx), ptr(cnt), B, d, self.temperature, self.ssl_lambda,
-                                                    ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s), "idg_infonce_fwd_bwd_dev")
-                else:
-                    check(l.idg_infonce_fwd_bwd_dev(ptr(cl_view), ptr(self.F), ptr(idx), ptr(cnt), B, d, self.temperature, self.ssl_lambda,
-                                                    ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s), "idg_infonce_fwd_bwd_dev")
+            Va, Vb, gA = (self.V1, self.V2, self.G) if self.kind == "SimGCL" else (cl_view, self.F, self.Gcl)
+            main = torch.cuda.current_stream()
+            self._nce_side.wait_stream(main)
+            for (idx, cnt), ws, st in (((self.iidx, self.icnt), self.nce_ws2, self._nce_side), ((self.uidx, self.ucnt), self.nce_ws, main)):
+                with torch.cuda.stream(st):     # disjoint gradient rows, separate workspaces: the two terms overlap
+                    check(l.idg_infonce_fwd_bwd_dev(ptr(Va), ptr(Vb), ptr(idx), ptr(cnt), B, d, self.temperature, self.ssl_lambda,
+                                                    ptr(self.loss[2:]), ptr(gA), ptr(self.G), ptr(ws), st.cuda_stream), "idg_infonce_fwd_bwd_dev")
+            main.wait_stream(self._nce_side)
             Gcl = self.Gcl
         self._mark('bpr')
         # backward Horner chain on the local rows: H_K = G (+cnt Gcl if cl = K); H_l = G + A H_{l+1} (+cnt Gcl if cl = l);

@@ -70,6 +70,9 @@ class FusedTrainer:
             self.noise = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev)
             self.noise_b = torch.empty(K, self.N, self.d, dtype=torch.float32, device=dev) if kind == "SimGCL" else None
             self.nce_ws = torch.empty(int(self.l.idg_infonce_workspace_bytes(max_batch, self.d)), dtype=torch.uint8, device=dev)
+            # the user-side and item-side contrast terms touch disjoint gradient rows: second workspace + stream, run concurrently
+            self.nce_ws2 = torch.empty_like(self.nce_ws)
+            self._nce_side = torch.cuda.Stream(device=dev)
             self.V1 = torch.empty_like(table)
             self.V2 = torch.empty_like(table) if kind == "SimGCL" else None
             self.Gcl = z() if kind == "XSimGCL" else None
@@ -232,6 +235,20 @@ class FusedTrainer:
                                         ptr(acc[0]), ptr(acc[1]), ptr(acc[2]), ptr(out), float(K), d, ptr(rows.rowlist), ptr(rows.count), rows.max_rows,
                                         ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
 
+    def _contrast_pair(self, uniq, B, Va, Vb, gA, gB):
+        """InfoNCE over the batch's unique users and over its unique positives (SimGCL.py:80-88, XSimGCL.py:84-92).  The two
+        terms read the same views and accumulate into disjoint rows (users < U <= items), so the item term runs on a second
+        stream with its own workspace; both add into the (zeroed) loss slot atomically -- two addends, order-free."""
+        l, main = self.l, torch.cuda.current_stream()
+        (uidx, ucnt), (iidx, icnt) = uniq
+        self._nce_side.wait_stream(main)
+        with torch.cuda.stream(self._nce_side):
+            check(l.idg_infonce_fwd_bwd_dev(ptr(Va), ptr(Vb), ptr(iidx), ptr(icnt), B, self.d, self.temperature, self.ssl_lambda,
+                                            ptr(self.loss[2:]), ptr(gA), ptr(gB), ptr(self.nce_ws2), cur_stream()), "idg_infonce_fwd_bwd_dev")
+        check(l.idg_infonce_fwd_bwd_dev(ptr(Va), ptr(Vb), ptr(uidx), ptr(ucnt), B, self.d, self.temperature, self.ssl_lambda,
+                                        ptr(self.loss[2:]), ptr(gA), ptr(gB), ptr(self.nce_ws), cur_stream()), "idg_infonce_fwd_bwd_dev")
+        main.wait_stream(self._nce_side)
+
     def _body(self, B, u, p, n, users_t=None, pos_t=None, fused=False):
         """Kernels of one step for batch pointers u/p/n (device int64).  ``fused``: Adam inside the last backward layer."""
         g, K = self.graph, self.K
@@ -294,20 +311,14 @@ class FusedTrainer:
                 self.loss[2:3].zero_()
                 # the three propagations share one linear backward operator: accumulate all row
                 # gradients into G and back-propagate once (9 backward SpMMs of the reference -> 3)
-                for idx, cnt in uniq:
-                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.V2), ptr(idx), ptr(cnt), B, self.d, self.temperature,
-                                                    self.ssl_lambda, ptr(self.loss[2:]), ptr(self.G), ptr(self.G), ptr(self.nce_ws), s),
-                          "idg_infonce_fwd_bwd_dev")
+                self._contrast_pair(uniq, B, self.V1, self.V2, self.G, self.G)
                 g.propagate_bwd(self.G, K, False, out=out, rows=rows, adam=adam)
             else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
                 self._draw_noise(0)
                 g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
                 self._bpr(B, u, p, n, fused)
                 self.loss[2:3].zero_()
-                for idx, cnt in uniq:
-                    check(l.idg_infonce_fwd_bwd_dev(ptr(self.V1), ptr(self.F), ptr(idx), ptr(cnt), B, self.d, self.temperature,
-                                                    self.ssl_lambda, ptr(self.loss[2:]), ptr(self.Gcl), ptr(self.G), ptr(self.nce_ws), s),
-                          "idg_infonce_fwd_bwd_dev")
+                self._contrast_pair(uniq, B, self.V1, self.F, self.Gcl, self.G)
                 g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=out, rows=rows, adam=adam)
                 for idx, _ in uniq:  # entries past the count are stale but valid rows of an all-zero table: harmless
                     check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), B, self.d, s), "idg_zero_rows")
