@@ -16,6 +16,8 @@
 // passes lose), tcgen05 with 2 loader warps 220 us, with 7 operand-builder warps and batched loads ~122 us (now bound by the
 // one-tile-per-CTA pipeline and the row-per-thread epilogue stores, not by the MMA).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include <curand_kernel.h>
 
 #include "idg_common.cuh"
@@ -25,6 +27,11 @@ namespace idg {
 // csrc/ngcf_tc.cu: the forward product on tcgen05 (3xTF32 split, TMEM accumulators)
 int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const float* bg, const float* Wb, const float* bb, const float* keep,
                       float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream);
+
+// csrc/ngcf_bwd_tc.cu: the backward products on tcgen05 (both contractions from one shared-memory image of dS)
+int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const float* Wb, const float* keep, float inv_keep, const float* S_pre,
+                      const float* D, const float* dO, int dO_stride, const float* dD_ext, int N, float* dside, float* dE_direct, float* dW_part,
+                      float* db_part, int max_parts, int* n_parts, cudaStream_t stream);
 
 constexpr int kNgTile = 64;     // rows per tile
 constexpr int kNgCtas = 296;    // persistent grid of the backward kernel (2 per SM)
@@ -244,12 +251,22 @@ extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const f
     cudaStream_t stream = (cudaStream_t)stream_;
     float* dW_part = (float*)d_ws;
     float* db_part = dW_part + (size_t)kNgCtas * 128 * 64;
-    const size_t smem = sizeof(float) * (kNgTile * 128 + kNgTile * 64 + 64 * 128);
-    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ngcf_dense_bwd_kernel<<<kNgCtas, 256, smem, stream>>>(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside,
-                                                          d_dE_direct, dW_part, db_part);
-    IDG_LAUNCH_CHECK("ngcf_dense_bwd_kernel");
-    ngcf_reduce_kernel<<<(128 * 64 + 64 + 63) / 64, 256, 0, stream>>>(dW_part, db_part, kNgCtas, d_dWg, d_dWb, d_db);
+    // IDG_NGCF_BWD=fma selects the CUDA-core tiles (kept as a cross-check of the tensor-core kernel)
+    static const bool use_tc = !(getenv("IDG_NGCF_BWD") && strcmp(getenv("IDG_NGCF_BWD"), "fma") == 0);
+    if (dO_stride & 3) return fail(-1, "idg_ngcf_dense_bwd: dO_stride must be a multiple of 4%s");
+    int n_parts = kNgCtas;
+    if (use_tc) {
+        if (int rc = ngcf_dense_bwd_tc(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside, d_dE_direct,
+                                       dW_part, db_part, kNgCtas, &n_parts, stream))
+            return rc;
+    } else {
+        const size_t smem = sizeof(float) * (kNgTile * 128 + kNgTile * 64 + 64 * 128);
+        IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ngcf_dense_bwd_kernel<<<kNgCtas, 256, smem, stream>>>(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N,
+                                                              d_dside, d_dE_direct, dW_part, db_part);
+        IDG_LAUNCH_CHECK("ngcf_dense_bwd_kernel");
+    }
+    ngcf_reduce_kernel<<<(128 * 64 + 64 + 63) / 64, 256, 0, stream>>>(dW_part, db_part, n_parts, d_dWg, d_dWb, d_db);
     IDG_LAUNCH_CHECK("ngcf_reduce_kernel");
     return 0;
 }
