@@ -4,197 +4,282 @@
 //   D = LeakyReLU_0.2(S) (*) keep / (1-p);   O = D / max(|D|_2, 1e-12)   (NGCF.py:98-106)
 //
 // The product is only 64 columns wide: 2.36 GFLOP against 185 MB of [N,64] streams per layer at the amazon-book shape, i.e.
-// stream-bound once it leaves the fp32 FMA pipe (the CUDA-core tiles of csrc/ngcf.cu run at 16-18 TFLOP/s = 130 us per layer;
-// the warp-level mma.sync tf32 path was measured slower than that).  tcgen05 has no fp32 input kind, so every product is the
-// 3xTF32 split  x*y ~= xh*yh + xh*yl + xl*yh  accumulated in one TMEM tile (error ~2^-21, inside the 1e-5 parity bar) -- the
-// same scheme and the same pipeline skeleton as nce_tc_gemm_kernel (csrc/infonce_tc.cu): one CTA per 128-row tile, K = 128 in
-// four chunks of 32 through a 2-stage shared-memory ring, loader warps that BUILD the operands (Z = [side | E*side] and the
-// transposed weights are split and stored in the 128B-swizzled K-major layout with plain stores + fence.proxy.async), one
-// MMA-issuing thread, four epilogue warps (thread <-> TMEM lane <-> row: bias, LeakyReLU, dropout, row norm without shuffles).
+// stream-bound once it leaves the fp32 FMA pipe (the CUDA-core tiles ran at 16-18 TFLOP/s = 130 us per layer; the warp-level
+// mma.sync tf32 path was measured slower than that).  tcgen05 has no fp32 input kind, so every product is the 3xTF32 split
+// x*y ~= xh*yh + xh*yl + xl*yh accumulated in one TMEM tile (error ~2^-21, inside the 1e-5 parity bar).
+//
+// Round 2: persistent CTAs (one per SM) instead of one tile per CTA (122 us per layer, bound by the un-overlapped
+// load -> build -> MMA -> epilogue chain and by row-per-thread epilogue stores):
+//   * Wcat^T (hi, lo) is split and laid out once per CTA and stays in shared memory (B operand, 4 k-chunks of 32).
+//   * side / E / keep arrive through a four-slot cp.async ring in 16 KB units ([128 rows x 32 columns] of one stream); a thread
+//     copies exactly the 16-byte pieces it later consumes, so the ring needs no barrier and keeps three units (48 KB per SM) in
+//     flight while earlier ones are processed.
+//   * a pair of units (side, E of one 32-column half) becomes two A chunks (k = the side half, k = 64 + the E*side half) in a
+//     two-stage ring of 128B-swizzled K-major tiles; one thread issues the MMAs; two TMEM accumulators, so the epilogue of tile
+//     t-1 runs after the operands of tile t have been handed over.
+//   * epilogue: TMEM (thread <-> row) + bias -> shared-memory tile -> 8 lanes per row: activation, dropout, row norm by shuffles,
+//     S / D / O written as full 128-byte lines.
 #include <math.h>
 
 #include "tc_common.cuh"
 
 namespace idg {
 
-constexpr int kNgLoaders = 224;           // warps 1..7 build the operands (warps 4..7 then run the epilogue)
-constexpr uint32_t kNgAtomA = 128 * 128;   // bytes: [128 rows x 128 B]  (32 k-values per row)
-constexpr uint32_t kNgAtomB = 64 * 128;    // bytes: [ 64 rows x 128 B]
-constexpr uint32_t kNgStage = 2 * kNgAtomA + 2 * kNgAtomB;   // A hi/lo + B hi/lo = 48 KB
-constexpr int kNgStages = 2;
+constexpr int kFwBuilders = 256;               // warps 1..8
+constexpr uint32_t kFwBlkA = 128 * 128;        // bytes: [128 rows x 32 fp32] A chunk (hi or lo)
+constexpr uint32_t kFwStage = 2 * kFwBlkA;     // hi | lo
+constexpr uint32_t kFwBlkB = 64 * 128;         // bytes: [64 rows x 32 fp32] B chunk
+constexpr uint32_t kFwWHalf = 4 * kFwBlkB;     // hi (or lo) of Wcat^T [64 x 128]
+constexpr uint32_t kFwUnit = 128 * 128;        // one staging slot: [128 rows x 32 fp32] of one stream
+constexpr int kFwSlots = 4, kFwAhead = 3, kFwUnits = 6;   // per iteration: side c0, E c0, side c1, E c1 (tile t), keep c0, keep c1 (tile t-1)
+constexpr uint32_t kFwTile = 128 * 256;        // epilogue tile: S + bias, [128 rows x 64 fp32]
+constexpr uint32_t kFwSmem = 2 * kFwWHalf + 2 * kFwStage + kFwSlots * kFwUnit + kFwTile;   // 64 + 64 + 64 + 32 KB
+constexpr uint32_t kFwTmemCols = 128;          // two accumulators of 64 columns
 
-__device__ __forceinline__ uint32_t ng_sw_atom(int r, int cc) {
+__device__ __forceinline__ uint32_t fw_sw(int r, int cc) {   // 128 B-row block, 128-byte swizzle: chunk cc ^ (r & 7)
     return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((cc ^ (r & 7)) << 4);
 }
-__device__ __forceinline__ void ng_st_shared4(uint32_t addr, float a, float b, float c, float d) {
+__device__ __forceinline__ void fw_st4(uint32_t addr, float a, float b, float c, float d) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+__device__ __forceinline__ float4 fw_ld4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fw_split_store(uint32_t hi_addr, uint32_t lo_addr, float4 x) {
+    float h[4], l[4];
+    split_tf32(x.x, h[0], l[0]); split_tf32(x.y, h[1], l[1]); split_tf32(x.z, h[2], l[2]); split_tf32(x.w, h[3], l[3]);
+    fw_st4(hi_addr, h[0], h[1], h[2], h[3]);
+    fw_st4(lo_addr, l[0], l[1], l[2], l[3]);
+}
 
-__global__ void __launch_bounds__(256, 2) ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
+__global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
                                                                    const float* __restrict__ Wg, const float* __restrict__ bg,
                                                                    const float* __restrict__ Wb, const float* __restrict__ bb,
                                                                    const float* __restrict__ keep, float inv_keep, int N,
                                                                    float* __restrict__ S_pre, float* __restrict__ D, float* __restrict__ out,
                                                                    int out_stride) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int S = kNgStages, kChunks = 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kNgStage);
-    uint64_t *full = bars, *empty = bars + S, *tfull = empty + S;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    unsigned char* sW = smem;                            // Wcat^T hi | lo
+    unsigned char* sA = sW + 2 * kFwWHalf;               // A ring: stage = chunk hi | lo
+    unsigned char* sG = sA + 2 * kFwStage;               // cp.async staging slots
+    unsigned char* sT = sG + kFwSlots * kFwUnit;         // epilogue tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT + kFwTile);
+    uint64_t *w_full = bars, *full = bars + 1, *empty = bars + 3, *tfull = bars + 5, *tempty = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* sBias = reinterpret_cast<float*>(bars + 10);  // [64] b_gcn + b_bi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r0 = blockIdx.x * 128;
+    const int ntiles = (N + 127) / 128;
+    const int T = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, kNgLoaders); mbar_init(empty + s, 1); }
-        mbar_init(tfull, 1);
+        mbar_init(w_full, kFwBuilders);
+        for (int s = 0; s < 2; ++s) { mbar_init(full + s, kFwBuilders); mbar_init(empty + s, 1); mbar_init(tfull + s, 1); mbar_init(tempty + s, kFwBuilders); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < 64) sBias[tid] = __ldg(bg + tid) + __ldg(bb + tid);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kFwTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t aW = smem_u32(sW), aA = smem_u32(sA), aG = smem_u32(sG), aT = smem_u32(sT);
 
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(128, 64);
-            for (int t = 0; t < kChunks; ++t) {
-                const int s = t % S;
-                mbar_wait(full + s, (t / S) & 1);
+            mbar_wait(w_full, 0);
+            tc_fence_after();
+            for (int it = 0; it < T; ++it) {
+                const int buf = it & 1;
+                mbar_wait(tempty + buf, ((it >> 1) & 1) ^ 1);      // the epilogue of tile it-2 has read this accumulator
                 tc_fence_after();
-                const uint32_t ah = smem_u32(smem + (size_t)s * kNgStage), al = ah + kNgAtomA, bh = al + kNgAtomA, bl = bh + kNgAtomB;
 #pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const uint32_t aa = (p == 2) ? al : ah, bb2 = (p == 1) ? bl : bh;
+                for (int p = 0; p < 2; ++p) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, umma_desc(aa + k * 32u), umma_desc(bb2 + k * 32u), idesc, (t | p | k) != 0);
+                    for (int st = 0; st < 2; ++st) {
+                        mbar_wait(full + st, (it * 2 + p) & 1);
+                        tc_fence_after();
+                        const int kc = st == 0 ? p : 2 + p;        // k-chunk: side half p, E*side half p
+                        const uint32_t ah = aA + (uint32_t)st * kFwStage, bh = aW + (uint32_t)kc * kFwBlkB;
+#pragma unroll
+                        for (int sp = 0; sp < 3; ++sp) {
+                            const uint32_t a = ah + (sp == 2 ? kFwBlkA : 0u), b = bh + (sp == 1 ? kFwWHalf : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                umma_tf32(tmem_base + (uint32_t)buf * 64u, umma_desc(a + ks * 32u), umma_desc(b + ks * 32u), idesc, (p | st | sp | ks) != 0);
+                        }
+                        umma_commit(empty + st);
+                    }
                 }
-                umma_commit(empty + s);
+                umma_commit(tfull + buf);
             }
-            umma_commit(tfull);
         }
     } else {
-        // operand builders (warps 1..7): chunk t covers k = 32 t .. 32 t + 31 of Z = [side | E*side] (rows) and of Wcat^T (the 64
-        // output columns).  All global loads of a chunk are issued before the first store so that they overlap.
-        const int bt = tid - 32;
-        for (int t = 0; t < kChunks; ++t) {
-            const int s = t % S;
-            const uint32_t dst = smem_u32(smem + (size_t)s * kNgStage);
-            const int k0 = (t & 1) * 32;          // column offset inside side / E
-            const bool second = t >= 2;           // chunks 2, 3: the E (*) side half
-            const float* Wsrc = second ? Wb : Wg;   // Wcat rows 0..63 = W_gcn, 64..127 = W_bi; B operand row n holds Wcat[k][n] over k
-            float4 zs[5], es[5];
-            float wv[3][4];
+        const int bt = tid - 32, urow = bt >> 3, uj = bt & 7;      // unit mapping: row urow + 32*pass, 16-byte chunk uj of the 128 B half-row
+        const int q = warp & 3, half = (warp - 1) >> 2;             // TMEM role: lane quadrant, column half
+        const uint32_t tq = tmem_base + (((uint32_t)(q * 32)) << 16);
+        // Wcat^T (hi, lo), once: B chunk kc, row n holds Wcat[32 kc .. 32 kc + 31][n]
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int c = bt + i * kNgLoaders;
-                const int r = c >> 3, cc = c & 7;
-                zs[i] = f4zero(); es[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (c < 128 * 8 && r0 + r < N) {
-                    zs[i] = ldg4(side + (size_t)(r0 + r) * 64 + k0 + cc * 4);
-                    if (second) es[i] = ldg4(E + (size_t)(r0 + r) * 64 + k0 + cc * 4);
-                }
+        for (int i = 0; i < 8; ++i) {
+            const int idx = bt + i * kFwBuilders;       // 64 columns n x 32 k-quads
+            const int n = idx & 63, kq = idx >> 6;
+            float wv[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int k = kq * 4 + jj;
+                wv[jj] = __ldg((k < 64 ? Wg + (size_t)k * 64 : Wb + (size_t)(k - 64) * 64) + n);
             }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int c = bt + i * kNgLoaders;
-                const int n = c >> 3, cc = c & 7;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wv[i][j] = (c < 64 * 8) ? __ldg(Wsrc + (size_t)(k0 + cc * 4 + j) * 64 + n) : 0.f;
-            }
-            mbar_wait(empty + s, ((t / S) & 1) ^ 1);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int c = bt + i * kNgLoaders;
-                if (c < 128 * 8) {
-                    const int r = c >> 3, cc = c & 7;
-                    const float z[4] = {zs[i].x * es[i].x, zs[i].y * es[i].y, zs[i].z * es[i].z, zs[i].w * es[i].w};
-                    float h[4], l[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) split_tf32(z[j], h[j], l[j]);
-                    const uint32_t o = ng_sw_atom(r, cc);
-                    ng_st_shared4(dst + o, h[0], h[1], h[2], h[3]);
-                    ng_st_shared4(dst + kNgAtomA + o, l[0], l[1], l[2], l[3]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int c = bt + i * kNgLoaders;
-                if (c < 64 * 8) {
-                    const int n = c >> 3, cc = c & 7;
-                    float h[4], l[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) split_tf32(wv[i][j], h[j], l[j]);
-                    const uint32_t o = ng_sw_atom(n, cc);
-                    ng_st_shared4(dst + 2 * kNgAtomA + o, h[0], h[1], h[2], h[3]);
-                    ng_st_shared4(dst + 2 * kNgAtomA + kNgAtomB + o, l[0], l[1], l[2], l[3]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(full + s);
+            const uint32_t o = (uint32_t)(kq >> 3) * kFwBlkB + fw_sw(n, kq & 7);
+            fw_split_store(aW + o, aW + kFwWHalf + o, make_float4(wv[0], wv[1], wv[2], wv[3]));
         }
-    }
-    if (warp >= 4) {
-        const int q = warp & 3;
-        const int r = r0 + q * 32 + lane;
-        const uint32_t lane_base = ((uint32_t)(q * 32)) << 16;
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        float sv[64];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(w_full);
+
+        // flat unit index U = 6 * iteration + w; slot U & 3; one commit group per unit, even when empty
+        auto issue = [&](int U) {
+            const int it_u = U / kFwUnits, w = U - it_u * kFwUnits;
+            const float* src = nullptr;
+            int tt = 0, col0 = 0;
+            if (w < 4) { if (it_u < T) { src = (w & 1) ? E : side; tt = (int)blockIdx.x + it_u * (int)gridDim.x; col0 = (w >> 1) * 32; } }
+            else if (keep && it_u >= 1 && it_u <= T) { src = keep; tt = (int)blockIdx.x + (it_u - 1) * (int)gridDim.x; col0 = (w - 4) * 32; }
+            if (src) {
+                const uint32_t dst = aG + (uint32_t)(U & 3) * kFwUnit + (uint32_t)bt * 16u;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + lane_base + (uint32_t)(c * 32), raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sv[c * 32 + j] = __uint_as_float(raw[j]);
-        }
-        if (r < N) {
-            float ss = 0.f;
-            float* ps = S_pre + (size_t)r * 64;
-            float* pd = D + (size_t)r * 64;
-            float* po = out + (size_t)r * out_stride;
-#pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4) {
-                const float4 b1 = ldg4(bg + j4 * 4), b2 = ldg4(bb + j4 * 4);
-                float4 kp = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (keep) kp = ldg4(keep + (size_t)r * 64 + j4 * 4);
-                const float bias[4] = {b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w}, kv[4] = {kp.x, kp.y, kp.z, kp.w};
-                float s4[4], d4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    s4[j] = sv[j4 * 4 + j] + bias[j];
-                    const float act = s4[j] > 0.f ? s4[j] : 0.2f * s4[j];
-                    d4[j] = keep ? act * kv[j] * inv_keep : act;
-                    ss = fmaf(d4[j], d4[j], ss);
-                    sv[j4 * 4 + j] = d4[j];
+                for (int ps = 0; ps < 4; ++ps) {
+                    const int r = tt * 128 + ps * 32 + urow;
+                    cp_async16(dst + (uint32_t)ps * 4096u, src + (size_t)(r < N ? r : 0) * 64 + col0 + uj * 4, r < N ? 16 : 0);
                 }
-                st4(ps + j4 * 4, make_float4(s4[0], s4[1], s4[2], s4[3]));
-                st4(pd + j4 * 4, make_float4(d4[0], d4[1], d4[2], d4[3]));
             }
-            const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // unit U has landed (three younger units stay in flight); returns this thread's first piece in its slot
+        auto get = [&](int U) -> uint32_t {
+            issue(U + kFwAhead);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kFwAhead) : "memory");
+            return aG + (uint32_t)(U & 3) * kFwUnit + (uint32_t)bt * 16u;
+        };
 #pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4)
-                st4(po + j4 * 4, make_float4(sv[j4 * 4] / nrm, sv[j4 * 4 + 1] / nrm, sv[j4 * 4 + 2] / nrm, sv[j4 * 4 + 3] / nrm));
+        for (int w = 0; w < kFwAhead; ++w) issue(w);
+
+        for (int it = 0; it <= T; ++it) {
+            const int U0 = it * kFwUnits;
+            // ---- operands of tile it: two pairs of units -> two A chunks each
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                float4 sd[4], e[4];
+                const uint32_t s0 = get(U0 + 2 * p);
+                if (it < T) {
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) sd[ps] = fw_ld4(s0 + (uint32_t)ps * 4096u);
+                }
+                const uint32_t s1 = get(U0 + 2 * p + 1);
+                if (it < T) {
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) e[ps] = fw_ld4(s1 + (uint32_t)ps * 4096u);
+                    const int n = it * 2 + p;
+                    mbar_wait(empty + 0, (n & 1) ^ 1);
+                    mbar_wait(empty + 1, (n & 1) ^ 1);
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) {
+                        const uint32_t o = fw_sw(ps * 32 + urow, uj);
+                        fw_split_store(aA + o, aA + kFwBlkA + o, sd[ps]);
+                        fw_split_store(aA + kFwStage + o, aA + kFwStage + kFwBlkA + o,
+                                       make_float4(e[ps].x * sd[ps].x, e[ps].y * sd[ps].y, e[ps].z * sd[ps].z, e[ps].w * sd[ps].w));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(full + 0);
+                    mbar_arrive(full + 1);
+                }
+            }
+            // ---- epilogue of tile it-1
+            float4 k0[4], k1[4];
+            const uint32_t g0 = get(U0 + 4);
+            if (keep && it >= 1) {
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) k0[ps] = fw_ld4(g0 + (uint32_t)ps * 4096u);
+            }
+            const uint32_t g1 = get(U0 + 5);
+            if (keep && it >= 1) {
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) k1[ps] = fw_ld4(g1 + (uint32_t)ps * 4096u);
+            }
+            if (it >= 1) {
+                const int pt = it - 1, buf = pt & 1;
+                const int r0 = ((int)blockIdx.x + pt * (int)gridDim.x) * 128;
+                mbar_wait(tfull + buf, (pt >> 1) & 1);
+                tc_fence_after();
+                {   // thread <-> row: S + bias into the tile, 16-byte chunk index XOR row (conflict-free here and for the reads below)
+                    const int row = q * 32 + lane;
+                    uint32_t raw[32];
+                    tmem_ld32(tq + (uint32_t)(buf * 64 + half * 32), raw);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(tempty + buf);
+                    const uint32_t rb = aT + (uint32_t)row * 256u + (uint32_t)half * 128u;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sBias + half * 32 + j4 * 4);
+                        fw_st4(rb + (uint32_t)(((j4 ^ row) & 7) << 4), __uint_as_float(raw[j4 * 4]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y,
+                               __uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) {     // 8 lanes per row: columns 4 uj .. +3 and 32 + 4 uj .. +3
+                    const int rr = ps * 32 + urow, r = r0 + rr;
+                    const uint32_t o = aT + (uint32_t)rr * 256u + (uint32_t)(((uj ^ rr) & 7) << 4);
+                    const float4 sa = fw_ld4(o), sb = fw_ld4(o + 128u);
+                    const float s8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                    const float kv[8] = {k0[ps].x, k0[ps].y, k0[ps].z, k0[ps].w, k1[ps].x, k1[ps].y, k1[ps].z, k1[ps].w};
+                    float d8[8], ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float act = s8[j] > 0.f ? s8[j] : 0.2f * s8[j];
+                        d8[j] = keep ? act * kv[j] * inv_keep : act;
+                        ss = fmaf(d8[j], d8[j], ss);
+                    }
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+                    if (r < N) {
+                        if (S_pre) { st4(S_pre + (size_t)r * 64 + uj * 4, sa); st4(S_pre + (size_t)r * 64 + 32 + uj * 4, sb); }
+                        st4(D + (size_t)r * 64 + uj * 4, make_float4(d8[0], d8[1], d8[2], d8[3]));
+                        st4(D + (size_t)r * 64 + 32 + uj * 4, make_float4(d8[4], d8[5], d8[6], d8[7]));
+                        st4(out + (size_t)r * out_stride + uj * 4, make_float4(d8[0] / nrm, d8[1] / nrm, d8[2] / nrm, d8[3] / nrm));
+                        st4(out + (size_t)r * out_stride + 32 + uj * 4, make_float4(d8[4] / nrm, d8[5] / nrm, d8[6] / nrm, d8[7] / nrm));
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // the tile is free for the next epilogue
+            }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kFwTmemCols) : "memory");
     }
 }
 
-// launched by idg_ngcf_dense_fwd (csrc/ngcf.cu) for the 64-wide layers of the reference configuration
+// launched by idg_ngcf_dense_fwd (csrc/ngcf.cu) for the 64-wide layers of the reference configuration; S_pre may be null
 int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const float* bg, const float* Wb, const float* bb, const float* keep,
                       float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream) {
-    const size_t smem = (size_t)kNgStages * kNgStage + 128;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        IDG_CUDA(cudaGetDevice(&dev));
+        IDG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int ntiles = (N + 127) / 128;
+    const int grid = sms < ntiles ? sms : ntiles;
+    const size_t smem = (size_t)kFwSmem + 512;
     IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ngcf_dense_fwd_tc_kernel<<<(N + 127) / 128, 256, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, inv_keep, N, S_pre, D, out, out_stride);
+    ngcf_dense_fwd_tc_kernel<<<grid, 288, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, inv_keep, N, S_pre, D, out, out_stride);
     IDG_LAUNCH_CHECK("ngcf_dense_fwd_tc_kernel");
     return 0;
 }
