@@ -235,7 +235,8 @@ extern "C" int idg_copy_rows_strided(const float* d_src, int32_t src_stride, con
 extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
                                   const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,
                                   int32_t out_stride, void* stream) {
-    if (!d_E || !d_side || !d_Wg || !d_bg || !d_Wb || !d_bb || !d_S || !d_D || !d_out || N <= 0) return fail(-1, "idg_ngcf_dense_fwd: bad argument%s");
+    // d_S (the pre-activation) may be null: only the CUDA-core backward (IDG_NGCF_BWD=fma) reads it, the tensor-core one takes the sign off D
+    if (!d_E || !d_side || !d_Wg || !d_bg || !d_Wb || !d_bb || !d_D || !d_out || N <= 0) return fail(-1, "idg_ngcf_dense_fwd: bad argument%s");
     if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "idg_ngcf_dense_fwd: drop_p must be in [0,1)%s");
     if (out_stride & 3) return fail(-1, "idg_ngcf_dense_fwd: out_stride must be a multiple of 4%s");
     return ngcf_dense_fwd_tc(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, 1.f / (1.f - drop_p), N, d_S, d_D, d_out, out_stride, (cudaStream_t)stream);
@@ -246,7 +247,7 @@ extern "C" int64_t idg_ngcf_workspace_bytes(void) { return (int64_t)sizeof(float
 extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep, float drop_p,
                                   const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
                                   float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream_) {
-    if (!d_E || !d_side || !d_Wg || !d_Wb || !d_S || !d_D || !d_dO || !d_dside || !d_dE_direct || !d_dWg || !d_dWb || !d_db || !d_ws || N <= 0)
+    if (!d_E || !d_side || !d_Wg || !d_Wb || !d_D || !d_dO || !d_dside || !d_dE_direct || !d_dWg || !d_dWb || !d_db || !d_ws || N <= 0)
         return fail(-1, "idg_ngcf_dense_bwd: bad argument%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     float* dW_part = (float*)d_ws;
@@ -254,6 +255,7 @@ extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const f
     // IDG_NGCF_BWD=fma selects the CUDA-core tiles (kept as a cross-check of the tensor-core kernel)
     static const bool use_tc = !(getenv("IDG_NGCF_BWD") && strcmp(getenv("IDG_NGCF_BWD"), "fma") == 0);
     if (dO_stride & 3) return fail(-1, "idg_ngcf_dense_bwd: dO_stride must be a multiple of 4%s");
+    if (!use_tc && !d_S) return fail(-1, "idg_ngcf_dense_bwd: the CUDA-core kernel needs the pre-activation d_S%s");
     int n_parts = kNgCtas;
     if (use_tc) {
         if (int rc = ngcf_dense_bwd_tc(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside, d_dE_direct,

@@ -48,8 +48,15 @@ __device__ __forceinline__ float4 fw_ld4(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void fw_split_store(uint32_t hi_addr, uint32_t lo_addr, float4 x) {
-    float h[4], l[4];
-    split_tf32(x.x, h[0], l[0]); split_tf32(x.y, h[1], l[1]); split_tf32(x.z, h[2], l[2]); split_tf32(x.w, h[3], l[3]);
+    float h[4], l[4];     // hi rounded to NEAREST tf32: |lo| <= 2^-12 |x|, half of what truncation leaves
+    const float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t r;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[j]));
+        h[j] = __uint_as_float(r);
+        l[j] = v[j] - h[j];
+    }
     fw_st4(hi_addr, h[0], h[1], h[2], h[3]);
     fw_st4(lo_addr, l[0], l[1], l[2], l[3]);
 }

@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -53,6 +55,8 @@ class NgcfFusedTrainer:
         N, d, K = self.N, self.d, self.K
         self.final = z(N, (K + 1) * d)
         self.side, self.S, self.D = ([z(N, d) for _ in range(K)] for _ in range(3))
+        if os.environ.get("IDG_NGCF_BWD") != "fma":
+            self.S = None                                # the tensor-core backward does not read the pre-activations
         self.keep_all = z(K, N, d)                       # the K dropout masks of a step, drawn in one launch
         self.keep = [self.keep_all[k] for k in range(K)]
         self._keep_prob = (C.c_float * K)(*[1.0 - float(p) for p in self.drop[:K]])
@@ -77,6 +81,10 @@ class NgcfFusedTrainer:
         self.injected_keep = None     # parity tests: K [N,d] 0/1 masks
 
     # ------------------------------------------------------------------------------------------------------------
+    def _S(self, layer):
+        """Pre-activation buffer of a layer: only the CUDA-core backward (IDG_NGCF_BWD=fma) reads it; otherwise it is not even written."""
+        return ptr(self.S[layer]) if self.S is not None else None
+
     def _body(self, B, u, p, n):
         l, s, g, K, d, N = self.l, cur_stream(), self.graph, self.K, self.d, self.N
         wd, W = self.w, (K + 1) * d
@@ -94,7 +102,7 @@ class NgcfFusedTrainer:
                 self.keep[layer].copy_(self.injected_keep[layer])
             g.spmm_layer(E, Y=self.side[layer])
             check(l.idg_ngcf_dense_fwd(ptr(E), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['b_gcn_%d' % layer]),
-                                       ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]), ptr(self.keep[layer]), pr, N, ptr(self.S[layer]),
+                                       ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]), ptr(self.keep[layer]), pr, N, self._S(layer),
                                        ptr(self.D[layer]), fbase + 4 * d * (layer + 1), W, s), "idg_ngcf_dense_fwd")
             E = self.D[layer]
         # BPR on the 256-d rows (NGCF.py:113-118); L2 on the item ego rows only (NGCF.py:120-125: reg mask 6)
@@ -109,7 +117,7 @@ class NgcfFusedTrainer:
             out = self.gE[layer & 1]
             db = self.gw['b_gcn_%d' % layer]
             check(l.idg_ngcf_dense_bwd(ptr(Ein), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['W_bi_%d' % layer]), ptr(self.keep[layer]),
-                                       self.drop[layer], ptr(self.S[layer]), ptr(self.D[layer]), gbase + 4 * d * (layer + 1), W,
+                                       self.drop[layer], self._S(layer), ptr(self.D[layer]), gbase + 4 * d * (layer + 1), W,
                                        ptr(ext) if ext is not None else None, N, ptr(self.dside), ptr(self.dEd),
                                        ptr(self.gw['W_gcn_%d' % layer]), ptr(self.gw['W_bi_%d' % layer]), ptr(db), ptr(self.ngws), s), "idg_ngcf_dense_bwd")
             self.gw['b_bi_%d' % layer].copy_(db)                       # both biases enter the same sum (NGCF.py:91-95)

@@ -234,7 +234,9 @@ int idg_infonce_fwd_bwd_dev(const float* d_V1, const float* d_V2, const int64_t*
 /* ---- a8: models/NGCF.py:87-106, dense part of one layer (side = A_hat.E comes from idg_spmm_layer) ----------
  * forward:  S = side W_gcn + b_gcn + (E*side) W_bi + b_bi;  D = LeakyReLU_0.2(S) * keep/(1-p);  out = D/max(|D|,1e-12)
  *           d_keep: [N,64] 0/1 dropout draws or NULL (no dropout); out rows have stride out_stride floats (a 64-column
- *           block of the [N,256] concat or a plain [N,64] tensor).  S and D are kept for the backward.
+ *           block of the [N,256] concat or a plain [N,64] tensor).  D is kept for the backward; d_S (the pre-activation)
+ *           may be NULL in both calls -- the tensor-core backward reads the sign of S off D (same sign wherever keep = 1,
+ *           zero gradient wherever keep = 0); only the CUDA-core cross-check (IDG_NGCF_BWD=fma) needs it.
  * backward: given dO (stride dO_stride) and dD_ext (gradient reaching D from the next layer, may be NULL):
  *           dside, dE_direct [N,64] (the caller finishes dE = dE_direct + A_hat.dside with idg_spmm_layer),
  *           dW_gcn, dW_bi [64,64], db [64] (same for both biases).  d_ws: idg_ngcf_workspace_bytes() bytes. */
