@@ -505,3 +505,53 @@ def test_contrastive_step_losses_and_gradient_vs_fp64(dev, kind, cl):
     err = np.abs(ft.gE0.cpu().numpy().astype(np.float64) - want_grad).max() / np.abs(want_grad).max()
     print("%s cl=%d: gradient max error / max entry = %.2e" % (kind, cl, err))
     assert err <= 1e-5, err
+
+
+# ---------------------------------------------------------------- NGCF dense layer on tcgen05: forward and backward against fp64
+@pytest.mark.parametrize("N,with_keep,with_ext", [(1000, True, True), (777, True, False), (130, False, True), (19001, True, True)])
+def test_ngcf_dense_layer_tensor_core_kernels_vs_fp64(dev, N, with_keep, with_ext):
+    """models/NGCF.py:87-106 for one layer, forward (persistent tcgen05 kernel, csrc/ngcf_tc.cu) and its autograd (csrc/ngcf_bwd_tc.cu:
+    dZ^T = Wcat . dS^T with Wcat in TMEM, dWcat = Z^T . dS from MN-major operands) against an fp64 restatement: every output within
+    1e-5 of the largest reference entry.  Ragged row counts (last tile partial, fewer tiles than SMs, several tiles per CTA), no
+    dropout mask, no incoming gradient from a next layer; the forward must not touch the other blocks of the [N,256] concat."""
+    from idgrec import _lib
+    from idgrec._lib import check, ptr, cur_stream
+    l = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(N)
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev)
+    E, side = rn(N, 64) * 0.3, rn(N, 64) * 0.3
+    Wg, Wb, bg, bb = rn(64, 64) * 0.2, rn(64, 64) * 0.2, rn(64) * 0.1, rn(64) * 0.1
+    keep = (torch.rand(N, 64, generator=g, device=dev) < 0.9).float() if with_keep else None
+    p = 0.1 if with_keep else 0.0
+    D = torch.empty(N, 64, device=dev)
+    out = torch.zeros(N, 256, device=dev)
+    kp = ptr(keep) if with_keep else None
+    check(l.idg_ngcf_dense_fwd(ptr(E), ptr(side), ptr(Wg), ptr(bg), ptr(Wb), ptr(bb), kp, p, N, None, ptr(D), out[:, 128:].data_ptr(), 256, cur_stream()), "fwd")
+    f = lambda t: t.double()
+    kd = f(keep) if with_keep else 1.0
+    Sd = f(side) @ f(Wg) + f(bg) + (f(E) * f(side)) @ f(Wb) + f(bb)
+    Dd = torch.where(Sd > 0, Sd, 0.2 * Sd) * kd / (1 - p)
+    nrm = Dd.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    Od = Dd / nrm
+    rel = lambda got, ref: float((f(got) - ref).abs().max() / ref.abs().max())
+    assert rel(D, Dd) < 1e-5 and rel(out[:, 128:192], Od) < 1e-5
+    assert float(out[:, :128].abs().max()) == 0.0 and float(out[:, 192:].abs().max()) == 0.0
+    # backward, from the kernel's own D (what the fused step passes)
+    dO_full, dDx = rn(N, 256), (rn(N, 64) * 0.5 if with_ext else None)
+    dO = dO_full[:, 128:192]
+    dside, dEd = torch.empty(N, 64, device=dev), torch.empty(N, 64, device=dev)
+    dWg, dWb, db = torch.empty(64, 64, device=dev), torch.empty(64, 64, device=dev), torch.empty(64, device=dev)
+    ws = torch.empty(int(l.idg_ngcf_workspace_bytes()), dtype=torch.uint8, device=dev)
+    check(l.idg_ngcf_dense_bwd(ptr(E), ptr(side), ptr(Wg), ptr(Wb), kp, p, None, ptr(D), dO.data_ptr(), 256, ptr(dDx) if with_ext else None, N, ptr(dside),
+                               ptr(dEd), ptr(dWg), ptr(dWb), ptr(db), ptr(ws), cur_stream()), "bwd")
+    D64 = f(D)
+    n64 = D64.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    O64 = D64 / n64
+    dD = (f(dDx) if with_ext else 0.0) + (f(dO) - O64 * (O64 * f(dO)).sum(1, keepdim=True)) / n64
+    dS = dD * kd / (1 - p) * torch.where(D64 > 0, 1.0, 0.2)
+    Wcat, Z = torch.cat([f(Wg), f(Wb)], 0), torch.cat([f(side), f(E) * f(side)], 1)
+    dZ = dS @ Wcat.T
+    dW = Z.T @ dS
+    for name, got, ref in (("dside", dside, dZ[:, :64] + dZ[:, 64:] * f(E)), ("dE_direct", dEd, dZ[:, 64:] * f(side)), ("dWg", dWg, dW[:64]),
+                           ("dWb", dWb, dW[64:]), ("db", db, dS.sum(0))):
+        assert rel(got, ref) < 1e-5, (name, rel(got, ref))
