@@ -25,6 +25,28 @@ __global__ void mc_push_kernel(const float4* __restrict__ src, float* mc_dst, in
     multimem_st4(mc_dst + 4 * i, src[i]);
 }
 
+// Persistent variants for the chunked exchange (idgrec/dist.py): a FEW CTAs stream a finished block of rows to the peers while
+// the next block is still being computed by the propagation kernel on the other SMs.  Measured at the XL shape on 8 GPUs: with
+// the peer stores inside the SpMM epilogue, a layer over 1/8 of the rows took 0.93 ms against 0.53 ms for the same layer without
+// them -- NVLink back-pressure on the store path stalls the gathers queued behind it on every SM.
+__global__ void __launch_bounds__(512) mc_push_persistent_kernel(const float4* __restrict__ src, float* mc_dst, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i + u * stride < n4) v[u] = src[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i + u * stride < n4) multimem_st4(mc_dst + 4 * (i + u * stride), v[u]);
+    }
+}
+__global__ void __launch_bounds__(512) peer_push_persistent_kernel(const float4* __restrict__ src, PeerPtrs dst, int n_dst, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = src[i];
+        for (int q = 0; q < n_dst; ++q) reinterpret_cast<float4*>(dst.p[q])[i] = v;
+    }
+}
+
 // state layout (ints, inside the slab): [0] = epoch counter (local), [1] = error word (0 = healthy, else
 // 1 + index of the first peer that did not arrive within the time limit), [8 + r] = last epoch announced by rank r.
 // The wait is bounded (a dead peer must surface as an error, not as a hung stream): after
@@ -132,6 +154,25 @@ extern "C" int idg_peers_push(const idg_peers* p, const void* d_src, int64_t byt
     for (int q = 0; q < p->world; ++q) if (q != p->rank) dst.p[n++] = p->bases[q] + off;
     peer_push_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_src, dst, n, n4);
     IDG_LAUNCH_CHECK("peer_push_kernel");
+    return 0;
+}
+
+extern "C" int idg_peers_push_ctas(const idg_peers* p, const void* d_src, int64_t bytes, int32_t n_ctas, void* stream) {
+    if (!p || !d_src || bytes < 0 || (bytes & 15) || ((uintptr_t)d_src & 15) || n_ctas < 1) return fail(-1, "idg_peers_push_ctas: bad argument (16-byte granularity)%s");
+    if (bytes == 0 || p->world == 1) return 0;
+    int64_t off;
+    if (int rc = slab_offset(p, d_src, bytes, &off)) return rc;
+    const int64_t n4 = bytes / 16;
+    if (p->mc_base) {
+        mc_push_persistent_kernel<<<(unsigned)n_ctas, 512, 0, (cudaStream_t)stream>>>((const float4*)d_src, (float*)(p->mc_base + off), n4);
+        IDG_LAUNCH_CHECK("mc_push_persistent_kernel");
+        return 0;
+    }
+    PeerPtrs dst;
+    int n = 0;
+    for (int q = 0; q < p->world; ++q) if (q != p->rank) dst.p[n++] = p->bases[q] + off;
+    peer_push_persistent_kernel<<<(unsigned)n_ctas, 512, 0, (cudaStream_t)stream>>>((const float4*)d_src, dst, n, n4);
+    IDG_LAUNCH_CHECK("peer_push_persistent_kernel");
     return 0;
 }
 

@@ -124,6 +124,7 @@ SIGNATURES = {
     "idg_peers_set_multicast": (C.c_int, [_p, _p]),
     "idg_graph_set_peers": (C.c_int, [_p, _p]),
     "idg_peers_push": (C.c_int, [_p, _p, _i64, _p]),
+    "idg_peers_push_ctas": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "idg_peers_barrier": (C.c_int, [_p, _p, _p]),
     "idg_peers_set_timeout_ms": (C.c_int, [_p, _i64]),
     "idg_peers_status": (C.c_int, [_p, _p, _p]),

@@ -350,6 +350,10 @@ void idg_peers_destroy(idg_peers* p);
 int idg_peers_set_multicast(idg_peers* p, void* mc_base);
 int idg_graph_set_peers(idg_graph* g, const idg_peers* p);
 int idg_peers_push(const idg_peers* p, const void* d_src, int64_t bytes, void* stream);
+/* Same copy by a persistent grid of n_ctas CTAs: a few SMs stream a finished block of rows to the peers while the rest of the
+ * GPU computes the next block (chunked exchange of idgrec/dist.py; replaces the in-epilogue peer stores where NVLink
+ * back-pressure stalled the propagation kernel's gathers). */
+int idg_peers_push_ctas(const idg_peers* p, const void* d_src, int64_t bytes, int32_t n_ctas, void* stream);
 int idg_peers_barrier(const idg_peers* p, int32_t* d_state, void* stream);
 /* The barrier's wait is bounded (default 20 s per barrier, idg_peers_set_timeout_ms): a peer that never arrives is
  * recorded in d_state[1] and the kernel returns instead of spinning; every later barrier on that slab returns at
