@@ -192,10 +192,13 @@ class DistFusedTrainer:
         # kernel's epilogue stores every finished row to all peers.  "chunked": the local rows are computed in a few nnz-balanced
         # blocks with plain local stores and each finished block is streamed to the peers by a handful of CTAs on a second
         # stream while the next block is computed.  At the XL shape on 8 GPUs the fused form runs a layer over 1/8 of the rows in
-        # 0.93 ms against 0.53 ms for the same layer without peer stores (NVLink back-pressure on the store path stalls the
-        # gathers behind it on every SM); with 2 GPUs the exchange is a small fraction of the layer and the fused form wins.
+        # 0.93 ms against 0.53 ms for the same layer without peer stores.  Measured (profiles/xl_exchange_r2.md): the chunked
+        # form is 2 % faster there (3.37 vs 3.45 ms per step) -- the layer is bound by the multicast ingress itself (448 MB per
+        # layer and GPU at ~480 GB/s), not by store back-pressure on the SMs; unicast peer stores are 15 % slower than multicast.
+        # "auto" picks it only where it was measured to help: 8 ranks and a large local share (>= 4 M non-zeros per rank).
         mode = os.environ.get("IDG_DIST_EXCHANGE", "auto")
-        self.chunked = world > 1 and (mode == "chunked" or (mode == "auto" and world >= 8))
+        local_nnz = int(csr.indptr[self.b1].item() - csr.indptr[self.b0].item())
+        self.chunked = world > 1 and (mode == "chunked" or (mode == "auto" and world >= 8 and local_nnz >= 4000000))
         self.chunks, self._push_side = [], None
         if self.chunked:
             n_chunks = max(1, int(os.environ.get("IDG_DIST_CHUNKS", "4")))

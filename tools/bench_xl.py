@@ -157,7 +157,7 @@ def run(rank, world, dev, users=1000000, items=1000000, edges=100000000, steps=2
                "nvlink_floor_ms_per_layer": recv / 770e6 if world > 1 else 0.0,
                "eval_users_total": int(nus.item()), "eval_ms": eval_ms, "eval_chunk_users": chunk, "eval_chunk_ms_rank0": chunk_ms, "eval_users_per_s_total": int(nus.item()) / eval_ms * 1e3,
                "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": bool(use_graph), "breakdown_ms": phases,
-               "closure_restrict": ft.use_closure, "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}
+               "closure_restrict": ft.use_closure, "exchange": ("chunked x%d, %d push CTAs" % (len(ft.chunks), ft.push_ctas)) if ft.chunked else "fused epilogue stores", "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}
     del ft, F, full, csr, ws
     torch.cuda.empty_cache()
     return rec
@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--closure", default="auto", choices=["auto", "0", "1"])
+    ap.add_argument("--no-one-gpu-ref", action="store_true", help="skip the same-job one-GPU reference run")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -182,7 +183,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rec = run(rank, world, dev, args.users, args.items, args.edges, args.steps, args.warmup, args.batch, args.eval_users or None,
-              not args.no_graph, args.breakdown, args.closure)
+              not args.no_graph, args.breakdown, args.closure, not args.no_one_gpu_ref)
     if rank == 0:
         print(json.dumps(rec))
     if world > 1:
