@@ -115,6 +115,12 @@ class FusedTrainer:
         # the batch row set does not depend on the first K-1 propagation layers: it is built on a side stream (a parallel
         # branch of the captured graph) while they run
         self._side = torch.cuda.Stream(device=dev) if (self.rows is not None and kind != "MFBPR") else None
+        # SimGCL: the batch-row last layers of the three propagations run concurrently, one stream each.  A propagation handle
+        # owns the scratch of its heavy rows (chunk partials + arrival counters), so concurrent launches need a handle each.
+        self._gviews = None
+        if kind == "SimGCL" and self.rows is not None and not self.use_closure and 2 <= K <= 4:
+            from .graph import Graph
+            self._gviews = [graph, Graph(graph.csr, graph.row_begin, graph.row_end), Graph(graph.csr, graph.row_begin, graph.row_end)]
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
@@ -222,18 +228,39 @@ class FusedTrainer:
             self._sg = [[torch.empty(N, d, dtype=torch.float32, device=self.dev) for _ in range(K - 1)] for _ in range(3)]
         X = self._sg
         nz = (None, self.noise, self.noise_b)
+        main, s1, s2 = torch.cuda.current_stream(), self._side, self._nce_side
+        # Noise draws in the reference's order (view 1 layers 0..K-1, then view 2: the generator is advanced on the host, call by
+        # call), but only the two first-layer draws sit in front of the first product: the others fill their buffers from a second
+        # stream while that product runs.
+        if self.injected_noise is not None:
+            self._draw_noise(0)
+            self._draw_noise(1, self.noise_b)
+        else:
+            s2.wait_stream(main)
+            for buf in (self.noise, self.noise_b):
+                buf[0].uniform_()
+                with torch.cuda.stream(s2):
+                    for k in range(1, K):
+                        buf[k].uniform_()
         check(l.idg_spmm_layer_views(g._h, ptr(self.E0), ptr(X[0][0]), ptr(self.noise[0]), ptr(X[1][0]), ptr(self.noise_b[0]), ptr(X[2][0]),
                                      float(self.eps), d, cur_stream()), "idg_spmm_layer_views")
+        if self.injected_noise is None:
+            main.wait_stream(s2)                                    # join: the later layers' noise is drawn
         for k in range(1, K - 1):
             for v in range(3):
                 g.spmm_layer(X[v][k - 1], Y=X[v][k], noise=None if v == 0 else nz[v][k], eps=0.0 if v == 0 else self.eps)
-        if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)     # join: the row set is ready
-        for v, out in enumerate((self.F, self.V1, self.V2)):
+        main.wait_stream(s1)                                        # join: the row set is ready
+        # the three batch-row last layers are latency-bound (a few thousand rows each): one per stream
+        s1.wait_stream(main)
+        s2.wait_stream(main)
+        for v, (out, st) in enumerate(((self.F, main), (self.V1, s1), (self.V2, s2))):
             acc = list(X[v]) + [None] * (3 - (K - 1))
+            g = self._gviews[v]
             check(l.idg_spmm_layer_rows(g._h, ptr(X[v][K - 2]), None, None if v == 0 else ptr(nz[v][K - 1]), 0.0 if v == 0 else float(self.eps),
                                         ptr(acc[0]), ptr(acc[1]), ptr(acc[2]), ptr(out), float(K), d, ptr(rows.rowlist), ptr(rows.count), rows.max_rows,
-                                        ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
+                                        ptr(rows.worklist(g, v)), st.cuda_stream), "idg_spmm_layer_rows")
+        main.wait_stream(s1)
+        main.wait_stream(s2)
 
     def _contrast_pair(self, uniq, B, Va, Vb, gA, gB):
         """InfoNCE over the batch's unique users and over its unique positives (SimGCL.py:80-88, XSimGCL.py:84-92).  The two
@@ -298,8 +325,6 @@ class FusedTrainer:
             uniq = ((self.uidx, self.ucnt), (self.iidx, self.icnt))
             if self.kind == "SimGCL":
                 if shared_fwd:
-                    self._draw_noise(0)
-                    self._draw_noise(1, self.noise_b)
                     self._simgcl_forward_shared()
                 else:
                     g.propagate_fwd(self.E0, K, False, out_mean=self.F, rows=rows)

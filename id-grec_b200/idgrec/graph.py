@@ -177,8 +177,10 @@ class BatchRows:
         self.closure = None  # optional bitmap: batch rows + their neighbours (enable_closure)
         self._wl = {}
 
-    def worklist(self, graph):
-        k = id(graph)
+    def worklist(self, graph, slot=0):
+        """Schedule scratch of the row-restricted layer over ``graph``; launches that run concurrently (one stream each) take
+        different ``slot``s -- the list is built with a counter, two launches must not share it."""
+        k = (id(graph), slot)
         if k not in self._wl:
             n = int(_lib.lib().idg_graph_worklist_ints(graph._h, self.max_rows))
             self._wl[k] = torch.zeros(n, dtype=torch.int32, device=self.rowlist.device)
