@@ -262,6 +262,39 @@ class FusedTrainer:
         main.wait_stream(s1)
         main.wait_stream(s2)
 
+    def _xsimgcl_forward_split(self):
+        """XSimGCL.py:69-82 for a step whose losses read the final mean (and, for cl_layer = K, the contrast view) at the batch
+        rows only: layers 1..K-1 are plain perturbed products, the last layer and the mean over layers 1..K run on the batch rows
+        (same launches as the row-partitioned trainer, dist.py:_forward).  Only the first layer's noise draw sits in front of the
+        first product; the later layers' draws fill their buffers from a second stream meanwhile (draw ORDER on the host, i.e.
+        the generator stream, is the reference's).  Returns the contrast view (post-noise output of layer cl_layer)."""
+        g, K, d, N, rows, l = self.graph, self.K, self.d, self.N, self.rows, self.l
+        if getattr(self, "_xg", None) is None:
+            self._xg = [torch.empty(N, d, dtype=torch.float32, device=self.dev) for _ in range(K - 1)]
+        W = self._xg
+        main, s2 = torch.cuda.current_stream(), self._nce_side
+        overlap = self.injected_noise is None
+        if overlap:
+            s2.wait_stream(main)
+            self.noise[0].uniform_()
+            with torch.cuda.stream(s2):
+                for k in range(1, K):
+                    self.noise[k].uniform_()
+        else:
+            self._draw_noise(0)
+        x = self.E0
+        for k in range(K - 1):
+            g.spmm_layer(x, Y=W[k], noise=self.noise[k], eps=self.eps)
+            if k == 0 and overlap:
+                main.wait_stream(s2)
+            x = W[k]
+        main.wait_stream(self._side)                                # join: the row set is ready
+        acc = list(W) + [None] * (3 - (K - 1))
+        y_cl = self.V1 if self.cl_layer == K else None
+        check(l.idg_spmm_layer_rows(g._h, ptr(x), ptr(y_cl), ptr(self.noise[K - 1]), float(self.eps), ptr(acc[0]), ptr(acc[1]), ptr(acc[2]), ptr(self.F),
+                                    float(K), d, ptr(rows.rowlist), ptr(rows.count), rows.max_rows, ptr(rows.worklist(g)), cur_stream()), "idg_spmm_layer_rows")
+        return self.V1 if self.cl_layer == K else W[self.cl_layer - 1]
+
     def _contrast_pair(self, uniq, B, Va, Vb, gA, gB):
         """InfoNCE over the batch's unique users and over its unique positives (SimGCL.py:80-88, XSimGCL.py:84-92).  The two
         terms read the same views and accumulate into disjoint rows (users < U <= items), so the item term runs on a second
@@ -286,7 +319,8 @@ class FusedTrainer:
         # forward of the LightGCN-encoder steps without the full-size layer sum, row set built on a parallel branch
         split_fwd = (rows is not None and not self.use_closure and 2 <= K <= 3 and (self.kind == "LightGCN" or self.kind in PAIR_MODELS))
         shared_fwd = rows is not None and not self.use_closure and 2 <= K <= 4 and self.kind == "SimGCL"
-        split_fwd = split_fwd or shared_fwd
+        xsplit = rows is not None and not self.use_closure and 2 <= K <= 4 and self.kind == "XSimGCL"
+        split_fwd = split_fwd or shared_fwd or xsplit
         if rows is not None and split_fwd and self._side is not None:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)                            # fork: after the batch copy / the previous step's clean-up
@@ -339,11 +373,15 @@ class FusedTrainer:
                 self._contrast_pair(uniq, B, self.V1, self.V2, self.G, self.G)
                 g.propagate_bwd(self.G, K, False, out=out, rows=rows, adam=adam)
             else:  # XSimGCL: one perturbed propagation, contrast view captured at cl_layer
-                self._draw_noise(0)
-                g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
+                if xsplit:
+                    cl_view = self._xsimgcl_forward_split()
+                else:
+                    self._draw_noise(0)
+                    g.propagate_fwd(self.E0, K, False, noise=self.noise, eps=self.eps, cl_layer=self.cl_layer, out_mean=self.F, out_cl=self.V1, rows=rows)
+                    cl_view = self.V1
                 self._bpr(B, u, p, n, fused)
                 self.loss[2:3].zero_()
-                self._contrast_pair(uniq, B, self.V1, self.F, self.Gcl, self.G)
+                self._contrast_pair(uniq, B, cl_view, self.F, self.Gcl, self.G)
                 g.propagate_bwd(self.G, K, False, Gcl=self.Gcl, cl_layer=self.cl_layer, out=out, rows=rows, adam=adam)
                 for idx, _ in uniq:  # entries past the count are stale but valid rows of an all-zero table: harmless
                     check(l.idg_zero_rows(ptr(self.Gcl), ptr(idx), B, self.d, s), "idg_zero_rows")
