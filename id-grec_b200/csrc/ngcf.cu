@@ -26,10 +26,11 @@ namespace idg {
 
 // csrc/ngcf_tc.cu: the forward product on tcgen05 (3xTF32 split, TMEM accumulators)
 int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const float* bg, const float* Wb, const float* bb, const float* keep,
-                      float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream);
+                      const uint32_t* keep_bits, float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream);
 
 // csrc/ngcf_bwd_tc.cu: the backward products on tcgen05 (both contractions from one shared-memory image of dS)
-int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const float* Wb, const float* keep, float inv_keep, const float* S_pre,
+int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const float* Wb, const float* keep, const uint32_t* keep_bits, float inv_keep,
+                      const float* S_pre,
                       const float* D, const float* dO, int dO_stride, const float* dD_ext, int N, float* dside, float* dE_direct, float* dW_part,
                       float* db_part, int max_parts, int* n_parts, cudaStream_t stream);
 
@@ -195,6 +196,27 @@ __global__ void __launch_bounds__(256) ngcf_keep_masks_kernel(float* __restrict_
     reinterpret_cast<float4*>(keep)[q] = make_float4(r.x <= pk ? 1.f : 0.f, r.y <= pk ? 1.f : 0.f, r.z <= pk ? 1.f : 0.f, r.w <= pk ? 1.f : 0.f);
 }
 
+// The same draws packed 64 bits per row (word w, bit b = column 32 w + b): what the tensor-core dense kernels read -- 8 bytes per
+// row instead of a 256-byte float mask row in the forward and again in the backward.  Same Philox stream as above, quad for quad.
+__global__ void __launch_bounds__(256) ngcf_keep_bits_kernel(uint2* __restrict__ bits, int N, int n_layers, float k0, float k1, float k2, float k3,
+                                                             unsigned long long seed, const int* __restrict__ d_step) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)N * n_layers) return;
+    const int layer = (int)(t / N);
+    const float pk = layer == 0 ? k0 : (layer == 1 ? k1 : (layer == 2 ? k2 : k3));
+    const unsigned long long step = (unsigned long long)(d_step ? *d_step : 0);
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)(t * 16 + c), step, &st);   // quad index = (layer N + row) 16 + c, as in ngcf_keep_masks_kernel
+        const float4 r = curand_uniform4(&st);
+        const uint32_t b = (r.x <= pk ? 1u : 0u) | (r.y <= pk ? 2u : 0u) | (r.z <= pk ? 4u : 0u) | (r.w <= pk ? 8u : 0u);
+        w[c >> 3] |= b << ((c & 7) * 4);
+    }
+    bits[t] = make_uint2(w[0], w[1]);
+}
+
 // dst[row] = src[row] for the rows idx[i] + row_offset (row strides in floats): the 64-column ego block of the [N,256] concat is
 // only read at the batch rows by the BPR kernels, so the step copies those instead of the whole table
 __global__ void __launch_bounds__(256) copy_rows_strided_kernel(const float* __restrict__ src, int src_stride, const int64_t* __restrict__ idx, int n,
@@ -222,6 +244,18 @@ extern "C" int idg_ngcf_keep_masks(float* d_keep, int64_t per_layer, int32_t n_l
     return 0;
 }
 
+extern "C" int idg_ngcf_keep_bits(uint32_t* d_bits, int32_t N, int32_t n_layers, const float* h_keep_prob, uint64_t seed, const int32_t* d_step,
+                                  void* stream) {
+    if (!d_bits || !h_keep_prob || N <= 0 || n_layers < 1 || n_layers > 4) return fail(-1, "idg_ngcf_keep_bits: bad argument%s");
+    float k[4] = {1.f, 1.f, 1.f, 1.f};
+    for (int l = 0; l < n_layers; ++l) k[l] = h_keep_prob[l];
+    const int64_t n = (int64_t)N * n_layers;
+    ngcf_keep_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint2*>(d_bits), N, n_layers, k[0], k[1], k[2], k[3],
+                                                                                      (unsigned long long)seed, d_step);
+    IDG_LAUNCH_CHECK("ngcf_keep_bits_kernel");
+    return 0;
+}
+
 extern "C" int idg_copy_rows_strided(const float* d_src, int32_t src_stride, const int64_t* d_idx, int32_t n, int32_t row_offset, int32_t d,
                                      float* d_dst, int32_t dst_stride, void* stream) {
     if (!d_src || !d_idx || !d_dst || n < 0 || d <= 0 || (d & 3) || (src_stride & 3) || (dst_stride & 3)) return fail(-1, "idg_copy_rows_strided: bad argument%s");
@@ -232,21 +266,34 @@ extern "C" int idg_copy_rows_strided(const float* d_src, int32_t src_stride, con
     return 0;
 }
 
-extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
-                                  const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,
-                                  int32_t out_stride, void* stream) {
+static int ngcf_fwd_impl(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb, const float* d_bb,
+                         const float* d_keep, const uint32_t* d_keep_bits, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out, int32_t out_stride,
+                         void* stream) {
     // d_S (the pre-activation) may be null: only the CUDA-core backward (IDG_NGCF_BWD=fma) reads it, the tensor-core one takes the sign off D
     if (!d_E || !d_side || !d_Wg || !d_bg || !d_Wb || !d_bb || !d_D || !d_out || N <= 0) return fail(-1, "idg_ngcf_dense_fwd: bad argument%s");
     if (drop_p < 0.f || drop_p >= 1.f) return fail(-1, "idg_ngcf_dense_fwd: drop_p must be in [0,1)%s");
     if (out_stride & 3) return fail(-1, "idg_ngcf_dense_fwd: out_stride must be a multiple of 4%s");
-    return ngcf_dense_fwd_tc(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, 1.f / (1.f - drop_p), N, d_S, d_D, d_out, out_stride, (cudaStream_t)stream);
+    return ngcf_dense_fwd_tc(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, d_keep_bits, 1.f / (1.f - drop_p), N, d_S, d_D, d_out, out_stride, (cudaStream_t)stream);
+}
+
+extern "C" int idg_ngcf_dense_fwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
+                                  const float* d_bb, const float* d_keep, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,
+                                  int32_t out_stride, void* stream) {
+    return ngcf_fwd_impl(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, d_keep, nullptr, drop_p, N, d_S, d_D, d_out, out_stride, stream);
+}
+
+extern "C" int idg_ngcf_dense_fwd_bits(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
+                                       const float* d_bb, const uint32_t* d_keep_bits, float drop_p, int32_t N, float* d_S, float* d_D, float* d_out,
+                                       int32_t out_stride, void* stream) {
+    if (!d_keep_bits) return fail(-1, "idg_ngcf_dense_fwd_bits: null mask%s");
+    return ngcf_fwd_impl(d_E, d_side, d_Wg, d_bg, d_Wb, d_bb, nullptr, d_keep_bits, drop_p, N, d_S, d_D, d_out, out_stride, stream);
 }
 
 extern "C" int64_t idg_ngcf_workspace_bytes(void) { return (int64_t)sizeof(float) * kNgCtas * (128 * 64 + 64); }
 
-extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep, float drop_p,
-                                  const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
-                                  float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream_) {
+static int ngcf_bwd_impl(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep, const uint32_t* d_keep_bits,
+                         float drop_p, const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
+                         float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream_) {
     if (!d_E || !d_side || !d_Wg || !d_Wb || !d_D || !d_dO || !d_dside || !d_dE_direct || !d_dWg || !d_dWb || !d_db || !d_ws || N <= 0)
         return fail(-1, "idg_ngcf_dense_bwd: bad argument%s");
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -256,10 +303,11 @@ extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const f
     static const bool use_tc = !(getenv("IDG_NGCF_BWD") && strcmp(getenv("IDG_NGCF_BWD"), "fma") == 0);
     if (dO_stride & 3) return fail(-1, "idg_ngcf_dense_bwd: dO_stride must be a multiple of 4%s");
     if (!use_tc && !d_S) return fail(-1, "idg_ngcf_dense_bwd: the CUDA-core kernel needs the pre-activation d_S%s");
+    if (!use_tc && d_keep_bits) return fail(-1, "idg_ngcf_dense_bwd_bits: the CUDA-core kernel takes the float mask%s");
     int n_parts = kNgCtas;
     if (use_tc) {
-        if (int rc = ngcf_dense_bwd_tc(d_E, d_side, d_Wg, d_Wb, d_keep, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside, d_dE_direct,
-                                       dW_part, db_part, kNgCtas, &n_parts, stream))
+        if (int rc = ngcf_dense_bwd_tc(d_E, d_side, d_Wg, d_Wb, d_keep, d_keep_bits, 1.f / (1.f - drop_p), d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside,
+                                       d_dE_direct, dW_part, db_part, kNgCtas, &n_parts, stream))
             return rc;
     } else {
         const size_t smem = sizeof(float) * (kNgTile * 128 + kNgTile * 64 + 64 * 128);
@@ -271,4 +319,19 @@ extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const f
     ngcf_reduce_kernel<<<(128 * 64 + 64 + 63) / 64, 256, 0, stream>>>(dW_part, db_part, n_parts, d_dWg, d_dWb, d_db);
     IDG_LAUNCH_CHECK("ngcf_reduce_kernel");
     return 0;
+}
+
+extern "C" int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const float* d_keep, float drop_p,
+                                  const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
+                                  float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream) {
+    return ngcf_bwd_impl(d_E, d_side, d_Wg, d_Wb, d_keep, nullptr, drop_p, d_S, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside, d_dE_direct, d_dWg, d_dWb, d_db,
+                         d_ws, stream);
+}
+
+extern "C" int idg_ngcf_dense_bwd_bits(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const uint32_t* d_keep_bits,
+                                       float drop_p, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
+                                       float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream) {
+    if (!d_keep_bits) return fail(-1, "idg_ngcf_dense_bwd_bits: null mask%s");
+    return ngcf_bwd_impl(d_E, d_side, d_Wg, d_Wb, nullptr, d_keep_bits, drop_p, nullptr, d_D, d_dO, dO_stride, d_dD_ext, N, d_dside, d_dE_direct, d_dWg, d_dWb,
+                         d_db, d_ws, stream);
 }

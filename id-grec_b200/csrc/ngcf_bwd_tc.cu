@@ -125,9 +125,13 @@ __device__ __forceinline__ void bw_split_store(uint32_t hi_addr, uint32_t lo_add
     bw_st4(lo_addr, l);
 }
 
+// KEEP: 0 = no dropout, 1 = float mask rows (keep), 2 = 64 mask bits per row (kbits); a template so that each variant stays inside
+// the 168-register budget of a 288-thread CTA (one generic kernel spilled in the streaming loop: 110 -> 124 us)
+template <int KEEP>
 __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
                                                                    const float* __restrict__ Wg, const float* __restrict__ Wb,
-                                                                   const float* __restrict__ keep, float inv_keep, const float* __restrict__ D,
+                                                                   const float* __restrict__ keep, const uint32_t* __restrict__ kbits, float inv_keep,
+                                                                   const float* __restrict__ D,
                                                                    const float* __restrict__ dO, int dO_stride, const float* __restrict__ dD_ext, int N,
                                                                    float* __restrict__ dside, float* __restrict__ dE_direct,
                                                                    float* __restrict__ dW_part, float* __restrict__ db_part) {
@@ -236,7 +240,9 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
                     cp_async16(dst, D + rc * 64 + tx * 4, ok);
                     cp_async16(dst + 4096u, dO + rc * dO_stride + tx * 4, ok);
                     if (dD_ext) cp_async16(dst + 8192u, dD_ext + rc * 64 + tx * 4, ok);
-                    if (keep) cp_async16(dst + 12288u, keep + rc * 64 + tx * 4, ok);
+                    if (KEEP == 1) cp_async16(dst + 12288u, keep + rc * 64 + tx * 4, ok);
+                    else if (KEEP == 2)   // 64 bits per row: every lane of the row fetches the same 8 bytes into its own piece (the ring is thread-private)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 12288u), "l"(kbits + rc * 2), "r"(ok >> 1) : "memory");
                 } else {              // side (two passes) | E (two passes), rows 32k + 16ps + ty
 #pragma unroll
                     for (int ps = 0; ps < 2; ++ps) {
@@ -271,7 +277,13 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
                     const bool in = r0 + rr < N;
                     const float4 d4 = bw_ld4(src), o4 = bw_ld4(src + 4096u);
                     const float4 x4 = dD_ext ? bw_ld4(src + 8192u) : f4zero();
-                    const float4 k4 = keep ? bw_ld4(src + 12288u) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    float4 k4 = KEEP == 1 ? bw_ld4(src + 12288u) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (KEEP == 2) {
+                        uint32_t w0, w1;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src + 12288u) : "memory");
+                        const uint32_t w = ((tx >> 3) ? w1 : w0) >> ((tx & 7) * 4);
+                        k4 = make_float4((float)(w & 1u), (float)((w >> 1) & 1u), (float)((w >> 2) & 1u), (float)((w >> 3) & 1u));
+                    }
                     float ss = d4.x * d4.x + d4.y * d4.y + d4.z * d4.z + d4.w * d4.w;
                     float dot = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;   // <D, dO>
 #pragma unroll
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const float dD = xv[jj] + (ov[jj] - dv[jj] * proj) / nrm;
-                        float v = keep ? dD * kv[jj] * inv_keep : dD;
+                        float v = KEEP ? dD * kv[jj] * inv_keep : dD;
                         v *= (dv[jj] > 0.f) ? 1.f : 0.2f;
                         ds[jj] = in ? v : 0.f;
                         bw_split(ds[jj], h[jj], l[jj]);
@@ -394,7 +406,8 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
 }
 
 // launched by idg_ngcf_dense_bwd (csrc/ngcf.cu); returns the number of per-CTA partials written (the reduce kernel's n_parts)
-int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const float* Wb, const float* keep, float inv_keep, const float* S_pre,
+int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const float* Wb, const float* keep, const uint32_t* keep_bits, float inv_keep,
+                      const float* S_pre,
                       const float* D, const float* dO, int dO_stride, const float* dD_ext, int N, float* dside, float* dE_direct, float* dW_part,
                       float* db_part, int max_parts, int* n_parts, cudaStream_t stream) {
     (void)S_pre;   // the sign of S is read off D (see the kernel)
@@ -408,8 +421,12 @@ int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const 
     int grid = sms < ntiles ? sms : ntiles;
     if (grid > max_parts) grid = max_parts;
     const size_t smem = (size_t)kBwSmem + 128;
-    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ngcf_dense_bwd_tc_kernel<<<grid, 288, smem, stream>>>(E, side, Wg, Wb, keep, inv_keep, D, dO, dO_stride, dD_ext, N, dside, dE_direct, dW_part, db_part);
+    auto launch = [&](auto kern) -> int {
+        IDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 288, smem, stream>>>(E, side, Wg, Wb, keep, keep_bits, inv_keep, D, dO, dO_stride, dD_ext, N, dside, dE_direct, dW_part, db_part);
+        return 0;
+    };
+    if (int rc = keep_bits ? launch(ngcf_dense_bwd_tc_kernel<2>) : (keep ? launch(ngcf_dense_bwd_tc_kernel<1>) : launch(ngcf_dense_bwd_tc_kernel<0>))) return rc;
     IDG_LAUNCH_CHECK("ngcf_dense_bwd_tc_kernel");
     *n_parts = grid;
     return 0;

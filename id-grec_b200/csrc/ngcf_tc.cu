@@ -61,12 +61,14 @@ __device__ __forceinline__ void fw_split_store(uint32_t hi_addr, uint32_t lo_add
     fw_st4(lo_addr, l[0], l[1], l[2], l[3]);
 }
 
+// KEEP: 0 = no dropout, 1 = float mask rows (keep, through the ring), 2 = 64 mask bits per row (kbits, read in the epilogue)
+template <int KEEP>
 __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
                                                                    const float* __restrict__ Wg, const float* __restrict__ bg,
                                                                    const float* __restrict__ Wb, const float* __restrict__ bb,
-                                                                   const float* __restrict__ keep, float inv_keep, int N,
-                                                                   float* __restrict__ S_pre, float* __restrict__ D, float* __restrict__ out,
-                                                                   int out_stride) {
+                                                                   const float* __restrict__ keep, const uint2* __restrict__ kbits, float inv_keep,
+                                                                   int N, float* __restrict__ S_pre, float* __restrict__ D,
+                                                                   float* __restrict__ out, int out_stride) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sW = smem;                            // Wcat^T hi | lo
     unsigned char* sA = sW + 2 * kFwWHalf;               // A ring: stage = chunk hi | lo
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
             const float* src = nullptr;
             int tt = 0, col0 = 0;
             if (w < 4) { if (it_u < T) { src = (w & 1) ? E : side; tt = (int)blockIdx.x + it_u * (int)gridDim.x; col0 = (w >> 1) * 32; } }
-            else if (keep && it_u >= 1 && it_u <= T) { src = keep; tt = (int)blockIdx.x + (it_u - 1) * (int)gridDim.x; col0 = (w - 4) * 32; }
+            else if (KEEP == 1 && it_u >= 1 && it_u <= T) { src = keep; tt = (int)blockIdx.x + (it_u - 1) * (int)gridDim.x; col0 = (w - 4) * 32; }
             if (src) {
                 const uint32_t dst = aG + (uint32_t)(U & 3) * kFwUnit + (uint32_t)bt * 16u;
 #pragma unroll
@@ -206,18 +208,26 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
             // ---- epilogue of tile it-1
             float4 k0[4], k1[4];
             const uint32_t g0 = get(U0 + 4);
-            if (keep && it >= 1) {
+            if (KEEP == 1 && it >= 1) {
 #pragma unroll
                 for (int ps = 0; ps < 4; ++ps) k0[ps] = fw_ld4(g0 + (uint32_t)ps * 4096u);
             }
             const uint32_t g1 = get(U0 + 5);
-            if (keep && it >= 1) {
+            if (KEEP == 1 && it >= 1) {
 #pragma unroll
                 for (int ps = 0; ps < 4; ++ps) k1[ps] = fw_ld4(g1 + (uint32_t)ps * 4096u);
             }
             if (it >= 1) {
                 const int pt = it - 1, buf = pt & 1;
                 const int r0 = ((int)blockIdx.x + pt * (int)gridDim.x) * 128;
+                uint2 kw[4];     // bit-packed dropout draws of this thread's four rows (64 bits per row): 8 B per row instead of 256
+                if (KEEP == 2) {
+#pragma unroll
+                    for (int ps = 0; ps < 4; ++ps) {
+                        const int r = r0 + ps * 32 + urow;
+                        kw[ps] = r < N ? __ldg(kbits + r) : make_uint2(0u, 0u);
+                    }
+                }
                 mbar_wait(tfull + buf, (pt >> 1) & 1);
                 tc_fence_after();
                 {   // thread <-> row: S + bias into the tile, 16-byte chunk index XOR row (conflict-free here and for the reads below)
@@ -242,12 +252,20 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
                     const uint32_t o = aT + (uint32_t)rr * 256u + (uint32_t)(((uj ^ rr) & 7) << 4);
                     const float4 sa = fw_ld4(o), sb = fw_ld4(o + 128u);
                     const float s8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-                    const float kv[8] = {k0[ps].x, k0[ps].y, k0[ps].z, k0[ps].w, k1[ps].x, k1[ps].y, k1[ps].z, k1[ps].w};
+                    float kv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+                    if (KEEP == 1) { kv[0] = k0[ps].x; kv[1] = k0[ps].y; kv[2] = k0[ps].z; kv[3] = k0[ps].w; kv[4] = k1[ps].x; kv[5] = k1[ps].y; kv[6] = k1[ps].z; kv[7] = k1[ps].w; }
+                    if (KEEP == 2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            kv[j] = (float)((kw[ps].x >> (uj * 4 + j)) & 1u);
+                            kv[4 + j] = (float)((kw[ps].y >> (uj * 4 + j)) & 1u);
+                        }
+                    }
                     float d8[8], ss = 0.f;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float act = s8[j] > 0.f ? s8[j] : 0.2f * s8[j];
-                        d8[j] = keep ? act * kv[j] * inv_keep : act;
+                        d8[j] = KEEP ? act * kv[j] * inv_keep : act;
                         ss = fmaf(d8[j], d8[j], ss);
                     }
                     ss += __shfl_xor_sync(0xffffffffu, ss, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -273,9 +291,10 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
     }
 }
 
-// launched by idg_ngcf_dense_fwd (csrc/ngcf.cu) for the 64-wide layers of the reference configuration; S_pre may be null
+// launched by idg_ngcf_dense_fwd / _bits (csrc/ngcf.cu) for the 64-wide layers of the reference configuration; S_pre may be null;
+// the dropout draws come as a float mask (keep), as 64 bits per row (keep_bits: word w, bit b = column 32 w + b) or not at all
 int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const float* bg, const float* Wb, const float* bb, const float* keep,
-                      float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream) {
+                      const uint32_t* keep_bits, float inv_keep, int N, float* S_pre, float* D, float* out, int out_stride, cudaStream_t stream) {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -285,8 +304,12 @@ int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const 
     const int ntiles = (N + 127) / 128;
     const int grid = sms < ntiles ? sms : ntiles;
     const size_t smem = (size_t)kFwSmem + 512;
-    IDG_CUDA(cudaFuncSetAttribute(ngcf_dense_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ngcf_dense_fwd_tc_kernel<<<grid, 288, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, inv_keep, N, S_pre, D, out, out_stride);
+    auto launch = [&](auto kern) -> int {
+        IDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 288, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, reinterpret_cast<const uint2*>(keep_bits), inv_keep, N, S_pre, D, out, out_stride);
+        return 0;
+    };
+    if (int rc = keep_bits ? launch(ngcf_dense_fwd_tc_kernel<2>) : (keep ? launch(ngcf_dense_fwd_tc_kernel<1>) : launch(ngcf_dense_fwd_tc_kernel<0>))) return rc;
     IDG_LAUNCH_CHECK("ngcf_dense_fwd_tc_kernel");
     return 0;
 }

@@ -101,6 +101,9 @@ SIGNATURES = {
     "idg_ngcf_keep_masks": (C.c_int, [_p, _i64, _i32, _p, C.c_uint64, _p, _p]),
     "idg_copy_rows_strided": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _p, _i32, _p]),
     "idg_ngcf_dense_bwd": (C.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
+    "idg_ngcf_keep_bits": (C.c_int, [_p, _i32, _i32, _p, C.c_uint64, _p, _p]),
+    "idg_ngcf_dense_fwd_bits": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _f32, _i32, _p, _p, _p, _i32, _p]),
+    "idg_ngcf_dense_bwd_bits": (C.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _i32, _p, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "idg_eval_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "idg_eval_topk": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p]),
     "idg_rating_matrix": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p, _p]),

@@ -60,6 +60,9 @@ class NgcfFusedTrainer:
         self.keep_all = z(K, N, d)                       # the K dropout masks of a step, drawn in one launch
         self.keep = [self.keep_all[k] for k in range(K)]
         self._keep_prob = (C.c_float * K)(*[1.0 - float(p) for p in self.drop[:K]])
+        # the draws packed 64 bits per row for the tensor-core dense kernels (8 B per row instead of a 256 B float mask row, read in
+        # the forward and again in the backward); the float masks remain for injected masks (parity tests) and IDG_NGCF_BWD=fma
+        self.keep_bits = torch.zeros(K, N, 2, dtype=torch.int32, device=dev) if os.environ.get("IDG_NGCF_BWD") != "fma" else None
         self._seed = int(torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()) & ((1 << 63) - 1)
         self.G = z(N, (K + 1) * d)                       # dL/dfinal: non-zero on the batch rows only, re-zeroed by bpr_finish
         self.G64 = z(N, d)                               # scratch for the reg-only BPR call (stays zero)
@@ -92,8 +95,11 @@ class NgcfFusedTrainer:
         # block 0 of the concat = the ego table, read by the BPR kernels at the batch rows only
         for idx, off in ((u, 0), (p, self.U), (n, self.U)):
             check(l.idg_copy_rows_strided(ptr(self.E0), d, idx, B, off, d, fbase, W, s), "idg_copy_rows_strided")
-        if self.injected_keep is None:
+        bits = self.keep_bits is not None and self.injected_keep is None
+        if bits:
             # nn.Dropout(p)'s draws (NGCF.py:99-100: always active): Bernoulli(1 - p) per element, all layers in one launch
+            check(l.idg_ngcf_keep_bits(ptr(self.keep_bits), N, K, self._keep_prob, self._seed, ptr(self.step_a), s), "idg_ngcf_keep_bits")
+        elif self.injected_keep is None:
             check(l.idg_ngcf_keep_masks(ptr(self.keep_all), N * d, K, self._keep_prob, self._seed, ptr(self.step_a), s), "idg_ngcf_keep_masks")
         E = self.E0
         for layer in range(K):
@@ -101,9 +107,10 @@ class NgcfFusedTrainer:
             if self.injected_keep is not None:
                 self.keep[layer].copy_(self.injected_keep[layer])
             g.spmm_layer(E, Y=self.side[layer])
-            check(l.idg_ngcf_dense_fwd(ptr(E), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['b_gcn_%d' % layer]),
-                                       ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]), ptr(self.keep[layer]), pr, N, self._S(layer),
-                                       ptr(self.D[layer]), fbase + 4 * d * (layer + 1), W, s), "idg_ngcf_dense_fwd")
+            check((l.idg_ngcf_dense_fwd_bits if bits else l.idg_ngcf_dense_fwd)(
+                ptr(E), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['b_gcn_%d' % layer]), ptr(wd['W_bi_%d' % layer]), ptr(wd['b_bi_%d' % layer]),
+                ptr(self.keep_bits[layer]) if bits else ptr(self.keep[layer]), pr, N, self._S(layer), ptr(self.D[layer]), fbase + 4 * d * (layer + 1), W, s),
+                "idg_ngcf_dense_fwd")
             E = self.D[layer]
         # BPR on the 256-d rows (NGCF.py:113-118); L2 on the item ego rows only (NGCF.py:120-125: reg mask 6)
         check(l.idg_bpr_forward(fbase, fbase, u, p, n, B, self.U, N, W, 0.0, 0, ptr(self.loss_a), ptr(self.ws256), s), "idg_bpr_forward")
@@ -116,10 +123,13 @@ class NgcfFusedTrainer:
             Ein = self.E0 if layer == 0 else self.D[layer - 1]
             out = self.gE[layer & 1]
             db = self.gw['b_gcn_%d' % layer]
-            check(l.idg_ngcf_dense_bwd(ptr(Ein), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['W_bi_%d' % layer]), ptr(self.keep[layer]),
-                                       self.drop[layer], self._S(layer), ptr(self.D[layer]), gbase + 4 * d * (layer + 1), W,
-                                       ptr(ext) if ext is not None else None, N, ptr(self.dside), ptr(self.dEd),
-                                       ptr(self.gw['W_gcn_%d' % layer]), ptr(self.gw['W_bi_%d' % layer]), ptr(db), ptr(self.ngws), s), "idg_ngcf_dense_bwd")
+            tail = (ptr(self.D[layer]), gbase + 4 * d * (layer + 1), W, ptr(ext) if ext is not None else None, N, ptr(self.dside), ptr(self.dEd),
+                    ptr(self.gw['W_gcn_%d' % layer]), ptr(self.gw['W_bi_%d' % layer]), ptr(db), ptr(self.ngws), s)
+            head = (ptr(Ein), ptr(self.side[layer]), ptr(wd['W_gcn_%d' % layer]), ptr(wd['W_bi_%d' % layer]))
+            if bits:
+                check(l.idg_ngcf_dense_bwd_bits(*head, ptr(self.keep_bits[layer]), self.drop[layer], *tail), "idg_ngcf_dense_bwd_bits")
+            else:
+                check(l.idg_ngcf_dense_bwd(*head, ptr(self.keep[layer]), self.drop[layer], self._S(layer), *tail), "idg_ngcf_dense_bwd")
             self.gw['b_bi_%d' % layer].copy_(db)                       # both biases enter the same sum (NGCF.py:91-95)
             g.spmm_layer(self.dside, Y=out, addend=self.dEd)           # d/dE_in = direct term + A_hat . dside (A_hat symmetric)
             ext = out

@@ -257,6 +257,17 @@ int idg_ngcf_dense_bwd(const float* d_E, const float* d_side, const float* d_Wg,
                        float drop_p, const float* d_S, const float* d_D, const float* d_dO, int32_t dO_stride,
                        const float* d_dD_ext, int32_t N, float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb,
                        float* d_db, void* d_ws, void* stream);
+/* The same three calls with the dropout draws packed 64 bits per row (d_bits [n_layers][N][2] words: word w, bit b = column
+ * 32 w + b; same Philox stream as idg_ngcf_keep_masks, draw for draw): the dense kernels read 8 bytes per row instead of a
+ * 256-byte float mask row.  Tensor-core kernels only; no pre-activation argument. */
+int idg_ngcf_keep_bits(uint32_t* d_bits, int32_t N, int32_t n_layers, const float* h_keep_prob, uint64_t seed, const int32_t* d_step,
+                       void* stream);
+int idg_ngcf_dense_fwd_bits(const float* d_E, const float* d_side, const float* d_Wg, const float* d_bg, const float* d_Wb,
+                            const float* d_bb, const uint32_t* d_keep_bits, float drop_p, int32_t N, float* d_S, float* d_D,
+                            float* d_out, int32_t out_stride, void* stream);
+int idg_ngcf_dense_bwd_bits(const float* d_E, const float* d_side, const float* d_Wg, const float* d_Wb, const uint32_t* d_keep_bits,
+                            float drop_p, const float* d_D, const float* d_dO, int32_t dO_stride, const float* d_dD_ext, int32_t N,
+                            float* d_dside, float* d_dE_direct, float* d_dWg, float* d_dWb, float* d_db, void* d_ws, void* stream);
 
 /* ---- a13/a14: get_rating_for_test + Test (models/LightGCN.py:74-80,
  * utility_train/batch_test.py:52-68) fused: score = <Fu[user], Fi[item]>, train

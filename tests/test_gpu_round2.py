@@ -555,3 +555,44 @@ def test_ngcf_dense_layer_tensor_core_kernels_vs_fp64(dev, N, with_keep, with_ex
     for name, got, ref in (("dside", dside, dZ[:, :64] + dZ[:, 64:] * f(E)), ("dE_direct", dEd, dZ[:, 64:] * f(side)), ("dWg", dWg, dW[:64]),
                            ("dWb", dWb, dW[64:]), ("db", db, dS.sum(0))):
         assert rel(got, ref) < 1e-5, (name, rel(got, ref))
+
+
+def test_ngcf_bit_packed_dropout_masks_match_the_float_masks(dev):
+    """idg_ngcf_keep_bits packs the SAME Philox draws as idg_ngcf_keep_masks (64 bits per row), and the dense kernels give the same
+    bits whether the mask arrives as floats or as bits (forward D / O, backward dside / dE_direct / dW / db)."""
+    import ctypes as C
+    from idgrec import _lib
+    from idgrec._lib import check, ptr, cur_stream
+    l = _lib.lib()
+    N, K = 1500, 2
+    probs = (C.c_float * K)(0.9, 0.6)
+    step = torch.full((1,), 3, dtype=torch.int32, device=dev)
+    keep = torch.empty(K, N, 64, device=dev)
+    bits = torch.zeros(K, N, 2, dtype=torch.int32, device=dev)
+    s = cur_stream()
+    check(l.idg_ngcf_keep_masks(ptr(keep), N * 64, K, probs, 77, ptr(step), s), "keep_masks")
+    check(l.idg_ngcf_keep_bits(ptr(bits), N, K, probs, 77, ptr(step), s), "keep_bits")
+    w = bits.cpu().numpy().astype(np.uint32)                                    # [K, N, 2]
+    unpacked = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(K, N, 64).astype(np.float32)
+    np.testing.assert_array_equal(unpacked, keep.cpu().numpy())
+    g = torch.Generator(device=dev).manual_seed(1)
+    rn = lambda *sh: torch.randn(*sh, generator=g, device=dev)
+    E, side, Wg, Wb, bg, bb = rn(N, 64) * 0.3, rn(N, 64) * 0.3, rn(64, 64) * 0.2, rn(64, 64) * 0.2, rn(64) * 0.1, rn(64) * 0.1
+    dO, dDx = rn(N, 64), rn(N, 64) * 0.5
+    ws = torch.empty(int(l.idg_ngcf_workspace_bytes()), dtype=torch.uint8, device=dev)
+    res = []
+    for use_bits in (False, True):
+        D, out = torch.empty(N, 64, device=dev), torch.empty(N, 64, device=dev)
+        outs = [torch.empty(N, 64, device=dev), torch.empty(N, 64, device=dev), torch.empty(64, 64, device=dev), torch.empty(64, 64, device=dev),
+                torch.empty(64, device=dev)]
+        if use_bits:
+            check(l.idg_ngcf_dense_fwd_bits(ptr(E), ptr(side), ptr(Wg), ptr(bg), ptr(Wb), ptr(bb), ptr(bits[1]), 0.4, N, None, ptr(D), ptr(out), 64, s), "fwd_bits")
+            check(l.idg_ngcf_dense_bwd_bits(ptr(E), ptr(side), ptr(Wg), ptr(Wb), ptr(bits[1]), 0.4, ptr(D), ptr(dO), 64, ptr(dDx), N, *[ptr(o) for o in outs],
+                                            ptr(ws), s), "bwd_bits")
+        else:
+            check(l.idg_ngcf_dense_fwd(ptr(E), ptr(side), ptr(Wg), ptr(bg), ptr(Wb), ptr(bb), ptr(keep[1]), 0.4, N, None, ptr(D), ptr(out), 64, s), "fwd")
+            check(l.idg_ngcf_dense_bwd(ptr(E), ptr(side), ptr(Wg), ptr(Wb), ptr(keep[1]), 0.4, None, ptr(D), ptr(dO), 64, ptr(dDx), N, *[ptr(o) for o in outs],
+                                       ptr(ws), s), "bwd")
+        res.append([D, out] + outs)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)

@@ -46,8 +46,15 @@ def main():
     ws = torch.empty(int(l.idg_ngcf_workspace_bytes()), dtype=torch.uint8, device=dev)
     bwd = lambda: check(l.idg_ngcf_dense_bwd(ptr(E), ptr(side), ptr(Wg), ptr(Wb), ptr(keep), p, ptr(S), ptr(D), dO[:, 64:].data_ptr(), 256, ptr(dDx), N, ptr(dside),
                                              ptr(dEd), ptr(dWg), ptr(dWb), ptr(db), ptr(ws), cur_stream()), "bwd")
+    import ctypes as C
+    bits = torch.zeros(N, 2, dtype=torch.int32, device=dev)
+    check(l.idg_ngcf_keep_bits(ptr(bits), N, 1, (C.c_float * 1)(0.9), 5, None, cur_stream()), "keep_bits")
+    fwd_b = lambda: check(l.idg_ngcf_dense_fwd_bits(ptr(E), ptr(side), ptr(Wg), ptr(bg), ptr(Wb), ptr(bb), ptr(bits), p, N, None, ptr(D), out[:, 64:].data_ptr(), 256,
+                                                    cur_stream()), "fwd_bits")
+    bwd_b = lambda: check(l.idg_ngcf_dense_bwd_bits(ptr(E), ptr(side), ptr(Wg), ptr(Wb), ptr(bits), p, ptr(D), dO[:, 64:].data_ptr(), 256, ptr(dDx), N, ptr(dside),
+                                                    ptr(dEd), ptr(dWg), ptr(dWb), ptr(db), ptr(ws), cur_stream()), "bwd_bits")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+    for name, fn in (("fwd", fwd), ("bwd", bwd), ("fwd, bit-packed mask", fwd_b), ("bwd, bit-packed mask", bwd_b)):
         for _ in range(5):
             fn()
         ts = []
