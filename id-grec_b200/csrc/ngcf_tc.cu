@@ -25,7 +25,9 @@
 
 namespace idg {
 
-constexpr int kFwBuilders = 256;               // warps 1..8
+constexpr int kFwBuilders = 512;               // warps 1..16 (8 warps left the SM issue-bound: `wait` stalls, two warps per scheduler)
+constexpr int kFwPasses = 1024 / kFwBuilders;  // a [128 rows x 8 chunks] unit in passes of kFwBuilders / 8 rows
+constexpr int kFwPassRows = kFwBuilders / 8;
 constexpr uint32_t kFwBlkA = 128 * 128;        // bytes: [128 rows x 32 fp32] A chunk (hi or lo)
 constexpr uint32_t kFwStage = 2 * kFwBlkA;     // hi | lo
 constexpr uint32_t kFwBlkB = 64 * 128;         // bytes: [64 rows x 32 fp32] B chunk
@@ -63,7 +65,7 @@ __device__ __forceinline__ void fw_split_store(uint32_t hi_addr, uint32_t lo_add
 
 // KEEP: 0 = no dropout, 1 = float mask rows (keep, through the ring), 2 = 64 mask bits per row (kbits, read in the epilogue)
 template <int KEEP>
-__global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
+__global__ void __launch_bounds__(kFwBuilders + 32, 1) ngcf_dense_fwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
                                                                    const float* __restrict__ Wg, const float* __restrict__ bg,
                                                                    const float* __restrict__ Wb, const float* __restrict__ bb,
                                                                    const float* __restrict__ keep, const uint2* __restrict__ kbits, float inv_keep,
@@ -129,12 +131,12 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
             }
         }
     } else {
-        const int bt = tid - 32, urow = bt >> 3, uj = bt & 7;      // unit mapping: row urow + 32*pass, 16-byte chunk uj of the 128 B half-row
-        const int q = warp & 3, half = (warp - 1) >> 2;             // TMEM role: lane quadrant, column half
+        const int bt = tid - 32, urow = bt >> 3, uj = bt & 7;      // unit mapping: row urow + kFwPassRows*pass, 16-byte chunk uj of the 128 B half-row
+        const int q = warp & 3, cq = (warp - 1) >> 2;               // TMEM role: lane quadrant, column quarter (16 columns)
         const uint32_t tq = tmem_base + (((uint32_t)(q * 32)) << 16);
         // Wcat^T (hi, lo), once: B chunk kc, row n holds Wcat[32 kc .. 32 kc + 31][n]
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 2048 / kFwBuilders; ++i) {
             const int idx = bt + i * kFwBuilders;       // 64 columns n x 32 k-quads
             const int n = idx & 63, kq = idx >> 6;
             float wv[4];
@@ -159,9 +161,9 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
             if (src) {
                 const uint32_t dst = aG + (uint32_t)(U & 3) * kFwUnit + (uint32_t)bt * 16u;
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {
-                    const int r = tt * 128 + ps * 32 + urow;
-                    cp_async16(dst + (uint32_t)ps * 4096u, src + (size_t)(r < N ? r : 0) * 64 + col0 + uj * 4, r < N ? 16 : 0);
+                for (int ps = 0; ps < kFwPasses; ++ps) {
+                    const int r = tt * 128 + ps * kFwPassRows + urow;
+                    cp_async16(dst + (uint32_t)ps * (kFwBuilders * 16u), src + (size_t)(r < N ? r : 0) * 64 + col0 + uj * 4, r < N ? 16 : 0);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -180,22 +182,22 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
             // ---- operands of tile it: two pairs of units -> two A chunks each
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                float4 sd[4], e[4];
+                float4 sd[kFwPasses], e[kFwPasses];
                 const uint32_t s0 = get(U0 + 2 * p);
                 if (it < T) {
 #pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) sd[ps] = fw_ld4(s0 + (uint32_t)ps * 4096u);
+                    for (int ps = 0; ps < kFwPasses; ++ps) sd[ps] = fw_ld4(s0 + (uint32_t)ps * (kFwBuilders * 16u));
                 }
                 const uint32_t s1 = get(U0 + 2 * p + 1);
                 if (it < T) {
 #pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) e[ps] = fw_ld4(s1 + (uint32_t)ps * 4096u);
+                    for (int ps = 0; ps < kFwPasses; ++ps) e[ps] = fw_ld4(s1 + (uint32_t)ps * (kFwBuilders * 16u));
                     const int n = it * 2 + p;
                     mbar_wait(empty + 0, (n & 1) ^ 1);
                     mbar_wait(empty + 1, (n & 1) ^ 1);
 #pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) {
-                        const uint32_t o = fw_sw(ps * 32 + urow, uj);
+                    for (int ps = 0; ps < kFwPasses; ++ps) {
+                        const uint32_t o = fw_sw(ps * kFwPassRows + urow, uj);
                         fw_split_store(aA + o, aA + kFwBlkA + o, sd[ps]);
                         fw_split_store(aA + kFwStage + o, aA + kFwStage + kFwBlkA + o,
                                        make_float4(e[ps].x * sd[ps].x, e[ps].y * sd[ps].y, e[ps].z * sd[ps].z, e[ps].w * sd[ps].w));
@@ -206,25 +208,25 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
                 }
             }
             // ---- epilogue of tile it-1
-            float4 k0[4], k1[4];
+            float4 k0[kFwPasses], k1[kFwPasses];
             const uint32_t g0 = get(U0 + 4);
             if (KEEP == 1 && it >= 1) {
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) k0[ps] = fw_ld4(g0 + (uint32_t)ps * 4096u);
+                for (int ps = 0; ps < kFwPasses; ++ps) k0[ps] = fw_ld4(g0 + (uint32_t)ps * (kFwBuilders * 16u));
             }
             const uint32_t g1 = get(U0 + 5);
             if (KEEP == 1 && it >= 1) {
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) k1[ps] = fw_ld4(g1 + (uint32_t)ps * 4096u);
+                for (int ps = 0; ps < kFwPasses; ++ps) k1[ps] = fw_ld4(g1 + (uint32_t)ps * (kFwBuilders * 16u));
             }
             if (it >= 1) {
                 const int pt = it - 1, buf = pt & 1;
                 const int r0 = ((int)blockIdx.x + pt * (int)gridDim.x) * 128;
-                uint2 kw[4];     // bit-packed dropout draws of this thread's four rows (64 bits per row): 8 B per row instead of 256
+                uint2 kw[kFwPasses];     // bit-packed dropout draws of this thread's rows (64 bits per row): 8 B per row instead of 256
                 if (KEEP == 2) {
 #pragma unroll
-                    for (int ps = 0; ps < 4; ++ps) {
-                        const int r = r0 + ps * 32 + urow;
+                    for (int ps = 0; ps < kFwPasses; ++ps) {
+                        const int r = r0 + ps * kFwPassRows + urow;
                         kw[ps] = r < N ? __ldg(kbits + r) : make_uint2(0u, 0u);
                     }
                 }
@@ -232,23 +234,29 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
                 tc_fence_after();
                 {   // thread <-> row: S + bias into the tile, 16-byte chunk index XOR row (conflict-free here and for the reads below)
                     const int row = q * 32 + lane;
-                    uint32_t raw[32];
-                    tmem_ld32(tq + (uint32_t)(buf * 64 + half * 32), raw);
+                    uint32_t raw[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]), "=r"(raw[8]),
+                          "=r"(raw[9]), "=r"(raw[10]), "=r"(raw[11]), "=r"(raw[12]), "=r"(raw[13]), "=r"(raw[14]), "=r"(raw[15])
+                        : "r"(tq + (uint32_t)(buf * 64 + cq * 16))
+                        : "memory");
                     tmem_ld_wait();
                     tc_fence_before();
                     mbar_arrive(tempty + buf);
-                    const uint32_t rb = aT + (uint32_t)row * 256u + (uint32_t)half * 128u;
+                    const uint32_t rb = aT + (uint32_t)row * 256u + (uint32_t)(cq >> 1) * 128u;
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 b = *reinterpret_cast<const float4*>(sBias + half * 32 + j4 * 4);
-                        fw_st4(rb + (uint32_t)(((j4 ^ row) & 7) << 4), __uint_as_float(raw[j4 * 4]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y,
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = *reinterpret_cast<const float4*>(sBias + cq * 16 + j4 * 4);
+                        const int c8 = (cq & 1) * 4 + j4;      // 16-byte chunk inside the 128 B half-row
+                        fw_st4(rb + (uint32_t)(((c8 ^ row) & 7) << 4), __uint_as_float(raw[j4 * 4]) + b.x, __uint_as_float(raw[j4 * 4 + 1]) + b.y,
                                __uint_as_float(raw[j4 * 4 + 2]) + b.z, __uint_as_float(raw[j4 * 4 + 3]) + b.w);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kFwBuilders) : "memory");
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {     // 8 lanes per row: columns 4 uj .. +3 and 32 + 4 uj .. +3
-                    const int rr = ps * 32 + urow, r = r0 + rr;
+                for (int ps = 0; ps < kFwPasses; ++ps) {     // 8 lanes per row: columns 4 uj .. +3 and 32 + 4 uj .. +3
+                    const int rr = ps * kFwPassRows + urow, r = r0 + rr;
                     const uint32_t o = aT + (uint32_t)rr * 256u + (uint32_t)(((uj ^ rr) & 7) << 4);
                     const float4 sa = fw_ld4(o), sb = fw_ld4(o + 128u);
                     const float s8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
@@ -278,7 +286,7 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_fwd_tc_kernel(const float* 
                         st4(out + (size_t)r * out_stride + 32 + uj * 4, make_float4(d8[4] / nrm, d8[5] / nrm, d8[6] / nrm, d8[7] / nrm));
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // the tile is free for the next epilogue
+                asm volatile("bar.sync 1, %0;" ::"n"(kFwBuilders) : "memory");     // the tile is free for the next epilogue
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -306,7 +314,7 @@ int ngcf_dense_fwd_tc(const float* E, const float* side, const float* Wg, const 
     const size_t smem = (size_t)kFwSmem + 512;
     auto launch = [&](auto kern) -> int {
         IDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 288, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, reinterpret_cast<const uint2*>(keep_bits), inv_keep, N, S_pre, D, out, out_stride);
+        kern<<<grid, kFwBuilders + 32, smem, stream>>>(E, side, Wg, bg, Wb, bb, keep, reinterpret_cast<const uint2*>(keep_bits), inv_keep, N, S_pre, D, out, out_stride);
         return 0;
     };
     if (int rc = keep_bits ? launch(ngcf_dense_fwd_tc_kernel<2>) : (keep ? launch(ngcf_dense_fwd_tc_kernel<1>) : launch(ngcf_dense_fwd_tc_kernel<0>))) return rc;
