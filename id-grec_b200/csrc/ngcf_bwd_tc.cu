@@ -34,7 +34,7 @@
 
 namespace idg {
 
-constexpr int kBwBuilders = 256;              // warps 1..8
+constexpr int kBwBuilders = 512;              // warps 1..16 (8 warps left the SM issue-bound: two warps per scheduler)
 constexpr uint32_t kBwBlk = 128 * 128;        // bytes of one [128 rows x 32 fp32] block
 constexpr uint32_t kBwHalf = 2 * kBwBlk;      // hi (or lo) of dS [128 x 64]: two blocks
 constexpr int kBwZRows = 16;                  // rows per Z ring stage (2 k-steps of the dW product)
@@ -43,9 +43,9 @@ constexpr uint32_t kBwZBlk = kBwZRows * 128;  // [16 rows x 32 fp32]
 constexpr uint32_t kBwZHalf = 4 * kBwZBlk;    // hi (or lo) of one stage: the four 32-feature blocks of Z
 constexpr uint32_t kBwZStage = 2 * kBwZHalf;
 constexpr int kBwZStages = 2;
-constexpr uint32_t kBwUnit = 4 * 16 * 256;    // one staging slot: four [16 rows x 64 fp32] pieces
+constexpr uint32_t kBwUnit = 2 * 32 * 256;    // one staging slot: two [32 rows x 64 fp32] pieces
 constexpr int kBwSlots = 4, kBwAhead = 3;     // units in flight per thread = kBwAhead
-constexpr int kBwUnits = 12;                  // per tile: for k = 0..3: dS rows 32k..+15, dS rows 32k+16..+31, Z rows 32k..+31
+constexpr int kBwUnits = 12;                  // per tile: for k = 0..3, rows 32k..32k+31: (D | dO), (dD_ext | mask), (side | E)
 // TMEM columns: dZ^T [0,128) | dWcat of the current tile [128,192) | running dWcat [192,256) | Wcat hi [256,320) | Wcat lo [320,384)
 constexpr uint32_t kBwTmemCols = 512, kTcDz = 0, kTcD2 = 128, kTcRun = 192, kTcWh = 256, kTcWl = 320;
 constexpr uint32_t kBwSmem = 4 * kBwHalf + kBwZStages * kBwZStage + kBwSlots * kBwUnit;   // dS K-major | dS MN-major | Z ring | staging = 224 KB
@@ -128,7 +128,7 @@ __device__ __forceinline__ void bw_split_store(uint32_t hi_addr, uint32_t lo_add
 // KEEP: 0 = no dropout, 1 = float mask rows (keep), 2 = 64 mask bits per row (kbits); a template so that each variant stays inside
 // the 168-register budget of a 288-thread CTA (one generic kernel spilled in the streaming loop: 110 -> 124 us)
 template <int KEEP>
-__global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
+__global__ void __launch_bounds__(kBwBuilders + 32, 1) ngcf_dense_bwd_tc_kernel(const float* __restrict__ E, const float* __restrict__ side,
                                                                    const float* __restrict__ Wg, const float* __restrict__ Wb,
                                                                    const float* __restrict__ keep, const uint32_t* __restrict__ kbits, float inv_keep,
                                                                    const float* __restrict__ D,
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
 
     if (tid == 0) {
         mbar_init(w_full, kBwBuilders); mbar_init(ds_full, kBwBuilders); mbar_init(d1_full, 1);
-        for (int s = 0; s < kBwZStages; ++s) { mbar_init(z_full + s, kBwBuilders); mbar_init(z_empty + s, 1); }
+        for (int s = 0; s < kBwZStages; ++s) { mbar_init(z_full + s, kBwBuilders / 2); mbar_init(z_empty + s, 1); }   // a 16-row chunk is built by half the builders
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -201,15 +201,15 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
             }
         }
     } else {
-        const int bt = tid - 32, ty = bt >> 4, tx = bt & 15;
-        const int q = warp & 3, half = (warp - 1) >> 2;     // TMEM role: lane quadrant, column half
+        const int bt = tid - 32, ty = bt >> 4, tx = bt & 15;    // 16 lanes per row, 32 rows per pass
+        const int q = warp & 3, cq = (warp - 1) >> 2;           // TMEM role: lane quadrant, column quarter
         const uint32_t tq = tmem_base + (((uint32_t)(q * 32)) << 16);
-        {   // Wcat (hi, lo) into TMEM, once: lane = Wcat row (0..63 W_gcn, 64..127 W_bi), this warp's 32 of its 64 columns; running dWcat = 0
+        {   // Wcat (hi, lo) into TMEM, once: lane = Wcat row (0..63 W_gcn, 64..127 W_bi), this warp's 16 of its 64 columns; running dWcat = 0
             const int kk = q * 32 + lane;
-            const float* wr = (kk < 64 ? Wg + (size_t)kk * 64 : Wb + (size_t)(kk - 64) * 64) + half * 32;
-            uint32_t h[32], l[32];
+            const float* wr = (kk < 64 ? Wg + (size_t)kk * 64 : Wb + (size_t)(kk - 64) * 64) + cq * 16;
+            uint32_t h[16], l[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 w = ldg4(wr + j4 * 4);
                 const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -219,39 +219,35 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
                     h[j4 * 4 + j] = __float_as_uint(hh); l[j4 * 4 + j] = __float_as_uint(ll);
                 }
             }
-            tmem_st32(tq + kTcWh + (uint32_t)(half * 32), h);
-            tmem_st32(tq + kTcWl + (uint32_t)(half * 32), l);
+            tmem_st16(tq + kTcWh + (uint32_t)(cq * 16), h);
+            tmem_st16(tq + kTcWl + (uint32_t)(cq * 16), l);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = 0u;
-            tmem_st32(tq + kTcRun + (uint32_t)(half * 32), h);
+            for (int j = 0; j < 16; ++j) h[j] = 0u;
+            tmem_st16(tq + kTcRun + (uint32_t)(cq * 16), h);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(w_full);
         }
-        // unit w of tile tt into staging slot w & 3 (kBwUnits is a multiple of kBwSlots); one commit group per unit, even when empty
+        // unit w of tile tt into staging slot w & 3 (kBwUnits is a multiple of kBwSlots); one commit group per unit, even when empty.
+        // Units of the 32-row group k = w / 3: (D | dO), (dD_ext | mask), (side | E); a piece is [32 rows x 64 fp32] = 8 KB.
         auto issue = [&](int tt, int w) {
             if (tt < ntiles) {
                 const uint32_t dst = aG + (uint32_t)(w & 3) * kBwUnit + (uint32_t)ty * 256u + (uint32_t)tx * 16u;
                 const int k = w / 3, j = w % 3;
-                if (j < 2) {          // D | dO | dD_ext | keep, rows 32k + 16j + ty
-                    const int r = tt * 128 + k * 32 + j * 16 + ty;
-                    const int ok = r < N ? 16 : 0;
-                    const size_t rc = r < N ? (size_t)r : 0;
+                const int r = tt * 128 + k * 32 + ty;
+                const int ok = r < N ? 16 : 0;
+                const size_t rc = r < N ? (size_t)r : 0;
+                if (j == 0) {
                     cp_async16(dst, D + rc * 64 + tx * 4, ok);
-                    cp_async16(dst + 4096u, dO + rc * dO_stride + tx * 4, ok);
-                    if (dD_ext) cp_async16(dst + 8192u, dD_ext + rc * 64 + tx * 4, ok);
-                    if (KEEP == 1) cp_async16(dst + 12288u, keep + rc * 64 + tx * 4, ok);
+                    cp_async16(dst + 8192u, dO + rc * dO_stride + tx * 4, ok);
+                } else if (j == 1) {
+                    if (dD_ext) cp_async16(dst, dD_ext + rc * 64 + tx * 4, ok);
+                    if (KEEP == 1) cp_async16(dst + 8192u, keep + rc * 64 + tx * 4, ok);
                     else if (KEEP == 2)   // 64 bits per row: every lane of the row fetches the same 8 bytes into its own piece (the ring is thread-private)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 12288u), "l"(kbits + rc * 2), "r"(ok >> 1) : "memory");
-                } else {              // side (two passes) | E (two passes), rows 32k + 16ps + ty
-#pragma unroll
-                    for (int ps = 0; ps < 2; ++ps) {
-                        const int r = tt * 128 + k * 32 + ps * 16 + ty;
-                        const int ok = r < N ? 16 : 0;
-                        const size_t rc = r < N ? (size_t)r : 0;
-                        cp_async16(dst + (uint32_t)ps * 4096u, side + rc * 64 + tx * 4, ok);
-                        cp_async16(dst + 8192u + (uint32_t)ps * 4096u, E + rc * 64 + tx * 4, ok);
-                    }
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8192u), "l"(kbits + rc * 2), "r"(ok >> 1) : "memory");
+                } else {
+                    cp_async16(dst, side + rc * 64 + tx * 4, ok);
+                    cp_async16(dst + 8192u, E + rc * 64 + tx * 4, ok);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -262,27 +258,28 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
         int it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int r0 = t * 128;
-            if (it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");       // every builder has left the previous epilogue's staging (= the K-major image)
-            float4 sd4[8], e4[8];
+            if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(kBwBuilders) : "memory");   // every builder has left the previous epilogue's staging (= the K-major image)
+            float4 sd4[4], e4[4], d4, o4;
 #pragma unroll
             for (int w = 0; w < kBwUnits; ++w) {
                 if (w + kBwAhead < kBwUnits) issue(t, w + kBwAhead); else issue(t + (int)gridDim.x, w + kBwAhead - kBwUnits);
                 asm volatile("cp.async.wait_group %0;" ::"n"(kBwAhead) : "memory");
                 const uint32_t src = aG + (uint32_t)(w & 3) * kBwUnit + (uint32_t)ty * 256u + (uint32_t)tx * 16u;
                 const int k = w / 3, j = w % 3;
-                if (j < 2) {
-                    // ---- dS, rows 32k + 16j + ty (16 lanes per row): the row norm and <D,dO> by shuffles.  S_pre is not read: where
-                    // keep = 1 the sign of S is the sign of D (D = LeakyReLU(S)/(1-p)), where keep = 0 the gradient is zero either way
-                    const int rr = k * 32 + j * 16 + ty;
+                if (j == 0) {
+                    d4 = bw_ld4(src); o4 = bw_ld4(src + 8192u);
+                } else if (j == 1) {
+                    // ---- dS, row 32k + ty (16 lanes per row): the row norm and <D,dO> by shuffles.  S_pre is not read: where keep = 1
+                    // the sign of S is the sign of D (D = LeakyReLU(S)/(1-p)), where keep = 0 the gradient is zero either way
+                    const int rr = k * 32 + ty;
                     const bool in = r0 + rr < N;
-                    const float4 d4 = bw_ld4(src), o4 = bw_ld4(src + 4096u);
-                    const float4 x4 = dD_ext ? bw_ld4(src + 8192u) : f4zero();
-                    float4 k4 = KEEP == 1 ? bw_ld4(src + 12288u) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 x4 = dD_ext ? bw_ld4(src) : f4zero();
+                    float4 k4 = KEEP == 1 ? bw_ld4(src + 8192u) : make_float4(1.f, 1.f, 1.f, 1.f);
                     if (KEEP == 2) {
                         uint32_t w0, w1;
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src + 12288u) : "memory");
-                        const uint32_t w = ((tx >> 3) ? w1 : w0) >> ((tx & 7) * 4);
-                        k4 = make_float4((float)(w & 1u), (float)((w >> 1) & 1u), (float)((w >> 2) & 1u), (float)((w >> 3) & 1u));
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(src + 8192u) : "memory");
+                        const uint32_t wd = ((tx >> 3) ? w1 : w0) >> ((tx & 7) * 4);
+                        k4 = make_float4((float)(wd & 1u), (float)((wd >> 1) & 1u), (float)((wd >> 2) & 1u), (float)((wd >> 3) & 1u));
                     }
                     float ss = d4.x * d4.x + d4.y * d4.y + d4.z * d4.z + d4.w * d4.w;
                     float dot = d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;   // <D, dO>
@@ -306,24 +303,20 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
                     bw_st4(aS + ok, h); bw_st4(aS + kBwHalf + ok, l);
                     bw_st4(aM + om, h); bw_st4(aM + kBwHalf + om, l);
                 } else {
-                    // ---- Z = [side | E (*) side], rows 32k .. 32k+31: two 16-row chunks into the ring (the dS rows they are contracted
-                    // with were written above; the fence before the arrive covers them)
-#pragma unroll
-                    for (int ps = 0; ps < 2; ++ps) {
-                        const int c = k * 2 + ps;
-                        sd4[c] = bw_ld4(src + (uint32_t)ps * 4096u);
-                        e4[c] = bw_ld4(src + 8192u + (uint32_t)ps * 4096u);
-                        const int g = it * kBwZChunks + c, s = g % kBwZStages;
-                        mbar_wait(z_empty + s, ((g / kBwZStages) & 1) ^ 1);
-                        const uint32_t zs = aZ + (uint32_t)s * kBwZStage;
-                        const float z1[4] = {sd4[c].x, sd4[c].y, sd4[c].z, sd4[c].w};
-                        const float z2[4] = {e4[c].x * sd4[c].x, e4[c].y * sd4[c].y, e4[c].z * sd4[c].z, e4[c].w * sd4[c].w};
-                        const uint32_t o = (uint32_t)(tx >> 3) * kBwZBlk + bw_sw32(ty, tx & 7);      // feature block tx/8 (side), 2 + tx/8 (E*side)
-                        bw_split_store(zs + o, zs + kBwZHalf + o, z1);
-                        bw_split_store(zs + 2 * kBwZBlk + o, zs + kBwZHalf + 2 * kBwZBlk + o, z2);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(z_full + s);
-                    }
+                    // ---- Z = [side | E (*) side], rows 32k .. 32k+31 = chunks 2k (the lanes with ty < 16) and 2k+1 (the others), each
+                    // into its own ring stage (the dS rows they are contracted with were written above; the fence covers them)
+                    sd4[k] = bw_ld4(src);
+                    e4[k] = bw_ld4(src + 8192u);
+                    const int s = ty >> 4;                      // chunk 2k + s lives in stage s (kBwZChunks is even)
+                    mbar_wait(z_empty + s, ((it * (kBwZChunks / 2) + k) & 1) ^ 1);
+                    const uint32_t zs = aZ + (uint32_t)s * kBwZStage;
+                    const float z1[4] = {sd4[k].x, sd4[k].y, sd4[k].z, sd4[k].w};
+                    const float z2[4] = {e4[k].x * sd4[k].x, e4[k].y * sd4[k].y, e4[k].z * sd4[k].z, e4[k].w * sd4[k].w};
+                    const uint32_t o = (uint32_t)(tx >> 3) * kBwZBlk + bw_sw32(ty & 15, tx & 7);      // feature block tx/8 (side), 2 + tx/8 (E*side)
+                    bw_split_store(zs + o, zs + kBwZHalf + o, z1);
+                    bw_split_store(zs + 2 * kBwZBlk + o, zs + kBwZHalf + 2 * kBwZBlk + o, z2);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(z_full + s);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -331,39 +324,35 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
             // ---- epilogue, after every product of the tile has completed
             mbar_wait(d1_full, it & 1);
             tc_fence_after();
-#pragma unroll
-            for (int hc = 0; hc < 2; ++hc) {     // running dWcat += this tile's (row q*32+lane of Wcat, this warp's 32 columns, 16 at a time)
+            {   // running dWcat += this tile's (row q*32+lane of Wcat, this warp's 16 columns)
                 uint32_t raw[16], run[16];
-                tmem_ld16(tq + kTcD2 + (uint32_t)(half * 32 + hc * 16), raw);
-                tmem_ld16(tq + kTcRun + (uint32_t)(half * 32 + hc * 16), run);
+                tmem_ld16(tq + kTcD2 + (uint32_t)(cq * 16), raw);
+                tmem_ld16(tq + kTcRun + (uint32_t)(cq * 16), run);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) run[j] = __float_as_uint(__uint_as_float(run[j]) + __uint_as_float(raw[j]));
-                tmem_st16(tq + kTcRun + (uint32_t)(half * 32 + hc * 16), run);
+                tmem_st16(tq + kTcRun + (uint32_t)(cq * 16), run);
             }
             {   // dZ^T: lane = feature kk (0..63 -> dZ1, 64..127 -> dZ2), columns = rows; un-transpose through the K-major dS image:
                 // plane kk/64, row-major [128 rows x 64], 16-byte chunk index XOR row (conflict-free for these stores and the reads below)
                 const int kk = q * 32 + lane;
                 const uint32_t pbase = aS + (uint32_t)(kk >> 6) * kBwHalf + (uint32_t)(kk & 3) * 4u;
                 const int chunk = (kk & 63) >> 2;
+                uint32_t zr[32];
+                tmem_ld32(tq + kTcDz + (uint32_t)(cq * 32), zr);
+                tmem_ld_wait();
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    uint32_t zr[32];
-                    tmem_ld32(tq + kTcDz + (uint32_t)(half * 64 + part * 32), zr);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int row = half * 64 + part * 32 + j;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(pbase + (uint32_t)row * 256u + (uint32_t)(((chunk & 8) | ((chunk ^ row) & 7)) << 4)), "r"(zr[j]) : "memory");
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const int row = cq * 32 + j;
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(pbase + (uint32_t)row * 256u + (uint32_t)(((chunk & 8) | ((chunk ^ row) & 7)) << 4)), "r"(zr[j]) : "memory");
                 }
             }
             tmem_st_wait();
             tc_fence_before();   // the next tile's products overwrite dZ^T and the tile accumulator: ordered through the arrives on z_full / ds_full
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kBwBuilders) : "memory");
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rr = i * 16 + ty, r = r0 + rr;
+            for (int i = 0; i < 4; ++i) {
+                const int rr = i * 32 + ty, r = r0 + rr;
                 const uint32_t o = aS + (uint32_t)rr * 256u + (uint32_t)(((tx & 8) | ((tx ^ rr) & 7)) << 4);
                 const float4 a = bw_ld4(o), b = bw_ld4(o + kBwHalf);
                 if (r < N) {
@@ -372,15 +361,15 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
                 }
             }
         }
-        // ---- dWcat partial of this CTA: the running sum (row = Wcat row, this warp's 32 columns)
+        // ---- dWcat partial of this CTA: the running sum (row = Wcat row, this warp's 16 columns)
         tc_fence_after();
         {
-            uint32_t run[32];
-            tmem_ld32(tq + kTcRun + (uint32_t)(half * 32), run);
+            uint32_t run[16];
+            tmem_ld16(tq + kTcRun + (uint32_t)(cq * 16), run);
             tmem_ld_wait();
-            float* wp = dW_part + ((size_t)blockIdx.x * 128 + q * 32 + lane) * 64 + half * 32;
+            float* wp = dW_part + ((size_t)blockIdx.x * 128 + q * 32 + lane) * 64 + cq * 16;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4)
+            for (int j4 = 0; j4 < 4; ++j4)
                 st4(wp + j4 * 4, make_float4(__uint_as_float(run[j4 * 4]), __uint_as_float(run[j4 * 4 + 1]), __uint_as_float(run[j4 * 4 + 2]), __uint_as_float(run[j4 * 4 + 3])));
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -390,13 +379,13 @@ __global__ void __launch_bounds__(288, 1) ngcf_dense_bwd_tc_kernel(const float* 
     float* scratch = reinterpret_cast<float*>(sZ);
     if (warp >= 1) {
         const int bt = tid - 32, ty = bt >> 4, tx = bt & 15;
-        *reinterpret_cast<float4*>(scratch + ty * 64 + tx * 4) = dbv;
+        *reinterpret_cast<float4*>(scratch + ty * 64 + tx * 4) = dbv;     // [32][64]
     }
     __syncthreads();
     if (tid < 64) {
         float a = 0.f;
 #pragma unroll
-        for (int y = 0; y < 16; ++y) a += scratch[y * 64 + tid];
+        for (int y = 0; y < kBwBuilders / 16; ++y) a += scratch[y * 64 + tid];
         db_part[(size_t)blockIdx.x * 64 + tid] = a;
     }
     if (warp == 0) {
@@ -423,7 +412,7 @@ int ngcf_dense_bwd_tc(const float* E, const float* side, const float* Wg, const 
     const size_t smem = (size_t)kBwSmem + 128;
     auto launch = [&](auto kern) -> int {
         IDG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 288, smem, stream>>>(E, side, Wg, Wb, keep, keep_bits, inv_keep, D, dO, dO_stride, dD_ext, N, dside, dE_direct, dW_part, db_part);
+        kern<<<grid, kBwBuilders + 32, smem, stream>>>(E, side, Wg, Wb, keep, keep_bits, inv_keep, D, dO, dO_stride, dD_ext, N, dside, dE_direct, dW_part, db_part);
         return 0;
     };
     if (int rc = keep_bits ? launch(ngcf_dense_bwd_tc_kernel<2>) : (keep ? launch(ngcf_dense_bwd_tc_kernel<1>) : launch(ngcf_dense_bwd_tc_kernel<0>))) return rc;
