@@ -121,6 +121,8 @@ class FusedTrainer:
         if kind == "SimGCL" and self.rows is not None and not self.use_closure and 2 <= K <= 4:
             from .graph import Graph
             self._gviews = [graph, Graph(graph.csr, graph.row_begin, graph.row_end), Graph(graph.csr, graph.row_begin, graph.row_end)]
+            for v, gv in enumerate(self._gviews):     # schedule scratch allocated (and zero-filled) here, not on first use: a lazy
+                self.rows.worklist(gv, v)              # torch.zeros on the main stream would race with the launch on the view's stream
         self.use_cuda_graph = use_cuda_graph
         self._graphs = {}
         self._graph_launches = {}
