@@ -198,7 +198,9 @@ class DistFusedTrainer:
         # "auto" picks it only where it was measured to help: 8 ranks and a large local share (>= 4 M non-zeros per rank).
         mode = os.environ.get("IDG_DIST_EXCHANGE", "auto")
         local_nnz = int(csr.indptr[self.b1].item() - csr.indptr[self.b0].item())
-        self.chunked = world > 1 and (mode == "chunked" or (mode == "auto" and world >= 8 and local_nnz >= 4000000))
+        # (forced "chunked" also applies to a world of one -- the pushes are no-ops there -- so that the block schedule and its
+        # fork / join are exercised on a single-GPU box)
+        self.chunked = mode == "chunked" or (mode == "auto" and world >= 8 and local_nnz >= 4000000)
         self.chunks, self._push_side = [], None
         if self.chunked:
             n_chunks = max(1, int(os.environ.get("IDG_DIST_CHUNKS", "4")))

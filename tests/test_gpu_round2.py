@@ -410,6 +410,42 @@ def test_ngcf_keep_masks_are_bernoulli_and_step_dependent(dev):
     assert not torch.equal(a[0], keep[0]) and abs(float((a[0] * keep[0]).mean()) - 0.81) < 5e-3      # independent draws
 
 
+@pytest.mark.parametrize("kind,use_graph", [("LightGCN", True), ("LightGCN", False), ("SimGCL", True), ("XSimGCL", True)])
+def test_row_partitioned_step_world1_chunked_exchange(dev, monkeypatch, kind, use_graph):
+    """The chunked exchange (local rows computed in nnz-balanced blocks on per-block propagation handles, each finished block pushed
+    from a second stream -- the default at 8 ranks on large graphs) with a single partition: same bits as the single-GPU fused
+    trainer.  The pushes are no-ops in a world of one; the block schedule, the per-block handles and the fork / join are real."""
+    from idgrec import datagen
+    from idgrec.dist import DistFusedTrainer
+    from idgrec.engine import FusedTrainer
+    from idgrec.graph import Graph, build_norm_adjacency
+    monkeypatch.setenv("IDG_DIST_EXCHANGE", "chunked")
+    monkeypatch.setenv("IDG_DIST_CHUNKS", "5")
+    g = datagen.gen_graph("small")
+    U, I = g.num_users, g.num_items
+    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
+    G = Graph(csr)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(15)
+    table = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
+    kw = dict(ssl_lambda=0.3, temperature=0.2, eps=0.1, cl_layer=2) if kind != "LightGCN" else {}
+    ref = FusedTrainer(kind, G, table.clone(), U, 3, 1e-4, 1e-3, max_batch=512, use_cuda_graph=False, **kw)
+    ft = DistFusedTrainer(kind, csr, table.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=512, use_cuda_graph=use_graph, full_graph=G, **kw)
+    assert ft.chunked and len(ft.chunks) >= 4
+    n_views = {"LightGCN": 0, "SimGCL": 2, "XSimGCL": 1}[kind]
+    rng = np.random.default_rng(18)
+    nz = [torch.empty(3, U + I, 64, device=dev) for _ in range(n_views)]
+    ref.injected_noise = ft.injected_noise = nz if n_views else None
+    for step in range(3):
+        e = rng.integers(0, len(g.train_user), 512)
+        b = tuple(torch.from_numpy(a).to(dev) for a in (g.train_user[e], g.train_item[e], rng.integers(0, I, 512)))
+        for t in nz:
+            t.copy_(torch.rand(3, U + I, 64, generator=gen, device=dev))
+        lr, ld = ref.step(*b).clone(), ft.step(*b).clone()
+        assert torch.equal(lr, ld), (step, lr, ld)
+    assert torch.equal(ref.E0, ft.E0)
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_row_partitioned_step_world1_with_neighbourhood_restriction(dev, use_graph):
     """Same bit-identity with the batch-neighbourhood (closure) restriction forced on: masked layer K-1, row-masked sparse first
