@@ -24,6 +24,9 @@ int nce_tc_stage(int stage, const float* A, const float* Bm, const float* beta, 
 
 constexpr int kNT = 64;      // tile edge
 constexpr int kNceSplits = 8;
+// csrc/infonce_flash.cu: the same contractions without the n x n matrices
+int nce_flash(const float* X, const float* Y, const float* V, const float* v_scale, const int* d_n, int n_max, float inv_tau, float* part_sum,
+              float* part_out, int splits, cudaStream_t stream);
 
 struct NceWs {
     float* A;      // [n,d] normalised view 1 rows
@@ -266,6 +269,19 @@ static int infonce_impl(const float* d_V1, const float* d_V2, const int64_t* d_i
     const dim3 grid((n + kNT - 1) / kNT, kNceSplits);
     nce_prep_kernel<<<(n + 7) / 8, 256, 0, stream>>>(d_V1, d_V2, d_idx, d_n, n, inv_tau, w);
     IDG_LAUNCH_CHECK("nce_prep_kernel");
+    // IDG_NCE_IMPL=split keeps the round-1 form (E and E^T materialised as (hi, lo) pairs, separate gemm launches) as a cross-check
+    static const bool flash = !(getenv("IDG_NCE_IMPL") && strcmp(getenv("IDG_NCE_IMPL"), "split") == 0);
+    if (nce_use_tc(n) && flash && (d_gV1 || d_gV2)) {
+        // fused tensor-core path (csrc/infonce_flash.cu): E = exp(A B^T / tau) never leaves the SM.  Pass 1: row sums and P B = E B;
+        // row kernel: loss, beta; pass 2 (mirrored): Q A = E^T (beta A); gradient kernel.
+        if (int rc = nce_flash(w.A, w.Bm, w.Bm, nullptr, d_n, n, inv_tau, w.part_sum, w.part_pb, kNceSplits, stream)) return rc;
+        nce_rows_kernel<<<1, 1024, 0, stream>>>(w, d_n, n, np, loss_scale, d_loss);
+        IDG_LAUNCH_CHECK("nce_rows_kernel");
+        if (int rc = nce_flash(w.Bm, w.A, w.A, w.beta, d_n, n, inv_tau, nullptr, w.part_qa, kNceSplits, stream)) return rc;
+        nce_grad_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, d_idx, d_n, n, np, inv_tau, loss_scale, d_gV1, d_gV2);
+        IDG_LAUNCH_CHECK("nce_grad_kernel");
+        return 0;
+    }
     if (nce_use_tc(n)) {
         // tensor-core path: E = exp(A B^T/tau) and its row sums, then (if gradients are wanted) E^T, PB = E B, QA = E^T (beta A)
         if (int rc = nce_tc_stage(0, w.A, w.Bm, nullptr, d_n, n, inv_tau, w.part_sum, nullptr, nullptr, w.extra, stream, (d_gV1 || d_gV2) ? 1 : 0, kNceSplits)) return rc;
