@@ -11,15 +11,18 @@
 // wrote E and E^T as (hi, lo) pairs (4 n^2 floats) and read them back in two more launches (csrc/infonce_tc.cu, kept for the
 // forward-only call and as the cross-check IDG_NCE_IMPL=split).
 //
-// grid (n_pad / 128, splits); warp 0 issues the MMAs, warps 1..8 build the operand images (16 lanes per row) and run the
-// epilogues (thread <-> TMEM lane = row; two warps per lane quadrant = two 64-column halves of the score tile).
+// grid (n_pad / 128, splits); warp 0 issues the MMAs, warps 1..16 build the operand images (16 lanes per row) and run the
+// epilogues (thread <-> TMEM lane = row; four warps per lane quadrant = four 32-column quarters of the score tile).  Measured at
+// n = 1,923: 65 us per InfoNCE call with 8 worker warps, 54 us with 16 (93 us with the materialised matrices).
 #include <math.h>
 
 #include "tc_common.cuh"
 
 namespace idg {
 
-constexpr int kFlWorkers = 256;
+constexpr int kFlWorkers = 512;               // 16 worker warps (8 left the SM issue-bound in the NGCF kernels of the same build)
+constexpr int kFlPasses = 2048 / kFlWorkers;  // a [128 rows x 16 chunks] operand in passes of kFlWorkers / 16 rows
+constexpr int kFlPassRows = kFlWorkers / 16;
 constexpr uint32_t kFlBlk = 128 * 128;          // [128 rows x 32 fp32]
 constexpr uint32_t kFlHalf = 2 * kFlBlk;        // hi (or lo) of a [128 x 64] operand
 constexpr uint32_t kFlSmem = 6 * kFlHalf;       // X hi|lo (K-major) | Y hi|lo (K-major) | V hi|lo (MN-major) = 192 KB
@@ -43,7 +46,7 @@ __device__ __forceinline__ void fl_split(float x, float& hi, float& lo) {   // h
 }
 
 template <bool ROWSUM>
-__global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ V,
+__global__ void __launch_bounds__(kFlWorkers + 32, 1) nce_flash_kernel(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ V,
                                                            const float* __restrict__ v_scale, const int* __restrict__ d_n, int n_in, int n_pad,
                                                            float inv_tau, float* __restrict__ part_sum, float* __restrict__ part_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFlSmem);
     uint64_t *x_full = bars, *y_full = bars + 1, *y_empty = bars + 2, *s_full = bars + 3, *e_full = bars + 4, *o_full = bars + 5;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    float* s_row = reinterpret_cast<float*>(bars + 8);     // [128] second column half's row sums
+    float* s_row = reinterpret_cast<float*>(bars + 8);     // [3][128] row sums of the column quarters 1..3
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_total = (n + 127) / 128;
     const int t_begin = (int)((long long)tiles_total * blockIdx.y / gridDim.y), t_end = (int)((long long)tiles_total * (blockIdx.y + 1) / gridDim.y);
@@ -107,14 +110,14 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
         }
     } else {
         const int bt = tid - 32, ty = bt >> 4, tx = bt & 15;
-        const int q = warp & 3, half = (warp - 1) >> 2;
+        const int q = warp & 3, cq = (warp - 1) >> 2;      // TMEM lane quadrant, column quarter (32 of the 128 score columns, 16 of the 64 out columns)
         const uint32_t tq = tmem_base + (((uint32_t)(q * 32)) << 16);
         const int row = q * 32 + lane;
         const bool rvalid = r0 + row < n;
         // X tile (hi, lo), once
 #pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-            const int rr = ps * 16 + ty;
+        for (int ps = 0; ps < kFlPasses; ++ps) {
+            const int rr = ps * kFlPassRows + ty;
             float4 x = f4zero();
             if (r0 + rr < n) x = ldg4(X + (size_t)(r0 + rr) * 64 + tx * 4);
             const float xv[4] = {x.x, x.y, x.z, x.w};
@@ -130,10 +133,10 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
         for (int t = 0; t < ntiles; ++t) {
             const int c0 = (t_begin + t) * 128;
             // ---- operand images of the column tile: Y rows K-major (scores), V rows MN-major (the contraction over these rows)
-            float4 yv[8], vv[8];
+            float4 yv[kFlPasses], vv[kFlPasses];
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int c = c0 + ps * 16 + ty;
+            for (int ps = 0; ps < kFlPasses; ++ps) {
+                const int c = c0 + ps * kFlPassRows + ty;
                 yv[ps] = f4zero(); vv[ps] = f4zero();
                 if (c < n) {
                     yv[ps] = ldg4(Y + (size_t)c * 64 + tx * 4);
@@ -147,8 +150,8 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
             }
             mbar_wait(y_empty, (t & 1) ^ 1);
 #pragma unroll
-            for (int ps = 0; ps < 8; ++ps) {
-                const int rr = ps * 16 + ty;
+            for (int ps = 0; ps < kFlPasses; ++ps) {
+                const int rr = ps * kFlPassRows + ty;
                 const float a[4] = {yv[ps].x, yv[ps].y, yv[ps].z, yv[ps].w}, b[4] = {vv[ps].x, vv[ps].y, vv[ps].z, vv[ps].w};
                 float h[4], l[4];
 #pragma unroll
@@ -165,9 +168,8 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
             // ---- scores -> E (hi, lo) in TMEM; row sums
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const uint32_t col = (uint32_t)(half * 64 + ch * 32);
+            {
+                const uint32_t col = (uint32_t)(cq * 32);
                 uint32_t raw[32], lo[32];
                 tmem_ld32(tq + kFlS + col, raw);
                 tmem_ld_wait();
@@ -191,24 +193,29 @@ __global__ void __launch_bounds__(288, 1) nce_flash_kernel(const float* __restri
             mbar_wait(o_full, 0);
             tc_fence_after();
         }
-        if (ROWSUM && half == 1) s_row[row] = rowsum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        float* out = part_out + ((size_t)blockIdx.y * n_pad + r0 + row) * 64 + half * 32;
+        if (ROWSUM && cq > 0) s_row[(cq - 1) * 128 + row] = rowsum;
+        asm volatile("bar.sync 1, %0;" ::"n"(kFlWorkers) : "memory");
+        float* out = part_out + ((size_t)blockIdx.y * n_pad + r0 + row) * 64 + cq * 16;
         if (ntiles > 0) {
-            uint32_t raw[32];
-            tmem_ld32(tq + kFlOut + (uint32_t)(half * 32), raw);
+            uint32_t raw[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]), "=r"(raw[8]), "=r"(raw[9]),
+                  "=r"(raw[10]), "=r"(raw[11]), "=r"(raw[12]), "=r"(raw[13]), "=r"(raw[14]), "=r"(raw[15])
+                : "r"(tq + kFlOut + (uint32_t)(cq * 16))
+                : "memory");
             tmem_ld_wait();
             if (rvalid) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
+                for (int j4 = 0; j4 < 4; ++j4)
                     st4(out + j4 * 4, make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
                                                   __uint_as_float(raw[4 * j4 + 3])));
             }
         } else if (rvalid) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) st4(out + j4 * 4, f4zero());
+            for (int j4 = 0; j4 < 4; ++j4) st4(out + j4 * 4, f4zero());
         }
-        if (ROWSUM && half == 0 && rvalid) part_sum[(size_t)blockIdx.y * n_pad + r0 + row] = rowsum + s_row[row];
+        if (ROWSUM && cq == 0 && rvalid) part_sum[(size_t)blockIdx.y * n_pad + r0 + row] = ((rowsum + s_row[row]) + s_row[128 + row]) + s_row[256 + row];
     }
     tc_fence_before();
     __syncthreads();
@@ -224,13 +231,13 @@ int nce_flash(const float* X, const float* Y, const float* V, const float* v_sca
               float* part_out, int splits, cudaStream_t stream) {
     const int np = (n_max + 127) / 128 * 128;
     const dim3 grid(np / 128, splits);
-    const size_t smem = (size_t)kFlSmem + 1024;
+    const size_t smem = (size_t)kFlSmem + 2048;
     if (part_sum) {
         IDG_CUDA(cudaFuncSetAttribute(nce_flash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nce_flash_kernel<true><<<grid, 288, smem, stream>>>(X, Y, V, v_scale, d_n, n_max, np, inv_tau, part_sum, part_out);
+        nce_flash_kernel<true><<<grid, kFlWorkers + 32, smem, stream>>>(X, Y, V, v_scale, d_n, n_max, np, inv_tau, part_sum, part_out);
     } else {
         IDG_CUDA(cudaFuncSetAttribute(nce_flash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nce_flash_kernel<false><<<grid, 288, smem, stream>>>(X, Y, V, v_scale, d_n, n_max, np, inv_tau, nullptr, part_out);
+        nce_flash_kernel<false><<<grid, kFlWorkers + 32, smem, stream>>>(X, Y, V, v_scale, d_n, n_max, np, inv_tau, nullptr, part_out);
     }
     IDG_LAUNCH_CHECK("nce_flash_kernel");
     return 0;
