@@ -180,41 +180,51 @@ __global__ void __launch_bounds__(256) ngcf_reduce_kernel(const float* __restric
 }
 
 // nn.Dropout's Bernoulli(1 - p) draws for all layers of one step in ONE launch (NGCF.py:99-100 constructs nn.Dropout inline, so
-// it is always active): keep[l][i] = 1 with probability 1 - p_l.  Counter-based Philox: element quad q of step t reads
-// stream (seed, subsequence q, offset t), so a captured step replays with fresh draws (t comes from the device step
-// counter) and the result does not depend on the launch geometry.  torch's own bernoulli_ costs three launches per mask
-// (uniform, compare, cast): 150 us of the 1.76 ms fused step at the amazon-book shape.
+// it is always active): keep[l][i] = 1 with probability 1 - p_l.  Counter-based Philox4x32-10 evaluated directly: element quad q of
+// step t is the block with counter (t, q) under the key `seed` -- every step reads a fresh block of every quad (t comes from the
+// device step counter, so a captured step replays with fresh draws) and the result does not depend on the launch geometry.
+// (An earlier version went through curand_init(seed, q, t) + curand_uniform4: offset t in VALUES, i.e. the quad of step t + 1 was
+// the quad of step t shifted by one element, and sixteen state initialisations per row made the bit-packed kernel 44 us.)
+// torch's own bernoulli_ costs three launches per mask (uniform, compare, cast): 150 us of the 1.76 ms round-1 step.
+__device__ __forceinline__ uint32_t keep_quad(unsigned long long seed, unsigned long long step, unsigned long long q, float pk) {
+    const uint4 r = curand_Philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), (unsigned)q, (unsigned)(q >> 32)),
+                                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float4 u = _curand_uniform4(r);   // (0, 1]
+    return (u.x <= pk ? 1u : 0u) | (u.y <= pk ? 2u : 0u) | (u.z <= pk ? 4u : 0u) | (u.w <= pk ? 8u : 0u);
+}
+
 __global__ void __launch_bounds__(256) ngcf_keep_masks_kernel(float* __restrict__ keep, int64_t per_layer4, int n_layers, float k0, float k1,
                                                               float k2, float k3, unsigned long long seed, const int* __restrict__ d_step) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= per_layer4 * n_layers) return;
     const int layer = (int)(q / per_layer4);
     const float pk = layer == 0 ? k0 : (layer == 1 ? k1 : (layer == 2 ? k2 : k3));
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed, (unsigned long long)q, (unsigned long long)(d_step ? *d_step : 0), &st);
-    const float4 r = curand_uniform4(&st);   // (0, 1]
-    reinterpret_cast<float4*>(keep)[q] = make_float4(r.x <= pk ? 1.f : 0.f, r.y <= pk ? 1.f : 0.f, r.z <= pk ? 1.f : 0.f, r.w <= pk ? 1.f : 0.f);
+    const uint32_t b = keep_quad(seed, (unsigned long long)(d_step ? *d_step : 0), (unsigned long long)q, pk);
+    reinterpret_cast<float4*>(keep)[q] = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
 }
 
 // The same draws packed 64 bits per row (word w, bit b = column 32 w + b): what the tensor-core dense kernels read -- 8 bytes per
-// row instead of a 256-byte float mask row in the forward and again in the backward.  Same Philox stream as above, quad for quad.
+// row instead of a 256-byte float mask row in the forward and again in the backward.  Quad for quad the blocks of the kernel above;
+// four lanes per row (four quads each), combined by shuffles.
 __global__ void __launch_bounds__(256) ngcf_keep_bits_kernel(uint2* __restrict__ bits, int N, int n_layers, float k0, float k1, float k2, float k3,
                                                              unsigned long long seed, const int* __restrict__ d_step) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)N * n_layers) return;
-    const int layer = (int)(t / N);
-    const float pk = layer == 0 ? k0 : (layer == 1 ? k1 : (layer == 2 ? k2 : k3));
-    const unsigned long long step = (unsigned long long)(d_step ? *d_step : 0);
-    uint32_t w[2] = {0u, 0u};
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-        curandStatePhilox4_32_10_t st;
-        curand_init(seed, (unsigned long long)(t * 16 + c), step, &st);   // quad index = (layer N + row) 16 + c, as in ngcf_keep_masks_kernel
-        const float4 r = curand_uniform4(&st);
-        const uint32_t b = (r.x <= pk ? 1u : 0u) | (r.y <= pk ? 2u : 0u) | (r.z <= pk ? 4u : 0u) | (r.w <= pk ? 8u : 0u);
-        w[c >> 3] |= b << ((c & 7) * 4);
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = g >> 2;                 // (layer, row)
+    const int part = (int)(g & 3);            // quads 4 part .. 4 part + 3 of the row = 16 mask bits
+    const bool in = t < (int64_t)N * n_layers;
+    uint32_t h = 0u;
+    if (in) {
+        const int layer = (int)(t / N);
+        const float pk = layer == 0 ? k0 : (layer == 1 ? k1 : (layer == 2 ? k2 : k3));
+        const unsigned long long step = (unsigned long long)(d_step ? *d_step : 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) h |= keep_quad(seed, step, (unsigned long long)(t * 16 + part * 4 + c), pk) << (c * 4);
     }
-    bits[t] = make_uint2(w[0], w[1]);
+    // lanes 4k .. 4k+3 hold the four 16-bit pieces of one row
+    const uint32_t nb = __shfl_down_sync(0xffffffffu, h, 1);
+    const uint32_t w = h | (nb << 16);        // valid on even parts: parts (0,1) -> word 0, parts (2,3) -> word 1
+    const uint32_t w1 = __shfl_down_sync(0xffffffffu, w, 2);
+    if (in && part == 0) bits[t] = make_uint2(w, w1);
 }
 
 // dst[row] = src[row] for the rows idx[i] + row_offset (row strides in floats): the 64-column ego block of the [N,256] concat is
@@ -249,7 +259,7 @@ extern "C" int idg_ngcf_keep_bits(uint32_t* d_bits, int32_t N, int32_t n_layers,
     if (!d_bits || !h_keep_prob || N <= 0 || n_layers < 1 || n_layers > 4) return fail(-1, "idg_ngcf_keep_bits: bad argument%s");
     float k[4] = {1.f, 1.f, 1.f, 1.f};
     for (int l = 0; l < n_layers; ++l) k[l] = h_keep_prob[l];
-    const int64_t n = (int64_t)N * n_layers;
+    const int64_t n = (int64_t)N * n_layers * 4;      // four lanes per row
     ngcf_keep_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint2*>(d_bits), N, n_layers, k[0], k[1], k[2], k[3],
                                                                                       (unsigned long long)seed, d_step);
     IDG_LAUNCH_CHECK("ngcf_keep_bits_kernel");

@@ -4,7 +4,8 @@
     python tools/prof_r2.py eval       # 400 graph-replayed train steps (so the table is not at its initial scale), then one Test()
     python tools/prof_r2.py infonce    # InfoNCE forward+backward at n = 1,923 rows (the SimGCL production size), tau = 0.2
     python tools/prof_r2.py simgcl     # 2 eager SimGCL steps on the yelp2018 shape, B = 2,048
-    python tools/prof_r2.py all        # everything above once (launch list)
+    python tools/prof_r2.py ngcf       # 2 eager NGCF steps on the amazon-book shape
+    python tools/prof_r2.py all        # everything above (except ngcf) once (launch list)
 """
 import os
 import sys
@@ -53,6 +54,18 @@ def simgcl(dev):
     torch.cuda.synchronize()
 
 
+def ngcf(dev):
+    import utility.utility_train.trainer as trainer
+    cfg, g, data, model = bc._build("NGCF", "amazon-book", dev)
+    cfg["cuda_graph"] = "0"
+    B = 1024
+    ft = model.fused_trainer(float(cfg["learn_rate"]), B)
+    users, pos, neg = trainer.sample_epoch(data, dev)
+    for s in range(2):
+        ft.step(users[s * B:(s + 1) * B], pos[s * B:(s + 1) * B], neg[s * B:(s + 1) * B])
+    torch.cuda.synchronize()
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     dev = torch.device("cuda:0")
@@ -65,6 +78,8 @@ def main():
         print(bc.infonce_record(dev, 1923, 0.2))
     if what in ("simgcl", "all"):
         simgcl(dev)
+    if what == "ngcf":
+        ngcf(dev)
 
 
 if __name__ == "__main__":
