@@ -126,14 +126,14 @@ def infonce_record(dev, n, tau, d=64):
         b.record()
     torch.cuda.synchronize()
     ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
-    flops = 4 * 2.0 * n * n * d          # S, and the three gradient contractions' worth (E V2, E^T V1 ...): 4 n x n x d products
+    flops = 4 * 2.0 * n * n * d          # two flash passes, each the score product and the E V product: 4 n x n x d products
     rec = {"rows": n, "ms_per_call": ms, "flops_fp32_equivalent": flops, "TFLOPs_fp32_equivalent": flops / ms / 1e9,
-           "passes": "3xTF32 split products on tcgen05 (x3 tensor-core work per fp32-equivalent flop)"}
+           "passes": "3xTF32 split products on tcgen05 (x3 tensor-core work per fp32-equivalent flop); E = exp(S/tau) stays in TMEM (csrc/infonce_flash.cu)"}
     try:
-        prof = json.load(open(os.path.join(REPO, "profiles", "infonce_n1923_r2_ncu.json")))
+        prof = json.load(open(os.path.join(REPO, "profiles", "infonce_flash_n1923_r2_ncu.json")))
         rec["tensor_pipe_active_pct_ncu"] = prof.get("tensor_pipe_active_pct")
         rec["kernel_us_ncu"] = prof.get("kernel_us")
-        rec["ncu_source"] = "profiles/infonce_n1923_r2_ncu.json"
+        rec["ncu_source"] = "profiles/infonce_flash_n1923_r2_ncu.json"
     except Exception:
         pass
     return rec
