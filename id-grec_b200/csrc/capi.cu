@@ -257,6 +257,26 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __rest
     if (i < n) { const float t = y[i]; gx[i] = gy[i] * (1.f - t * t); }
 }
 
+// The step's mini-batch out of the epoch's sample arrays, as the FIRST node of the captured step graph: the host then only replays
+// (three small device-to-device copies per step were 8 us of the 438 us amazon-book step).  d_ptrs (device, 4 x int64): the three
+// array base addresses and the value of the step counter when the epoch's first batch runs; the batch of this replay starts at
+// (*d_step - start) * stride.
+__global__ void __launch_bounds__(256) batch_fetch_kernel(const long long* __restrict__ ptrs, const int* __restrict__ d_step, int stride, int B,
+                                                          int64_t* __restrict__ slab, int slab_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int k = blockIdx.y;
+    const long long cursor = ((long long)*d_step - ptrs[3]) * stride;
+    slab[(size_t)k * slab_stride + i] = reinterpret_cast<const int64_t*>(ptrs[k])[cursor + i];
+}
+
+extern "C" int idg_batch_fetch(const void* d_ptrs, const int32_t* d_step, int32_t stride, int32_t B, int64_t* d_slab, int32_t slab_stride, void* stream) {
+    if (!d_ptrs || !d_step || !d_slab || stride <= 0 || B <= 0 || B > slab_stride) return fail(-1, "idg_batch_fetch: bad argument%s");
+    batch_fetch_kernel<<<dim3((B + 255) / 256, 3), 256, 0, (cudaStream_t)stream>>>((const long long*)d_ptrs, d_step, stride, B, d_slab, slab_stride);
+    IDG_LAUNCH_CHECK("batch_fetch_kernel");
+    return 0;
+}
+
 extern "C" int idg_tanh_fwd(const float* d_x, float* d_y, int64_t n, void* stream) {
     if (!d_x || !d_y || n < 0) return fail(-1, "idg_tanh_fwd: bad argument%s");
     if (n == 0) return 0;

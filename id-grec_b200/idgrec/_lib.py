@@ -134,6 +134,7 @@ SIGNATURES = {
     "idg_neg_sample_replay": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64)]),
     "idg_neg_sample_walk": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p, C.POINTER(_i64), C.POINTER(_i64)]),
     "idg_permute3": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "idg_batch_fetch": (C.c_int, [_p, _p, _i32, _i32, _p, _i32, _p]),
     "idg_tanh_fwd": (C.c_int, [_p, _p, _i64, _p]),
     "idg_tanh_bwd": (C.c_int, [_p, _p, _p, _i64, _p]),
     "idg_parse_ratings": (C.c_int, [C.c_char_p, _p, _p, _i64, C.POINTER(_i64), _p, _p, _i64, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

@@ -102,6 +102,7 @@ class FusedTrainer:
         # Adam applied in the epilogue of the last backward layer (no gradient pass through memory)
         self.fuse_adam = fuse_adam and kind != "MFBPR"
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ep, self._ep_ptrs = None, torch.zeros(4, dtype=torch.int64, device=dev)     # registered epoch arrays (see _epoch_cursor)
         self.regc = torch.zeros(self.N, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
@@ -409,14 +410,48 @@ class FusedTrainer:
             self.loss_acc += self.loss
         return self._report(self.loss)
 
+    def _epoch_cursor(self, B, users, pos, neg):
+        """trainer.py:40-47 walks the epoch's three (shuffled) sample arrays in slices of batch_size.  When the three batch tensors
+        are such slices -- views at the same offset of three contiguous int64 arrays, taken in order from offset 0 -- the step graph
+        fetches its batch itself (idg_batch_fetch, first node) and the host only replays.  Returns True if this call is the next
+        slice of the registered epoch; registers a new epoch when it is the slice at offset 0."""
+        bases = (users._base, pos._base, neg._base)
+        if any(b is None for b in bases) or self.d_step is None:
+            return False
+        offs, starts = [], []
+        for t, b in zip((users, pos, neg), bases):
+            # the array is the base itself (1-D) or one row of a contiguous 2-D base (trainer.py's [3, E] sample block)
+            if t.dtype != torch.int64 or b.dtype != torch.int64 or not t.is_contiguous() or not b.is_contiguous() or b.dim() not in (1, 2):
+                return False
+            cols = b.shape[-1]
+            o = (t.data_ptr() - b.data_ptr()) // 8
+            if o % cols + B > cols:
+                return False
+            offs.append(o % cols)
+            starts.append(b.data_ptr() + (o // cols) * cols * 8)
+        if offs[0] != offs[1] or offs[0] != offs[2]:
+            return False
+        key = tuple(starts)
+        if offs[0] == 0 and B == min(self.max_batch, bases[0].shape[-1]):
+            # first slice of an epoch: (re)register -- also when the same arrays are walked again
+            self._ep = (key, self.step_count, B, bases)
+            self._ep_ptrs.copy_(torch.tensor(list(key) + [self.step_count], dtype=torch.int64), non_blocking=False)
+            return True
+        ep = self._ep
+        return ep is not None and ep[0] == key and B <= ep[2] and offs[0] == (self.step_count - ep[1]) * ep[2]
+
     def _step_graph(self, B, users, pos, neg):
-        """CUDA-graph replay: the step's kernels (incl. the device-side Adam step counter) are captured
-        once per batch size; each call only copies the batch into the static slab and replays."""
-        self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
-        if B not in self._graphs:
-            self._capture(B)
-        self._graphs[B].replay()
-        self.replayed_launches += self._graph_launches[B]
+        """CUDA-graph replay: the step's kernels (incl. the device-side Adam step counter) are captured once per batch size.  Batches
+        that are consecutive slices of the epoch's sample arrays are fetched by the graph itself; any other batch is copied into
+        the static slab first."""
+        fetch = self._epoch_cursor(B, users, pos, neg)
+        key = ("f", B, self._ep[2]) if fetch else B
+        if not fetch:
+            self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
+        if key not in self._graphs:
+            self._capture(B, key)
+        self._graphs[key].replay()
+        self.replayed_launches += self._graph_launches[key]
         self.step_count += 1
         return self._report(self.loss)
 
@@ -424,10 +459,13 @@ class FusedTrainer:
         """Losses in the order of the model's loss list (raw slots: bpr, reg, pair terms)."""
         return raw[:self.n_loss] if self.loss_order is None else raw[self.loss_order]
 
-    def _capture(self, B):
+    def _capture(self, B, key=None):
+        key = B if key is None else key
         u, p, n = (self.batch[k].data_ptr() for k in range(3))
 
         def run():
+            if isinstance(key, tuple):      # ("f", B, stride): the batch comes from the registered epoch arrays
+                check(self.l.idg_batch_fetch(ptr(self._ep_ptrs), ptr(self.d_step), key[2], B, ptr(self.batch), self.max_batch, cur_stream()), "idg_batch_fetch")
             self._body(B, u, p, n, fused=self.fuse_adam)
             if not self.fuse_adam:
                 self._adam()
@@ -440,8 +478,8 @@ class FusedTrainer:
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
             run()
-        self._graph_launches[B] = int(self.l.idg_launch_count() - n0)
-        self._graphs[B] = gr
+        self._graph_launches[key] = int(self.l.idg_launch_count() - n0)
+        self._graphs[key] = gr
 
     def pop_epoch_losses(self):
         out = self._report(self.loss_acc).tolist()

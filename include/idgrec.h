@@ -395,6 +395,11 @@ int idg_neg_sample_walk(const int64_t* h_train_user, int64_t e_begin, int64_t E,
  * of one epoch; only the permutation and the negatives cross PCIe, the train edges are resident). */
 int idg_permute3(const int64_t* d_a, const int64_t* d_b, const int64_t* d_c, const int64_t* d_perm, int64_t n,
                  int64_t* d_out, void* stream);
+/* The step's mini-batch fetched on the device from the epoch's (shuffled) sample arrays -- the first node of a captured train step,
+ * so that an epoch is nothing but graph replays on the host (trainer.py:40-47 slices the three arrays per batch).  d_ptrs: device
+ * int64[4] = base addresses of the user / positive / negative arrays and the step-counter value of the epoch's first batch; the
+ * batch read is [(*d_step - start) * stride, + B); d_slab: [3, slab_stride] int64. */
+int idg_batch_fetch(const void* d_ptrs, const int32_t* d_step, int32_t stride, int32_t B, int64_t* d_slab, int32_t slab_stride, void* stream);
 
 /* nn.Tanh between the propagation layers of EGCF (models/EGCF.py:42,52-53,71): y = tanh(x); gx = gy (1 - y^2). */
 int idg_tanh_fwd(const float* d_x, float* d_y, int64_t n, void* stream);

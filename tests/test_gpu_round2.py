@@ -632,3 +632,36 @@ def test_ngcf_bit_packed_dropout_masks_match_the_float_masks(dev):
         res.append([D, out] + outs)
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_step_graph_fetches_epoch_slices_itself(dev):
+    """trainer.py:40-47 walks the epoch's sample arrays in slices.  When step() is handed such slices in order, the captured step
+    fetches its batch on the device (idg_batch_fetch as the first graph node); any other batch goes through the copy path.  Same
+    tables and losses either way, across an epoch boundary, a ragged last batch and an out-of-order call in the middle."""
+    from idgrec import datagen
+    from idgrec.engine import FusedTrainer
+    from idgrec.graph import Graph, build_norm_adjacency
+    g = datagen.gen_graph("small")
+    U, I = g.num_users, g.num_items
+    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(21)
+    table = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
+    B, E = 256, 256 * 5 + 77
+    rng = np.random.default_rng(4)
+    a = FusedTrainer("LightGCN", Graph(csr), table.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=True)
+    b = FusedTrainer("LightGCN", Graph(csr), table.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=True)
+    for epoch in range(2):
+        e = rng.integers(0, len(g.train_user), E)
+        block = torch.from_numpy(np.stack([g.train_user[e], g.train_item[e], rng.integers(0, I, E)])).to(dev)      # [3, E], like trainer.py's
+        users, pos, neg = block[0], block[1], block[2]
+        for s in range(0, E, B):
+            sl = (users[s:s + B], pos[s:s + B], neg[s:s + B])
+            la = a.step(*sl).clone()
+            lb = b.step(*[t.clone() for t in sl]).clone()          # clones are not views: always the copy path
+            assert torch.equal(la, lb), (epoch, s)
+            if epoch == 1 and s == 2 * B:                          # an extra, out-of-order batch: a falls back to the copy path from here on
+                la, lb = a.step(users[:B], pos[:B], neg[:B]).clone(), b.step(users[:B].clone(), pos[:B].clone(), neg[:B].clone()).clone()
+                assert torch.equal(la, lb)
+    assert any(isinstance(k, tuple) for k in a._graphs) and not any(isinstance(k, tuple) for k in b._graphs)
+    assert ("f", 77, B) in a._graphs
+    assert torch.equal(a.E0, b.E0)
