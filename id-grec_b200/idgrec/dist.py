@@ -20,6 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import check, cur_stream, ptr
+from .engine import EpochFetch
 from .graph import BatchRows, Graph
 
 
@@ -143,7 +144,7 @@ class PeerSlab:
         check(self.l.idg_peers_status(self.handle, ptr(self.state), cur_stream()), "idg_peers_status")
 
 
-class DistFusedTrainer:
+class DistFusedTrainer(EpochFetch):
     """LightGCN / SimGCL / XSimGCL training step, row-partitioned over `world` GPUs (same public surface as FusedTrainer).
 
     The contrastive models run their extra propagations the same way (local rows, finished rows stored to all peers by the
@@ -235,6 +236,7 @@ class DistFusedTrainer:
         self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
         self.batch = torch.zeros(3, max_batch, dtype=torch.int64, device=dev)
         self.d_step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ep, self._ep_ptrs = None, torch.zeros(4, dtype=torch.int64, device=dev)     # registered epoch arrays (EpochFetch)
         self.regc = torch.zeros(N, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.adam_args = _lib.AdamArgs(ptr(self.E0), ptr(self.m), ptr(self.v), ptr(self.regc), ptr(self.adam_scalars), betas[0], betas[1], adam_eps)
@@ -423,21 +425,27 @@ class DistFusedTrainer:
     def step(self, users, pos, neg, apply_adam=True):
         assert apply_adam, "the distributed step always applies Adam"
         B = int(users.numel())
-        self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
+        # consecutive slices of the epoch's sample arrays are fetched by the captured step itself (engine.py:EpochFetch)
+        fetch = self.use_cuda_graph and self._epoch_cursor(B, users, pos, neg)
+        key = ("f", B, self._ep[2]) if fetch else B
+        if not fetch:
+            self.batch[0, :B].copy_(users); self.batch[1, :B].copy_(pos); self.batch[2, :B].copy_(neg)
         u, p, n = (self.batch[k].data_ptr() for k in range(3))
         if not self.use_cuda_graph:
             self._body(B, u, p, n)
         else:
-            if B not in self._graphs:
+            if key not in self._graphs:
                 torch.cuda.synchronize()
                 n0 = self.l.idg_launch_count()
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
+                    if fetch:
+                        self._fetch_batch(B, key[2])
                     self._body(B, u, p, n)
-                self._graph_launches[B] = int(self.l.idg_launch_count() - n0)
-                self._graphs[B] = gr
-            self._graphs[B].replay()
-            self.replayed_launches += self._graph_launches[B]
+                self._graph_launches[key] = int(self.l.idg_launch_count() - n0)
+                self._graphs[key] = gr
+            self._graphs[key].replay()
+            self.replayed_launches += self._graph_launches[key]
         self.step_count += 1
         return self.loss[:self.n_loss]
 

@@ -30,7 +30,46 @@ PAIR_MODELS = {
 }
 
 
-class FusedTrainer:
+class EpochFetch:
+    """Shared by the fused trainers: recognise consecutive slices of the epoch's sample arrays so that the captured step can fetch
+    its own mini-batch (idg_batch_fetch).  Needs self.d_step (device step counter, +1 per applied step), self.step_count (its host
+    twin), self.max_batch, and self._ep / self._ep_ptrs (None / device int64[4])."""
+
+    def _epoch_cursor(self, B, users, pos, neg):
+        """trainer.py:40-47 walks the epoch's three (shuffled) sample arrays in slices of batch_size.  When the three batch tensors
+        are such slices -- views at the same offset of three contiguous int64 arrays, taken in order from offset 0 -- the step graph
+        fetches its batch itself (idg_batch_fetch, first node) and the host only replays.  Returns True if this call is the next
+        slice of the registered epoch; registers a new epoch when it is the slice at offset 0."""
+        bases = (users._base, pos._base, neg._base)
+        if any(b is None for b in bases) or self.d_step is None:
+            return False
+        offs, starts = [], []
+        for t, b in zip((users, pos, neg), bases):
+            # the array is the base itself (1-D) or one row of a contiguous 2-D base (trainer.py's [3, E] sample block)
+            if t.dtype != torch.int64 or b.dtype != torch.int64 or not t.is_contiguous() or not b.is_contiguous() or b.dim() not in (1, 2):
+                return False
+            cols = b.shape[-1]
+            o = (t.data_ptr() - b.data_ptr()) // 8
+            if o % cols + B > cols:
+                return False
+            offs.append(o % cols)
+            starts.append(b.data_ptr() + (o // cols) * cols * 8)
+        if offs[0] != offs[1] or offs[0] != offs[2]:
+            return False
+        key = tuple(starts)
+        if offs[0] == 0 and B == min(self.max_batch, bases[0].shape[-1]):
+            # first slice of an epoch: (re)register -- also when the same arrays are walked again
+            self._ep = (key, self.step_count, B, bases)
+            self._ep_ptrs.copy_(torch.tensor(list(key) + [self.step_count], dtype=torch.int64), non_blocking=False)
+            return True
+        ep = self._ep
+        return ep is not None and ep[0] == key and B <= ep[2] and offs[0] == (self.step_count - ep[1]) * ep[2]
+
+    def _fetch_batch(self, B, stride):
+        check(self.l.idg_batch_fetch(ptr(self._ep_ptrs), ptr(self.d_step), stride, B, ptr(self.batch), self.batch.shape[1], cur_stream()), "idg_batch_fetch")
+
+
+class FusedTrainer(EpochFetch):
     def __init__(self, kind, graph, table, num_users, K, reg_lambda, lr, ssl_lambda=0.0, temperature=0.2,
                  eps=0.0, cl_layer=1, max_batch=2048, use_cuda_graph=True, betas=(0.9, 0.999), adam_eps=1e-8,
                  restrict_rows=True, fuse_adam=True, closure_restrict="auto", margin=0.0, gamma=0.0):
@@ -410,36 +449,6 @@ class FusedTrainer:
             self.loss_acc += self.loss
         return self._report(self.loss)
 
-    def _epoch_cursor(self, B, users, pos, neg):
-        """trainer.py:40-47 walks the epoch's three (shuffled) sample arrays in slices of batch_size.  When the three batch tensors
-        are such slices -- views at the same offset of three contiguous int64 arrays, taken in order from offset 0 -- the step graph
-        fetches its batch itself (idg_batch_fetch, first node) and the host only replays.  Returns True if this call is the next
-        slice of the registered epoch; registers a new epoch when it is the slice at offset 0."""
-        bases = (users._base, pos._base, neg._base)
-        if any(b is None for b in bases) or self.d_step is None:
-            return False
-        offs, starts = [], []
-        for t, b in zip((users, pos, neg), bases):
-            # the array is the base itself (1-D) or one row of a contiguous 2-D base (trainer.py's [3, E] sample block)
-            if t.dtype != torch.int64 or b.dtype != torch.int64 or not t.is_contiguous() or not b.is_contiguous() or b.dim() not in (1, 2):
-                return False
-            cols = b.shape[-1]
-            o = (t.data_ptr() - b.data_ptr()) // 8
-            if o % cols + B > cols:
-                return False
-            offs.append(o % cols)
-            starts.append(b.data_ptr() + (o // cols) * cols * 8)
-        if offs[0] != offs[1] or offs[0] != offs[2]:
-            return False
-        key = tuple(starts)
-        if offs[0] == 0 and B == min(self.max_batch, bases[0].shape[-1]):
-            # first slice of an epoch: (re)register -- also when the same arrays are walked again
-            self._ep = (key, self.step_count, B, bases)
-            self._ep_ptrs.copy_(torch.tensor(list(key) + [self.step_count], dtype=torch.int64), non_blocking=False)
-            return True
-        ep = self._ep
-        return ep is not None and ep[0] == key and B <= ep[2] and offs[0] == (self.step_count - ep[1]) * ep[2]
-
     def _step_graph(self, B, users, pos, neg):
         """CUDA-graph replay: the step's kernels (incl. the device-side Adam step counter) are captured once per batch size.  Batches
         that are consecutive slices of the epoch's sample arrays are fetched by the graph itself; any other batch is copied into
@@ -465,7 +474,7 @@ class FusedTrainer:
 
         def run():
             if isinstance(key, tuple):      # ("f", B, stride): the batch comes from the registered epoch arrays
-                check(self.l.idg_batch_fetch(ptr(self._ep_ptrs), ptr(self.d_step), key[2], B, ptr(self.batch), self.max_batch, cur_stream()), "idg_batch_fetch")
+                self._fetch_batch(B, key[2])
             self._body(B, u, p, n, fused=self.fuse_adam)
             if not self.fuse_adam:
                 self._adam()

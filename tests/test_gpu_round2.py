@@ -650,6 +650,8 @@ def test_step_graph_fetches_epoch_slices_itself(dev):
     rng = np.random.default_rng(4)
     a = FusedTrainer("LightGCN", Graph(csr), table.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=True)
     b = FusedTrainer("LightGCN", Graph(csr), table.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=True)
+    from idgrec.dist import DistFusedTrainer
+    c = DistFusedTrainer("LightGCN", csr, table.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=B, use_cuda_graph=True)     # row-partitioned trainer, one partition
     for epoch in range(2):
         e = rng.integers(0, len(g.train_user), E)
         block = torch.from_numpy(np.stack([g.train_user[e], g.train_item[e], rng.integers(0, I, E)])).to(dev)      # [3, E], like trainer.py's
@@ -658,10 +660,13 @@ def test_step_graph_fetches_epoch_slices_itself(dev):
             sl = (users[s:s + B], pos[s:s + B], neg[s:s + B])
             la = a.step(*sl).clone()
             lb = b.step(*[t.clone() for t in sl]).clone()          # clones are not views: always the copy path
-            assert torch.equal(la, lb), (epoch, s)
+            lc = c.step(*sl).clone()
+            assert torch.equal(la, lb) and torch.equal(la, lc), (epoch, s)
             if epoch == 1 and s == 2 * B:                          # an extra, out-of-order batch: a falls back to the copy path from here on
                 la, lb = a.step(users[:B], pos[:B], neg[:B]).clone(), b.step(users[:B].clone(), pos[:B].clone(), neg[:B].clone()).clone()
-                assert torch.equal(la, lb)
+                lc = c.step(users[:B], pos[:B], neg[:B]).clone()
+                assert torch.equal(la, lb) and torch.equal(la, lc)
     assert any(isinstance(k, tuple) for k in a._graphs) and not any(isinstance(k, tuple) for k in b._graphs)
     assert ("f", 77, B) in a._graphs
-    assert torch.equal(a.E0, b.E0)
+    assert any(isinstance(k, tuple) for k in c._graphs)
+    assert torch.equal(a.E0, b.E0) and torch.equal(a.E0, c.E0)
