@@ -83,7 +83,7 @@ struct idg_graph {
     const unsigned* closure = nullptr;  // optional: batch rows + their neighbours (idg_graph_set_closure)
     int32_t n_rows = 0, n_cols = 0, row_offset = 0;
     int64_t nnz = 0;
-    int n_items = 0, n_heavy = 0, n_parts = 0;
+    int n_items = 0, n_heavy = 0, n_parts = 0, n_classes = 1;
     int2* colval = nullptr;
     int4* items = nullptr;
     int2* row_items = nullptr;  // per local row: {first item, item count}
@@ -104,7 +104,17 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
 template <bool NA>
 __device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
 
-template <int LPR, bool ADAM>
+// (col, val) stream of a graph whose gather table does not fit the L2 (BIG kernels): the 8 nnz bytes are read once per launch,
+// so they are fetched with an L2 evict-first policy and leave the L2 to the gathered rows (L1 still serves the group's broadcast)
+template <bool BIG>
+__device__ __forceinline__ int2 ldcv(const int2* p, unsigned long long pol) {
+    if (!BIG) return __ldg(p);
+    int2 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+
+template <int LPR, bool ADAM, bool BIG = false>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
     constexpr int d = 4 * LPR;
     const size_t off = (size_t)grow * d + sub * 4;
@@ -144,7 +154,8 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
     if (a.mcY) {
         multimem_st4(a.mcY + off, y);  // one NVLink store, replicated by the switch (NVLS)
     } else if (a.Y) {
-        st4(a.Y + off, y);
+        if (BIG) stcs4(a.Y + off, y);  // the layer output (N d 4 bytes > L2) streams through
+        else st4(a.Y + off, y);
 #pragma unroll 1
         for (int p = 0; p < a.n_peers; ++p) st4(a.peerY[p] + off, y);  // NVLink peer stores, fire-and-forget
     }
@@ -189,7 +200,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false, bool BIG = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -220,6 +231,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_v + poff));
     }
 
+    unsigned long long pol = 0;
+    if (BIG) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     float4 acc = f4zero();
     int k = it.y;
     const int end = it.z;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
 #pragma unroll
             for (int u = 0; u < kSU; ++u) {
                 const int kk = base + u * LPR + sub;
-                c[u] = (kk < end) ? __ldg(cvp + kk) : make_int2(0, 0);
+                c[u] = (kk < end) ? ldcv<BIG>(cvp + kk, pol) : make_int2(0, 0);
             }
 #pragma unroll
             for (int u = 0; u < kSU; ++u) {
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     if (k + kU <= end) {
         int2 cv[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + u);
+        for (int u = 0; u < kU; ++u) cv[u] = ldcv<BIG>(cvp + k + u, pol);
         for (; k + kU <= end; k += kU) {
             float4 x[kU];
 #pragma unroll
@@ -270,14 +283,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             for (int u = 0; u < kU; ++u) w[u] = __int_as_float(cv[u].y);
             if (k + 2 * kU <= end) {  // software pipeline: next (col,val) quad while the gathers fly
 #pragma unroll
-                for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + kU + u);
+                for (int u = 0; u < kU; ++u) cv[u] = ldcv<BIG>(cvp + k + kU + u, pol);
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) acc = f4fma(w[u], x[u], acc);
         }
     }
     for (; k < end; ++k) {
-        const int2 c = __ldg(cvp + k);
+        const int2 c = ldcv<BIG>(cvp + k, pol);
         acc = f4fma(__int_as_float(c.y), gat<NA>(X + (size_t)c.x * d), acc);
     }
 
@@ -289,7 +302,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             const bool nz = (acc.x != 0.f) | (acc.y != 0.f) | (acc.z != 0.f) | (acc.w != 0.f) | (g.x != 0.f) | (g.y != 0.f) | (g.z != 0.f) | (g.w != 0.f);
             if (!__any_sync(gmask, nz)) return;
         }
-        finish_row<LPR, ADAM>(a, a.row_offset + it.x, sub, gmask, acc);
+        finish_row<LPR, ADAM, BIG>(a, a.row_offset + it.x, sub, gmask, acc);
         return;
     }
     // chunk of a heavy row: publish the partial; the last chunk to arrive sums them in chunk order
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     float4 s = ldcg4(a.partials + (size_t)h.part_begin * d + sub * 4);
     for (int p = 1; p < h.n_parts; ++p) s = f4add(s, ldcg4(a.partials + (size_t)(h.part_begin + p) * d + sub * 4));
     if (sub == 0) a.counters[it.x] = 0;  // ready for the next launch
-    finish_row<LPR, ADAM>(a, a.row_offset + h.row, sub, gmask, s);
+    finish_row<LPR, ADAM, BIG>(a, a.row_offset + h.row, sub, gmask, s);
 }
 
 __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int2* __restrict__ out, int64_t nnz) {
@@ -313,9 +326,54 @@ __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* 
     if (i < nnz) out[i] = make_int2(col[i], __float_as_int(val[i]));
 }
 
+// first and last column of every row (rows hold ascending columns); {-1, -1} for an empty row
+__global__ void row_first_last_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int n_rows, int2* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int s = indptr[r], e = indptr[r + 1];
+    out[r] = (e > s) ? make_int2(indices[s], indices[e - 1]) : make_int2(-1, -1);
+}
 }  // namespace idg
 
 using namespace idg;
+
+// Schedule classes for tables that do not fit the L2 (IDG_SPMM_CLASS_SPLIT = 1 forces, 0 disables; default: gather table of
+// n_cols 256-byte rows beyond kClassSplitBytes).  In the bipartite adjacency every user row gathers item rows only and every item
+// row gathers user rows only, so running all user rows before all item rows halves the table the L2 has to hold at any time
+// (XL shape: 512 MB -> 2 x 256 MB; ncu of the mixed schedule: 29.5 GB of DRAM traffic per layer, L2 hit rate 34 %).  A row is
+// "upper" when all its columns lie above its own global index and "lower" when all lie below; the split is used only when every
+// non-empty row is one or the other.  The order of the work items is scheduling only: every item's sum, the heavy rows' partial
+// slots and their chunk-order reduction are unchanged, so results are bit-identical with either schedule.
+static const int64_t kClassSplitBytes = 100ll << 20;
+
+static int classify_rows(const int32_t* d_indptr, const int32_t* d_indices, int32_t n_rows, int32_t n_cols, int64_t nnz, int32_t row_offset,
+                         cudaStream_t stream, std::vector<unsigned char>& cls, bool* split) {
+    *split = false;
+    const char* env = getenv("IDG_SPMM_CLASS_SPLIT");
+    const int mode = env ? atoi(env) : -1;
+    if (nnz == 0 || n_rows == 0 || mode == 0 || (mode != 1 && (int64_t)n_cols * 256 <= kClassSplitBytes)) return 0;
+    int2* d_fl = nullptr;
+    IDG_CUDA(cudaMalloc(&d_fl, sizeof(int2) * (size_t)n_rows));
+    row_first_last_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(d_indptr, d_indices, n_rows, d_fl);
+    g_launches.fetch_add(1);
+    std::vector<int2> fl((size_t)n_rows);
+    cudaError_t e = cudaMemcpyAsync(fl.data(), d_fl, sizeof(int2) * (size_t)n_rows, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d_fl);
+    if (e != cudaSuccess) return cuda_fail(e, "classify_rows");
+    cls.assign((size_t)n_rows, 0);
+    size_t n_upper = 0, n_lower = 0;
+    unsigned char last = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const int grow = row_offset + r;
+        if (fl[r].x < 0) { cls[r] = last; continue; }  // empty row: nothing to gather, stays with its neighbours
+        if (fl[r].x > grow) { cls[r] = last = 0; ++n_upper; }
+        else if (fl[r].y < grow) { cls[r] = last = 1; ++n_lower; }
+        else return 0;  // a row reaching across its own index (self loops, general graphs): keep the single schedule
+    }
+    *split = n_upper > 0 && n_lower > 0;
+    return 0;
+}
 
 extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indices, const float* d_data, int32_t n_rows,
                                 int32_t n_cols, int64_t nnz, int32_t row_offset, idg_graph** out, void* stream_) {
@@ -331,30 +389,47 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
     idg_graph* g = new idg_graph();
     g->n_rows = n_rows; g->n_cols = n_cols; g->row_offset = row_offset; g->nnz = nnz;
 
-    std::vector<int4> light, parts;
+    std::vector<unsigned char> cls;
+    bool split = false;
+    if (int rc = classify_rows(d_indptr, d_indices, n_rows, n_cols, nnz, row_offset, stream, cls, &split)) { delete g; return rc; }
+    const int n_cls = split ? 2 : 1;
+
+    // per class: chunks of heavy rows first (contiguous per row), then whole rows longest-first (stable => deterministic);
+    // it.w of a chunk is its slot in the partials buffer (numbered in row order, independent of where the item sits)
+    std::vector<int4> light[2], parts[2];
     std::vector<HeavyRow> heavy;
-    light.reserve(n_rows);
+    int n_parts_total = 0;
+    light[0].reserve(n_rows);
     for (int r = 0; r < n_rows; ++r) {
         const int s = ptr[r], e = ptr[r + 1];
         if (e < s) { delete g; return fail(-1, "idg_graph_create: indptr not monotone%s"); }
+        const int c = split ? cls[r] : 0;
         if (e - s <= kChunk) {
-            light.push_back(make_int4(r, s, e, -1));
+            light[c].push_back(make_int4(r, s, e, -1));
         } else {
-            HeavyRow h{r, (int)parts.size(), (e - s + kChunk - 1) / kChunk, 0};
+            HeavyRow h{r, n_parts_total, (e - s + kChunk - 1) / kChunk, 0};
             for (int p = 0; p < h.n_parts; ++p)
-                parts.push_back(make_int4((int)heavy.size(), s + p * kChunk, std::min(e, s + (p + 1) * kChunk), h.part_begin + p));
+                parts[c].push_back(make_int4((int)heavy.size(), s + p * kChunk, std::min(e, s + (p + 1) * kChunk), h.part_begin + p));
+            n_parts_total += h.n_parts;
             heavy.push_back(h);
         }
     }
-    // degree-sorted schedule: chunks of heavy rows first (contiguous per row), then whole rows
-    // longest-first (stable => deterministic)
-    std::stable_sort(light.begin(), light.end(), [](const int4& x, const int4& y) { return (x.z - x.y) > (y.z - y.y); });
-    std::vector<int4> items(parts);
-    items.insert(items.end(), light.begin(), light.end());
+    std::vector<int4> items;
+    items.reserve(light[0].size() + light[1].size() + (size_t)n_parts_total);
     std::vector<int2> row_items((size_t)std::max(n_rows, 1));
-    for (size_t h = 0; h < heavy.size(); ++h) row_items[heavy[h].row] = make_int2(heavy[h].part_begin, heavy[h].n_parts);
-    for (size_t i = 0; i < light.size(); ++i) row_items[light[i].x] = make_int2((int)(parts.size() + i), 1);
-    g->n_items = (int)items.size(); g->n_heavy = (int)heavy.size(); g->n_parts = (int)parts.size();
+    for (int c = 0; c < n_cls; ++c) {
+        std::stable_sort(light[c].begin(), light[c].end(), [](const int4& x, const int4& y) { return (x.z - x.y) > (y.z - y.y); });
+        for (size_t i = 0; i < parts[c].size(); ++i) {
+            const HeavyRow& h = heavy[parts[c][i].x];
+            if (parts[c][i].w == h.part_begin) row_items[h.row] = make_int2((int)items.size(), h.n_parts);  // first chunk of the row
+            items.push_back(parts[c][i]);
+        }
+        for (size_t i = 0; i < light[c].size(); ++i) {
+            row_items[light[c][i].x] = make_int2((int)items.size(), 1);
+            items.push_back(light[c][i]);
+        }
+    }
+    g->n_items = (int)items.size(); g->n_heavy = (int)heavy.size(); g->n_parts = n_parts_total; g->n_classes = n_cls;
 
 #define G_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { idg_graph_destroy(g); return cuda_fail(_e, #expr); } } while (0)
     G_CUDA(cudaMalloc(&g->colval, sizeof(int2) * (size_t)std::max<int64_t>(nnz, 1)));
@@ -390,6 +465,7 @@ extern "C" int idg_graph_set_peers(idg_graph* g, const idg_peers* p) {
 }
 extern "C" int64_t idg_graph_nnz(const idg_graph* g) { return g ? g->nnz : -1; }
 extern "C" int32_t idg_graph_rows(const idg_graph* g) { return g ? g->n_rows : -1; }
+extern "C" int32_t idg_graph_classes(const idg_graph* g) { return g ? g->n_classes : -1; }
 
 struct SpmmExtra {
     const float* acc_in2 = nullptr;
@@ -468,6 +544,23 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     const int T = warps_per_cta * 32;
     // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
     // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
+    // gather table beyond the L2 (XL shape: 512 MB): (col, val) with an L2 evict-first policy, streaming Y stores (d = 64 kernels,
+    // 6 resident CTAs = 40 registers: the policy operand does not fit the 32 of the L2-resident kernels without spills;
+    // IDG_SPMM_STREAM = 0 | 1 overrides the size rule)
+    const char* big_env = getenv("IDG_SPMM_STREAM");
+    const bool big = d == 64 && !ex.worklist && (big_env ? atoi(big_env) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
+    if (big) {
+        if (ex.adam) {
+            if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
+            spmm_kernel<16, 2, false, 6, false, true, false, true><<<grid, T, 0, stream>>>(a);
+        } else if (ex.bitmap && ex.rowmask) spmm_kernel<16, 2, false, 6, true, false, true, true><<<grid, T, 0, stream>>>(a);
+        else if (ex.bitmap) spmm_kernel<16, 2, false, 6, true, false, false, true><<<grid, T, 0, stream>>>(a);
+        else if (ex.rowmask) spmm_kernel<16, 2, false, 6, false, false, true, true><<<grid, T, 0, stream>>>(a);
+        else if (big_env && atoi(big_env) == 2) spmm_kernel<16, 4, false, 6, false, false, false, true><<<grid, T, 0, stream>>>(a);  // experiment: 4 gathers in flight
+        else spmm_kernel<16, 2, false, 6, false, false, false, true><<<grid, T, 0, stream>>>(a);
+        IDG_LAUNCH_CHECK("spmm_kernel");
+        return 0;
+    }
     if (ex.adam) {
         if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
         // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step

@@ -90,6 +90,10 @@ int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indices, const fl
 void idg_graph_destroy(idg_graph* g);
 int64_t idg_graph_nnz(const idg_graph* g);
 int32_t idg_graph_rows(const idg_graph* g);
+/* schedule classes of the handle: 2 when the work items run "all rows that gather from above their own index, then all rows that
+ * gather from below" (bipartite adjacency whose gather table exceeds the L2: user rows, then item rows), else 1.  Scheduling
+ * only -- results are bit-identical (IDG_SPMM_CLASS_SPLIT = 0 | 1 overrides the size rule). */
+int32_t idg_graph_classes(const idg_graph* g);
 
 /* ---- a6/a7/a11: one propagation layer = torch.sparse.mm(self.Graph, X) -----
  * (models/LightGCN.py:44, SimGCL.py:48, XSimGCL.py:51, NGCF.py:85) with the
