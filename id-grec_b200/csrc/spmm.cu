@@ -104,17 +104,7 @@ __device__ __forceinline__ float4 ldg4_stream(const float* p) {
 template <bool NA>
 __device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
 
-// (col, val) stream of a graph whose gather table does not fit the L2 (BIG kernels): the 8 nnz bytes are read once per launch,
-// so they are fetched with an L2 evict-first policy and leave the L2 to the gathered rows (L1 still serves the group's broadcast)
-template <bool BIG>
-__device__ __forceinline__ int2 ldcv(const int2* p, unsigned long long pol) {
-    if (!BIG) return __ldg(p);
-    int2 r;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-
-template <int LPR, bool ADAM, bool BIG = false>
+template <int LPR, bool ADAM>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
     constexpr int d = 4 * LPR;
     const size_t off = (size_t)grow * d + sub * 4;
@@ -154,8 +144,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
     if (a.mcY) {
         multimem_st4(a.mcY + off, y);  // one NVLink store, replicated by the switch (NVLS)
     } else if (a.Y) {
-        if (BIG) stcs4(a.Y + off, y);  // the layer output (N d 4 bytes > L2) streams through
-        else st4(a.Y + off, y);
+        st4(a.Y + off, y);
 #pragma unroll 1
         for (int p = 0; p < a.n_peers; ++p) st4(a.peerY[p] + off, y);  // NVLink peer stores, fire-and-forget
     }
@@ -200,7 +189,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false, bool BIG = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -231,8 +220,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_v + poff));
     }
 
-    unsigned long long pol = 0;
-    if (BIG) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     float4 acc = f4zero();
     int k = it.y;
     const int end = it.z;
@@ -248,7 +235,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
 #pragma unroll
             for (int u = 0; u < kSU; ++u) {
                 const int kk = base + u * LPR + sub;
-                c[u] = (kk < end) ? ldcv<BIG>(cvp + kk, pol) : make_int2(0, 0);
+                c[u] = (kk < end) ? __ldg(cvp + kk) : make_int2(0, 0);
             }
 #pragma unroll
             for (int u = 0; u < kSU; ++u) {
@@ -273,7 +260,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     if (k + kU <= end) {
         int2 cv[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) cv[u] = ldcv<BIG>(cvp + k + u, pol);
+        for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + u);
         for (; k + kU <= end; k += kU) {
             float4 x[kU];
 #pragma unroll
@@ -283,14 +270,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             for (int u = 0; u < kU; ++u) w[u] = __int_as_float(cv[u].y);
             if (k + 2 * kU <= end) {  // software pipeline: next (col,val) quad while the gathers fly
 #pragma unroll
-                for (int u = 0; u < kU; ++u) cv[u] = ldcv<BIG>(cvp + k + kU + u, pol);
+                for (int u = 0; u < kU; ++u) cv[u] = __ldg(cvp + k + kU + u);
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) acc = f4fma(w[u], x[u], acc);
         }
     }
     for (; k < end; ++k) {
-        const int2 c = ldcv<BIG>(cvp + k, pol);
+        const int2 c = __ldg(cvp + k);
         acc = f4fma(__int_as_float(c.y), gat<NA>(X + (size_t)c.x * d), acc);
     }
 
@@ -302,7 +289,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             const bool nz = (acc.x != 0.f) | (acc.y != 0.f) | (acc.z != 0.f) | (acc.w != 0.f) | (g.x != 0.f) | (g.y != 0.f) | (g.z != 0.f) | (g.w != 0.f);
             if (!__any_sync(gmask, nz)) return;
         }
-        finish_row<LPR, ADAM, BIG>(a, a.row_offset + it.x, sub, gmask, acc);
+        finish_row<LPR, ADAM>(a, a.row_offset + it.x, sub, gmask, acc);
         return;
     }
     // chunk of a heavy row: publish the partial; the last chunk to arrive sums them in chunk order
@@ -318,7 +305,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     float4 s = ldcg4(a.partials + (size_t)h.part_begin * d + sub * 4);
     for (int p = 1; p < h.n_parts; ++p) s = f4add(s, ldcg4(a.partials + (size_t)(h.part_begin + p) * d + sub * 4));
     if (sub == 0) a.counters[it.x] = 0;  // ready for the next launch
-    finish_row<LPR, ADAM, BIG>(a, a.row_offset + h.row, sub, gmask, s);
+    finish_row<LPR, ADAM>(a, a.row_offset + h.row, sub, gmask, s);
 }
 
 __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int2* __restrict__ out, int64_t nnz) {
@@ -544,27 +531,15 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     const int T = warps_per_cta * 32;
     // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
     // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
-    // gather table beyond the L2 (XL shape: 512 MB): (col, val) with an L2 evict-first policy, streaming Y stores (d = 64 kernels,
-    // 6 resident CTAs = 40 registers: the policy operand does not fit the 32 of the L2-resident kernels without spills;
-    // IDG_SPMM_STREAM = 0 | 1 overrides the size rule)
-    const char* big_env = getenv("IDG_SPMM_STREAM");
-    const bool big = d == 64 && !ex.worklist && (big_env ? atoi(big_env) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
-    if (big) {
-        if (ex.adam) {
-            if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
-            spmm_kernel<16, 2, false, 6, false, true, false, true><<<grid, T, 0, stream>>>(a);
-        } else if (ex.bitmap && ex.rowmask) spmm_kernel<16, 2, false, 6, true, false, true, true><<<grid, T, 0, stream>>>(a);
-        else if (ex.bitmap) spmm_kernel<16, 2, false, 6, true, false, false, true><<<grid, T, 0, stream>>>(a);
-        else if (ex.rowmask) spmm_kernel<16, 2, false, 6, false, false, true, true><<<grid, T, 0, stream>>>(a);
-        else if (big_env && atoi(big_env) == 2) spmm_kernel<16, 4, false, 6, false, false, false, true><<<grid, T, 0, stream>>>(a);  // experiment: 4 gathers in flight
-        else spmm_kernel<16, 2, false, 6, false, false, false, true><<<grid, T, 0, stream>>>(a);
-        IDG_LAUNCH_CHECK("spmm_kernel");
-        return 0;
-    }
     if (ex.adam) {
         if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
         // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step
-        if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        // ... at the amazon-book shape.  With a gather table beyond the L2 (XL shape) the layer is bound by HBM latency and the
+        // 64 resident warps of the 32-register build win (IDG_SPMM_ADAM8 = 0 | 1 overrides the size rule)
+        const char* a8 = getenv("IDG_SPMM_ADAM8");
+        const bool adam8 = d == 64 && (a8 ? atoi(a8) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
+        if (adam8) spmm_kernel<16, 2, false, 8, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
         else if (d == 32) spmm_kernel<8, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
         else spmm_kernel<32, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
     } else if (ex.bitmap && ex.rowmask) {
