@@ -84,7 +84,6 @@ struct idg_graph {
     int32_t n_rows = 0, n_cols = 0, row_offset = 0;
     int64_t nnz = 0;
     int n_items = 0, n_heavy = 0, n_parts = 0, n_classes = 1;
-    bool cold_bits = false;  // colval column indices carry the cold flag in their sign bit (kernels instantiated with COLD)
     int2* colval = nullptr;
     int4* items = nullptr;
     int2* row_items = nullptr;  // per local row: {first item, item count}
@@ -95,20 +94,15 @@ struct idg_graph {
 
 namespace idg {
 
-// Gather of one embedding row.  COLD graphs (gather table beyond the L2, idg_graph_create) flag the rarely gathered columns in the
-// sign bit of the stored column index: those rows are fetched with the streaming hint (ld.global.cs: evict-first in L1 and L2) so that
-// the frequently gathered rows, which do fit, stay resident instead of being evicted by rows that will not be seen again in time.
-__device__ __forceinline__ float4 ldcs4g(const float* p) {
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    // embedding gathers have ~no L1 reuse (ncu: 2.5% hit rate): keep L1 for the (col,val) stream
     float4 r;
-    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-template <bool COLD, int d>
-__device__ __forceinline__ float4 gat(const float* X, int c) {
-    if (!COLD) return ldg4(X + (size_t)c * d);
-    const float* p = X + (size_t)(c & 0x7fffffff) * d;
-    return (c < 0) ? ldcs4g(p) : ldg4(p);
-}
+
+template <bool NA>
+__device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
 
 template <int LPR, bool ADAM>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
@@ -195,7 +189,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool COLD = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -242,7 +236,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
             for (int u = 0; u < kSU; ++u) {
                 const int kk = base + u * LPR + sub;
                 c[u] = (kk < end) ? __ldg(cvp + kk) : make_int2(0, 0);
-                if (COLD) c[u].x &= 0x7fffffff;
             }
 #pragma unroll
             for (int u = 0; u < kSU; ++u) {
@@ -271,7 +264,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
         for (; k + kU <= end; k += kU) {
             float4 x[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) x[u] = gat<COLD, d>(X, cv[u].x);
+            for (int u = 0; u < kU; ++u) x[u] = gat<NA>(X + (size_t)cv[u].x * d);
             float w[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) w[u] = __int_as_float(cv[u].y);
@@ -285,7 +278,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     }
     for (; k < end; ++k) {
         const int2 c = __ldg(cvp + k);
-        acc = f4fma(__int_as_float(c.y), gat<COLD, d>(X, c.x), acc);
+        acc = f4fma(__int_as_float(c.y), gat<NA>(X + (size_t)c.x * d), acc);
     }
 
     if (it.w < 0) {
@@ -319,19 +312,6 @@ __global__ void interleave_kernel(const int32_t* __restrict__ col, const float* 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) out[i] = make_int2(col[i], __float_as_int(val[i]));
 }
-// same, with the sign bit of the column index set for the columns flagged in the bitmap (cold columns, see gat<COLD>)
-__global__ void interleave_cold_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int2* __restrict__ out, int64_t nnz,
-                                       const unsigned* __restrict__ cold) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    const int c = col[i];
-    const unsigned f = (__ldg(cold + (c >> 5)) >> (c & 31)) & 1u;
-    out[i] = make_int2(c | (int)(f << 31), __float_as_int(val[i]));
-}
-__global__ void col_count_kernel(const int32_t* __restrict__ col, int64_t nnz, int* __restrict__ counts) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) atomicAdd(counts + col[i], 1);
-}
 
 // first and last column of every row (rows hold ascending columns); {-1, -1} for an empty row
 __global__ void row_first_last_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices, int n_rows, int2* __restrict__ out) {
@@ -354,9 +334,8 @@ using namespace idg;
 static const int64_t kClassSplitBytes = 100ll << 20;
 
 static int classify_rows(const int32_t* d_indptr, const int32_t* d_indices, int32_t n_rows, int32_t n_cols, int64_t nnz, int32_t row_offset,
-                         cudaStream_t stream, std::vector<unsigned char>& cls, bool* split, int* boundary) {
+                         cudaStream_t stream, std::vector<unsigned char>& cls, bool* split) {
     *split = false;
-    *boundary = -1;
     const char* env = getenv("IDG_SPMM_CLASS_SPLIT");
     const int mode = env ? atoi(env) : -1;
     if (nnz == 0 || n_rows == 0 || mode == 0 || (mode != 1 && (int64_t)n_cols * 256 <= kClassSplitBytes)) return 0;
@@ -380,54 +359,6 @@ static int classify_rows(const int32_t* d_indptr, const int32_t* d_indices, int3
         else return 0;  // a row reaching across its own index (self loops, general graphs): keep the single schedule
     }
     *split = n_upper > 0 && n_lower > 0;
-    if (*split)
-        for (int r = 0; r < n_rows; ++r)
-            if (cls[r]) { *boundary = row_offset + r; break; }  // upper rows gather columns >= boundary, lower rows columns < boundary
-    return 0;
-}
-
-// Cold columns of a gather table beyond the L2 (IDG_SPMM_COLD = 1 forces, 0 disables; default: the size rule of the class split).
-// Per column class (the columns one schedule class gathers) the most frequently gathered columns up to IDG_SPMM_HOT_MB (default 72)
-// of 256-byte rows are "hot"; every other column that is gathered at all is flagged cold.  ncu at the XL shape: the plain LRU-like
-// replacement keeps an L2 hit rate of 34 % (mixed schedule) although the hottest 30 % of the rows receive ~70 % of the gathers.
-static int flag_cold_columns(const int32_t* d_indices, int32_t n_cols, int64_t nnz, int boundary, cudaStream_t stream, unsigned** d_cold) {
-    *d_cold = nullptr;
-    const char* env = getenv("IDG_SPMM_COLD");
-    const int mode = env ? atoi(env) : -1;
-    if (nnz == 0 || mode == 0 || (mode != 1 && (int64_t)n_cols * 256 <= kClassSplitBytes)) return 0;
-    const char* mb = getenv("IDG_SPMM_HOT_MB");
-    const double hot_mb = mb ? atof(mb) : 72.0;
-    const size_t budget = (size_t)std::max(1.0, hot_mb * 1048576.0 / 256.0);
-    int* d_counts = nullptr;
-    IDG_CUDA(cudaMalloc(&d_counts, sizeof(int) * (size_t)n_cols));
-    std::vector<int> counts((size_t)n_cols);
-    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)n_cols, stream);
-    if (e == cudaSuccess) {
-        col_count_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(d_indices, nnz, d_counts);
-        g_launches.fetch_add(1);
-        e = cudaMemcpyAsync(counts.data(), d_counts, sizeof(int) * (size_t)n_cols, cudaMemcpyDeviceToHost, stream);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(d_counts);
-    if (e != cudaSuccess) return cuda_fail(e, "flag_cold_columns");
-    std::vector<unsigned> bits(((size_t)n_cols + 31) / 32, 0u);
-    bool any = false;
-    const int b = std::min(std::max(boundary, 0), (int)n_cols);
-    const int lo[2] = {0, b}, hi[2] = {b, n_cols};
-    for (int c = 0; c < 2; ++c) {
-        std::vector<int> v;
-        for (int j = lo[c]; j < hi[c]; ++j) if (counts[j] > 0) v.push_back(counts[j]);
-        if (v.size() <= budget) continue;  // everything this class gathers fits: nothing is cold
-        std::nth_element(v.begin(), v.begin() + budget, v.end(), [](int x, int y) { return x > y; });
-        const int T = v[budget];  // hot <=> gathered more often than the (budget+1)-th most frequent column
-        for (int j = lo[c]; j < hi[c]; ++j)
-            if (counts[j] > 0 && counts[j] <= T) { bits[(size_t)j >> 5] |= 1u << (j & 31); any = true; }
-    }
-    if (!any) return 0;
-    IDG_CUDA(cudaMalloc(d_cold, sizeof(unsigned) * bits.size()));
-    e = cudaMemcpyAsync(*d_cold, bits.data(), sizeof(unsigned) * bits.size(), cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e != cudaSuccess) { cudaFree(*d_cold); *d_cold = nullptr; return cuda_fail(e, "flag_cold_columns"); }
     return 0;
 }
 
@@ -447,8 +378,7 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
 
     std::vector<unsigned char> cls;
     bool split = false;
-    int boundary = -1;
-    if (int rc = classify_rows(d_indptr, d_indices, n_rows, n_cols, nnz, row_offset, stream, cls, &split, &boundary)) { delete g; return rc; }
+    if (int rc = classify_rows(d_indptr, d_indices, n_rows, n_cols, nnz, row_offset, stream, cls, &split)) { delete g; return rc; }
     const int n_cls = split ? 2 : 1;
 
     // per class: chunks of heavy rows first (contiguous per row), then whole rows longest-first (stable => deterministic);
@@ -500,16 +430,9 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
     if (g->n_items) G_CUDA(cudaMemcpyAsync(g->items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, stream));
     if (g->n_heavy) G_CUDA(cudaMemcpyAsync(g->heavy, heavy.data(), sizeof(HeavyRow) * heavy.size(), cudaMemcpyHostToDevice, stream));
     if (nnz) {
-        unsigned* d_cold = nullptr;
-        if (int rc = flag_cold_columns(d_indices, n_cols, nnz, boundary, stream, &d_cold)) { idg_graph_destroy(g); return rc; }
-        if (d_cold) interleave_cold_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(d_indices, d_data, g->colval, nnz, d_cold);
-        else interleave_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(d_indices, d_data, g->colval, nnz);
+        interleave_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream>>>(d_indices, d_data, g->colval, nnz);
         g_launches.fetch_add(1);
-        cudaError_t le = cudaGetLastError();
-        if (le == cudaSuccess && d_cold) le = cudaStreamSynchronize(stream);
-        cudaFree(d_cold);
-        g->cold_bits = d_cold != nullptr;
-        G_CUDA(le);
+        G_CUDA(cudaGetLastError());
     }
     G_CUDA(cudaStreamSynchronize(stream));
 #undef G_CUDA
@@ -545,49 +468,6 @@ struct SpmmExtra {
     int skip_zero_rows = 0;
     const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
-
-// kernel variant for one launch; COLD = the handle's column indices carry the cold flag (gat<COLD>)
-template <bool COLD>
-static int spmm_dispatch(const idg_graph* g, const SpmmArgs& a, const SpmmExtra& ex, int32_t d, unsigned grid, int T, cudaStream_t stream) {
-    // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
-    // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
-    if (ex.adam) {
-        if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
-        // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step
-        // ... at the amazon-book shape.  With a gather table beyond the L2 (XL shape) the layer is bound by HBM latency and the
-        // 64 resident warps of the 32-register build win (IDG_SPMM_ADAM8 = 0 | 1 overrides the size rule)
-        const char* a8 = getenv("IDG_SPMM_ADAM8");
-        const bool adam8 = d == 64 && (a8 ? atoi(a8) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
-        if (adam8) spmm_kernel<16, 2, COLD, 8, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 64) spmm_kernel<16, 2, COLD, 6, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, COLD, 6, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, COLD, 6, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.bitmap && ex.rowmask) {
-        // sparse-input product restricted to the rows that can come out non-zero (batch rows + their neighbours): the other
-        // rows would stream their whole (col, val) list only to find no flagged column
-        if (d == 64) spmm_kernel<16, 2, COLD, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, COLD, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, COLD, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.bitmap) {
-        if (d == 64) spmm_kernel<16, 2, COLD, 8, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, COLD, 8, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, COLD, 8, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.rowmask) {
-        if (d == 64) spmm_kernel<16, 2, COLD, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, COLD, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, COLD, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.worklist) {
-        // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
-        if (d == 64) spmm_kernel<16, 8, COLD, 1><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 8, COLD, 1><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 8, COLD, 1><<<grid, T, 0, stream>>>(a);
-    } else {
-        if (d == 64) spmm_kernel<16, 2, COLD, 8><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, COLD, 8><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, COLD, 8><<<grid, T, 0, stream>>>(a);
-    }
-    return 0;
-}
 
 static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
                        float scale2, const float* d_noise, float eps, const float* d_acc_in, float* d_acc_out, float acc_div,
@@ -649,7 +529,43 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     const unsigned grid = (unsigned)((n_slots + per_cta - 1) / per_cta);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int T = warps_per_cta * 32;
-    if (int rc = g->cold_bits ? spmm_dispatch<true>(g, a, ex, d, grid, T, stream) : spmm_dispatch<false>(g, a, ex, d, grid, T, stream)) return rc;
+    // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
+    // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
+    if (ex.adam) {
+        if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
+        // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step
+        // ... at the amazon-book shape.  With a gather table beyond the L2 (XL shape) the layer is bound by HBM latency and the
+        // 64 resident warps of the 32-register build win (IDG_SPMM_ADAM8 = 0 | 1 overrides the size rule)
+        const char* a8 = getenv("IDG_SPMM_ADAM8");
+        const bool adam8 = d == 64 && (a8 ? atoi(a8) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
+        if (adam8) spmm_kernel<16, 2, false, 8, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap && ex.rowmask) {
+        // sparse-input product restricted to the rows that can come out non-zero (batch rows + their neighbours): the other
+        // rows would stream their whole (col, val) list only to find no flagged column
+        if (d == 64) spmm_kernel<16, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.rowmask) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.worklist) {
+        // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
+        if (d == 64) spmm_kernel<16, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 8, false, 1><<<grid, T, 0, stream>>>(a);
+    } else {
+        if (d == 64) spmm_kernel<16, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8><<<grid, T, 0, stream>>>(a);
+    }
     IDG_LAUNCH_CHECK("spmm_kernel");
     return 0;
 }
@@ -737,7 +653,7 @@ __global__ void __launch_bounds__(256) closure_kernel(const int4* __restrict__ i
     for (int base = it.y; base < it.z && !any; base += LPR) {
         const int k = base + sub;
         bool hit = false;
-        if (k < it.z) { const int c = __ldg(colval + k).x & 0x7fffffff; hit = (__ldg(batch + (c >> 5)) >> (c & 31)) & 1u; }
+        if (k < it.z) { const int c = __ldg(colval + k).x; hit = (__ldg(batch + (c >> 5)) >> (c & 31)) & 1u; }
         any = __any_sync(gmask, hit);
     }
     if (any && sub == 0) {
@@ -761,7 +677,7 @@ __global__ void __launch_bounds__(256) closure_from_rows_kernel(const int* __res
     for (int q = warp; q < ri.y; q += 8) {
         const int4 it = __ldg(items + ri.x + q);
         for (int k = it.y + lane; k < it.z; k += 32) {
-            const int c = __ldg(colval + k).x & 0x7fffffff;
+            const int c = __ldg(colval + k).x;
             atomicOr(closure + (c >> 5), 1u << (c & 31));
         }
     }

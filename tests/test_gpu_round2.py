@@ -723,45 +723,3 @@ def test_class_split_schedule_is_bit_identical(dev, monkeypatch, closure):
         assert torch.equal(la, lb), (step, la, lb)
     assert torch.equal(a.E0, b.E0)
 
-
-
-@pytest.mark.parametrize("closure", [False, True])
-def test_cold_column_flags_are_bit_identical(dev, monkeypatch, closure):
-    """Gather tables beyond the L2: idg_graph_create flags the rarely gathered columns in the sign bit of the stored column index
-    and the COLD instantiations of spmm_kernel fetch those rows with the streaming hint (csrc/spmm.cu:flag_cold_columns, gat<COLD>).
-    Forced here on the small graph with a hot budget of 300 rows per class: the plain layer, every layer variant of the fused step
-    (row-restricted work list, sparse-input, row-masked, closure-column, Adam-fused, both register builds) and the closure bitmaps
-    (which read the same column stream) give the same bits as an unflagged handle."""
-    from idgrec import datagen
-    from idgrec.engine import FusedTrainer
-    from idgrec.graph import Graph, build_norm_adjacency
-    g = datagen.gen_graph("small")
-    U, I = g.num_users, g.num_items
-    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
-    gen = torch.Generator(device=dev).manual_seed(35)
-    X = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
-    B = 64 if closure else 256
-    kw = dict(closure_restrict=True) if closure else {}
-    rng = np.random.default_rng(7)
-    batches = []
-    for step in range(3):
-        e = rng.integers(0, len(g.train_user), B)
-        batches.append(tuple(torch.from_numpy(t).to(dev) for t in (g.train_user[e], g.train_item[e], rng.integers(0, I, B))))
-    out = {}
-    for mode, split, adam8 in (("0", "0", "0"), ("1", "0", "0"), ("1", "1", "1")):
-        monkeypatch.setenv("IDG_SPMM_COLD", mode)
-        monkeypatch.setenv("IDG_SPMM_HOT_MB", str(300 * 256 / 1048576.0))
-        monkeypatch.setenv("IDG_SPMM_CLASS_SPLIT", split)
-        monkeypatch.setenv("IDG_SPMM_ADAM8", adam8)
-        G = Graph(csr)
-        Y = torch.empty_like(X)
-        G.spmm_layer(X, Y=Y)
-        ft = FusedTrainer("LightGCN", G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=(split == "1"), **kw)
-        losses = [ft.step(*b).clone() for b in batches]
-        torch.cuda.synchronize()
-        out[(mode, split)] = (Y, losses, ft.E0.clone())
-    ref = out[("0", "0")]
-    for key in (("1", "0"), ("1", "1")):
-        assert torch.equal(ref[0], out[key][0]) and float(ref[0].abs().sum()) > 0
-        assert all(torch.equal(a, b) for a, b in zip(ref[1], out[key][1]))
-        assert torch.equal(ref[2], out[key][2])
