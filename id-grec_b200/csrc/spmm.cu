@@ -74,11 +74,6 @@ struct SpmmArgs {
     // the clean row to Y and row + sign(row) * normalize(noise_v) * eps to view_Y[v] (SimGCL.py:47-51 for each view)
     const float* view_noise[2];
     float* view_Y[2];
-    // column-blocked passes (BLK kernels): pass `block` of n_blocks covers, of every work item, the nonzeros whose column lies in
-    // the pass's column range; blk[item * (n_blocks - 1) + j] = first nonzero of the item at or beyond boundary j
-    const int* blk;
-    float* carry;  // [n_rows, d]: running sums of the whole rows between passes (chunks of heavy rows use their partials slot)
-    int block, n_blocks;
 };
 
 }  // namespace idg
@@ -89,9 +84,6 @@ struct idg_graph {
     int32_t n_rows = 0, n_cols = 0, row_offset = 0;
     int64_t nnz = 0;
     int n_items = 0, n_heavy = 0, n_parts = 0, n_classes = 1;
-    int n_blocks = 1;       // > 1: column-blocked passes available (blk, carry)
-    int* blk = nullptr;
-    float* carry = nullptr;
     int2* colval = nullptr;
     int4* items = nullptr;
     int2* row_items = nullptr;  // per local row: {first item, item count}
@@ -101,6 +93,16 @@ struct idg_graph {
 };
 
 namespace idg {
+
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    // embedding gathers have ~no L1 reuse (ncu: 2.5% hit rate): keep L1 for the (col,val) stream
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <bool NA>
+__device__ __forceinline__ float4 gat(const float* p) { return NA ? ldg4_stream(p) : ldg4(p); }
 
 template <int LPR, bool ADAM>
 __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub, unsigned gmask, float4 y) {
@@ -187,7 +189,7 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int grow, int sub,
 // One lane group (LPR lanes = one 4*LPR-float row per 128-bit load) per work item; a warp carries
 // 32/LPR items of adjacent (hence similar) length.  Per nonzero: one broadcast 8-byte (col,val)
 // load (L1-resident: 16 nonzeros per line), one 128-bit gather per lane, four FFMA.
-template <int LPR, int UNROLL = kUnroll, bool BLK = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
+template <int LPR, int UNROLL = kUnroll, bool NA = false, int MINB = 1, bool SPARSE = false, bool ADAM = false, bool ROWMASK = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const SpmmArgs a) {
     constexpr int kU = UNROLL;
     constexpr int d = 4 * LPR;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     }
     const float* __restrict__ X = a.X + sub * 4;
     const int2* __restrict__ cvp = a.colval;
-    if (ADAM && (!BLK || a.block == a.n_blocks - 1) && (sub & 7) == 0) {
+    if (ADAM && (sub & 7) == 0) {
         // the epilogue reads this row of p / m / v from HBM: start those lines towards L2 now, under the gather loop
         const size_t poff = (size_t)(a.row_offset + ((it.w < 0) ? it.x : a.heavy[it.x].row)) * d + sub * 4;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.adam_p + poff));
@@ -220,19 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
 
     float4 acc = f4zero();
     int k = it.y;
-    int end = it.z;
-    if (BLK) {
-        // Column-blocked pass: a row's columns ascend, so the passes continue ONE sequential sum -- accumulator in, same FMAs in the
-        // same order, accumulator out -- and the result has the bits of the single-pass kernel.  Between passes the sum of a whole
-        // row lives in carry[row], that of a heavy row's chunk in the chunk's partials slot.
-        const int nb1 = a.n_blocks - 1;
-        const int* bp = a.blk + (size_t)item * nb1;
-        if (a.block > 0) k = __ldg(bp + a.block - 1);
-        if (a.block < nb1) end = __ldg(bp + a.block);
-        if (a.block != nb1 && k >= end) return;  // no nonzero in this column range: the carried sum (if any) stays as it is
-        if (k > it.y)  // earlier passes contributed
-            acc = ldcg4(((it.w < 0) ? a.carry + (size_t)it.x * d : a.partials + (size_t)it.w * d) + sub * 4);
-    }
+    const int end = it.z;
     if (SPARSE) {
         // X is zero outside the rows flagged in the bitmap (first backward layer: dL/dF touches only
         // the batch rows): stream the (col,val) list, gather only flagged columns, same ascending order.
@@ -274,7 +264,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
         for (; k + kU <= end; k += kU) {
             float4 x[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) x[u] = ldg4(X + (size_t)cv[u].x * d);
+            for (int u = 0; u < kU; ++u) x[u] = gat<NA>(X + (size_t)cv[u].x * d);
             float w[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) w[u] = __int_as_float(cv[u].y);
@@ -288,13 +278,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB) spmm_kernel(const Spm
     }
     for (; k < end; ++k) {
         const int2 c = __ldg(cvp + k);
-        acc = f4fma(__int_as_float(c.y), ldg4(X + (size_t)c.x * d), acc);
+        acc = f4fma(__int_as_float(c.y), gat<NA>(X + (size_t)c.x * d), acc);
     }
 
-    if (BLK && a.block != a.n_blocks - 1) {
-        stcg4(((it.w < 0) ? a.carry + (size_t)it.x * d : a.partials + (size_t)it.w * d) + sub * 4, acc);
-        return;
-    }
     if (it.w < 0) {
         if (SPARSE && a.skip_zero_rows) {
             // first backward product: most rows have no batch neighbour and a zero addend -> nothing to publish
@@ -334,21 +320,6 @@ __global__ void row_first_last_kernel(const int32_t* __restrict__ indptr, const 
     const int s = indptr[r], e = indptr[r + 1];
     out[r] = (e > s) ? make_int2(indices[s], indices[e - 1]) : make_int2(-1, -1);
 }
-// column-blocked passes: per work item, the first nonzero at or beyond each column boundary (binary search in the ascending columns)
-__global__ void item_block_bounds_kernel(const int4* __restrict__ items, int n_items, const int32_t* __restrict__ indices, int first_boundary,
-                                         int cols_per_block, int nb1, int* __restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)n_items * nb1) return;
-    const int item = (int)(t / nb1), j = (int)(t % nb1);
-    const int4 it = items[item];
-    const int bound = first_boundary + j * cols_per_block;
-    int lo = it.y, hi = it.z;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (indices[mid] < bound) lo = mid + 1; else hi = mid;
-    }
-    out[t] = lo;
-}
 }  // namespace idg
 
 using namespace idg;
@@ -363,14 +334,11 @@ using namespace idg;
 static const int64_t kClassSplitBytes = 100ll << 20;
 
 static int classify_rows(const int32_t* d_indptr, const int32_t* d_indices, int32_t n_rows, int32_t n_cols, int64_t nnz, int32_t row_offset,
-                         cudaStream_t stream, std::vector<unsigned char>& cls, bool* split, int* min_col, int* max_col) {
+                         cudaStream_t stream, std::vector<unsigned char>& cls, bool* split) {
     *split = false;
-    *min_col = 0; *max_col = n_cols - 1;
     const char* env = getenv("IDG_SPMM_CLASS_SPLIT");
     const int mode = env ? atoi(env) : -1;
-    const bool want_blocks = getenv("IDG_SPMM_BLOCKS") && atoi(getenv("IDG_SPMM_BLOCKS")) != 0;
-    const bool want_split = !(mode == 0 || (mode != 1 && (int64_t)n_cols * 256 <= kClassSplitBytes));
-    if (nnz == 0 || n_rows == 0 || (!want_split && !want_blocks)) return 0;
+    if (nnz == 0 || n_rows == 0 || mode == 0 || (mode != 1 && (int64_t)n_cols * 256 <= kClassSplitBytes)) return 0;
     int2* d_fl = nullptr;
     IDG_CUDA(cudaMalloc(&d_fl, sizeof(int2) * (size_t)n_rows));
     row_first_last_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(d_indptr, d_indices, n_rows, d_fl);
@@ -380,11 +348,6 @@ static int classify_rows(const int32_t* d_indptr, const int32_t* d_indices, int3
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(d_fl);
     if (e != cudaSuccess) return cuda_fail(e, "classify_rows");
-    int mn = n_cols, mx = -1;
-    for (int r = 0; r < n_rows; ++r)
-        if (fl[r].x >= 0) { mn = std::min(mn, fl[r].x); mx = std::max(mx, fl[r].y); }
-    if (mx >= mn) { *min_col = mn; *max_col = mx; }
-    if (!want_split) return 0;
     cls.assign((size_t)n_rows, 0);
     size_t n_upper = 0, n_lower = 0;
     unsigned char last = 0;
@@ -415,8 +378,7 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
 
     std::vector<unsigned char> cls;
     bool split = false;
-    int min_col = 0, max_col = n_cols - 1;
-    if (int rc = classify_rows(d_indptr, d_indices, n_rows, n_cols, nnz, row_offset, stream, cls, &split, &min_col, &max_col)) { delete g; return rc; }
+    if (int rc = classify_rows(d_indptr, d_indices, n_rows, n_cols, nnz, row_offset, stream, cls, &split)) { delete g; return rc; }
     const int n_cls = split ? 2 : 1;
 
     // per class: chunks of heavy rows first (contiguous per row), then whole rows longest-first (stable => deterministic);
@@ -472,24 +434,6 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
         g_launches.fetch_add(1);
         G_CUDA(cudaGetLastError());
     }
-    // Column-blocked passes (IDG_SPMM_BLOCKS != 0; IDG_SPMM_BLOCK_MB = megabytes of 256-byte table rows per pass, default 64): the
-    // gathers of one pass stay inside a slice of the table that fits the L2
-    if (nnz && g->n_items && getenv("IDG_SPMM_BLOCKS") && atoi(getenv("IDG_SPMM_BLOCKS")) != 0) {
-        const double mb = getenv("IDG_SPMM_BLOCK_MB") ? atof(getenv("IDG_SPMM_BLOCK_MB")) : 64.0;
-        const int64_t range = (int64_t)max_col - min_col + 1;
-        int64_t per = std::max<int64_t>(1, (int64_t)(mb * 1048576.0 / 256.0));
-        int nb = (int)std::min<int64_t>(16, (range + per - 1) / per);
-        if (nb > 1) {
-            per = (range + nb - 1) / nb;
-            G_CUDA(cudaMalloc(&g->blk, sizeof(int) * (size_t)g->n_items * (nb - 1)));
-            G_CUDA(cudaMalloc(&g->carry, sizeof(float) * 64 * (size_t)std::max(n_rows, 1)));
-            const int64_t total = (int64_t)g->n_items * (nb - 1);
-            item_block_bounds_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g->items, g->n_items, d_indices, min_col + (int)per, (int)per, nb - 1, g->blk);
-            g_launches.fetch_add(1);
-            G_CUDA(cudaGetLastError());
-            g->n_blocks = nb;
-        }
-    }
     G_CUDA(cudaStreamSynchronize(stream));
 #undef G_CUDA
     *out = g;
@@ -498,7 +442,7 @@ extern "C" int idg_graph_create(const int32_t* d_indptr, const int32_t* d_indice
 
 extern "C" void idg_graph_destroy(idg_graph* g) {
     if (!g) return;
-    cudaFree(g->colval); cudaFree(g->items); cudaFree(g->row_items); cudaFree(g->heavy); cudaFree(g->partials); cudaFree(g->counters); cudaFree(g->blk); cudaFree(g->carry);
+    cudaFree(g->colval); cudaFree(g->items); cudaFree(g->row_items); cudaFree(g->heavy); cudaFree(g->partials); cudaFree(g->counters);
     delete g;
 }
 extern "C" int idg_graph_set_peers(idg_graph* g, const idg_peers* p) {
@@ -509,7 +453,6 @@ extern "C" int idg_graph_set_peers(idg_graph* g, const idg_peers* p) {
 extern "C" int64_t idg_graph_nnz(const idg_graph* g) { return g ? g->nnz : -1; }
 extern "C" int32_t idg_graph_rows(const idg_graph* g) { return g ? g->n_rows : -1; }
 extern "C" int32_t idg_graph_classes(const idg_graph* g) { return g ? g->n_classes : -1; }
-extern "C" int32_t idg_graph_blocks(const idg_graph* g) { return g ? g->n_blocks : -1; }
 
 struct SpmmExtra {
     const float* acc_in2 = nullptr;
@@ -525,49 +468,6 @@ struct SpmmExtra {
     int skip_zero_rows = 0;
     const idg_adam_args* adam = nullptr;  // Adam-fused epilogue (last backward layer)
 };
-
-// kernel variant for one launch; BLK = one pass of the column-blocked form (a.block of a.n_blocks)
-template <bool BLK>
-static int spmm_dispatch(const idg_graph* g, const SpmmArgs& a, const SpmmExtra& ex, int32_t d, unsigned grid, int T, cudaStream_t stream) {
-    // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
-    // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
-    if (ex.adam) {
-        if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
-        // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step
-        // ... at the amazon-book shape.  With a gather table beyond the L2 (XL shape) the layer is bound by HBM latency and the
-        // 64 resident warps of the 32-register build win (IDG_SPMM_ADAM8 = 0 | 1 overrides the size rule)
-        const char* a8 = getenv("IDG_SPMM_ADAM8");
-        const bool adam8 = d == 64 && (a8 ? atoi(a8) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
-        if (adam8) spmm_kernel<16, 2, BLK, 8, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 64) spmm_kernel<16, 2, BLK, 6, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, BLK, 6, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, BLK, 6, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.bitmap && ex.rowmask) {
-        // sparse-input product restricted to the rows that can come out non-zero (batch rows + their neighbours): the other
-        // rows would stream their whole (col, val) list only to find no flagged column
-        if (d == 64) spmm_kernel<16, 2, BLK, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, BLK, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, BLK, 8, true, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.bitmap) {
-        if (d == 64) spmm_kernel<16, 2, BLK, 8, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, BLK, 8, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, BLK, 8, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.rowmask) {
-        if (d == 64) spmm_kernel<16, 2, BLK, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, BLK, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, BLK, 8, false, false, true><<<grid, T, 0, stream>>>(a);
-    } else if (ex.worklist) {
-        // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
-        if (d == 64) spmm_kernel<16, 8, BLK, 1><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 8, BLK, 1><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 8, BLK, 1><<<grid, T, 0, stream>>>(a);
-    } else {
-        if (d == 64) spmm_kernel<16, 2, BLK, 8><<<grid, T, 0, stream>>>(a);
-        else if (d == 32) spmm_kernel<8, 2, BLK, 8><<<grid, T, 0, stream>>>(a);
-        else spmm_kernel<32, 2, BLK, 8><<<grid, T, 0, stream>>>(a);
-    }
-    return 0;
-}
 
 static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const float* d_addend, const float* d_addend2,
                        float scale2, const float* d_noise, float eps, const float* d_acc_in, float* d_acc_out, float acc_div,
@@ -629,18 +529,43 @@ static int spmm_launch(const idg_graph* g, const float* d_X, float* d_Y, const f
     const unsigned grid = (unsigned)((n_slots + per_cta - 1) / per_cta);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int T = warps_per_cta * 32;
-    // column-blocked passes: d = 64 layers over all rows of a handle that holds block bounds (IDG_SPMM_BLOCKS at idg_graph_create)
-    a.blk = g->blk; a.carry = g->carry; a.block = 0; a.n_blocks = 1;
-    if (g->n_blocks > 1 && d == 64 && !ex.worklist) {
-        a.n_blocks = g->n_blocks;
-        for (int c = 0; c < g->n_blocks; ++c) {
-            a.block = c;
-            if (int rc = spmm_dispatch<true>(g, a, ex, d, grid, T, stream)) return rc;
-            IDG_LAUNCH_CHECK("spmm_kernel");
-        }
-        return 0;
+    // tuned on B200 (amazon-book shape): 2 gathers in flight per lane at full occupancy (<= 32 registers,
+    // 64 warps/SM) beats deeper unrolling at lower occupancy; L1-allocating gathers beat .L1::no_allocate.
+    if (ex.adam) {
+        if (ex.bitmap) return fail(-1, "idg_spmm_layer_adam: the Adam-fused layer cannot be the sparse-input one (K >= 2)%s");
+        // 6 resident CTAs (40 registers): forcing 32 registers for 8 CTAs spills in the epilogue and measured 1.7 % slower per step
+        // ... at the amazon-book shape.  With a gather table beyond the L2 (XL shape) the layer is bound by HBM latency and the
+        // 64 resident warps of the 32-register build win (IDG_SPMM_ADAM8 = 0 | 1 overrides the size rule)
+        const char* a8 = getenv("IDG_SPMM_ADAM8");
+        const bool adam8 = d == 64 && (a8 ? atoi(a8) != 0 : (int64_t)g->n_cols * d * 4 > kClassSplitBytes);
+        if (adam8) spmm_kernel<16, 2, false, 8, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 64) spmm_kernel<16, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 6, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap && ex.rowmask) {
+        // sparse-input product restricted to the rows that can come out non-zero (batch rows + their neighbours): the other
+        // rows would stream their whole (col, val) list only to find no flagged column
+        if (d == 64) spmm_kernel<16, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.bitmap) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.rowmask) {
+        if (d == 64) spmm_kernel<16, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8, false, false, true><<<grid, T, 0, stream>>>(a);
+    } else if (ex.worklist) {
+        // row-restricted launch: a few thousand rows, latency-bound per row -> deep unrolling instead of occupancy
+        if (d == 64) spmm_kernel<16, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 8, false, 1><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 8, false, 1><<<grid, T, 0, stream>>>(a);
+    } else {
+        if (d == 64) spmm_kernel<16, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else if (d == 32) spmm_kernel<8, 2, false, 8><<<grid, T, 0, stream>>>(a);
+        else spmm_kernel<32, 2, false, 8><<<grid, T, 0, stream>>>(a);
     }
-    if (int rc = spmm_dispatch<false>(g, a, ex, d, grid, T, stream)) return rc;
     IDG_LAUNCH_CHECK("spmm_kernel");
     return 0;
 }

@@ -69,7 +69,6 @@ SIGNATURES = {
     "idg_graph_nnz": (_i64, [_p]),
     "idg_graph_rows": (_i32, [_p]),
     "idg_graph_classes": (_i32, [_p]),
-    "idg_graph_blocks": (_i32, [_p]),
     "idg_spmm_layer": (C.c_int, [_p, _p, _p, _p, _p, _f32, _p, _p, _f32, _i32, _p]),
     "idg_propagate_fwd": (C.c_int, [_p, _p, _i32, _i32, C.c_int, _p, _f32, _i32, _p, _p, _p, _p]),
     "idg_propagate_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_int, _i32, _p, _p, _p]),

@@ -94,10 +94,6 @@ int32_t idg_graph_rows(const idg_graph* g);
  * gather from below" (bipartite adjacency whose gather table exceeds the L2: user rows, then item rows), else 1.  Scheduling
  * only -- results are bit-identical (IDG_SPMM_CLASS_SPLIT = 0 | 1 overrides the size rule). */
 int32_t idg_graph_classes(const idg_graph* g);
-/* number of column-blocked passes a d = 64 layer of this handle runs (1 = single pass).  IDG_SPMM_BLOCKS != 0 at
- * idg_graph_create splits the columns into ranges of IDG_SPMM_BLOCK_MB (default 64) megabytes of 256-byte table rows; the
- * accumulators are carried through memory between passes in the single-pass order -- results are bit-identical. */
-int32_t idg_graph_blocks(const idg_graph* g);
 
 /* ---- a6/a7/a11: one propagation layer = torch.sparse.mm(self.Graph, X) -----
  * (models/LightGCN.py:44, SimGCL.py:48, XSimGCL.py:51, NGCF.py:85) with the

@@ -723,49 +723,3 @@ def test_class_split_schedule_is_bit_identical(dev, monkeypatch, closure):
         assert torch.equal(la, lb), (step, la, lb)
     assert torch.equal(a.E0, b.E0)
 
-
-
-@pytest.mark.parametrize("closure", [False, True])
-def test_column_blocked_passes_are_bit_identical(dev, monkeypatch, closure):
-    """IDG_SPMM_BLOCKS: a layer runs as several passes, each over the nonzeros of one column range, the accumulators carried through
-    memory in between (csrc/spmm.cu, BLK kernels).  A row's columns ascend, so the passes continue one sequential sum: same bits as
-    the single pass -- plain layer, and every layer variant of the fused step (sparse-input, row-masked, closure-column, Adam-fused;
-    heavy rows carry per chunk in their partials slot), single-GPU trainer and row-partitioned trainer with one partition."""
-    from idgrec import datagen
-    from idgrec.dist import DistFusedTrainer
-    from idgrec.engine import FusedTrainer
-    from idgrec.graph import Graph, build_norm_adjacency
-    g = datagen.gen_graph("small")
-    U, I = g.num_users, g.num_items
-    csr = build_norm_adjacency(g.train_user, g.train_item, U, I, device=dev)
-    gen = torch.Generator(device=dev).manual_seed(36)
-    X = (torch.rand(U + I, 64, generator=gen, device=dev) - 0.5) * 0.2
-    B = 64 if closure else 256
-    kw = dict(closure_restrict=True) if closure else {}
-    rng = np.random.default_rng(8)
-    batches = []
-    for step in range(3):
-        e = rng.integers(0, len(g.train_user), B)
-        batches.append(tuple(torch.from_numpy(t).to(dev) for t in (g.train_user[e], g.train_item[e], rng.integers(0, I, B))))
-    out = {}
-    for blocks, mb, split in (("0", "64", "0"), ("1", "0.08", "0"), ("1", "0.3", "1")):
-        monkeypatch.setenv("IDG_SPMM_BLOCKS", blocks)
-        monkeypatch.setenv("IDG_SPMM_BLOCK_MB", mb)          # 0.08 MB = 328 rows per pass -> the 16-pass cap; 0.3 MB -> 5 passes
-        monkeypatch.setenv("IDG_SPMM_CLASS_SPLIT", split)
-        G = Graph(csr)
-        from idgrec import _lib
-        assert _lib.lib().idg_graph_blocks(G._h) == {"64": 1, "0.08": 16, "0.3": 5}[mb]
-        Y = torch.empty_like(X)
-        G.spmm_layer(X, Y=Y)
-        ft = FusedTrainer("LightGCN", G, X.clone(), U, 3, 1e-4, 1e-3, max_batch=B, use_cuda_graph=(split == "1"), **kw)
-        dt = DistFusedTrainer("LightGCN", csr, X.clone(), U, 3, 1e-4, 1e-3, 0, 1, max_batch=B, use_cuda_graph=(split == "0"), **kw)
-        losses = [ft.step(*b).clone() for b in batches]
-        losses_d = [dt.step(*b).clone() for b in batches]
-        torch.cuda.synchronize()
-        out[(blocks, mb)] = (Y, losses, ft.E0.clone(), losses_d, dt.E0.clone())
-    ref = out[("0", "64")]
-    assert float(ref[0].abs().sum()) > 0
-    for key in (("1", "0.08"), ("1", "0.3")):
-        assert torch.equal(ref[0], out[key][0])
-        assert all(torch.equal(a, b) for a, b in zip(ref[1], out[key][1])) and all(torch.equal(a, b) for a, b in zip(ref[1], out[key][3]))
-        assert torch.equal(ref[2], out[key][2]) and torch.equal(ref[2], out[key][4])
