@@ -157,7 +157,10 @@ def run(rank, world, dev, users=1000000, items=1000000, edges=100000000, steps=2
                "nvlink_floor_ms_per_layer": recv / 770e6 if world > 1 else 0.0,
                "eval_users_total": int(nus.item()), "eval_ms": eval_ms, "eval_chunk_users": chunk, "eval_chunk_ms_rank0": chunk_ms, "eval_users_per_s_total": int(nus.item()) / eval_ms * 1e3,
                "gen_s": t_gen, "csr_build_s": t_csr, "bounds": ft.bounds, "cuda_graph": bool(use_graph), "breakdown_ms": phases,
-               "closure_restrict": ft.use_closure, "exchange": ("chunked x%d, %d push CTAs" % (len(ft.chunks), ft.push_ctas)) if ft.chunked else "fused epilogue stores", "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast}
+               "closure_restrict": ft.use_closure, "exchange": ("chunked x%d, %d push CTAs" % (len(ft.chunks), ft.push_ctas)) if ft.chunked else "fused epilogue stores", "slab_backend": ft.slab.backend, "multicast": ft.slab.multicast,
+               "one_gpu_schedule_note": "the one-GPU figure runs the class-split schedule of csrc/spmm.cu:classify_rows (all user rows, then all item rows: the L2 holds one "
+                                        "256 MB half of the table at a time; 18.9 -> 16.1 ms per step); a rank of a multi-GPU job holds (almost) one class already and gains nothing, "
+                                        "so speedup_vs_one_gpu is smaller than before that change (5.6x -> ~4.8x at 8 GPUs) although no step got slower"}
     del ft, F, full, csr, ws
     torch.cuda.empty_cache()
     return rec
